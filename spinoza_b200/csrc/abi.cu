@@ -1,0 +1,585 @@
+// abi.cu -- the C ABI of libspinoza_b200 (include/spinoza_b200.h): state management, the gate entry points
+// mirroring gates.rs:215-320, and QuantumCircuit::execute (circuit.rs:552-600) with the fusion scheduler.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "engine.h"
+
+namespace spz {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) in `%s` at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    if (e == cudaErrorMemoryAllocation) return SPZ_ERR_OOM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return SPZ_ERR_NO_DEVICE;
+    return SPZ_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int resolve_gate(int kind, const double *p, GateK *out) {
+    out->kind = kind;
+    for (double &v : out->s) v = 0.0;
+    switch (kind) {
+    case SPZ_GATE_H: case SPZ_GATE_X: case SPZ_GATE_Y: case SPZ_GATE_Z: return SPZ_OK;
+    case SPZ_GATE_P: { // p_apply gates.rs:865: sin_cos(angle)
+        out->s[0] = std::cos(p[0]); out->s[1] = std::sin(p[0]); return SPZ_OK; }
+    case SPZ_GATE_RX: { // rx_apply gates.rs:749-751: theta = angle*0.5; ct = cos; nst = -sin
+        const double th = p[0] * 0.5; out->s[0] = std::cos(th); out->s[1] = -std::sin(th); return SPZ_OK; }
+    case SPZ_GATE_RY: { // ry_apply gates.rs:1125-1126: (sin, cos) of angle*0.5
+        const double th = p[0] * 0.5; out->s[0] = std::sin(th); out->s[1] = std::cos(th); return SPZ_OK; }
+    case SPZ_GATE_RZ: { // rz_apply gates.rs:970-973: d0 = (c, -s), d1 = (c, s)
+        const double th = p[0] * 0.5; out->s[0] = std::cos(th); out->s[1] = std::sin(th); return SPZ_OK; }
+    case SPZ_GATE_U: { // u_apply gates.rs:1286-1304
+        const double st = std::sin(p[0] * 0.5), ct = std::cos(p[0] * 0.5);
+        const double sl = std::sin(p[2]), cl = std::cos(p[2]);
+        const double spl = std::sin(p[1] + p[2]), cpl = std::cos(p[1] + p[2]);
+        const double sp = std::sin(p[1]), cp = std::cos(p[1]);
+        out->s[0] = ct; out->s[1] = -cl * st; out->s[2] = -sl * st; out->s[3] = cp * st; out->s[4] = sp * st;
+        out->s[5] = cpl * ct; out->s[6] = spl * ct;
+        return SPZ_OK; }
+    default:
+        set_error("gate kind %d cannot be applied as a 2x2 pair update", kind);
+        return SPZ_ERR_UNSUPPORTED;
+    }
+}
+
+static inline uint64_t splitmix64(uint64_t *x) {
+    uint64_t z = (*x += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+static inline double next_u01(spz_state *st) { return (double)(splitmix64(&st->rng) >> 11) * (1.0 / 9007199254740992.0); }
+
+static int bind(const spz_state *st) {
+    SPZ_CUDA(cudaSetDevice(st->device));
+    return SPZ_OK;
+}
+
+#define SPZ_CHECK_STATE(st)                                              \
+    do {                                                                 \
+        if (!(st)) { ::spz::set_error("null state handle"); return SPZ_ERR_INVALID_ARG; } \
+        SPZ_TRY(::spz::bind(st));                                        \
+    } while (0)
+
+// ---- one op, unfused ---------------------------------------------------------------------------------
+static int apply_masked(spz_state *st, int kind, const double *p, uint64_t ctrl_mask, int target) {
+    GateK g;
+    SPZ_TRY(resolve_gate(kind, p, &g));
+    return launch_gate(st, g, ctrl_mask, target);
+}
+
+static int measure_impl(spz_state *st, int target, int reset, int forced_v, int *out_bit) {
+    if (target < 0 || target >= st->n) { set_error("target %d out of range", target); return SPZ_ERR_INVALID_ARG; }
+    if (forced_v > 1) { set_error("forced outcome must be 0, 1 or -1"); return SPZ_ERR_INVALID_ARG; } // assert measurement.rs:32
+    double prob0 = 0.0;
+    SPZ_TRY(reduce_scalar(st, 0, target, &prob0));
+    int val;
+    if (forced_v >= 0) val = forced_v;
+    else val = next_u01(st) < 1.0 - prob0 ? 1 : 0; // Binomial(1, 1 - prob0) measurement.rs:35-36
+    double k;
+    if (val == 0) k = 1.0 / std::sqrt(prob0);       // prob0.sqrt().recip() measurement.rs:40
+    else k = 1.0 / std::sqrt(1.0 - prob0);          // measurement.rs:63-64
+    SPZ_TRY(launch_collapse(st, target, val, reset, k));
+    if (out_bit) *out_bit = val;
+    return SPZ_OK;
+}
+
+// ---- fusion scheduler -----------------------------------------------------------------------------------
+struct ROp { // an op resolved to what the kernels need
+    int kind;
+    int target, t2;
+    uint64_t cmask;
+    GateK g;
+};
+
+struct Fuser {
+    spz_state *st;
+    int T;      // tile bits (<= n)
+    int Lmin;   // smallest contiguous run we accept (coalescing)
+    std::vector<ROp> ops;
+    uint64_t high_set = 0;
+    int low_need = 0;
+
+    Fuser(spz_state *s) : st(s) {
+        T = std::min(max_tile_bits(), s->n);
+        Lmin = std::min(6, T);
+    }
+    int n_high() const { return __builtin_popcountll(high_set); }
+
+    bool try_add_target(int q, uint64_t &hs, int &ln) const {
+        const int Lcur = T - __builtin_popcountll(hs);
+        if (q < Lcur) { ln = std::max(ln, q + 1); return true; }
+        if ((hs >> q) & 1ull) return true;
+        const int Lnew = Lcur - 1;
+        if (Lnew < std::max(ln, Lmin) || __builtin_popcountll(hs) + 1 > 8) return false;
+        hs |= 1ull << q;
+        return true;
+    }
+
+    bool fits(const ROp &op, uint64_t &hs, int &ln) const {
+        hs = high_set; ln = low_need;
+        // low_need records every target accepted as a low tile bit, so L can never shrink below it
+        if (op.kind == SPZ_GATE_SWAP) return try_add_target(op.target, hs, ln) && try_add_target(op.t2, hs, ln);
+        if (is_diagonal_kind(op.kind)) return true;
+        return try_add_target(op.target, hs, ln);
+    }
+
+    int flush() {
+        if (ops.empty()) return SPZ_OK;
+        int rc = SPZ_OK;
+        if (ops.size() == 1 && ops[0].kind != SPZ_GATE_SWAP) {
+            rc = launch_gate(st, ops[0].g, ops[0].cmask, ops[0].target);
+        } else if (ops.size() == 1) {
+            rc = launch_swap(st, ops[0].target, ops[0].t2);
+        } else {
+            TilePlan plan{};
+            plan.n_high = n_high();
+            plan.tile_bits = T;
+            plan.low_bits = T - plan.n_high;
+            int k = 0;
+            for (int q = 0; q < 64; ++q) if ((high_set >> q) & 1ull) plan.high[k++] = q;
+            auto tile_bit = [&](int q) -> int {
+                if (q < plan.low_bits) return q;
+                for (int i = 0; i < plan.n_high; ++i) if (plan.high[i] == q) return plan.low_bits + i;
+                return -1;
+            };
+            std::vector<TileOp> tops(ops.size());
+            for (size_t i = 0; i < ops.size(); ++i) {
+                const ROp &o = ops[i];
+                TileOp &t = tops[i];
+                std::memset(&t, 0, sizeof t);
+                t.kind = o.kind;
+                t.tbit = tile_bit(o.target);
+                t.tbit2 = o.kind == SPZ_GATE_SWAP ? tile_bit(o.t2) : -1;
+                t.outer_target = t.tbit < 0 ? o.target : -1;
+                for (int q = 0; q < st->n; ++q) {
+                    if (!((o.cmask >> q) & 1ull)) continue;
+                    const int b = tile_bit(q);
+                    if (b >= 0) t.inner_cmask |= 1u << b; else t.outer_cmask |= 1ull << q;
+                }
+                for (int j = 0; j < 7; ++j) t.s[j] = o.g.s[j];
+                if (t.tbit < 0 && !is_diagonal_kind(o.kind)) { set_error("internal: non-diagonal op left outside its tile"); return SPZ_ERR_INVALID_ARG; }
+                if (o.kind == SPZ_GATE_SWAP && t.tbit2 < 0) { set_error("internal: swap operand left outside its tile"); return SPZ_ERR_INVALID_ARG; }
+            }
+            rc = launch_tile_group(st, plan, tops.data(), (int)tops.size());
+        }
+        ops.clear();
+        high_set = 0;
+        low_need = 0;
+        return rc;
+    }
+
+    int add(const ROp &op) {
+        uint64_t hs; int ln;
+        if (!fits(op, hs, ln) || ops.size() >= 8192) {
+            SPZ_TRY(flush());
+            if (!fits(op, hs, ln)) { set_error("internal: op does not fit an empty tile"); return SPZ_ERR_INVALID_ARG; }
+        }
+        high_set = hs; low_need = ln;
+        ops.push_back(op);
+        return SPZ_OK;
+    }
+};
+
+} // namespace spz
+
+using namespace spz;
+
+extern "C" {
+
+int spz_abi_version(void) { return SPZ_ABI_VERSION; }
+const char *spz_last_error(void) { return g_err; }
+
+const char *spz_status_string(int status) {
+    switch (status) {
+    case SPZ_OK: return "ok";
+    case SPZ_ERR_INVALID_ARG: return "invalid argument";
+    case SPZ_ERR_UNSUPPORTED: return "unsupported gate/control combination";
+    case SPZ_ERR_CUDA: return "CUDA error";
+    case SPZ_ERR_OOM: return "out of device memory";
+    case SPZ_ERR_COMM: return "communication error";
+    case SPZ_ERR_NO_DEVICE: return "no CUDA device";
+    default: return "unknown status";
+    }
+}
+
+int spz_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+
+int spz_device_name(int device, char *buf, int buflen) {
+    cudaDeviceProp prop;
+    SPZ_CUDA(cudaGetDeviceProperties(&prop, device));
+    snprintf(buf, (size_t)buflen, "%s (sm_%d%d, %d SMs)", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+    return SPZ_OK;
+}
+
+int spz_mem_info(int device, uint64_t *free_bytes, uint64_t *total_bytes) {
+    SPZ_CUDA(cudaSetDevice(device));
+    size_t f = 0, t = 0;
+    SPZ_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return SPZ_OK;
+}
+
+int spz_create(int n_qubits, int device, spz_state **out) {
+    if (!out) { set_error("null out pointer"); return SPZ_ERR_INVALID_ARG; }
+    *out = nullptr;
+    if (n_qubits < 1 || n_qubits > 40) { set_error("n_qubits must be in 1..40 (assert!(n > 0) core.rs:33)"); return SPZ_ERR_INVALID_ARG; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device visible: libspinoza_b200 has no CPU fallback");
+        return SPZ_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) { set_error("device %d out of range (%d visible)", device, count); return SPZ_ERR_INVALID_ARG; }
+    SPZ_CUDA(cudaSetDevice(device));
+    spz_state *st = new (std::nothrow) spz_state();
+    if (!st) return SPZ_ERR_OOM;
+    st->n = n_qubits;
+    st->device = device;
+    st->len = (int64_t)1 << n_qubits;
+    const size_t bytes = sizeof(double) * (size_t)st->len;
+    auto fail = [&](cudaError_t err, const char *what) {
+        int rc = cuda_fail(err, what, __FILE__, __LINE__);
+        spz_destroy(st);
+        return rc;
+    };
+    if ((e = cudaMalloc(&st->re, bytes)) != cudaSuccess) return fail(e, "cudaMalloc(re)");
+    if ((e = cudaMalloc(&st->im, bytes)) != cudaSuccess) return fail(e, "cudaMalloc(im)");
+    if ((e = cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreate(&st->ev0)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&st->ev1)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    int rc = launch_fill_basis(st, 0);
+    if (rc != SPZ_OK) { spz_destroy(st); return rc; }
+    *out = st;
+    return SPZ_OK;
+}
+
+int spz_destroy(spz_state *st) {
+    if (!st) return SPZ_OK;
+    cudaSetDevice(st->device);
+    if (st->stream) cudaStreamSynchronize(st->stream);
+    cudaFree(st->re);
+    cudaFree(st->im);
+    cudaFree(st->scratch.partials);
+    if (st->scratch.h_result) cudaFreeHost(st->scratch.h_result);
+    cudaFree(st->d_ops);
+    if (st->ev0) cudaEventDestroy(st->ev0);
+    if (st->ev1) cudaEventDestroy(st->ev1);
+    if (st->stream) cudaStreamDestroy(st->stream);
+    cudaGetLastError();
+    delete st;
+    return SPZ_OK;
+}
+
+int spz_clone(const spz_state *src, spz_state **out) {
+    if (!src || !out) { set_error("null argument"); return SPZ_ERR_INVALID_ARG; }
+    SPZ_TRY(spz_create(src->n, src->device, out));
+    spz_state *dst = *out;
+    const size_t bytes = sizeof(double) * (size_t)src->len;
+    SPZ_CUDA(cudaStreamSynchronize(src->stream));
+    SPZ_CUDA(cudaMemcpyAsync(dst->re, src->re, bytes, cudaMemcpyDeviceToDevice, dst->stream));
+    SPZ_CUDA(cudaMemcpyAsync(dst->im, src->im, bytes, cudaMemcpyDeviceToDevice, dst->stream));
+    SPZ_CUDA(cudaStreamSynchronize(dst->stream));
+    dst->rng = src->rng;
+    return SPZ_OK;
+}
+
+int spz_num_qubits(const spz_state *st) { return st ? st->n : -1; }
+int64_t spz_len(const spz_state *st) { return st ? st->len : -1; }
+
+int spz_reset_zero(spz_state *st) { SPZ_CHECK_STATE(st); return launch_fill_basis(st, 0); }
+int spz_set_basis(spz_state *st, uint64_t index) { SPZ_CHECK_STATE(st); return launch_fill_basis(st, index); }
+int spz_init_random(spz_state *st, uint64_t seed) { SPZ_CHECK_STATE(st); return launch_init_random(st, seed); }
+int spz_set_seed(spz_state *st, uint64_t seed) { if (!st) return SPZ_ERR_INVALID_ARG; st->rng = seed; return SPZ_OK; }
+
+int spz_upload(spz_state *st, const double *re, const double *im, int64_t offset, int64_t count) {
+    SPZ_CHECK_STATE(st);
+    if (offset < 0 || count < 0 || offset + count > st->len) { set_error("upload range [%lld, +%lld) outside the state", (long long)offset, (long long)count); return SPZ_ERR_INVALID_ARG; }
+    const size_t bytes = sizeof(double) * (size_t)count;
+    if (re) SPZ_CUDA(cudaMemcpyAsync(st->re + offset, re, bytes, cudaMemcpyHostToDevice, st->stream));
+    if (im) SPZ_CUDA(cudaMemcpyAsync(st->im + offset, im, bytes, cudaMemcpyHostToDevice, st->stream));
+    SPZ_CUDA(cudaStreamSynchronize(st->stream));
+    return SPZ_OK;
+}
+
+int spz_download(const spz_state *st, double *re, double *im, int64_t offset, int64_t count) {
+    SPZ_CHECK_STATE(st);
+    if (offset < 0 || count < 0 || offset + count > st->len) { set_error("download range [%lld, +%lld) outside the state", (long long)offset, (long long)count); return SPZ_ERR_INVALID_ARG; }
+    const size_t bytes = sizeof(double) * (size_t)count;
+    if (re) SPZ_CUDA(cudaMemcpyAsync(re, st->re + offset, bytes, cudaMemcpyDeviceToHost, st->stream));
+    if (im) SPZ_CUDA(cudaMemcpyAsync(im, st->im + offset, bytes, cudaMemcpyDeviceToHost, st->stream));
+    SPZ_CUDA(cudaStreamSynchronize(st->stream));
+    return SPZ_OK;
+}
+
+int spz_sync(spz_state *st) {
+    SPZ_CHECK_STATE(st);
+    SPZ_CUDA(cudaStreamSynchronize(st->stream));
+    return SPZ_OK;
+}
+
+int spz_alloc_host(uint64_t bytes, void **out) {
+    if (!out) return SPZ_ERR_INVALID_ARG;
+    *out = nullptr;
+    SPZ_CUDA(cudaMallocHost(out, (size_t)bytes));
+    return SPZ_OK;
+}
+
+int spz_free_host(void *ptr) {
+    if (ptr) SPZ_CUDA(cudaFreeHost(ptr));
+    return SPZ_OK;
+}
+
+// ---- gates ---------------------------------------------------------------------------------------------
+int spz_apply(spz_state *st, const spz_gate *gate, int target) {
+    SPZ_CHECK_STATE(st);
+    if (!gate) { set_error("null gate"); return SPZ_ERR_INVALID_ARG; }
+    switch (gate->kind) {
+    case SPZ_GATE_SWAP: return launch_swap(st, gate->t0, gate->t1); // gates.rs:225 (ignores `target`)
+    case SPZ_GATE_BITFLIP: { // bit_flip_noise_apply gates.rs:1365-1374
+        if (target < 0 || target >= st->n) { set_error("target %d out of range", target); return SPZ_ERR_INVALID_ARG; }
+        const double eps = next_u01(st);
+        if (eps <= gate->p[0]) return apply_masked(st, SPZ_GATE_X, nullptr, 0, target);
+        return SPZ_OK; }
+    case SPZ_GATE_M: case SPZ_GATE_UNITARY: // unimplemented!() gates.rs:230
+        set_error("apply: gate kind %d is not applicable here (reference: unimplemented!())", gate->kind);
+        return SPZ_ERR_UNSUPPORTED;
+    default: return apply_masked(st, gate->kind, gate->p, 0, target);
+    }
+}
+
+static int controlled_ok(const spz_gate *gate, const char *fn) {
+    if (!gate) { set_error("null gate"); return SPZ_ERR_INVALID_ARG; }
+    switch (gate->kind) {
+    case SPZ_GATE_M: case SPZ_GATE_SWAP: case SPZ_GATE_UNITARY: case SPZ_GATE_BITFLIP: // todo!() gates.rs:267,275,318
+        set_error("%s: gate kind %d has no controlled form (reference: todo!())", fn, gate->kind);
+        return SPZ_ERR_UNSUPPORTED;
+    default: return SPZ_OK;
+    }
+}
+
+int spz_c_apply(spz_state *st, const spz_gate *gate, int control, int target) {
+    SPZ_CHECK_STATE(st);
+    SPZ_TRY(controlled_ok(gate, "c_apply"));
+    if (control < 0 || control >= st->n || control == target) { set_error("bad control %d (target %d, %d qubits)", control, target, st->n); return SPZ_ERR_INVALID_ARG; }
+    return apply_masked(st, gate->kind, gate->p, 1ull << control, target);
+}
+
+int spz_cc_apply(spz_state *st, const spz_gate *gate, int c0, int c1, int target) {
+    SPZ_CHECK_STATE(st);
+    SPZ_TRY(controlled_ok(gate, "cc_apply"));
+    if (c0 < 0 || c1 < 0 || c0 >= st->n || c1 >= st->n || c0 == target || c1 == target) { set_error("bad controls (%d,%d)", c0, c1); return SPZ_ERR_INVALID_ARG; }
+    return apply_masked(st, gate->kind, gate->p, (1ull << c0) | (1ull << c1), target);
+}
+
+int spz_mc_apply_mask(spz_state *st, const spz_gate *gate, uint64_t ctrl_mask, int target) {
+    SPZ_CHECK_STATE(st);
+    SPZ_TRY(controlled_ok(gate, "mc_apply"));
+    return apply_masked(st, gate->kind, gate->p, ctrl_mask, target);
+}
+
+int spz_mc_apply(spz_state *st, const spz_gate *gate, const int32_t *controls, int n_controls, const int32_t *zeros,
+                 int n_zeros, int target) {
+    SPZ_CHECK_STATE(st);
+    SPZ_TRY(controlled_ok(gate, "mc_apply"));
+    if (n_controls < 0 || (n_controls && !controls) || !(st->n > n_controls)) { // debug_assert gates.rs:297
+        set_error("mc_apply needs n_qubits > n_controls"); return SPZ_ERR_INVALID_ARG;
+    }
+    uint64_t mask = 0; // gates.rs:298-311: controls listed in `zeros` are dropped from the mask
+    for (int i = 0; i < n_controls; ++i) {
+        const int c = controls[i];
+        if (c < 0 || c >= st->n || c == target) { set_error("bad control %d", c); return SPZ_ERR_INVALID_ARG; }
+        bool skip = false;
+        for (int j = 0; j < n_zeros; ++j) if (zeros && zeros[j] == c) skip = true;
+        if (!skip) mask |= 1ull << c;
+    }
+    return apply_masked(st, gate->kind, gate->p, mask, target);
+}
+
+int spz_iqft(spz_state *st, const int32_t *targets, int m) {
+    SPZ_CHECK_STATE(st);
+    if (m < 0 || (m && !targets)) return SPZ_ERR_INVALID_ARG;
+    // core.rs:184-191
+    for (int j = m - 1; j >= 0; --j) {
+        SPZ_TRY(apply_masked(st, SPZ_GATE_H, nullptr, 0, targets[j]));
+        for (int k = j - 1; k >= 0; --k) {
+            const double ang = -3.14159265358979323846 / std::ldexp(1.0, j - k);
+            if (targets[j] == targets[k] || targets[j] < 0 || targets[j] >= st->n) { set_error("bad iqft targets"); return SPZ_ERR_INVALID_ARG; }
+            SPZ_TRY(apply_masked(st, SPZ_GATE_P, &ang, 1ull << targets[j], targets[k]));
+        }
+    }
+    return SPZ_OK;
+}
+
+// ---- execute -------------------------------------------------------------------------------------------
+int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags, uint64_t *measured_mask,
+                uint64_t *measured_vals) {
+    SPZ_CHECK_STATE(st);
+    if (n_ops < 0 || (n_ops && !ops)) { set_error("bad op list"); return SPZ_ERR_INVALID_ARG; }
+    uint64_t local_m = 0, local_v = 0;
+    uint64_t *mm = measured_mask ? measured_mask : &local_m;
+    uint64_t *mv = measured_vals ? measured_vals : &local_v;
+    const bool fuse = (flags & SPZ_EXEC_FUSE) != 0;
+    Fuser fuser(st);
+
+    auto emit = [&](int kind, const double *p, uint64_t cmask, int target, int t2) -> int {
+        if (kind != SPZ_GATE_SWAP) {
+            if (target < 0 || target >= st->n) { set_error("target %d out of range", target); return SPZ_ERR_INVALID_ARG; }
+            if ((cmask >> target) & 1ull) { set_error("target %d is also a control", target); return SPZ_ERR_INVALID_ARG; }
+            if (st->n < 64 && (cmask >> st->n)) { set_error("control outside the register"); return SPZ_ERR_INVALID_ARG; }
+        } else if (target < 0 || t2 < 0 || target >= st->n || t2 >= st->n) {
+            set_error("swap operands out of range"); return SPZ_ERR_INVALID_ARG;
+        }
+        if (!fuse) {
+            if (kind == SPZ_GATE_SWAP) return launch_swap(st, target, t2);
+            return apply_masked(st, kind, p, cmask, target);
+        }
+        ROp r{};
+        r.kind = kind; r.target = target; r.t2 = t2; r.cmask = cmask;
+        if (kind == SPZ_GATE_SWAP) { if (target == t2) return SPZ_OK; r.g.kind = kind; }
+        else SPZ_TRY(resolve_gate(kind, p, &r.g));
+        return fuser.add(r);
+    };
+
+    for (int64_t i = 0; i < n_ops; ++i) {
+        const spz_op &op = ops[i];
+        const int kind = op.kind;
+        if (kind == SPZ_GATE_UNITARY) { // transform_u / c_transform_u (circuit.rs:555-558): dense fallback, out of scope
+            set_error("execute: dense Unitary gates are not supported by the B200 engine");
+            return SPZ_ERR_UNSUPPORTED;
+        }
+        if (op.ctrl_kind == SPZ_CTRL_NONE) {
+            if (kind == SPZ_GATE_M) { // circuit.rs:559-566
+                if (op.target < 0 || op.target >= st->n) { set_error("target %d out of range", op.target); return SPZ_ERR_INVALID_ARG; }
+                if (!((*mm >> op.target) & 1ull)) {
+                    SPZ_TRY(fuser.flush());
+                    int bit = 0;
+                    SPZ_TRY(measure_impl(st, op.target, 1, -1, &bit));
+                    *mm |= 1ull << op.target;
+                    *mv &= ~(1ull << op.target);
+                    *mv |= (uint64_t)bit << op.target;
+                }
+            } else if (kind == SPZ_GATE_BITFLIP) { // gates.rs:1365-1374
+                const double eps = next_u01(st);
+                if (eps <= op.p[0]) SPZ_TRY(emit(SPZ_GATE_X, nullptr, 0, op.target, 0));
+            } else if (kind == SPZ_GATE_SWAP) {
+                SPZ_TRY(emit(SPZ_GATE_SWAP, nullptr, 0, op.t0, op.t1)); // apply() ignores target for SWAP, gates.rs:225
+            } else { // circuit.rs:567-569
+                SPZ_TRY(emit(kind, op.p, 0, op.target, 0));
+            }
+            continue;
+        }
+        if (kind == SPZ_GATE_M || kind == SPZ_GATE_SWAP || kind == SPZ_GATE_BITFLIP) {
+            set_error("execute: gate kind %d has no controlled form (reference: todo!())", kind);
+            return SPZ_ERR_UNSUPPORTED;
+        }
+        if (op.ctrl_kind == SPZ_CTRL_SINGLE) { // circuit.rs:570-578
+            if (__builtin_popcountll(op.ctrl_mask) != 1) { set_error("Single control needs exactly one control bit"); return SPZ_ERR_INVALID_ARG; }
+            const int c = __builtin_ctzll(op.ctrl_mask);
+            if ((*mm >> c) & 1ull) {
+                if ((*mv >> c) & 1ull) SPZ_TRY(emit(kind, op.p, 0, op.target, 0)); // classical control
+            } else {
+                SPZ_TRY(emit(kind, op.p, op.ctrl_mask, op.target, 0));
+            }
+        } else if (op.ctrl_kind == SPZ_CTRL_ONES) { // circuit.rs:579-587 (X only in the reference)
+            SPZ_TRY(emit(kind, op.p, op.ctrl_mask, op.target, 0));
+        } else if (op.ctrl_kind == SPZ_CTRL_MIXED) { // circuit.rs:588-596 -> mc_apply drops the zeros (gates.rs:298-311)
+            SPZ_TRY(emit(kind, op.p, op.ctrl_mask & ~op.zeros_mask, op.target, 0));
+        } else {
+            set_error("bad ctrl_kind %d", op.ctrl_kind);
+            return SPZ_ERR_INVALID_ARG;
+        }
+    }
+    return fuser.flush();
+}
+
+// ---- reductions --------------------------------------------------------------------------------------------
+int spz_prob0(spz_state *st, int target, double *out) {
+    SPZ_CHECK_STATE(st);
+    if (!out) return SPZ_ERR_INVALID_ARG;
+    return reduce_scalar(st, 0, target, out);
+}
+
+int spz_norm2(spz_state *st, double *out) {
+    SPZ_CHECK_STATE(st);
+    if (!out) return SPZ_ERR_INVALID_ARG;
+    return reduce_scalar(st, 1, 0, out);
+}
+
+int spz_measure_qubit(spz_state *st, int target, int reset, int forced_v, int *out_bit) {
+    SPZ_CHECK_STATE(st);
+    return measure_impl(st, target, reset, forced_v, out_bit);
+}
+
+int spz_qubit_expectation_value(spz_state *st, int target, double *out) {
+    SPZ_CHECK_STATE(st);
+    if (!out) return SPZ_ERR_INVALID_ARG;
+    double p0 = 0.0;
+    SPZ_TRY(reduce_scalar(st, 0, target, &p0));
+    *out = 2.0 * p0 - 1.0; // core.rs:217-218
+    return SPZ_OK;
+}
+
+int spz_xyz_expectation_value(spz_state *st, char observable, const int32_t *targets, int n_targets, double *out) {
+    SPZ_CHECK_STATE(st);
+    int mode;
+    switch (observable) { // panic!("observable {observable} not supported") core.rs:223-225
+    case 'x': mode = 2; break;
+    case 'y': mode = 3; break;
+    case 'z': mode = 4; break;
+    default: set_error("observable %c not supported", observable); return SPZ_ERR_INVALID_ARG;
+    }
+    if (n_targets < 0 || (n_targets && (!targets || !out))) return SPZ_ERR_INVALID_ARG;
+    for (int i = 0; i < n_targets; ++i) SPZ_TRY(reduce_scalar(st, mode, targets[i], &out[i]));
+    return SPZ_OK;
+}
+
+int spz_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_index) {
+    SPZ_CHECK_STATE(st);
+    if (shots < 0 || (shots && (!u01 || !out_index))) return SPZ_ERR_INVALID_ARG;
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64_t layout");
+    return launch_sample(st, u01, shots, out_index);
+}
+
+// ---- instrumentation -----------------------------------------------------------------------------------------
+int spz_timer_start(spz_state *st) {
+    SPZ_CHECK_STATE(st);
+    SPZ_CUDA(cudaEventRecord(st->ev0, st->stream));
+    return SPZ_OK;
+}
+
+int spz_timer_stop(spz_state *st, double *out_ms) {
+    SPZ_CHECK_STATE(st);
+    SPZ_CUDA(cudaEventRecord(st->ev1, st->stream));
+    SPZ_CUDA(cudaEventSynchronize(st->ev1));
+    float ms = 0.f;
+    SPZ_CUDA(cudaEventElapsedTime(&ms, st->ev0, st->ev1));
+    if (out_ms) *out_ms = (double)ms;
+    return SPZ_OK;
+}
+
+int64_t spz_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+} // extern "C"

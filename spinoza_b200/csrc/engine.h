@@ -1,0 +1,108 @@
+// engine.h -- internal declarations shared by the CUDA translation units of libspinoza_b200.
+// Nothing here is part of the ABI (see include/spinoza_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spinoza_b200.h"
+
+namespace spz {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define SPZ_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return ::spz::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define SPZ_TRY(call)                   \
+    do {                                \
+        int rc__ = (call);              \
+        if (rc__ != SPZ_OK) return rc__; \
+    } while (0)
+
+void count_launch(int n = 1);
+
+// ---- gates resolved to scalars (host side) ----------------------------------------------------
+// Scalars are computed once on the host exactly as each reference *_apply does, so that the device
+// arithmetic can mirror the reference operation by operation:
+//   P  : s0=cos(theta) s1=sin(theta)                         gates.rs:865
+//   RX : s0=cos(theta/2) s1=-sin(theta/2)                    gates.rs:749-751
+//   RY : s0=sin(theta/2) s1=cos(theta/2)                     gates.rs:1125-1126
+//   RZ : s0=cos(theta/2) s1=sin(theta/2)  (d0=(c,-s) d1=(c,s)) gates.rs:970-973
+//   U  : s0..s6 = a,k,l,q,r,s,t                              gates.rs:1286-1304
+struct GateK {
+    int kind;
+    double s[7];
+};
+int resolve_gate(int kind, const double *p, GateK *out); // SPZ_ERR_UNSUPPORTED for M/SWAP/UNITARY/BITFLIP
+
+inline bool is_diagonal_kind(int kind) { return kind == SPZ_GATE_Z || kind == SPZ_GATE_P || kind == SPZ_GATE_RZ; }
+
+// ---- the state --------------------------------------------------------------------------------
+struct Scratch {
+    double *partials = nullptr; // device, reduction partials
+    size_t n_partials = 0;
+    double *h_result = nullptr; // pinned host, small
+};
+
+} // namespace spz
+
+struct spz_state {
+    int n = 0;           // total qubits of the register
+    int device = 0;
+    int64_t len = 0;     // amplitudes held by this handle (2^n single-GPU)
+    double *re = nullptr;
+    double *im = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    spz::Scratch scratch;
+    uint64_t rng = 0x853c49e6748fea9bULL; // splitmix64 state for M / BitFlipNoise draws
+    // fused-execute scratch
+    void *d_ops = nullptr;
+    size_t d_ops_bytes = 0;
+    size_t d_ops_cursor = 0;
+};
+
+namespace spz {
+
+// ---- kernel launchers (kernels_direct.cu) -------------------------------------------------------
+// Apply resolved gate g to `target` for every amplitude whose index has all bits of ctrl_mask set.
+int launch_gate(spz_state *st, const GateK &g, uint64_t ctrl_mask, int target);
+int launch_swap(spz_state *st, int t0, int t1);
+
+// ---- reductions and state utilities (kernels_reduce.cu) -----------------------------------------
+int ensure_scratch(spz_state *st);
+int launch_fill_basis(spz_state *st, uint64_t index);
+int launch_init_random(spz_state *st, uint64_t seed);
+// mode: 0 = sum |amp|^2 over amps with bit `target` clear (prob0); 1 = all amps (norm2; target ignored)
+// 2/3/4 = <X>/<Y>/<Z> on `target`
+int reduce_scalar(spz_state *st, int mode, int target, double *out);
+int launch_collapse(spz_state *st, int target, int outcome, int reset, double scale);
+int launch_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_index);
+
+// ---- fused execution (kernels_tile.cu) ------------------------------------------------------------
+struct TileOp {
+    int kind;            // spz_gate_kind (H X Y Z P RX RY RZ U) or SPZ_GATE_SWAP
+    int tbit;            // in-tile bit of the target, or -1 when the target is an outer (non-tile) qubit
+    int tbit2;           // SWAP: in-tile bit of the second operand
+    int outer_target;    // absolute qubit of an outer target (diagonal gates only), else -1
+    uint32_t inner_cmask; // control bits inside the tile (in-tile bit positions)
+    uint32_t pad;
+    uint64_t outer_cmask; // control bits outside the tile (absolute positions)
+    double s[7];
+};
+struct TilePlan {
+    int tile_bits;       // T
+    int low_bits;        // L: tile bits 0..L-1 are qubits 0..L-1
+    int n_high;          // tile bits L.. are qubits high[0..n_high)
+    int high[16];
+};
+int launch_tile_group(spz_state *st, const TilePlan &plan, const TileOp *ops, int n_ops);
+int max_tile_bits();
+
+} // namespace spz

@@ -1,0 +1,136 @@
+// kernels_direct.cu -- host-side dispatch of the one-gate-per-pass kernels (see kernels_direct.cuh).
+#include <algorithm>
+
+#include "kernels_direct.cuh"
+
+namespace spz {
+
+// Tuned on B200 with tools/bw_probe.cu (profiles/round1_bw_probe.md).
+#ifndef SPZ_W
+#define SPZ_W 4
+#endif
+#ifndef SPZ_U
+#define SPZ_U 2
+#endif
+#ifndef SPZ_THREADS
+#define SPZ_THREADS 256
+#endif
+#ifndef SPZ_POL
+#define SPZ_POL 0
+#endif
+
+constexpr int W = SPZ_W, U = SPZ_U, THREADS = SPZ_THREADS, POL = SPZ_POL;
+constexpr int LOGW = LogW<W>::v;
+
+template <int KIND, int NINS>
+static void launch_vec(const PairArgs &a, cudaStream_t s) {
+    const long long per_block = (long long)THREADS * U;
+    const unsigned grid = (unsigned)((a.nvec + per_block - 1) / per_block);
+    k_pair_vec<KIND, NINS, W, U, THREADS, POL><<<grid, THREADS, 0, s>>>(a);
+}
+template <int KIND, int NINS>
+static void launch_low(const PairArgs &a, cudaStream_t s) {
+    const long long per_block = (long long)THREADS * U;
+    const unsigned grid = (unsigned)((a.nvec + per_block - 1) / per_block);
+    k_pair_low<KIND, NINS, W, U, THREADS, POL><<<grid, THREADS, 0, s>>>(a);
+}
+
+template <int KIND>
+static void dispatch_kind(bool low, const PairArgs &a, cudaStream_t s) {
+    if (low) {
+        switch (a.nins) {
+        case 0: launch_low<KIND, 0>(a, s); break;
+        case 1: launch_low<KIND, 1>(a, s); break;
+        default: launch_low<KIND, -1>(a, s); break;
+        }
+    } else {
+        switch (a.nins) {
+        case 1: launch_vec<KIND, 1>(a, s); break;
+        case 2: launch_vec<KIND, 2>(a, s); break;
+        case 3: launch_vec<KIND, 3>(a, s); break;
+        default: launch_vec<KIND, -1>(a, s); break;
+        }
+    }
+}
+
+int launch_gate(spz_state *st, const GateK &g, uint64_t ctrl_mask, int target) {
+    const int n = st->n;
+    if (target < 0 || target >= n) { set_error("target %d out of range for %d qubits", target, n); return SPZ_ERR_INVALID_ARG; }
+    if ((ctrl_mask >> target) & 1ull) { set_error("target %d is also a control", target); return SPZ_ERR_INVALID_ARG; }
+    if (n < 64 && (ctrl_mask >> n)) { set_error("control mask 0x%llx exceeds %d qubits", (unsigned long long)ctrl_mask, n); return SPZ_ERR_INVALID_ARG; }
+
+    const uint64_t low_bits_mask = (1ull << LOGW) - 1ull;
+    const int n_ctrl = __builtin_popcountll(ctrl_mask);
+    const int n_ctrl_hi = __builtin_popcountll(ctrl_mask & ~low_bits_mask);
+    const bool low = target < LOGW;
+    const int nins_vec = n_ctrl_hi + (low ? 0 : 1);
+
+    if (n - LOGW - nins_vec >= 0 && nins_vec <= kMaxIns) {
+        PairArgs a{};
+        a.re = st->re; a.im = st->im;
+        a.nvec = 1ll << (n - LOGW - nins_vec);
+        a.setmask = ctrl_mask & ~low_bits_mask;
+        a.tbit = low ? 0ull : (1ull << target);
+        a.lane_cmask = (int)(ctrl_mask & low_bits_mask);
+        a.tlow = low ? target : 0;
+        int k = 0;
+        for (int q = LOGW; q < n; ++q)
+            if (((ctrl_mask >> q) & 1ull) || (!low && q == target)) a.pos[k++] = (unsigned char)q;
+        a.nins = k;
+        for (int i = 0; i < 7; ++i) a.s[i] = g.s[i];
+        switch (g.kind) {
+        case SPZ_GATE_H: dispatch_kind<SPZ_GATE_H>(low, a, st->stream); break;
+        case SPZ_GATE_X: dispatch_kind<SPZ_GATE_X>(low, a, st->stream); break;
+        case SPZ_GATE_Y: dispatch_kind<SPZ_GATE_Y>(low, a, st->stream); break;
+        case SPZ_GATE_Z: dispatch_kind<SPZ_GATE_Z>(low, a, st->stream); break;
+        case SPZ_GATE_P: dispatch_kind<SPZ_GATE_P>(low, a, st->stream); break;
+        case SPZ_GATE_RX: dispatch_kind<SPZ_GATE_RX>(low, a, st->stream); break;
+        case SPZ_GATE_RY: dispatch_kind<SPZ_GATE_RY>(low, a, st->stream); break;
+        case SPZ_GATE_RZ: dispatch_kind<SPZ_GATE_RZ>(low, a, st->stream); break;
+        case SPZ_GATE_U: dispatch_kind<SPZ_GATE_U>(low, a, st->stream); break;
+        default: set_error("gate kind %d has no pair kernel", g.kind); return SPZ_ERR_UNSUPPORTED;
+        }
+    } else {
+        if (n_ctrl + 1 > kMaxIns) { set_error("too many controls"); return SPZ_ERR_INVALID_ARG; }
+        ScalarArgs a{};
+        a.re = st->re; a.im = st->im;
+        a.npairs = 1ll << (n - 1 - n_ctrl);
+        a.setmask = ctrl_mask;
+        a.tbit = 1ull << target;
+        a.kind = g.kind;
+        int k = 0;
+        for (int q = 0; q < n; ++q)
+            if (((ctrl_mask >> q) & 1ull) || q == target) a.pos[k++] = (unsigned char)q;
+        a.nins = k;
+        for (int i = 0; i < 7; ++i) a.s[i] = g.s[i];
+        const unsigned grid = (unsigned)std::min<long long>((a.npairs + 255) / 256, 148 * 8);
+        k_pair_scalar<<<grid, 256, 0, st->stream>>>(a);
+    }
+    count_launch();
+    SPZ_CUDA(cudaGetLastError());
+    return SPZ_OK;
+}
+
+int launch_swap(spz_state *st, int t0, int t1) {
+    const int n = st->n;
+    // assert!(state.n > t0 && state.n > t1) gates.rs:1377
+    if (t0 < 0 || t1 < 0 || t0 >= n || t1 >= n) { set_error("swap operands (%d,%d) out of range for %d qubits", t0, t1, n); return SPZ_ERR_INVALID_ARG; }
+    if (t0 == t1) return SPZ_OK; // the reference's scan finds no index with bit t0 = 0 and bit t0 = 1
+    SwapArgs a{};
+    a.re = st->re; a.im = st->im;
+    a.lo = std::min(t0, t1); a.hi = std::max(t0, t1);
+    if (a.lo >= LOGW && n - 2 - LOGW >= 0) {
+        a.nvec = 1ll << (n - 2 - LOGW);
+        const unsigned grid = (unsigned)((a.nvec + THREADS - 1) / THREADS);
+        k_swap_vec<W, THREADS><<<grid, THREADS, 0, st->stream>>>(a);
+    } else {
+        a.nvec = 1ll << (n - 2);
+        const unsigned grid = (unsigned)std::min<long long>((a.nvec + 255) / 256, 148 * 16);
+        k_swap_scalar<<<grid, 256, 0, st->stream>>>(a);
+    }
+    count_launch();
+    SPZ_CUDA(cudaGetLastError());
+    return SPZ_OK;
+}
+
+} // namespace spz
