@@ -146,6 +146,40 @@ SPZ_API int spz_xyz_expectation_value(spz_state *st, char observable, const int3
    cdf(i) > u01[k] * norm2. */
 SPZ_API int spz_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_index);
 
+/* ---- multi-GPU: one process per GPU, amplitudes sharded by the top log2(world) index bits ------ */
+/* The reference has no distributed layer; this is the engine's own.  Every rank calls the
+   same sequence of spz_* functions on its handle (SPMD).  Local-qubit gates and all diagonal gates need no
+   communication; a non-diagonal gate on a global qubit first trades that qubit for a local one by a pairwise
+   half-shard exchange written directly into the partner's HBM through CUDA IPC peer pointers over NVLink. */
+typedef struct {
+    int32_t type;    /* 0 skip, 1 local gate, 2 diagonal constant factor, 3 exchange */
+    int32_t kind;    /* spz_gate_kind */
+    int32_t target;  /* type 1: local physical bit */
+    int32_t hi;      /* type 2: value of the (global) target bit on this rank */
+    uint64_t cmask;  /* types 1,2: local physical control mask */
+    int32_t gbit;    /* type 3: which bit of the rank is exchanged */
+    int32_t lq;      /* type 3: local physical bit it trades places with */
+    int32_t partner; /* type 3: rank ^ (1 << gbit) */
+    int32_t reserved;
+    double p[3];
+} spz_dist_action;
+
+#define SPZ_IPC_BLOB_BYTES 256
+SPZ_API int spz_dist_create(int n_qubits, int rank, int world, int device, spz_state **out);
+SPZ_API int spz_dist_export(spz_state *st, void *blob);        /* SPZ_IPC_BLOB_BYTES of IPC handles */
+SPZ_API int spz_dist_connect(spz_state *st, const void *blobs); /* world blobs, rank order (all-gathered by the host) */
+/* same-process variant (one host thread per shard; shards on one or several GPUs): direct peer pointers, no IPC */
+SPZ_API int spz_dist_connect_local(spz_state **states, int world);
+SPZ_API int spz_dist_perm(const spz_state *st, int32_t *perm_out); /* logical qubit -> physical bit, n_qubits entries */
+SPZ_API int spz_dist_local_qubits(const spz_state *st);
+SPZ_API int spz_dist_stats(const spz_state *st, double *out4);  /* exchanges, bytes sent, exchange ms, reserved */
+/* planning only (pure host code, no CUDA): what the CPU tests of the sharding logic drive */
+typedef struct spz_dist_plan spz_dist_plan;
+SPZ_API int spz_dist_plan_create(int n_qubits, int world, spz_dist_plan **out);
+SPZ_API int spz_dist_plan_destroy(spz_dist_plan *p);
+SPZ_API int spz_dist_plan_lower(spz_dist_plan *p, int rank, const spz_op *op, spz_dist_action *out, int max_out, int *n_out);
+SPZ_API int spz_dist_plan_perm(const spz_dist_plan *p, int32_t *perm_out);
+
 /* ---- instrumentation --------------------------------------------------------------------------- */
 SPZ_API int spz_timer_start(spz_state *st);               /* cudaEventRecord on the state's stream */
 SPZ_API int spz_timer_stop(spz_state *st, double *out_ms); /* record + synchronise + elapsed */

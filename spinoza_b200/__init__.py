@@ -61,6 +61,12 @@ class _Gate(C.Structure):
                 ("p", C.c_double * 3)]
 
 
+class _DistAction(C.Structure):
+    _fields_ = [("type", C.c_int32), ("kind", C.c_int32), ("target", C.c_int32), ("hi", C.c_int32),
+                ("cmask", C.c_uint64), ("gbit", C.c_int32), ("lq", C.c_int32), ("partner", C.c_int32),
+                ("reserved", C.c_int32), ("p", C.c_double * 3)]
+
+
 class _Op(C.Structure):
     _fields_ = [("kind", C.c_int32), ("target", C.c_int32), ("t0", C.c_int32), ("t1", C.c_int32),
                 ("p", C.c_double * 3), ("ctrl_kind", C.c_int32), ("reserved", C.c_int32),
@@ -104,6 +110,17 @@ _SIGNATURES = {
     "spz_qubit_expectation_value": (C.c_int, [_vp, C.c_int, _dp]),
     "spz_xyz_expectation_value": (C.c_int, [_vp, C.c_char, _i32p, C.c_int, _dp]),
     "spz_sample": (C.c_int, [_vp, _dp, C.c_int64, C.POINTER(C.c_int64)]),
+    "spz_dist_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "spz_dist_export": (C.c_int, [_vp, C.c_char_p]),
+    "spz_dist_connect": (C.c_int, [_vp, C.c_char_p]),
+    "spz_dist_connect_local": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "spz_dist_perm": (C.c_int, [_vp, _i32p]),
+    "spz_dist_local_qubits": (C.c_int, [_vp]),
+    "spz_dist_stats": (C.c_int, [_vp, _dp]),
+    "spz_dist_plan_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_vp)]),
+    "spz_dist_plan_destroy": (C.c_int, [_vp]),
+    "spz_dist_plan_lower": (C.c_int, [_vp, C.c_int, C.POINTER(_Op), C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "spz_dist_plan_perm": (C.c_int, [_vp, _i32p]),
     "spz_timer_start": (C.c_int, [_vp]),
     "spz_timer_stop": (C.c_int, [_vp, _dp]),
     "spz_launch_count": (C.c_int64, []),
@@ -495,6 +512,7 @@ def sample(state: State, shots: int, seed: int = 0, u01: Optional[np.ndarray] = 
 from .circuit import (Controls, QuantumCircuit, QuantumRegister, QuantumTransformation,  # noqa: E402
                       EXEC_FUSE, EXEC_NO_FUSE)
 from . import openqasm  # noqa: E402
+from . import distributed  # noqa: E402
 
 __all__ = [
     "PI", "SpinozaError", "Gate", "State", "HostBuffer", "apply", "c_apply", "cc_apply", "mc_apply", "mc_apply_mask", "iqft",

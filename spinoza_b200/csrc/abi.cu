@@ -8,6 +8,7 @@
 #include <new>
 #include <vector>
 
+#include "dist_plan.h"
 #include "engine.h"
 
 namespace spz {
@@ -77,35 +78,54 @@ static int bind(const spz_state *st) {
         SPZ_TRY(::spz::bind(st));                                        \
     } while (0)
 
+static inline int total_qubits(const spz_state *st) { return st->dist ? dist_total_qubits(st) : st->n; }
+
 // ---- one op, unfused ---------------------------------------------------------------------------------
 static int apply_masked(spz_state *st, int kind, const double *p, uint64_t ctrl_mask, int target) {
+    if (st->dist) {
+        GateK probe;
+        SPZ_TRY(resolve_gate(kind, p, &probe)); // same UNSUPPORTED behaviour as the single-GPU path
+        return dist_apply_masked(st, kind, p, 0, 0, ctrl_mask, target);
+    }
     GateK g;
     SPZ_TRY(resolve_gate(kind, p, &g));
     return launch_gate(st, g, ctrl_mask, target);
 }
 
+static int swap_impl(spz_state *st, int t0, int t1) {
+    if (st->dist) return dist_apply_masked(st, SPZ_GATE_SWAP, nullptr, t0, t1, 0, 0); // relabel, no data moves
+    return launch_swap(st, t0, t1);
+}
+
 static int measure_impl(spz_state *st, int target, int reset, int forced_v, int *out_bit) {
-    if (target < 0 || target >= st->n) { set_error("target %d out of range", target); return SPZ_ERR_INVALID_ARG; }
+    if (target < 0 || target >= total_qubits(st)) { set_error("target %d out of range", target); return SPZ_ERR_INVALID_ARG; }
     if (forced_v > 1) { set_error("forced outcome must be 0, 1 or -1"); return SPZ_ERR_INVALID_ARG; } // assert measurement.rs:32
     double prob0 = 0.0;
-    SPZ_TRY(reduce_scalar(st, 0, target, &prob0));
+    if (st->dist) SPZ_TRY(dist_reduce_scalar(st, 0, target, &prob0));
+    else SPZ_TRY(reduce_scalar(st, 0, target, &prob0));
     int val;
     if (forced_v >= 0) val = forced_v;
     else val = next_u01(st) < 1.0 - prob0 ? 1 : 0; // Binomial(1, 1 - prob0) measurement.rs:35-36
     double k;
     if (val == 0) k = 1.0 / std::sqrt(prob0);       // prob0.sqrt().recip() measurement.rs:40
     else k = 1.0 / std::sqrt(1.0 - prob0);          // measurement.rs:63-64
-    SPZ_TRY(launch_collapse(st, target, val, reset, k));
+    if (st->dist) {
+        SPZ_TRY(dist_collapse(st, target, val, k));
+        if (val == 1 && reset) SPZ_TRY(apply_masked(st, SPZ_GATE_X, nullptr, 0, target)); // measurement.rs:87-89
+    } else {
+        SPZ_TRY(launch_collapse(st, target, val, reset, k));
+    }
     if (out_bit) *out_bit = val;
     return SPZ_OK;
 }
 
 // ---- fusion scheduler -----------------------------------------------------------------------------------
-struct ROp { // an op resolved to what the kernels need
+struct ROp { // an op resolved to what the kernels need (physical qubits of this handle's shard)
     int kind;
     int target, t2;
     uint64_t cmask;
     GateK g;
+    int const_hi = -1; // >= 0: diagonal gate whose target is a rank bit of a sharded register; value of that bit
 };
 
 struct Fuser {
@@ -136,14 +156,16 @@ struct Fuser {
         hs = high_set; ln = low_need;
         // low_need records every target accepted as a low tile bit, so L can never shrink below it
         if (op.kind == SPZ_GATE_SWAP) return try_add_target(op.target, hs, ln) && try_add_target(op.t2, hs, ln);
-        if (is_diagonal_kind(op.kind)) return true;
+        if (is_diagonal_kind(op.kind)) return true; // includes const_hi ops
         return try_add_target(op.target, hs, ln);
     }
 
     int flush() {
         if (ops.empty()) return SPZ_OK;
         int rc = SPZ_OK;
-        if (ops.size() == 1 && ops[0].kind != SPZ_GATE_SWAP) {
+        if (ops.size() == 1 && ops[0].const_hi >= 0) {
+            rc = dist_diag_const(st, ops[0].g, ops[0].cmask, ops[0].const_hi);
+        } else if (ops.size() == 1 && ops[0].kind != SPZ_GATE_SWAP) {
             rc = launch_gate(st, ops[0].g, ops[0].cmask, ops[0].target);
         } else if (ops.size() == 1) {
             rc = launch_swap(st, ops[0].target, ops[0].t2);
@@ -165,7 +187,8 @@ struct Fuser {
                 TileOp &t = tops[i];
                 std::memset(&t, 0, sizeof t);
                 t.kind = o.kind;
-                t.tbit = tile_bit(o.target);
+                t.const_hi = o.const_hi >= 0 ? (uint32_t)(o.const_hi + 1) : 0u;
+                t.tbit = o.const_hi >= 0 ? -1 : tile_bit(o.target);
                 t.tbit2 = o.kind == SPZ_GATE_SWAP ? tile_bit(o.t2) : -1;
                 t.outer_target = t.tbit < 0 ? o.target : -1;
                 for (int q = 0; q < st->n; ++q) {
@@ -280,6 +303,7 @@ int spz_destroy(spz_state *st) {
     if (!st) return SPZ_OK;
     cudaSetDevice(st->device);
     if (st->stream) cudaStreamSynchronize(st->stream);
+    if (st->dist) dist_destroy(st);
     cudaFree(st->re);
     cudaFree(st->im);
     cudaFree(st->scratch.partials);
@@ -295,6 +319,7 @@ int spz_destroy(spz_state *st) {
 
 int spz_clone(const spz_state *src, spz_state **out) {
     if (!src || !out) { set_error("null argument"); return SPZ_ERR_INVALID_ARG; }
+    if (src->dist) { set_error("clone of a sharded register is not supported"); return SPZ_ERR_UNSUPPORTED; }
     SPZ_TRY(spz_create(src->n, src->device, out));
     spz_state *dst = *out;
     const size_t bytes = sizeof(double) * (size_t)src->len;
@@ -306,12 +331,12 @@ int spz_clone(const spz_state *src, spz_state **out) {
     return SPZ_OK;
 }
 
-int spz_num_qubits(const spz_state *st) { return st ? st->n : -1; }
+int spz_num_qubits(const spz_state *st) { return st ? total_qubits(st) : -1; }
 int64_t spz_len(const spz_state *st) { return st ? st->len : -1; }
 
-int spz_reset_zero(spz_state *st) { SPZ_CHECK_STATE(st); return launch_fill_basis(st, 0); }
-int spz_set_basis(spz_state *st, uint64_t index) { SPZ_CHECK_STATE(st); return launch_fill_basis(st, index); }
-int spz_init_random(spz_state *st, uint64_t seed) { SPZ_CHECK_STATE(st); return launch_init_random(st, seed); }
+int spz_reset_zero(spz_state *st) { SPZ_CHECK_STATE(st); return st->dist ? dist_fill_basis(st, 0) : launch_fill_basis(st, 0); }
+int spz_set_basis(spz_state *st, uint64_t index) { SPZ_CHECK_STATE(st); return st->dist ? dist_fill_basis(st, index) : launch_fill_basis(st, index); }
+int spz_init_random(spz_state *st, uint64_t seed) { SPZ_CHECK_STATE(st); return st->dist ? dist_init_random(st, seed) : launch_init_random(st, seed); }
 int spz_set_seed(spz_state *st, uint64_t seed) { if (!st) return SPZ_ERR_INVALID_ARG; st->rng = seed; return SPZ_OK; }
 
 int spz_upload(spz_state *st, const double *re, const double *im, int64_t offset, int64_t count) {
@@ -357,9 +382,9 @@ int spz_apply(spz_state *st, const spz_gate *gate, int target) {
     SPZ_CHECK_STATE(st);
     if (!gate) { set_error("null gate"); return SPZ_ERR_INVALID_ARG; }
     switch (gate->kind) {
-    case SPZ_GATE_SWAP: return launch_swap(st, gate->t0, gate->t1); // gates.rs:225 (ignores `target`)
+    case SPZ_GATE_SWAP: return swap_impl(st, gate->t0, gate->t1); // gates.rs:225 (ignores `target`)
     case SPZ_GATE_BITFLIP: { // bit_flip_noise_apply gates.rs:1365-1374
-        if (target < 0 || target >= st->n) { set_error("target %d out of range", target); return SPZ_ERR_INVALID_ARG; }
+        if (target < 0 || target >= total_qubits(st)) { set_error("target %d out of range", target); return SPZ_ERR_INVALID_ARG; }
         const double eps = next_u01(st);
         if (eps <= gate->p[0]) return apply_masked(st, SPZ_GATE_X, nullptr, 0, target);
         return SPZ_OK; }
@@ -383,14 +408,14 @@ static int controlled_ok(const spz_gate *gate, const char *fn) {
 int spz_c_apply(spz_state *st, const spz_gate *gate, int control, int target) {
     SPZ_CHECK_STATE(st);
     SPZ_TRY(controlled_ok(gate, "c_apply"));
-    if (control < 0 || control >= st->n || control == target) { set_error("bad control %d (target %d, %d qubits)", control, target, st->n); return SPZ_ERR_INVALID_ARG; }
+    if (control < 0 || control >= total_qubits(st) || control == target) { set_error("bad control %d (target %d, %d qubits)", control, target, total_qubits(st)); return SPZ_ERR_INVALID_ARG; }
     return apply_masked(st, gate->kind, gate->p, 1ull << control, target);
 }
 
 int spz_cc_apply(spz_state *st, const spz_gate *gate, int c0, int c1, int target) {
     SPZ_CHECK_STATE(st);
     SPZ_TRY(controlled_ok(gate, "cc_apply"));
-    if (c0 < 0 || c1 < 0 || c0 >= st->n || c1 >= st->n || c0 == target || c1 == target) { set_error("bad controls (%d,%d)", c0, c1); return SPZ_ERR_INVALID_ARG; }
+    if (c0 < 0 || c1 < 0 || c0 >= total_qubits(st) || c1 >= total_qubits(st) || c0 == target || c1 == target) { set_error("bad controls (%d,%d)", c0, c1); return SPZ_ERR_INVALID_ARG; }
     return apply_masked(st, gate->kind, gate->p, (1ull << c0) | (1ull << c1), target);
 }
 
@@ -404,13 +429,13 @@ int spz_mc_apply(spz_state *st, const spz_gate *gate, const int32_t *controls, i
                  int n_zeros, int target) {
     SPZ_CHECK_STATE(st);
     SPZ_TRY(controlled_ok(gate, "mc_apply"));
-    if (n_controls < 0 || (n_controls && !controls) || !(st->n > n_controls)) { // debug_assert gates.rs:297
+    if (n_controls < 0 || (n_controls && !controls) || !(total_qubits(st) > n_controls)) { // debug_assert gates.rs:297
         set_error("mc_apply needs n_qubits > n_controls"); return SPZ_ERR_INVALID_ARG;
     }
     uint64_t mask = 0; // gates.rs:298-311: controls listed in `zeros` are dropped from the mask
     for (int i = 0; i < n_controls; ++i) {
         const int c = controls[i];
-        if (c < 0 || c >= st->n || c == target) { set_error("bad control %d", c); return SPZ_ERR_INVALID_ARG; }
+        if (c < 0 || c >= total_qubits(st) || c == target) { set_error("bad control %d", c); return SPZ_ERR_INVALID_ARG; }
         bool skip = false;
         for (int j = 0; j < n_zeros; ++j) if (zeros && zeros[j] == c) skip = true;
         if (!skip) mask |= 1ull << c;
@@ -426,7 +451,7 @@ int spz_iqft(spz_state *st, const int32_t *targets, int m) {
         SPZ_TRY(apply_masked(st, SPZ_GATE_H, nullptr, 0, targets[j]));
         for (int k = j - 1; k >= 0; --k) {
             const double ang = -3.14159265358979323846 / std::ldexp(1.0, j - k);
-            if (targets[j] == targets[k] || targets[j] < 0 || targets[j] >= st->n) { set_error("bad iqft targets"); return SPZ_ERR_INVALID_ARG; }
+            if (targets[j] == targets[k] || targets[j] < 0 || targets[j] >= total_qubits(st)) { set_error("bad iqft targets"); return SPZ_ERR_INVALID_ARG; }
             SPZ_TRY(apply_masked(st, SPZ_GATE_P, &ang, 1ull << targets[j], targets[k]));
         }
     }
@@ -444,35 +469,72 @@ int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags,
     const bool fuse = (flags & SPZ_EXEC_FUSE) != 0;
     Fuser fuser(st);
 
-    auto emit = [&](int kind, const double *p, uint64_t cmask, int target, int t2) -> int {
-        if (kind != SPZ_GATE_SWAP) {
-            if (target < 0 || target >= st->n) { set_error("target %d out of range", target); return SPZ_ERR_INVALID_ARG; }
-            if ((cmask >> target) & 1ull) { set_error("target %d is also a control", target); return SPZ_ERR_INVALID_ARG; }
-            if (st->n < 64 && (cmask >> st->n)) { set_error("control outside the register"); return SPZ_ERR_INVALID_ARG; }
-        } else if (target < 0 || t2 < 0 || target >= st->n || t2 >= st->n) {
-            set_error("swap operands out of range"); return SPZ_ERR_INVALID_ARG;
+    const int nq = total_qubits(st);
+    int64_t cur = 0; // index of the op being emitted (for the exchange look-ahead)
+    // distance from op `cur` to the next non-diagonal use of every logical qubit (sharded registers only)
+    auto next_uses = [&](uint64_t *nu) {
+        for (int q = 0; q < 64; ++q) nu[q] = UINT64_MAX;
+        for (int64_t j = cur + 1; j < n_ops; ++j) {
+            const spz_op &o = ops[j];
+            if (o.kind == SPZ_GATE_SWAP || is_diagonal_kind(o.kind) || o.kind == SPZ_GATE_UNITARY) continue;
+            if (o.target >= 0 && o.target < 64 && nu[o.target] == UINT64_MAX) nu[o.target] = (uint64_t)(j - cur);
         }
+    };
+
+    auto emit_local = [&](int kind, const double *p, uint64_t cmask, int target, int t2, int const_hi) -> int {
         if (!fuse) {
             if (kind == SPZ_GATE_SWAP) return launch_swap(st, target, t2);
-            return apply_masked(st, kind, p, cmask, target);
+            GateK g;
+            SPZ_TRY(resolve_gate(kind, p, &g));
+            if (const_hi >= 0) return dist_diag_const(st, g, cmask, const_hi);
+            return launch_gate(st, g, cmask, target);
         }
         ROp r{};
-        r.kind = kind; r.target = target; r.t2 = t2; r.cmask = cmask;
+        r.kind = kind; r.target = target; r.t2 = t2; r.cmask = cmask; r.const_hi = const_hi;
         if (kind == SPZ_GATE_SWAP) { if (target == t2) return SPZ_OK; r.g.kind = kind; }
         else SPZ_TRY(resolve_gate(kind, p, &r.g));
         return fuser.add(r);
     };
 
+    auto emit = [&](int kind, const double *p, uint64_t cmask, int target, int t2) -> int {
+        if (kind != SPZ_GATE_SWAP) {
+            if (target < 0 || target >= nq) { set_error("target %d out of range", target); return SPZ_ERR_INVALID_ARG; }
+            if ((cmask >> target) & 1ull) { set_error("target %d is also a control", target); return SPZ_ERR_INVALID_ARG; }
+            if (nq < 64 && (cmask >> nq)) { set_error("control outside the register"); return SPZ_ERR_INVALID_ARG; }
+        } else if (target < 0 || t2 < 0 || target >= nq || t2 >= nq) {
+            set_error("swap operands out of range"); return SPZ_ERR_INVALID_ARG;
+        }
+        if (!st->dist) return emit_local(kind, p, cmask, target, t2, -1);
+        // sharded register: lower the logical op to per-rank actions (dist_plan.h)
+        if (kind != SPZ_GATE_SWAP) { GateK probe; SPZ_TRY(resolve_gate(kind, p, &probe)); }
+        uint64_t nu[64];
+        next_uses(nu);
+        std::vector<spz_dist_action> acts;
+        int rc = dist_lower(st, kind, p, target, t2, cmask, target, nu, acts);
+        if (rc != SPZ_OK) { set_error("cannot lower gate kind %d onto the sharded register", kind); return rc; }
+        for (const spz_dist_action &a : acts) {
+            switch (a.type) {
+            case ACT_SKIP: break;
+            case ACT_EXCHANGE: SPZ_TRY(fuser.flush()); SPZ_TRY(dist_exchange(st, a.gbit, a.lq)); break;
+            case ACT_LOCAL_GATE: SPZ_TRY(emit_local(a.kind, a.p, a.cmask, a.target, 0, -1)); break;
+            case ACT_DIAG_CONST: SPZ_TRY(emit_local(a.kind, a.p, a.cmask, 0, 0, a.hi)); break;
+            default: return SPZ_ERR_INVALID_ARG;
+            }
+        }
+        return SPZ_OK;
+    };
+
     for (int64_t i = 0; i < n_ops; ++i) {
         const spz_op &op = ops[i];
         const int kind = op.kind;
+        cur = i;
         if (kind == SPZ_GATE_UNITARY) { // transform_u / c_transform_u (circuit.rs:555-558): dense fallback, out of scope
             set_error("execute: dense Unitary gates are not supported by the B200 engine");
             return SPZ_ERR_UNSUPPORTED;
         }
         if (op.ctrl_kind == SPZ_CTRL_NONE) {
             if (kind == SPZ_GATE_M) { // circuit.rs:559-566
-                if (op.target < 0 || op.target >= st->n) { set_error("target %d out of range", op.target); return SPZ_ERR_INVALID_ARG; }
+                if (op.target < 0 || op.target >= total_qubits(st)) { set_error("target %d out of range", op.target); return SPZ_ERR_INVALID_ARG; }
                 if (!((*mm >> op.target) & 1ull)) {
                     SPZ_TRY(fuser.flush());
                     int bit = 0;
@@ -519,13 +581,13 @@ int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags,
 int spz_prob0(spz_state *st, int target, double *out) {
     SPZ_CHECK_STATE(st);
     if (!out) return SPZ_ERR_INVALID_ARG;
-    return reduce_scalar(st, 0, target, out);
+    return st->dist ? dist_reduce_scalar(st, 0, target, out) : reduce_scalar(st, 0, target, out);
 }
 
 int spz_norm2(spz_state *st, double *out) {
     SPZ_CHECK_STATE(st);
     if (!out) return SPZ_ERR_INVALID_ARG;
-    return reduce_scalar(st, 1, 0, out);
+    return st->dist ? dist_reduce_scalar(st, 1, 0, out) : reduce_scalar(st, 1, 0, out);
 }
 
 int spz_measure_qubit(spz_state *st, int target, int reset, int forced_v, int *out_bit) {
@@ -537,7 +599,8 @@ int spz_qubit_expectation_value(spz_state *st, int target, double *out) {
     SPZ_CHECK_STATE(st);
     if (!out) return SPZ_ERR_INVALID_ARG;
     double p0 = 0.0;
-    SPZ_TRY(reduce_scalar(st, 0, target, &p0));
+    if (st->dist) SPZ_TRY(dist_reduce_scalar(st, 0, target, &p0));
+    else SPZ_TRY(reduce_scalar(st, 0, target, &p0));
     *out = 2.0 * p0 - 1.0; // core.rs:217-218
     return SPZ_OK;
 }
@@ -552,7 +615,10 @@ int spz_xyz_expectation_value(spz_state *st, char observable, const int32_t *tar
     default: set_error("observable %c not supported", observable); return SPZ_ERR_INVALID_ARG;
     }
     if (n_targets < 0 || (n_targets && (!targets || !out))) return SPZ_ERR_INVALID_ARG;
-    for (int i = 0; i < n_targets; ++i) SPZ_TRY(reduce_scalar(st, mode, targets[i], &out[i]));
+    for (int i = 0; i < n_targets; ++i) {
+        if (st->dist) SPZ_TRY(dist_reduce_scalar(st, mode, targets[i], &out[i]));
+        else SPZ_TRY(reduce_scalar(st, mode, targets[i], &out[i]));
+    }
     return SPZ_OK;
 }
 
@@ -560,6 +626,7 @@ int spz_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_ind
     SPZ_CHECK_STATE(st);
     if (shots < 0 || (shots && (!u01 || !out_index))) return SPZ_ERR_INVALID_ARG;
     static_assert(sizeof(long long) == sizeof(int64_t), "int64_t layout");
+    if (st->dist) { set_error("sampling a sharded register is not implemented yet"); return SPZ_ERR_UNSUPPORTED; }
     return launch_sample(st, u01, shots, out_index);
 }
 

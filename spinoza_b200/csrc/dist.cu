@@ -1,0 +1,518 @@
+// dist.cu -- multi-GPU layer: one process per GPU, shards exchanged over NVLink through CUDA IPC peer pointers.
+//
+// See dist_plan.h for the lowering rules.  This file holds the device side:
+//   * k_exchange_*   : the pairwise half-shard exchange.  Rank pair (r, r ^ 2^k) swaps r's [local bit lq = 1]
+//                      half with the partner's [lq = 0] half IN PLACE: every thread loads one vector from its own
+//                      HBM and one from the partner's HBM (ld.global on the IPC-mapped peer pointer, i.e. over
+//                      NVLink) and stores them crosswise (one local store, one peer store).  The pair list is split
+//                      between the two ranks, so each direction of the link carries exactly half a shard
+//                      (16 * 2^(n_local-1) bytes) and no staging buffer is needed next to a 137 GB shard.
+//   * k_handshake    : stream-ordered cross-process barrier between the two partners (epoch flags in IPC-shared
+//                      device memory, st.release.sys / ld.acquire.sys), before and after each exchange.
+//   * k_allreduce    : scalar sum across all ranks through the same IPC control blocks (prob0 / norm / <O>).
+// No NCCL: the data path is peer loads/stores issued by our own kernels.
+#include <cstring>
+#include <vector>
+
+#include "dist_plan.h"
+#include "kernels_direct.cuh"
+
+namespace spz {
+
+constexpr int kMaxRanks = 16;
+constexpr unsigned long long kSpinTimeoutNs = 60ull * 1000ull * 1000ull * 1000ull;
+
+struct CtrlBlock { // lives in device memory of each rank, mapped by every peer
+    unsigned long long ready[kMaxRanks];
+    unsigned long long done[kMaxRanks];
+    unsigned long long red_epoch[2][kMaxRanks];
+    double red_slot[2][kMaxRanks];
+    double red_result;
+    unsigned long long error;
+};
+
+struct IpcBlob {
+    cudaIpcMemHandle_t re, im, ctrl;
+    int rank, device;
+    long long len;
+    char pad[SPZ_IPC_BLOB_BYTES - 3 * sizeof(cudaIpcMemHandle_t) - 2 * sizeof(int) - sizeof(long long)];
+};
+static_assert(sizeof(IpcBlob) == SPZ_IPC_BLOB_BYTES, "blob size");
+
+struct DistCtx {
+    DistPlan plan;
+    int rank = 0, world = 1;
+    CtrlBlock *ctrl = nullptr;
+    CtrlBlock *peer_ctrl[kMaxRanks] = {};
+    double *peer_re[kMaxRanks] = {}, *peer_im[kMaxRanks] = {};
+    CtrlBlock **d_table = nullptr; // device copy of peer_ctrl[] for k_allreduce
+    bool connected = false, ipc = false;
+    unsigned long long epoch = 0, red_epoch = 0;
+    // stats
+    double n_exchanges = 0, bytes_sent = 0, ms_accum = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, free_events;
+};
+
+static DistCtx *ctx_of(const spz_state *st) { return static_cast<DistCtx *>(st->dist); }
+
+int dist_total_qubits(const spz_state *st) { return ctx_of(st)->plan.n; }
+
+// ---- device helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Tell the partner "I reached epoch e" and wait until it has too.  One thread.
+__global__ void k_handshake(unsigned long long *partner_slot, const unsigned long long *my_slot, unsigned long long epoch,
+                            unsigned long long *err) {
+    __threadfence_system();
+    st_release_sys(partner_slot, epoch);
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(my_slot) < epoch) {
+        if (globaltimer_ns() - t0 > kSpinTimeoutNs) { *err = epoch; break; }
+        __nanosleep(200);
+    }
+}
+
+// Scalar all-reduce (sum) over all ranks.  One thread per peer writes, thread 0 sums in rank order, so every
+// rank obtains the bitwise-identical total.
+__global__ void k_allreduce(CtrlBlock *mine, CtrlBlock *const *peers, int rank, int world, unsigned long long epoch,
+                            const double *value_ptr, double value_imm, double *out) {
+    __shared__ CtrlBlock *sp[kMaxRanks];
+    const int par = (int)(epoch & 1ull);
+    const double v = value_ptr ? *value_ptr : value_imm;
+    if (threadIdx.x < world) sp[threadIdx.x] = peers[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x < world) {
+        CtrlBlock *p = sp[threadIdx.x];
+        p->red_slot[par][rank] = v;
+        __threadfence_system();
+        st_release_sys(&p->red_epoch[par][rank], epoch);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = globaltimer_ns();
+        double acc = 0.0;
+        for (int r = 0; r < world; ++r) {
+            while (ld_acquire_sys(&mine->red_epoch[par][r]) < epoch) {
+                if (globaltimer_ns() - t0 > kSpinTimeoutNs) { mine->error = epoch; break; }
+                __nanosleep(200);
+            }
+            acc += *(volatile double *)&mine->red_slot[par][r];
+        }
+        *out = acc;
+        mine->red_result = acc;
+    }
+}
+
+// ---- the exchange ------------------------------------------------------------------------------------------
+struct XArgs {
+    double *mine_re, *mine_im, *peer_re, *peer_im;
+    long long nvec_begin, nvec_end; // range of pair-list vectors this rank handles
+    int lq;                         // local physical bit traded with the rank bit
+    int my_bit;                     // this rank's value of the rank bit
+};
+
+template <int W, int U, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_exchange_vec(const XArgs a) {
+    const long long v0 = a.nvec_begin + (long long)blockIdx.x * (THREADS * U) + threadIdx.x;
+    const unsigned long long lbit = 1ull << a.lq;
+    unsigned long long im_[U], ip_[U];
+    Vec<W> mr[U], mi[U], pr[U], pi[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long v = v0 + (long long)u * THREADS;
+        if (v < a.nvec_end) {
+            const unsigned long long base = insert_zero((unsigned long long)v << LogW<W>::v, a.lq);
+            // low rank (bit 0) gives its lq=1 half and takes the partner's lq=0 half
+            im_[u] = a.my_bit ? base : (base | lbit);
+            ip_[u] = a.my_bit ? (base | lbit) : base;
+            pr[u] = ldv<W, 0>(a.peer_re + ip_[u]); // NVLink loads first: longest latency
+            pi[u] = ldv<W, 0>(a.peer_im + ip_[u]);
+            mr[u] = ldv<W, 0>(a.mine_re + im_[u]);
+            mi[u] = ldv<W, 0>(a.mine_im + im_[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long v = v0 + (long long)u * THREADS;
+        if (v < a.nvec_end) {
+            stv<W, 0>(a.peer_re + ip_[u], mr[u]);
+            stv<W, 0>(a.peer_im + ip_[u], mi[u]);
+            stv<W, 0>(a.mine_re + im_[u], pr[u]);
+            stv<W, 0>(a.mine_im + im_[u], pi[u]);
+        }
+    }
+}
+
+__global__ void k_exchange_scalar(const XArgs a) {
+    const unsigned long long lbit = 1ull << a.lq;
+    for (long long v = a.nvec_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; v < a.nvec_end;
+         v += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long base = insert_zero((unsigned long long)v, a.lq);
+        const unsigned long long im_ = a.my_bit ? base : (base | lbit), ip_ = a.my_bit ? (base | lbit) : base;
+        const double pr = a.peer_re[ip_], pi = a.peer_im[ip_], mr = a.mine_re[im_], mi = a.mine_im[im_];
+        a.peer_re[ip_] = mr; a.peer_im[ip_] = mi; a.mine_re[im_] = pr; a.mine_im[im_] = pi;
+    }
+}
+
+// Constant diagonal factor on every amplitude of the shard whose local controls are set (a diagonal gate whose
+// target is a global qubit).  Same per-amplitude arithmetic as the pair kernels (gate_math.cuh).
+__global__ void __launch_bounds__(256) k_diag_const(double *__restrict__ re, double *__restrict__ im, long long count,
+                                                    unsigned long long cmask, int kind, int hi, GateK g) {
+    const int nc = __popcll(cmask);
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < count; p += (long long)gridDim.x * blockDim.x) {
+        unsigned long long x = (unsigned long long)p, m = cmask;
+        for (int k = 0; k < nc; ++k) { const int b = __ffsll((long long)m) - 1; x = insert_zero(x, b); m &= m - 1; }
+        x |= cmask;
+        double a = re[x], b = im[x];
+        diag_update_rt(kind, g.s, hi != 0, a, b);
+        re[x] = a; im[x] = b;
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+static int check_comm_error(spz_state *st) {
+    DistCtx *c = ctx_of(st);
+    unsigned long long err = 0;
+    SPZ_CUDA(cudaMemcpyAsync(&err, &c->ctrl->error, sizeof err, cudaMemcpyDeviceToHost, st->stream));
+    SPZ_CUDA(cudaStreamSynchronize(st->stream));
+    if (err) { set_error("rank %d: peer did not arrive at epoch %llu within the spin timeout", c->rank, err); return SPZ_ERR_COMM; }
+    return SPZ_OK;
+}
+
+int dist_exchange(spz_state *st, int gbit, int lq) {
+    DistCtx *c = ctx_of(st);
+    if (!c->connected) { set_error("dist state used before spz_dist_connect"); return SPZ_ERR_COMM; }
+    const int partner = c->rank ^ (1 << gbit);
+    const int my_bit = (c->rank >> gbit) & 1;
+    const unsigned long long e = ++c->epoch;
+    k_handshake<<<1, 1, 0, st->stream>>>(&c->peer_ctrl[partner]->ready[c->rank], &c->ctrl->ready[partner], e, &c->ctrl->error);
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!c->free_events.empty()) { ev = c->free_events.back(); c->free_events.pop_back(); }
+    else { SPZ_CUDA(cudaEventCreate(&ev.first)); SPZ_CUDA(cudaEventCreate(&ev.second)); }
+    SPZ_CUDA(cudaEventRecord(ev.first, st->stream));
+    XArgs a{};
+    a.mine_re = st->re; a.mine_im = st->im; a.peer_re = c->peer_re[partner]; a.peer_im = c->peer_im[partner];
+    a.lq = lq; a.my_bit = my_bit;
+    const int n_local = st->n;
+    constexpr int W = 4, U = 4, THREADS = 256;
+    if (lq >= LogW<W>::v && n_local - 1 - LogW<W>::v >= 1) {
+        const long long nvec = 1ll << (n_local - 1 - LogW<W>::v);
+        a.nvec_begin = my_bit ? nvec / 2 : 0;
+        a.nvec_end = my_bit ? nvec : nvec / 2;
+        const long long cnt = a.nvec_end - a.nvec_begin, per = (long long)THREADS * U;
+        k_exchange_vec<W, U, THREADS><<<(unsigned)((cnt + per - 1) / per), THREADS, 0, st->stream>>>(a);
+    } else {
+        const long long nvec = 1ll << (n_local - 1);
+        a.nvec_begin = my_bit ? nvec / 2 : 0;
+        a.nvec_end = my_bit ? nvec : nvec / 2;
+        const long long cnt = a.nvec_end - a.nvec_begin;
+        k_exchange_scalar<<<(unsigned)std::max<long long>(1, std::min<long long>((cnt + 255) / 256, 148 * 8)), 256, 0, st->stream>>>(a);
+    }
+    SPZ_CUDA(cudaEventRecord(ev.second, st->stream));
+    c->pending.push_back(ev);
+    k_handshake<<<1, 1, 0, st->stream>>>(&c->peer_ctrl[partner]->done[c->rank], &c->ctrl->done[partner], e, &c->ctrl->error);
+    count_launch(3);
+    SPZ_CUDA(cudaGetLastError());
+    c->n_exchanges += 1;
+    c->bytes_sent += 16.0 * (double)(1ll << (n_local - 1)); // half a shard leaves this GPU (re + im)
+    return SPZ_OK;
+}
+
+int dist_allreduce(spz_state *st, const double *dev_value, double host_value, double *host_out, double **dev_out) {
+    DistCtx *c = ctx_of(st);
+    if (!c->connected) { set_error("dist state used before spz_dist_connect"); return SPZ_ERR_COMM; }
+    SPZ_TRY(ensure_scratch(st));
+    const unsigned long long e = ++c->red_epoch;
+    if (!c->d_table) { // device-resident table of peer control blocks
+        SPZ_CUDA(cudaMalloc(&c->d_table, sizeof(CtrlBlock *) * kMaxRanks));
+        SPZ_CUDA(cudaMemcpy(c->d_table, c->peer_ctrl, sizeof(CtrlBlock *) * kMaxRanks, cudaMemcpyHostToDevice));
+    }
+    k_allreduce<<<1, 32, 0, st->stream>>>(c->ctrl, c->d_table, c->rank, c->world, e, dev_value, host_value, st->scratch.partials + 0);
+    count_launch();
+    SPZ_CUDA(cudaGetLastError());
+    if (dev_out) *dev_out = st->scratch.partials + 0;
+    if (host_out) {
+        SPZ_CUDA(cudaMemcpyAsync(st->scratch.h_result, st->scratch.partials + 0, sizeof(double), cudaMemcpyDeviceToHost, st->stream));
+        SPZ_CUDA(cudaStreamSynchronize(st->stream));
+        *host_out = st->scratch.h_result[0];
+        SPZ_TRY(check_comm_error(st));
+    }
+    return SPZ_OK;
+}
+
+int dist_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int hi) {
+    const long long count = st->len >> __builtin_popcountll(local_cmask);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((count + 255) / 256, 148 * 16));
+    k_diag_const<<<grid, 256, 0, st->stream>>>(st->re, st->im, count, local_cmask, g.kind, hi, g);
+    count_launch();
+    SPZ_CUDA(cudaGetLastError());
+    return SPZ_OK;
+}
+
+// Lower one logical gate and run the resulting actions immediately (the unfused path).
+int dist_apply_masked(spz_state *st, int kind, const double *p, int t0, int t1, uint64_t cmask, int target) {
+    DistCtx *c = ctx_of(st);
+    std::vector<spz_dist_action> acts;
+    int rc = c->plan.lower(c->rank, kind, p, t0, t1, cmask, target, nullptr, acts);
+    if (rc != SPZ_OK) { set_error("cannot lower gate kind %d target %d onto the sharded register", kind, target); return rc; }
+    for (const spz_dist_action &a : acts) {
+        switch (a.type) {
+        case ACT_SKIP: break;
+        case ACT_EXCHANGE: SPZ_TRY(dist_exchange(st, a.gbit, a.lq)); break;
+        case ACT_LOCAL_GATE: { GateK g; SPZ_TRY(resolve_gate(a.kind, a.p, &g)); SPZ_TRY(launch_gate(st, g, a.cmask, a.target)); break; }
+        case ACT_DIAG_CONST: { GateK g; SPZ_TRY(resolve_gate(a.kind, a.p, &g)); SPZ_TRY(dist_diag_const(st, g, a.cmask, a.hi)); break; }
+        default: return SPZ_ERR_INVALID_ARG;
+        }
+    }
+    return SPZ_OK;
+}
+
+int dist_lower(spz_state *st, int kind, const double *p, int t0, int t1, uint64_t cmask, int target, const uint64_t *next_use,
+               std::vector<spz_dist_action> &acts) {
+    DistCtx *c = ctx_of(st);
+    return c->plan.lower(c->rank, kind, p, t0, t1, cmask, target, next_use, acts);
+}
+
+// Reductions on a sharded register.  mode as in reduce_scalar(); `target` is a LOGICAL qubit.
+int dist_reduce_scalar(spz_state *st, int mode, int target, double *out) {
+    DistCtx *c = ctx_of(st);
+    double local = 0.0;
+    if (mode == 1) {
+        SPZ_TRY(reduce_scalar(st, 1, 0, &local));
+    } else {
+        if (target < 0 || target >= c->plan.n) { set_error("target %d out of range", target); return SPZ_ERR_INVALID_ARG; }
+        if (mode == 2 || mode == 3) { // <X>, <Y> pair amplitudes across the target bit: make it resident first
+            std::vector<spz_dist_action> acts;
+            SPZ_TRY(c->plan.ensure_local(target, nullptr, 0, acts, c->rank));
+            for (const spz_dist_action &a : acts) SPZ_TRY(dist_exchange(st, a.gbit, a.lq));
+        }
+        const int pt = c->plan.perm[target];
+        if (pt < c->plan.n_local) {
+            SPZ_TRY(reduce_scalar(st, mode, pt, &local));
+        } else { // global target: prob0 / <Z> are per-rank constants times the shard's norm
+            const int bit = (c->rank >> (pt - c->plan.n_local)) & 1;
+            double nrm = 0.0;
+            SPZ_TRY(reduce_scalar(st, 1, 0, &nrm));
+            if (mode == 0) local = bit ? 0.0 : nrm;
+            else local = bit ? -nrm : nrm; // mode 4
+        }
+    }
+    return dist_allreduce(st, nullptr, local, out, nullptr);
+}
+
+int dist_collapse(spz_state *st, int target, int outcome, double scale) {
+    DistCtx *c = ctx_of(st);
+    const int pt = c->plan.perm[target];
+    if (pt < c->plan.n_local) return launch_collapse(st, pt, outcome, 0, scale);
+    const int bit = (c->rank >> (pt - c->plan.n_local)) & 1;
+    if (bit == outcome) return launch_scale(st, scale);
+    SPZ_CUDA(cudaMemsetAsync(st->re, 0, sizeof(double) * (size_t)st->len, st->stream));
+    SPZ_CUDA(cudaMemsetAsync(st->im, 0, sizeof(double) * (size_t)st->len, st->stream));
+    return SPZ_OK;
+}
+
+int dist_fill_basis(spz_state *st, uint64_t logical_index) {
+    DistCtx *c = ctx_of(st);
+    if (c->plan.n < 64 && (logical_index >> c->plan.n)) { set_error("basis index out of range"); return SPZ_ERR_INVALID_ARG; }
+    uint64_t phys = 0;
+    for (int q = 0; q < c->plan.n; ++q) if ((logical_index >> q) & 1ull) phys |= 1ull << c->plan.perm[q];
+    const int owner = (int)(phys >> c->plan.n_local);
+    if (owner == c->rank) return launch_fill_basis(st, phys & ((1ull << c->plan.n_local) - 1ull));
+    SPZ_CUDA(cudaMemsetAsync(st->re, 0, sizeof(double) * (size_t)st->len, st->stream));
+    SPZ_CUDA(cudaMemsetAsync(st->im, 0, sizeof(double) * (size_t)st->len, st->stream));
+    return SPZ_OK;
+}
+
+int dist_init_random(spz_state *st, uint64_t seed) {
+    DistCtx *c = ctx_of(st);
+    const long long total_len = 1ll << c->plan.n;
+    double *d_local = nullptr, *d_total = nullptr;
+    SPZ_TRY(launch_rand_probs(st, seed, (long long)c->rank * st->len, &d_local));
+    SPZ_TRY(dist_allreduce(st, d_local, 0.0, nullptr, &d_total));
+    return launch_rand_finish(st, seed, (long long)c->rank * st->len, total_len, d_total);
+}
+
+void dist_destroy(spz_state *st) {
+    DistCtx *c = ctx_of(st);
+    if (!c) return;
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank || !c->connected || !c->ipc) continue;
+        if (c->peer_re[r]) cudaIpcCloseMemHandle(c->peer_re[r]);
+        if (c->peer_im[r]) cudaIpcCloseMemHandle(c->peer_im[r]);
+        if (c->peer_ctrl[r]) cudaIpcCloseMemHandle(c->peer_ctrl[r]);
+    }
+    for (auto &e : c->pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto &e : c->free_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    cudaFree(c->d_table);
+    cudaFree(c->ctrl);
+    delete c;
+    st->dist = nullptr;
+}
+
+} // namespace spz
+
+using namespace spz;
+
+struct spz_dist_plan {
+    DistPlan plan;
+};
+
+extern "C" {
+
+int spz_dist_create(int n_qubits, int rank, int world, int device, spz_state **out) {
+    if (!out) return SPZ_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (world < 1 || world > kMaxRanks || (world & (world - 1)) || rank < 0 || rank >= world) {
+        set_error("world size must be a power of two <= %d and 0 <= rank < world", kMaxRanks); return SPZ_ERR_INVALID_ARG;
+    }
+    int g = 0;
+    while ((1 << g) < world) ++g;
+    if (n_qubits - g < 2 || n_qubits > 48) { set_error("need at least 2 local qubits per rank"); return SPZ_ERR_INVALID_ARG; }
+    spz_state *st = nullptr;
+    SPZ_TRY(spz_create(n_qubits - g, device, &st));
+    DistCtx *c = new DistCtx();
+    c->plan.init(n_qubits, world);
+    c->rank = rank; c->world = world;
+    st->dist = c;
+    cudaError_t e = cudaMalloc(&c->ctrl, sizeof(CtrlBlock));
+    if (e == cudaSuccess) e = cudaMemset(c->ctrl, 0, sizeof(CtrlBlock));
+    if (e != cudaSuccess) { int rc = cuda_fail(e, "cudaMalloc(ctrl)", __FILE__, __LINE__); spz_destroy(st); return rc; }
+    c->peer_ctrl[rank] = c->ctrl; c->peer_re[rank] = st->re; c->peer_im[rank] = st->im;
+    if (world == 1) c->connected = true;
+    int rc = dist_fill_basis(st, 0); // |0..0> lives on rank 0 only
+    if (rc != SPZ_OK) { spz_destroy(st); return rc; }
+    *out = st;
+    return SPZ_OK;
+}
+
+int spz_dist_export(spz_state *st, void *blob) {
+    if (!st || !st->dist || !blob) return SPZ_ERR_INVALID_ARG;
+    SPZ_CUDA(cudaSetDevice(st->device));
+    DistCtx *c = ctx_of(st);
+    IpcBlob b;
+    std::memset(&b, 0, sizeof b);
+    SPZ_CUDA(cudaIpcGetMemHandle(&b.re, st->re));
+    SPZ_CUDA(cudaIpcGetMemHandle(&b.im, st->im));
+    SPZ_CUDA(cudaIpcGetMemHandle(&b.ctrl, c->ctrl));
+    b.rank = c->rank; b.device = st->device; b.len = st->len;
+    std::memcpy(blob, &b, sizeof b);
+    return SPZ_OK;
+}
+
+int spz_dist_connect(spz_state *st, const void *blobs) {
+    if (!st || !st->dist || !blobs) return SPZ_ERR_INVALID_ARG;
+    SPZ_CUDA(cudaSetDevice(st->device));
+    DistCtx *c = ctx_of(st);
+    const IpcBlob *b = static_cast<const IpcBlob *>(blobs);
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) continue;
+        if (b[r].rank != r || b[r].len != st->len) { set_error("blob %d does not describe rank %d's shard", r, r); return SPZ_ERR_COMM; }
+        void *p = nullptr;
+        SPZ_CUDA(cudaIpcOpenMemHandle(&p, b[r].re, cudaIpcMemLazyEnablePeerAccess)); c->peer_re[r] = static_cast<double *>(p);
+        SPZ_CUDA(cudaIpcOpenMemHandle(&p, b[r].im, cudaIpcMemLazyEnablePeerAccess)); c->peer_im[r] = static_cast<double *>(p);
+        SPZ_CUDA(cudaIpcOpenMemHandle(&p, b[r].ctrl, cudaIpcMemLazyEnablePeerAccess)); c->peer_ctrl[r] = static_cast<CtrlBlock *>(p);
+    }
+    c->connected = true;
+    c->ipc = true;
+    return SPZ_OK;
+}
+
+int spz_dist_connect_local(spz_state **states, int world) {
+    if (!states || world < 1 || world > kMaxRanks) return SPZ_ERR_INVALID_ARG;
+    for (int r = 0; r < world; ++r) {
+        if (!states[r] || !states[r]->dist) { set_error("state %d is not a shard", r); return SPZ_ERR_INVALID_ARG; }
+        DistCtx *c = ctx_of(states[r]);
+        if (c->rank != r || c->world != world || states[r]->len != states[0]->len) { set_error("state %d: wrong rank/world/length", r); return SPZ_ERR_INVALID_ARG; }
+    }
+    for (int r = 0; r < world; ++r) {
+        DistCtx *c = ctx_of(states[r]);
+        SPZ_CUDA(cudaSetDevice(states[r]->device));
+        for (int q = 0; q < world; ++q) {
+            if (q == r) continue;
+            if (states[q]->device != states[r]->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(states[q]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+                cudaGetLastError();
+            }
+            c->peer_re[q] = states[q]->re; c->peer_im[q] = states[q]->im; c->peer_ctrl[q] = ctx_of(states[q])->ctrl;
+        }
+        c->connected = true;
+        c->ipc = false;
+    }
+    return SPZ_OK;
+}
+
+int spz_dist_perm(const spz_state *st, int32_t *perm_out) {
+    if (!st || !st->dist || !perm_out) return SPZ_ERR_INVALID_ARG;
+    const DistCtx *c = ctx_of(st);
+    for (int q = 0; q < c->plan.n; ++q) perm_out[q] = c->plan.perm[q];
+    return SPZ_OK;
+}
+
+int spz_dist_local_qubits(const spz_state *st) { return st ? st->n : -1; }
+
+int spz_dist_stats(const spz_state *cst, double *out4) {
+    if (!cst || !cst->dist || !out4) return SPZ_ERR_INVALID_ARG;
+    spz_state *st = const_cast<spz_state *>(cst);
+    DistCtx *c = ctx_of(st);
+    SPZ_CUDA(cudaSetDevice(st->device));
+    SPZ_CUDA(cudaStreamSynchronize(st->stream));
+    for (auto &e : c->pending) {
+        float ms = 0.f;
+        SPZ_CUDA(cudaEventElapsedTime(&ms, e.first, e.second));
+        c->ms_accum += ms;
+        c->free_events.push_back(e);
+    }
+    c->pending.clear();
+    out4[0] = c->n_exchanges; out4[1] = c->bytes_sent; out4[2] = c->ms_accum; out4[3] = 0.0;
+    return SPZ_OK;
+}
+
+int spz_dist_plan_create(int n_qubits, int world, spz_dist_plan **out) {
+    if (!out || world < 1 || (world & (world - 1)) || n_qubits < 1 || n_qubits > 63) return SPZ_ERR_INVALID_ARG;
+    spz_dist_plan *p = new spz_dist_plan();
+    p->plan.init(n_qubits, world);
+    if (p->plan.n_local < 1) { delete p; return SPZ_ERR_INVALID_ARG; }
+    *out = p;
+    return SPZ_OK;
+}
+
+int spz_dist_plan_destroy(spz_dist_plan *p) { delete p; return SPZ_OK; }
+
+int spz_dist_plan_lower(spz_dist_plan *p, int rank, const spz_op *op, spz_dist_action *out, int max_out, int *n_out) {
+    if (!p || !op || !out || !n_out) return SPZ_ERR_INVALID_ARG;
+    uint64_t cmask = 0;
+    switch (op->ctrl_kind) { // same resolution as spz_execute (circuit.rs:567-596)
+    case SPZ_CTRL_NONE: break;
+    case SPZ_CTRL_SINGLE: case SPZ_CTRL_ONES: cmask = op->ctrl_mask; break;
+    case SPZ_CTRL_MIXED: cmask = op->ctrl_mask & ~op->zeros_mask; break;
+    default: return SPZ_ERR_INVALID_ARG;
+    }
+    if (op->kind == SPZ_GATE_M || op->kind == SPZ_GATE_UNITARY || op->kind == SPZ_GATE_BITFLIP) return SPZ_ERR_UNSUPPORTED;
+    std::vector<spz_dist_action> acts;
+    SPZ_TRY(p->plan.lower(rank, op->kind, op->p, op->t0, op->t1, cmask, op->target, nullptr, acts));
+    if ((int)acts.size() > max_out) return SPZ_ERR_INVALID_ARG;
+    for (size_t i = 0; i < acts.size(); ++i) out[i] = acts[i];
+    *n_out = (int)acts.size();
+    return SPZ_OK;
+}
+
+int spz_dist_plan_perm(const spz_dist_plan *p, int32_t *perm_out) {
+    if (!p || !perm_out) return SPZ_ERR_INVALID_ARG;
+    for (int q = 0; q < p->plan.n; ++q) perm_out[q] = p->plan.perm[q];
+    return SPZ_OK;
+}
+
+} // extern "C"

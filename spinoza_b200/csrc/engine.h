@@ -66,6 +66,7 @@ struct spz_state {
     void *d_ops = nullptr;
     size_t d_ops_bytes = 0;
     size_t d_ops_cursor = 0;
+    void *dist = nullptr; // spz::DistCtx* when this handle is one shard of a multi-GPU register (dist.cu)
 };
 
 namespace spz {
@@ -83,6 +84,10 @@ int launch_init_random(spz_state *st, uint64_t seed);
 // 2/3/4 = <X>/<Y>/<Z> on `target`
 int reduce_scalar(spz_state *st, int mode, int target, double *out);
 int launch_collapse(spz_state *st, int target, int outcome, int reset, double scale);
+int launch_scale(spz_state *st, double scale); // every amplitude *= scale
+// gen_random_state split in two so that a sharded register can insert its cross-rank sum between the halves
+int launch_rand_probs(spz_state *st, uint64_t seed, long long index_offset, double **d_local_total);
+int launch_rand_finish(spz_state *st, uint64_t seed, long long index_offset, long long total_len, const double *d_total);
 int launch_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_index);
 
 // ---- fused execution (kernels_tile.cu) ------------------------------------------------------------
@@ -92,7 +97,8 @@ struct TileOp {
     int tbit2;           // SWAP: in-tile bit of the second operand
     int outer_target;    // absolute qubit of an outer target (diagonal gates only), else -1
     uint32_t inner_cmask; // control bits inside the tile (in-tile bit positions)
-    uint32_t pad;
+    uint32_t const_hi;    // outer-target diagonal gates: 0 = read the bit from the tile base, 1 = bit is 0, 2 = bit is 1
+                          // (a target that is a rank bit of a sharded register)
     uint64_t outer_cmask; // control bits outside the tile (absolute positions)
     double s[7];
 };
@@ -104,5 +110,16 @@ struct TilePlan {
 };
 int launch_tile_group(spz_state *st, const TilePlan &plan, const TileOp *ops, int n_ops);
 int max_tile_bits();
+
+// ---- multi-GPU (dist.cu) ----------------------------------------------------------------------------
+int dist_total_qubits(const spz_state *st);
+int dist_apply_masked(spz_state *st, int kind, const double *p, int t0, int t1, uint64_t cmask, int target);
+int dist_exchange(spz_state *st, int gbit, int lq);
+int dist_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int hi);
+int dist_reduce_scalar(spz_state *st, int mode, int target, double *out);
+int dist_collapse(spz_state *st, int target, int outcome, double scale);
+int dist_fill_basis(spz_state *st, uint64_t logical_index);
+int dist_init_random(spz_state *st, uint64_t seed);
+void dist_destroy(spz_state *st);
 
 } // namespace spz

@@ -10,7 +10,7 @@ namespace spz {
 #define SPZ_W 4
 #endif
 #ifndef SPZ_U
-#define SPZ_U 2
+#define SPZ_U 4
 #endif
 #ifndef SPZ_THREADS
 #define SPZ_THREADS 256

@@ -200,7 +200,7 @@ struct ScalarArgs {
     double s[7];
 };
 
-__global__ void k_pair_scalar(const ScalarArgs a) {
+static __global__ void k_pair_scalar(const ScalarArgs a) {
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.npairs;
          p += (long long)gridDim.x * blockDim.x) {
         unsigned long long x = (unsigned long long)p;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(THREADS) k_swap_vec(const SwapArgs a) {
     stv<W, 0>(a.re + ib, ra); stv<W, 0>(a.im + ib, ma);
 }
 
-__global__ void k_swap_scalar(const SwapArgs a) {
+static __global__ void k_swap_scalar(const SwapArgs a) {
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.nvec;
          p += (long long)gridDim.x * blockDim.x) {
         unsigned long long x = insert_zero(insert_zero((unsigned long long)p, a.lo), a.hi);

@@ -174,12 +174,13 @@ __host__ __device__ __forceinline__ uint64_t splitmix_at(uint64_t seed, uint64_t
 __host__ __device__ __forceinline__ double u01_of(uint64_t r) { return (double)(r >> 11) * (1.0 / 9007199254740992.0); }
 
 // gen_random_state utils.rs:168-201: p_i ~ U(0,1) normalised by their sum, phase ~ U(0, 2 pi).
-__global__ void __launch_bounds__(256) k_rand_probs(double *__restrict__ re, long long len, uint64_t seed,
+// `offset` is the global index of this shard's first amplitude (0 on a single GPU).
+__global__ void __launch_bounds__(256) k_rand_probs(double *__restrict__ re, long long len, long long offset, uint64_t seed,
                                                     double *__restrict__ partials) {
     double acc = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
-        const double u = u01_of(splitmix_at(seed, (uint64_t)i));
+        const double u = u01_of(splitmix_at(seed, (uint64_t)(offset + i)));
         re[i] = u;
         acc += u;
     }
@@ -187,12 +188,13 @@ __global__ void __launch_bounds__(256) k_rand_probs(double *__restrict__ re, lon
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
 __global__ void __launch_bounds__(256) k_rand_finish(double *__restrict__ re, double *__restrict__ im, long long len,
-                                                     uint64_t seed, const double *__restrict__ total) {
+                                                     long long offset, long long total_len, uint64_t seed,
+                                                     const double *__restrict__ total) {
     const double recip = 1.0 / *total;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
         const double p = re[i] * recip;
-        const double ang = u01_of(splitmix_at(seed, (uint64_t)(len + i))) * (2.0 * 3.14159265358979323846);
+        const double ang = u01_of(splitmix_at(seed, (uint64_t)(total_len + offset + i))) * (2.0 * 3.14159265358979323846);
         const double ps = sqrt(p);
         double sn, cs;
         sincos(ang, &sn, &cs);
@@ -201,14 +203,44 @@ __global__ void __launch_bounds__(256) k_rand_finish(double *__restrict__ re, do
     }
 }
 
-int launch_init_random(spz_state *st, uint64_t seed) {
+int launch_rand_probs(spz_state *st, uint64_t seed, long long index_offset, double **d_local_total) {
     SPZ_TRY(ensure_scratch(st));
     const int grid = (int)std::max<long long>(1, std::min<long long>((st->len + 255) / 256, kRedBlocks));
     double *part = st->scratch.partials;
-    k_rand_probs<<<grid, 256, 0, st->stream>>>(st->re, st->len, seed, part);
+    k_rand_probs<<<grid, 256, 0, st->stream>>>(st->re, st->len, index_offset, seed, part);
     k_final_sum<<<1, kRedThreads, 0, st->stream>>>(part, grid, part + kRedBlocks);
-    k_rand_finish<<<grid, 256, 0, st->stream>>>(st->re, st->im, st->len, seed, part + kRedBlocks);
-    count_launch(3);
+    count_launch(2);
+    SPZ_CUDA(cudaGetLastError());
+    *d_local_total = part + kRedBlocks;
+    return SPZ_OK;
+}
+
+int launch_rand_finish(spz_state *st, uint64_t seed, long long index_offset, long long total_len, const double *d_total) {
+    const int grid = (int)std::max<long long>(1, std::min<long long>((st->len + 255) / 256, kRedBlocks));
+    k_rand_finish<<<grid, 256, 0, st->stream>>>(st->re, st->im, st->len, index_offset, total_len, seed, d_total);
+    count_launch();
+    SPZ_CUDA(cudaGetLastError());
+    return SPZ_OK;
+}
+
+int launch_init_random(spz_state *st, uint64_t seed) {
+    double *d_total = nullptr;
+    SPZ_TRY(launch_rand_probs(st, seed, 0, &d_total));
+    return launch_rand_finish(st, seed, 0, st->len, d_total);
+}
+
+__global__ void __launch_bounds__(256) k_scale_all(double *__restrict__ re, double *__restrict__ im, long long len, double k) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        re[i] = __dmul_rn(re[i], k);
+        im[i] = __dmul_rn(im[i], k);
+    }
+}
+
+int launch_scale(spz_state *st, double scale) {
+    const int grid = (int)std::max<long long>(1, std::min<long long>((st->len + 255) / 256, 148 * 16));
+    k_scale_all<<<grid, 256, 0, st->stream>>>(st->re, st->im, st->len, scale);
+    count_launch();
     SPZ_CUDA(cudaGetLastError());
     return SPZ_OK;
 }

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kTileThreads) k_tile(const TileArgs a) {
             }
         } else {
             // diagonal gate whose target is an outer qubit: constant factor for this tile
-            const bool hi = (base >> op.outer_target) & 1ull;
+            const bool hi = op.const_hi ? (op.const_hi == 2) : (bool)((base >> op.outer_target) & 1ull);
             if (!hi && kind != SPZ_GATE_RZ) continue; // Z / P leave target-bit-0 amplitudes alone
             const unsigned cnt = tile_len >> __popc(icm);
             for (unsigned p = threadIdx.x; p < cnt; p += kTileThreads) {

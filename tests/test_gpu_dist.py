@@ -1,0 +1,187 @@
+"""GPU tests of the sharded register (csrc/dist.cu).
+
+* `local group`: 2/4/8 shards inside this process on one GPU, one host thread per shard -- the same kernels,
+  epoch flags and exchange protocol as one-process-per-GPU, minus IPC.  Runs on a 1-GPU box.
+* `torchrun`: 2 real processes on 2 GPUs with CUDA IPC over NVLink (skipped when fewer than 2 GPUs).
+Parity: the gathered, un-permuted state must equal the unsharded single-GPU engine bit for bit (same
+arithmetic per amplitude) and the oracle within 1e-12.
+"""
+import math
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle as orc
+import spinoza_b200 as sb
+from spinoza_b200 import Gate, QuantumCircuit
+from spinoza_b200.distributed import DistState, unpermute
+from tests.test_gpu_parity import GATES, G, build_circuit, random_ops, run_dense
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def run_group(states, fn):
+    """Run fn(rank, state) on one thread per shard (calls block on device-side handshakes)."""
+    with ThreadPoolExecutor(max_workers=len(states)) as ex:
+        futs = [ex.submit(fn, r, s) for r, s in enumerate(states)]
+        return [f.result(timeout=300) for f in futs]
+
+
+def upload_shards(states, cpu):
+    n_local = states[0].n_local
+    for r, s in enumerate(states):
+        s.upload(cpu.reals[r << n_local:(r + 1) << n_local], cpu.imags[r << n_local:(r + 1) << n_local])
+
+
+def gather(states):
+    parts = [s.download() for s in states]
+    re = np.concatenate([p[0] for p in parts]); im = np.concatenate([p[1] for p in parts])
+    perms = [s.perm() for s in states]
+    assert all(p == perms[0] for p in perms)
+    return unpermute(re, im, perms[0])
+
+
+@pytest.mark.parametrize("n,world", [(6, 2), (9, 4), (12, 8), (14, 2)])
+def test_direct_gates_sharded_vs_single_gpu(n, world):
+    cpu = orc.gen_random_state(n, 11 * n + world)
+    ref = sb.State.from_arrays(cpu.reals, cpu.imags)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, cpu)
+    rng = np.random.default_rng(n + world)
+    seq = []
+    for _ in range(60):
+        kind, p = GATES[int(rng.integers(len(GATES)))]
+        t = int(rng.integers(n))
+        c = int(rng.integers(n - 1)); c += c >= t
+        seq.append((kind, p, t, c, rng.random() < 0.5))
+    seq += [(orc.H, (), n - 1, 0, False), (orc.RX, (1.0,), n - 1, 0, False), (orc.X, (), n - 2, n - 1, True)]
+
+    def body(rank, s):
+        for kind, p, t, c, ctl in seq:
+            if ctl and kind != orc.Z:
+                sb.c_apply(G(kind, p), s, c, t)
+            else:
+                sb.apply(G(kind, p), s, t)
+        s.sync()
+    run_group(states, body)
+    for kind, p, t, c, ctl in seq:
+        if ctl and kind != orc.Z:
+            sb.c_apply(G(kind, p), ref, c, t)
+        else:
+            sb.apply(G(kind, p), ref, t)
+    re, im = gather(states)
+    rre, rim = ref.download()
+    assert np.array_equal(re, rre) and np.array_equal(im, rim)
+    assert states[0].stats()["exchanges"] > 0
+
+
+@pytest.mark.parametrize("n,world,fuse", [(8, 2, True), (10, 4, True), (10, 4, False), (13, 8, True), (16, 4, True)])
+def test_execute_sharded_vs_dense(n, world, fuse):
+    ops = random_ops(n, 150, seed=n * 7 + world, with_swap=True)
+    cpu = orc.gen_random_state(n, 3 * n + world)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, cpu)
+
+    def body(rank, s):
+        build_circuit(n, ops, s, fuse=fuse).execute()
+        s.sync()
+    run_group(states, body)
+    re, im = gather(states)
+    want = run_dense(n, cpu.amps(), ops)
+    assert np.max(np.abs((re + 1j * im) - want)) < 1e-12
+    ref = sb.State.from_arrays(cpu.reals, cpu.imags)
+    build_circuit(n, ops, ref, fuse=False).execute()
+    rre, rim = ref.download()
+    assert np.array_equal(re, rre) and np.array_equal(im, rim)
+
+
+@pytest.mark.parametrize("n,world", [(10, 8), (14, 4)])
+def test_qft_sharded_closed_form_and_reductions(n, world):
+    x = 0x9E3779B97F4A7C15 % (1 << n)
+    states = DistState.create_local_group(n, world)
+
+    def body(rank, s):
+        s.set_basis(x)
+        qc = QuantumCircuit.from_state(s, fuse=True)
+        qc.qft()
+        qc.execute()
+        out = {"norm": sb.norm2(s), "p0": [sb.prob0(s, t) for t in range(n)],
+               "x": sb.xyz_expectation_value("x", s, [0, n - 1]), "z": sb.xyz_expectation_value("z", s, [n - 1]),
+               "qev": sb.qubit_expectation_value(s, n - 2)}
+        s.sync()
+        return out
+    res = run_group(states, body)
+    assert all(r == res[0] for r in res)  # every rank sees the bitwise-identical reduction
+    re, im = gather(states)
+    k = np.arange(1 << n)
+    rev = np.zeros_like(k)
+    for b in range(n):
+        rev |= ((k >> b) & 1) << (n - 1 - b)
+    want = 2.0 ** (-n / 2) * np.exp(2j * np.pi * ((x * rev) % (1 << n)) / (1 << n))
+    assert np.max(np.abs((re + 1j * im) - want)) < 1e-12
+    assert abs(res[0]["norm"] - 1.0) < 1e-10
+    cpu = orc.State(n, re, im)
+    for t in range(n):
+        assert abs(res[0]["p0"][t] - orc.prob0(cpu, t)) < 1e-12
+    assert np.max(np.abs(np.array(res[0]["x"]) - orc.xyz_expectation_value("x", cpu, [0, n - 1]))) < 1e-12
+    assert abs(res[0]["z"][0] - orc.xyz_expectation_value("z", cpu, [n - 1])[0]) < 1e-12
+    assert states[0].stats()["exchanges"] == int(math.log2(world)) + 1  # revolving door: g + 1
+
+
+@pytest.mark.parametrize("n,world", [(7, 4), (11, 2)])
+def test_measure_sharded(n, world):
+    cpu = orc.gen_random_state(n, 19 + n)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, cpu)
+    plan = [(n - 1, 1, True), (0, 0, True), (n - 2, 1, False), (1, 1, True)]
+
+    def body(rank, s):
+        bits = [sb.measure_qubit(s, t, reset, v) for t, v, reset in plan]
+        s.sync()
+        return bits
+    res = run_group(states, body)
+    for t, v, reset in plan:
+        orc.measure_qubit(cpu, t, reset, v)
+    assert all(r == [v for _, v, _ in plan] for r in res)
+    re, im = gather(states)
+    assert np.max(np.abs(re - cpu.reals)) < 1e-12 and np.max(np.abs(im - cpu.imags)) < 1e-12
+
+
+def test_init_random_sharded_matches_single_gpu():
+    n, world = 12, 4
+    states = DistState.create_local_group(n, world)
+    run_group(states, lambda r, s: (s.init_random(42), s.sync()))
+    re, im = gather(states)
+    ref = sb.State(n); ref.init_random(42)
+    rre, rim = ref.download()
+    assert np.max(np.abs(re - rre)) < 1e-14 and np.max(np.abs(im - rim)) < 1e-14
+
+
+def test_world_one_dist_state_behaves_like_state():
+    from spinoza_b200.distributed import DistEnv
+    n = 8
+    cpu = orc.gen_random_state(n, 2)
+    s = DistState(n, DistEnv(0, 1, 0))
+    s.upload(cpu.reals, cpu.imags)
+    sb.apply(Gate.H, s, n - 1); orc.apply(orc.H, cpu, n - 1)
+    sb.c_apply(Gate.P(0.3), s, 0, n - 1); orc.c_apply(orc.P, cpu, 0, n - 1, (0.3,))
+    re, im = s.download()
+    assert np.array_equal(re, cpu.reals) and np.array_equal(im, cpu.imags)
+    assert abs(sb.prob0(s, 3) - orc.prob0(cpu, 3)) < 1e-12
+
+
+@pytest.mark.skipif(sb.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpus_ipc_nvlink():
+    env = dict(os.environ)
+    env["PYTHONPATH"] = str(ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(ROOT / "tests" / "_dist_gpu_worker.py")],
+                       capture_output=True, text=True, env=env, timeout=600, cwd=str(ROOT))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "GPU_DIST_OK" in r.stdout
