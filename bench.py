@@ -240,10 +240,7 @@ def main():
             dist.barrier()
 
     def apply(gate, t):
-        if dist is not None:
-            state.apply(gate, t)
-        else:
-            sb.apply(gate, state, t)
+        sb.apply(gate, state, t)  # same call for a single-GPU State and for one shard of a DistState
 
     def step():
         for gate in gates:
@@ -265,8 +262,15 @@ def main():
     state.sync(); barrier()
     launches = sb.launch_count() - l0
     clocks = sampler.stop()
+    nvlink = None
     if dist is not None:
         ms = dist.max_float(ms)
+        st_ = state.stats()
+        nvlink = {"exchanges_total": st_["exchanges"], "bytes_sent_per_gpu": st_["bytes_sent"],
+                  "exchange_kernel_ms": st_["exchange_ms"], "GBps_per_direction_per_gpu": st_["nvlink_GBps_per_direction"],
+                  "peak_GBps_per_direction": 770.0, "peak_source": "B200_PROFILING.md measured peer copy",
+                  "frac": (st_["nvlink_GBps_per_direction"] or 0.0) / 770.0,
+                  "note": "covers warm-up + timed steps; each exchange moves half a shard out and half a shard in"}
     ms_per_step = ms / args.steps
     value = gates_per_step * bytes_per_gate_total / (ms_per_step * 1e-3) / 1e9
     per_gate_ms = ms_per_step / gates_per_step
@@ -286,6 +290,8 @@ def main():
                      "traffic": None},
         "clocks": clocks, "gpu_launches": int(launches),
     }
+    if nvlink is not None:
+        line["nvlink"] = nvlink
 
     # ---- per-(gate, target) table, single GPU only: 1 warm-up + 5 timed reps each ----
     if rank == 0 and dist is None and not args.no_extras:
@@ -310,12 +316,8 @@ def main():
         qft = {}
         n_gates = n + n * (n - 1) // 2
         for label, fuse in (("fused", True), ("unfused", False)):
-            if dist is not None:
-                state.set_basis(0x9E3779B97F4A7C15 % (1 << n))
-                qc = state.circuit(fuse=fuse)
-            else:
-                state.set_basis(0x9E3779B97F4A7C15 % (1 << n))
-                qc = QuantumCircuit.from_state(state, fuse=fuse)
+            state.set_basis(0x9E3779B97F4A7C15 % (1 << n))
+            qc = QuantumCircuit.from_state(state, fuse=fuse)
             qc.qft()
             state.sync(); barrier()
             l1 = sb.launch_count()

@@ -85,8 +85,11 @@ typedef struct {
 } spz_op;
 
 /* spz_execute flags */
-#define SPZ_EXEC_FUSE 1u     /* batch runs of gates into shared-memory tiles (one HBM pass per batch) */
 #define SPZ_EXEC_NO_FUSE 0u  /* one kernel per gate, arithmetic bit-identical to spz_apply & co. */
+#define SPZ_EXEC_FUSE 1u     /* batch runs of gates into on-chip tiles (one HBM pass per batch); runs of diagonal
+                                gates are merged into phase accumulators (differs from gate-by-gate by a few ulp) */
+#define SPZ_EXEC_EXACT 2u    /* with SPZ_EXEC_FUSE: apply every gate with the reference arithmetic -> results are
+                                bit-identical to SPZ_EXEC_NO_FUSE (slower on long diagonal runs) */
 
 /* ---- library -------------------------------------------------------------------------------- */
 SPZ_API int spz_abi_version(void);

@@ -510,13 +510,13 @@ def sample(state: State, shots: int, seed: int = 0, u01: Optional[np.ndarray] = 
 
 
 from .circuit import (Controls, QuantumCircuit, QuantumRegister, QuantumTransformation,  # noqa: E402
-                      EXEC_FUSE, EXEC_NO_FUSE)
+                      EXEC_FUSE, EXEC_NO_FUSE, EXEC_EXACT)
 from . import openqasm  # noqa: E402
 from . import distributed  # noqa: E402
 
 __all__ = [
     "PI", "SpinozaError", "Gate", "State", "HostBuffer", "apply", "c_apply", "cc_apply", "mc_apply", "mc_apply_mask", "iqft",
     "measure_qubit", "prob0", "norm2", "qubit_expectation_value", "xyz_expectation_value", "sample", "uniforms",
-    "Controls", "QuantumCircuit", "QuantumRegister", "QuantumTransformation", "EXEC_FUSE", "EXEC_NO_FUSE",
+    "Controls", "QuantumCircuit", "QuantumRegister", "QuantumTransformation", "EXEC_FUSE", "EXEC_NO_FUSE", "EXEC_EXACT",
     "openqasm", "device_count", "device_name", "mem_info", "launch_count", "library_path",
 ]

@@ -10,7 +10,8 @@ import ctypes as C
 from typing import Iterable, List, Optional, Sequence
 
 EXEC_NO_FUSE = 0
-EXEC_FUSE = 1
+EXEC_FUSE = 1   # fused tiles, runs of diagonal gates merged into phase accumulators (few-ulp rounding difference)
+EXEC_EXACT = 2  # with EXEC_FUSE: every gate applied with the reference arithmetic (bit-identical to unfused)
 
 
 class QuantumRegister:
@@ -106,7 +107,7 @@ class QuantumTransformation:
 class QuantumCircuit:
     """circuit.rs:168-601"""
 
-    def __init__(self, *registers: QuantumRegister, device: int = 0, state=None, fuse: bool = True):
+    def __init__(self, *registers: QuantumRegister, device: int = 0, state=None, fuse: bool = True, exact: bool = False):
         bits = 0
         self.quantum_registers_info: List[int] = []
         for r in registers:  # circuit.rs:186-190
@@ -123,6 +124,7 @@ class QuantumCircuit:
         self._measured_qubits = 0
         self._measured_qubits_vals = 0
         self.fuse = fuse
+        self.exact = exact
 
     @property
     def state(self):
@@ -137,9 +139,9 @@ class QuantumCircuit:
         self.n_qubits = value.n
 
     @classmethod
-    def from_state(cls, state, fuse: bool = True) -> "QuantumCircuit":
+    def from_state(cls, state, fuse: bool = True, exact: bool = False) -> "QuantumCircuit":
         """The tests' `QuantumCircuit { state, transformations: Vec::new(), .. }` literal (circuit.rs:839-844)."""
-        return cls(state=state, fuse=fuse)
+        return cls(state=state, fuse=fuse, exact=exact)
 
     def get_statevector(self):  # circuit.rs:200-202
         return self.state
@@ -306,7 +308,7 @@ class QuantumCircuit:
         arr, n = self._encode()
         m = C.c_uint64(self._measured_qubits)
         v = C.c_uint64(self._measured_qubits_vals)
-        flags = EXEC_FUSE if self.fuse else EXEC_NO_FUSE
+        flags = (EXEC_FUSE | (EXEC_EXACT if self.exact else 0)) if self.fuse else EXEC_NO_FUSE
         self.transformations = []  # drain(..): the list is consumed even if a gate "panics"
         _check(_lib.spz_execute(self.state._h, arr, n, flags, C.byref(m), C.byref(v)))
         self._measured_qubits, self._measured_qubits_vals = m.value, v.value

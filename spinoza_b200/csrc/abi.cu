@@ -126,6 +126,7 @@ struct ROp { // an op resolved to what the kernels need (physical qubits of this
     uint64_t cmask;
     GateK g;
     int const_hi = -1; // >= 0: diagonal gate whose target is a rank bit of a sharded register; value of that bit
+    double theta = 0.0; // first gate parameter (merged diagonal factors are computed from the angle itself)
 };
 
 struct Fuser {
@@ -135,6 +136,7 @@ struct Fuser {
     std::vector<ROp> ops;
     uint64_t high_set = 0;
     int low_need = 0;
+    bool exact = false;
 
     Fuser(spz_state *s) : st(s) {
         T = std::min(max_tile_bits(), s->n);
@@ -160,6 +162,82 @@ struct Fuser {
         return try_add_target(op.target, hs, ln);
     }
 
+    // Compile the group into the tile kernel's micro-program (see kernels_tile.cu).
+    int compile(const TilePlan &plan, std::vector<TileInstr> &prog) const {
+        auto tile_bit = [&](int q) -> int {
+            if (q < plan.low_bits) return q;
+            for (int i = 0; i < plan.n_high; ++i) if (plan.high[i] == q) return plan.low_bits + i;
+            return -1;
+        };
+        // SWAP(a, b) = CX(a,b) CX(b,a) CX(a,b) (utils.rs:204-208): exact, and each CX is a register butterfly
+        std::vector<ROp> lops;
+        lops.reserve(ops.size() + 8);
+        for (const ROp &o : ops) {
+            if (o.kind != SPZ_GATE_SWAP) { lops.push_back(o); continue; }
+            ROp cx{};
+            cx.kind = SPZ_GATE_X; cx.g.kind = SPZ_GATE_X;
+            cx.target = o.t2; cx.cmask = 1ull << o.target; lops.push_back(cx);
+            cx.target = o.target; cx.cmask = 1ull << o.t2; lops.push_back(cx);
+            cx.target = o.t2; cx.cmask = 1ull << o.target; lops.push_back(cx);
+        }
+        int R[4] = {0, 1, 2, 3};
+        bool haveR = false;
+        auto idx_in_R = [&](int b) -> int { for (int i = 0; i < 4; ++i) if (R[i] == b) return i; return -1; };
+        auto choose_layout = [&](size_t from, int must) {
+            int pick[4], np = 0;
+            auto add = [&](int b) { for (int i = 0; i < np; ++i) if (pick[i] == b) return; if (np < 4) pick[np++] = b; };
+            if (must >= 0) add(must);
+            for (size_t j = from; j < lops.size() && np < 4; ++j) {
+                const ROp &o = lops[j];
+                if (is_diagonal_kind(o.kind) || o.const_hi >= 0) continue;
+                const int b = tile_bit(o.target);
+                if (b >= 0) add(b);
+            }
+            for (int b = T - 1; b >= 0 && np < 4; --b) add(b);
+            std::sort(pick, pick + 4);
+            for (int i = 0; i < 4; ++i) R[i] = pick[i];
+            haveR = true;
+            TileInstr li{};
+            li.op = TI_LAYOUT;
+            for (int i = 0; i < 4; ++i) li.rbit[i] = R[i];
+            prog.push_back(li);
+        };
+        for (size_t i = 0; i < lops.size(); ++i) {
+            const ROp &o = lops[i];
+            const bool diag = is_diagonal_kind(o.kind);
+            const int tb = o.const_hi >= 0 ? -1 : tile_bit(o.target);
+            if (!diag && tb < 0) { set_error("internal: non-diagonal op left outside its tile"); return SPZ_ERR_INVALID_ARG; }
+            if (!diag) { if (!haveR || idx_in_R(tb) < 0) choose_layout(i, tb); }
+            else if (!haveR) choose_layout(i, -1);
+            TileInstr t{};
+            t.op = diag ? TI_DIAG : TI_GATE;
+            t.kind = o.kind;
+            t.outer_target = -1;
+            for (int q = 0; q < st->n; ++q) {
+                if (!((o.cmask >> q) & 1ull)) continue;
+                const int b = tile_bit(q);
+                if (b < 0) t.outer_cmask |= 1ull << q;
+                else if (idx_in_R(b) >= 0) t.reg_cmask |= 1u << idx_in_R(b);
+                else t.thr_cmask |= 1u << b;
+            }
+            for (int j = 0; j < 7; ++j) t.s[j] = o.g.s[j];
+            if (!diag) {
+                t.rpos = idx_in_R(tb);
+            } else {
+                if (o.const_hi >= 0) { t.t_where = 0; t.const_hi = (uint32_t)(o.const_hi + 1); }
+                else if (tb < 0) { t.t_where = 0; t.outer_target = o.target; }
+                else if (idx_in_R(tb) >= 0) { t.t_where = 2; t.t_mask = 1u << idx_in_R(tb); }
+                else { t.t_where = 1; t.t_mask = 1u << tb; }
+                t.f0[0] = 1.0; t.f0[1] = 0.0;
+                if (o.kind == SPZ_GATE_Z) { t.f1[0] = -1.0; t.f1[1] = 0.0; }
+                else { t.f1[0] = std::cos(o.theta); t.f1[1] = std::sin(o.theta); } // P and RZ: e^{i theta} on target-bit-1
+                if (o.kind == SPZ_GATE_RZ) { t.has_f0 = 1; t.f0[0] = o.g.s[0]; t.f0[1] = -o.g.s[1]; } // d0 = (cos, -sin)(theta/2)
+            }
+            prog.push_back(t);
+        }
+        return SPZ_OK;
+    }
+
     int flush() {
         if (ops.empty()) return SPZ_OK;
         int rc = SPZ_OK;
@@ -176,31 +254,10 @@ struct Fuser {
             plan.low_bits = T - plan.n_high;
             int k = 0;
             for (int q = 0; q < 64; ++q) if ((high_set >> q) & 1ull) plan.high[k++] = q;
-            auto tile_bit = [&](int q) -> int {
-                if (q < plan.low_bits) return q;
-                for (int i = 0; i < plan.n_high; ++i) if (plan.high[i] == q) return plan.low_bits + i;
-                return -1;
-            };
-            std::vector<TileOp> tops(ops.size());
-            for (size_t i = 0; i < ops.size(); ++i) {
-                const ROp &o = ops[i];
-                TileOp &t = tops[i];
-                std::memset(&t, 0, sizeof t);
-                t.kind = o.kind;
-                t.const_hi = o.const_hi >= 0 ? (uint32_t)(o.const_hi + 1) : 0u;
-                t.tbit = o.const_hi >= 0 ? -1 : tile_bit(o.target);
-                t.tbit2 = o.kind == SPZ_GATE_SWAP ? tile_bit(o.t2) : -1;
-                t.outer_target = t.tbit < 0 ? o.target : -1;
-                for (int q = 0; q < st->n; ++q) {
-                    if (!((o.cmask >> q) & 1ull)) continue;
-                    const int b = tile_bit(q);
-                    if (b >= 0) t.inner_cmask |= 1u << b; else t.outer_cmask |= 1ull << q;
-                }
-                for (int j = 0; j < 7; ++j) t.s[j] = o.g.s[j];
-                if (t.tbit < 0 && !is_diagonal_kind(o.kind)) { set_error("internal: non-diagonal op left outside its tile"); return SPZ_ERR_INVALID_ARG; }
-                if (o.kind == SPZ_GATE_SWAP && t.tbit2 < 0) { set_error("internal: swap operand left outside its tile"); return SPZ_ERR_INVALID_ARG; }
-            }
-            rc = launch_tile_group(st, plan, tops.data(), (int)tops.size());
+            std::vector<TileInstr> prog;
+            prog.reserve(ops.size() + 16);
+            rc = compile(plan, prog);
+            if (rc == SPZ_OK) rc = launch_tile_program(st, plan, prog.data(), (int)prog.size(), exact);
         }
         ops.clear();
         high_set = 0;
@@ -466,8 +523,9 @@ int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags,
     uint64_t local_m = 0, local_v = 0;
     uint64_t *mm = measured_mask ? measured_mask : &local_m;
     uint64_t *mv = measured_vals ? measured_vals : &local_v;
-    const bool fuse = (flags & SPZ_EXEC_FUSE) != 0;
+    const bool fuse = (flags & SPZ_EXEC_FUSE) != 0 && st->n >= min_tile_bits();
     Fuser fuser(st);
+    fuser.exact = (flags & SPZ_EXEC_EXACT) != 0;
 
     const int nq = total_qubits(st);
     int64_t cur = 0; // index of the op being emitted (for the exchange look-ahead)
@@ -491,6 +549,7 @@ int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags,
         }
         ROp r{};
         r.kind = kind; r.target = target; r.t2 = t2; r.cmask = cmask; r.const_hi = const_hi;
+        r.theta = p ? p[0] : 0.0;
         if (kind == SPZ_GATE_SWAP) { if (target == t2) return SPZ_OK; r.g.kind = kind; }
         else SPZ_TRY(resolve_gate(kind, p, &r.g));
         return fuser.add(r);

@@ -91,16 +91,24 @@ int launch_rand_finish(spz_state *st, uint64_t seed, long long index_offset, lon
 int launch_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_index);
 
 // ---- fused execution (kernels_tile.cu) ------------------------------------------------------------
-struct TileOp {
-    int kind;            // spz_gate_kind (H X Y Z P RX RY RZ U) or SPZ_GATE_SWAP
-    int tbit;            // in-tile bit of the target, or -1 when the target is an outer (non-tile) qubit
-    int tbit2;           // SWAP: in-tile bit of the second operand
-    int outer_target;    // absolute qubit of an outer target (diagonal gates only), else -1
-    uint32_t inner_cmask; // control bits inside the tile (in-tile bit positions)
-    uint32_t const_hi;    // outer-target diagonal gates: 0 = read the bit from the tile base, 1 = bit is 0, 2 = bit is 1
-                          // (a target that is a rank bit of a sharded register)
-    uint64_t outer_cmask; // control bits outside the tile (absolute positions)
-    double s[7];
+// Micro-program of the fused tile kernel (kernels_tile.cu).  128 bytes per instruction.
+enum { TI_LAYOUT = 0, TI_GATE = 1, TI_DIAG = 2 };
+struct TileInstr {
+    int op;               // TI_*
+    int kind;             // spz_gate_kind
+    int rbit[4];          // TI_LAYOUT: the 4 register-resident tile bits, ascending
+    int rpos;             // TI_GATE: which register bit (0..3) the target is
+    uint32_t reg_cmask;   // controls on register bits (mask over k = 0..15)
+    uint32_t thr_cmask;   // controls on thread bits (mask in tile-index space)
+    int t_where;          // TI_DIAG target: 0 = outside the tile, 1 = thread bit, 2 = register bit
+    uint32_t t_mask;      // t_where 1: tile-index mask; t_where 2: mask over k
+    int outer_target;     // t_where 0: absolute qubit, unless const_hi is set
+    uint32_t const_hi;    // t_where 0: 0 = read the bit from the tile base, 1 = bit is 0, 2 = bit is 1 (a rank bit)
+    int has_f0;           // merged mode: f0 is not the identity
+    uint64_t outer_cmask; // controls outside the tile (absolute positions)
+    double s[7];          // gate scalars for the exact arithmetic (gate_math.cuh)
+    double f0[2];         // merged mode: factor when all controls are set (RZ's d0)
+    double f1[2];         // merged mode: extra factor when the target bit is set too (e^{i theta}, -1)
 };
 struct TilePlan {
     int tile_bits;       // T
@@ -108,8 +116,9 @@ struct TilePlan {
     int n_high;          // tile bits L.. are qubits high[0..n_high)
     int high[16];
 };
-int launch_tile_group(spz_state *st, const TilePlan &plan, const TileOp *ops, int n_ops);
+int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, bool exact);
 int max_tile_bits();
+int min_tile_bits();
 
 // ---- multi-GPU (dist.cu) ----------------------------------------------------------------------------
 int dist_total_qubits(const spz_state *st);

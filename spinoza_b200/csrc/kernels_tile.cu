@@ -1,18 +1,29 @@
-// kernels_tile.cu -- fused execution: a run of gates applied tile-by-tile in shared memory so that one
-// HBM pass (32 * 2^n bytes) serves the whole run.  This is the engine behind spz_execute(SPZ_EXEC_FUSE);
-// the reference applies one gate per full pass (circuit.rs:553-599, "no fusion").
+// kernels_tile.cu -- fused execution: a run of gates applied tile-by-tile on chip so that one HBM pass
+// (32 * 2^n bytes) serves the whole run.  This is the engine behind spz_execute(SPZ_EXEC_FUSE); the reference
+// applies one gate per full pass (circuit.rs:553-599, "no fusion").
 //
-// A tile is the set of 2^T amplitudes that share all index bits OUTSIDE the tile's bit set
-//   { 0 .. L-1 }  U  { high[0] < high[1] < ... }         (T = L + n_high)
-// i.e. 2^n_high contiguous segments of 2^L amplitudes each.  Any gate whose target is a tile qubit can be
-// applied inside the tile; controls may be anywhere (outer controls are constant per tile, so the CTA skips
-// the gate or applies it unconditionally); diagonal gates (Z, P, RZ) may even target an outer qubit, where
-// they reduce to a per-tile constant factor.  Gates are applied one after another with the same per-pair
-// arithmetic as the unfused kernels (gate_math.cuh), so fused results are bit-identical to unfused ones.
+// Tile.  The 2^T amplitudes (T = 12: 64 KB of re+im) that share all index bits OUTSIDE the tile bit set
+//   { 0 .. L-1 }  U  { high[0] < high[1] < ... }            (T = L + n_high)
+// i.e. 2^n_high contiguous segments of 2^L amplitudes.  A gate whose target is a tile qubit can be applied inside
+// the tile; controls may be anywhere (outer controls are constant per tile: the CTA skips the gate or applies it
+// unconditionally); diagonal gates (Z, P, RZ) may even target an outer qubit (constant factor per tile).
 //
-// One CTA per tile: coalesced 128-bit loads of every segment into shared memory (SoA: re[2^T], im[2^T]),
-// the op list applied with a __syncthreads between ops, coalesced stores back.  T = 12 -> 64 KB of shared
-// memory per CTA, 3 CTAs per SM so loads of one tile overlap the arithmetic of another.
+// Execution model.  One CTA per tile, 2^(T-4) threads.  Shared memory is the tile's home (XOR-swizzled so every
+// register layout below is bank-conflict free); each thread keeps 16 amplitudes in REGISTERS: the 4 tile bits of
+// the current "register layout" R index the thread's amplitudes k = 0..15, the other T-4 tile bits come from the
+// thread id.  The host compiles the op run into a micro-program (TileInstr, engine.h):
+//   LAYOUT R      write registers back, barrier, re-read with 4 other bits register-resident
+//   GATE          non-diagonal gate on a register bit: a butterfly among the thread's own 16 amplitudes, with the
+//                 same per-pair arithmetic as the unfused kernels (gate_math.cuh) -> bit-identical results
+//   DIAG          diagonal gate.  Exact mode: applied per amplitude with the reference arithmetic (bit-identical).
+//                 Merged mode (default): a run of diagonal gates is folded into per-thread phase accumulators
+//                 F0 (all 16 amplitudes) and F1..F4 (amplitudes whose register bit i is 1); only gates whose
+//                 support has >= 2 register bits touch amplitudes directly.  At the end of the run the 16
+//                 per-amplitude factors are expanded from the 5 accumulators (15 complex multiplies) and
+//                 applied once.  A QFT pass with ~280 controlled-phase gates then costs ~1 complex multiply per
+//                 gate per THREAD instead of 16 per gate.  Rounding differs from gate-by-gate application by a few
+//                 ulp per run (documented in DESIGN.md; tests hold it to 1e-12 absolute).
+// No barrier is needed between gates that act on register bits; barriers only surround LAYOUT changes.
 #include <algorithm>
 #include <vector>
 
@@ -20,36 +31,59 @@
 
 namespace spz {
 
-constexpr int kTileThreads = 256;
 constexpr int kMaxTileBits = 12;
 constexpr int kMaxHigh = 8;
+constexpr int kRegBits = 4; // 16 amplitudes per thread
 
 int max_tile_bits() { return kMaxTileBits; }
+int min_tile_bits() { return kRegBits; }
 
 struct TileArgs {
     double *re;
     double *im;
-    const TileOp *ops;
-    int n_ops;
+    const TileInstr *prog;
+    int n_instr;
     int T, L, n_high;
     int high[kMaxHigh];
 };
 
-// deposit the bits of x into the positions of the zero bits... insert a zero at every set bit of `mask`
-// (ascending), leaving room for the tile bits.
-__device__ __forceinline__ unsigned insert_zeros_mask(unsigned x, unsigned mask) {
-    while (mask) {
-        const int b = __ffs(mask) - 1;
-        x = (unsigned)insert_zero(x, b);
-        mask &= mask - 1;
-    }
-    return x;
+__device__ __forceinline__ unsigned swz(unsigned j) { return j ^ (((j >> 4) ^ (j >> 8)) & 15u); }
+
+__device__ __forceinline__ void cmul(double &xr, double &xi, double fr, double fi) {
+    const double nr = xr * fr - xi * fi;
+    const double ni = xr * fi + xi * fr;
+    xr = nr; xi = ni;
 }
 
-__global__ void __launch_bounds__(kTileThreads) k_tile(const TileArgs a) {
+// Butterfly of a non-diagonal gate over register bit RPOS: pairs (k, k | 1 << RPOS).
+template <int KIND, int RPOS>
+__device__ __forceinline__ void butterfly(double (&ar)[16], double (&ai)[16], const double *__restrict__ s, unsigned creg,
+                                          bool ok) {
+#pragma unroll
+    for (int k0 = 0; k0 < 16; ++k0) {
+        if (k0 & (1 << RPOS)) continue;
+        const int k1 = k0 | (1 << RPOS);
+        if (ok && ((unsigned)k0 & creg) == creg) pair_update<KIND>(s, ar[k0], ai[k0], ar[k1], ai[k1]);
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ void butterfly_pos(int rpos, double (&ar)[16], double (&ai)[16], const double *__restrict__ s,
+                                              unsigned creg, bool ok) {
+    switch (rpos) {
+    case 0: butterfly<KIND, 0>(ar, ai, s, creg, ok); break;
+    case 1: butterfly<KIND, 1>(ar, ai, s, creg, ok); break;
+    case 2: butterfly<KIND, 2>(ar, ai, s, creg, ok); break;
+    default: butterfly<KIND, 3>(ar, ai, s, creg, ok); break;
+    }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
     extern __shared__ double smem[];
     const int T = a.T, L = a.L;
     const unsigned tile_len = 1u << T;
+    const unsigned nthr = blockDim.x;
     double *sre = smem;
     double *sim = smem + tile_len;
     __shared__ unsigned long long seg_off[1 << kMaxHigh];
@@ -57,9 +91,8 @@ __global__ void __launch_bounds__(kTileThreads) k_tile(const TileArgs a) {
     // absolute index of the tile's first amplitude: CTA id bits go to the non-tile positions
     unsigned long long base = (unsigned long long)blockIdx.x << L;
     for (int k = 0; k < a.n_high; ++k) base = insert_zero(base, a.high[k]);
-
     const int n_seg = 1 << a.n_high;
-    for (int sgi = threadIdx.x; sgi < n_seg; sgi += kTileThreads) {
+    for (int sgi = threadIdx.x; sgi < n_seg; sgi += nthr) {
         unsigned long long off = 0;
         for (int k = 0; k < a.n_high; ++k)
             if ((sgi >> k) & 1) off |= 1ull << a.high[k];
@@ -67,86 +100,178 @@ __global__ void __launch_bounds__(kTileThreads) k_tile(const TileArgs a) {
     }
     __syncthreads();
 
-    // ---- load: 2^(T-1) double2 vectors per array ----
+    // ---- global -> shared (coalesced 128-bit loads; swizzled placement) ----
     const unsigned n_vec = tile_len >> 1;
     const unsigned seg_mask = (1u << L) - 1u;
-    for (unsigned v = threadIdx.x; v < n_vec; v += kTileThreads) {
+    for (unsigned v = threadIdx.x; v < n_vec; v += nthr) {
         const unsigned j = v << 1;
         const unsigned long long g = base + seg_off[j >> L] + (j & seg_mask);
         const double2 r = *reinterpret_cast<const double2 *>(a.re + g);
         const double2 m = *reinterpret_cast<const double2 *>(a.im + g);
-        *reinterpret_cast<double2 *>(sre + j) = r;
-        *reinterpret_cast<double2 *>(sim + j) = m;
+        const unsigned s0 = swz(j), s1 = swz(j + 1); // s1 == s0 ^ 1
+        sre[s0] = r.x; sre[s1] = r.y;
+        sim[s0] = m.x; sim[s1] = m.y;
     }
     __syncthreads();
 
-    // ---- apply the op list ----
-    for (int oi = 0; oi < a.n_ops; ++oi) {
-        const TileOp &op = a.ops[oi];
-        const unsigned long long ocm = op.outer_cmask;
-        if ((base & ocm) != ocm) continue; // an outer control is 0 for this whole tile
-        const int kind = op.kind;
-        const unsigned icm = op.inner_cmask;
-        if (kind == SPZ_GATE_SWAP) {
-            // swap_apply gates.rs:1376-1386 restricted to the tile: (lo=1,hi=0) <-> (lo=0,hi=1)
-            const unsigned blo = 1u << min(op.tbit, op.tbit2), bhi = 1u << max(op.tbit, op.tbit2);
-            const unsigned ins = blo | bhi;
-            const unsigned cnt = tile_len >> 2;
-            for (unsigned p = threadIdx.x; p < cnt; p += kTileThreads) {
-                const unsigned x = insert_zeros_mask(p, ins);
-                const unsigned ia = x | blo, ib = x | bhi;
-                double t = sre[ia]; sre[ia] = sre[ib]; sre[ib] = t;
-                t = sim[ia]; sim[ia] = sim[ib]; sim[ib] = t;
-            }
-        } else if (op.tbit >= 0) {
-            const unsigned tb = 1u << op.tbit;
-            const unsigned ins = tb | icm;
-            const unsigned cnt = tile_len >> __popc(ins);
-            const bool s0_too = !(kind == SPZ_GATE_Z || kind == SPZ_GATE_P);
-            for (unsigned p = threadIdx.x; p < cnt; p += kTileThreads) {
-                const unsigned i0 = insert_zeros_mask(p, ins) | icm;
-                const unsigned i1 = i0 | tb;
-                double x0 = 0.0, y0 = 0.0;
-                if (s0_too) { x0 = sre[i0]; y0 = sim[i0]; }
-                double x1 = sre[i1], y1 = sim[i1];
-                pair_update_rt(kind, op.s, x0, y0, x1, y1);
-                if (s0_too) { sre[i0] = x0; sim[i0] = y0; }
-                sre[i1] = x1; sim[i1] = y1;
-            }
-        } else {
-            // diagonal gate whose target is an outer qubit: constant factor for this tile
-            const bool hi = op.const_hi ? (op.const_hi == 2) : (bool)((base >> op.outer_target) & 1ull);
-            if (!hi && kind != SPZ_GATE_RZ) continue; // Z / P leave target-bit-0 amplitudes alone
-            const unsigned cnt = tile_len >> __popc(icm);
-            for (unsigned p = threadIdx.x; p < cnt; p += kTileThreads) {
-                const unsigned i = insert_zeros_mask(p, icm) | icm;
-                double x = sre[i], y = sim[i];
-                diag_update_rt(kind, op.s, hi, x, y);
-                sre[i] = x; sim[i] = y;
+    double ar[16], ai[16];
+    // merged-mode phase accumulators: F0 multiplies all 16 amplitudes, Fi those whose register bit i-1 is set
+    double f0r = 1.0, f0i = 0.0, f1r = 1.0, f1i = 0.0, f2r = 1.0, f2i = 0.0, f3r = 1.0, f3i = 0.0, f4r = 1.0, f4i = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
+    bool dirty = false, have_regs = false;
+    unsigned tj = 0;                       // this thread's tile index with the register bits cleared
+    int r0 = 0, r1 = 1, r2 = 2, r3 = 3;    // the register-resident tile bits
+
+    auto koff = [&](int k) -> unsigned {
+        return ((k & 1u) << r0) | (((k >> 1) & 1u) << r1) | (((k >> 2) & 1u) << r2) | (((k >> 3) & 1u) << r3);
+    };
+
+    auto flush_diag = [&]() {
+        if (!dirty) return;
+        // expand the 5 accumulators into the 16 per-amplitude factors, depth first (15 + 16 complex multiplies)
+#pragma unroll
+        for (int b3 = 0; b3 < 2; ++b3) {
+            double g3r = f0r, g3i = f0i;
+            if (b3) cmul(g3r, g3i, f4r, f4i);
+#pragma unroll
+            for (int b2 = 0; b2 < 2; ++b2) {
+                double g2r = g3r, g2i = g3i;
+                if (b2) cmul(g2r, g2i, f3r, f3i);
+#pragma unroll
+                for (int b1 = 0; b1 < 2; ++b1) {
+                    double g1r = g2r, g1i = g2i;
+                    if (b1) cmul(g1r, g1i, f2r, f2i);
+#pragma unroll
+                    for (int b0 = 0; b0 < 2; ++b0) {
+                        double gr = g1r, gi = g1i;
+                        if (b0) cmul(gr, gi, f1r, f1i);
+                        cmul(ar[b0 | (b1 << 1) | (b2 << 2) | (b3 << 3)], ai[b0 | (b1 << 1) | (b2 << 2) | (b3 << 3)], gr, gi);
+                    }
+                }
             }
         }
+        f0r = f1r = f2r = f3r = f4r = 1.0;
+        f0i = f1i = f2i = f3i = f4i = 0.0;
+        dirty = false;
+    };
+
+    auto store_regs = [&]() {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const unsigned s = swz(tj | koff(k));
+            sre[s] = ar[k]; sim[s] = ai[k];
+        }
+    };
+
+    // one merged-mode phase term: amplitudes with (thread bits >= thr) and (k >= m) are multiplied by f
+    auto add_term = [&](unsigned thr, unsigned m, double fr, double fi) {
+        const bool ok = (tj & thr) == thr;
+        dirty = true;
+        switch (m) {
+        case 0: if (ok) cmul(f0r, f0i, fr, fi); break;
+        case 1: if (ok) cmul(f1r, f1i, fr, fi); break;
+        case 2: if (ok) cmul(f2r, f2i, fr, fi); break;
+        case 4: if (ok) cmul(f3r, f3i, fr, fi); break;
+        case 8: if (ok) cmul(f4r, f4i, fr, fi); break;
+        default:
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (ok && ((unsigned)k & m) == m) cmul(ar[k], ai[k], fr, fi);
+            break;
+        }
+    };
+
+    for (int pc = 0; pc < a.n_instr; ++pc) {
+        const TileInstr &ins = a.prog[pc];
+        const int op = ins.op;
+        if (op == TI_LAYOUT) {
+            if (have_regs) {
+                flush_diag();
+                store_regs();
+                __syncthreads();
+            }
+            r0 = ins.rbit[0]; r1 = ins.rbit[1]; r2 = ins.rbit[2]; r3 = ins.rbit[3];
+            tj = (unsigned)insert_zero(insert_zero(insert_zero(insert_zero(threadIdx.x, r0), r1), r2), r3);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const unsigned s = swz(tj | koff(k));
+                ar[k] = sre[s]; ai[k] = sim[s];
+            }
+            have_regs = true;
+            __syncthreads(); // everyone has read before anyone's next store_regs
+            continue;
+        }
+        const unsigned long long ocm = ins.outer_cmask;
+        if ((base & ocm) != ocm) continue; // an outer control is 0 for this whole tile
+        if (op == TI_GATE) {
+            flush_diag();
+            const bool ok = (tj & ins.thr_cmask) == ins.thr_cmask;
+            const unsigned creg = ins.reg_cmask;
+            switch (ins.kind) {
+            case SPZ_GATE_H: butterfly_pos<SPZ_GATE_H>(ins.rpos, ar, ai, ins.s, creg, ok); break;
+            case SPZ_GATE_X: butterfly_pos<SPZ_GATE_X>(ins.rpos, ar, ai, ins.s, creg, ok); break;
+            case SPZ_GATE_Y: butterfly_pos<SPZ_GATE_Y>(ins.rpos, ar, ai, ins.s, creg, ok); break;
+            case SPZ_GATE_RX: butterfly_pos<SPZ_GATE_RX>(ins.rpos, ar, ai, ins.s, creg, ok); break;
+            case SPZ_GATE_RY: butterfly_pos<SPZ_GATE_RY>(ins.rpos, ar, ai, ins.s, creg, ok); break;
+            case SPZ_GATE_U: butterfly_pos<SPZ_GATE_U>(ins.rpos, ar, ai, ins.s, creg, ok); break;
+            default: break;
+            }
+            continue;
+        }
+        // ---- TI_DIAG ----
+        const int kind = ins.kind;
+        const int tw = ins.t_where;
+        bool outer_hi = false;
+        if (tw == 0) outer_hi = ins.const_hi ? (ins.const_hi == 2) : (bool)((base >> ins.outer_target) & 1ull);
+        if constexpr (EXACT) {
+            if (tw == 0 && !outer_hi && kind != SPZ_GATE_RZ) continue; // Z / P leave target-bit-0 amplitudes alone
+            const bool ok = (tj & ins.thr_cmask) == ins.thr_cmask;
+            const bool thr_hi = tw == 1 ? ((tj & ins.t_mask) != 0) : outer_hi;
+            const unsigned creg = ins.reg_cmask;
+            const unsigned tmask = ins.t_mask;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (ok && ((unsigned)k & creg) == creg) {
+                    const bool hi = tw == 2 ? (((unsigned)k & tmask) != 0) : thr_hi;
+                    diag_update_rt(kind, ins.s, hi, ar[k], ai[k]);
+                }
+            }
+        } else {
+            // term A: controls set, any target value (RZ's d0);  term B: controls and target set (e^{i theta}, -1)
+            const unsigned thr = ins.thr_cmask, m = ins.reg_cmask;
+            if (ins.has_f0) add_term(thr, m, ins.f0[0], ins.f0[1]);
+            if (tw == 0) { if (outer_hi) add_term(thr, m, ins.f1[0], ins.f1[1]); }
+            else if (tw == 1) add_term(thr | ins.t_mask, m, ins.f1[0], ins.f1[1]);
+            else add_term(thr, m | ins.t_mask, ins.f1[0], ins.f1[1]);
+        }
+    }
+    if (have_regs) {
+        flush_diag();
+        store_regs();
         __syncthreads();
     }
 
-    // ---- store ----
-    for (unsigned v = threadIdx.x; v < n_vec; v += kTileThreads) {
+    // ---- shared -> global ----
+    for (unsigned v = threadIdx.x; v < n_vec; v += nthr) {
         const unsigned j = v << 1;
         const unsigned long long g = base + seg_off[j >> L] + (j & seg_mask);
-        *reinterpret_cast<double2 *>(a.re + g) = *reinterpret_cast<const double2 *>(sre + j);
-        *reinterpret_cast<double2 *>(a.im + g) = *reinterpret_cast<const double2 *>(sim + j);
+        const unsigned s0 = swz(j), s1 = swz(j + 1);
+        *reinterpret_cast<double2 *>(a.re + g) = make_double2(sre[s0], sre[s1]);
+        *reinterpret_cast<double2 *>(a.im + g) = make_double2(sim[s0], sim[s1]);
     }
 }
 
-int launch_tile_group(spz_state *st, const TilePlan &plan, const TileOp *ops, int n_ops) {
-    if (n_ops <= 0) return SPZ_OK;
-    if (plan.tile_bits > kMaxTileBits || plan.n_high > kMaxHigh || plan.low_bits < 1 ||
+int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, bool exact) {
+    if (n_instr <= 0) return SPZ_OK;
+    if (plan.tile_bits > kMaxTileBits || plan.tile_bits < kRegBits || plan.n_high > kMaxHigh || plan.low_bits < 1 ||
         plan.tile_bits != plan.low_bits + plan.n_high || plan.tile_bits > st->n) {
         set_error("bad tile plan T=%d L=%d H=%d n=%d", plan.tile_bits, plan.low_bits, plan.n_high, st->n);
         return SPZ_ERR_INVALID_ARG;
     }
-    // Op lists are staged in a device ring buffer: a group's list must stay intact until its kernel has
-    // run, so the cursor only wraps after a stream synchronise.
-    const size_t bytes = (sizeof(TileOp) * (size_t)n_ops + 255) & ~(size_t)255;
+    // Programs are staged in a device ring buffer: a group's program must stay intact until its kernel has run,
+    // so the cursor only wraps after a stream synchronise.
+    const size_t bytes = (sizeof(TileInstr) * (size_t)n_instr + 255) & ~(size_t)255;
     if (st->d_ops_bytes < bytes || !st->d_ops) {
         if (st->d_ops) { SPZ_CUDA(cudaStreamSynchronize(st->stream)); SPZ_CUDA(cudaFree(st->d_ops)); st->d_ops = nullptr; }
         const size_t cap = std::max<size_t>(bytes * 2, (size_t)4 << 20);
@@ -160,23 +285,26 @@ int launch_tile_group(spz_state *st, const TilePlan &plan, const TileOp *ops, in
     }
     char *slot = static_cast<char *>(st->d_ops) + st->d_ops_cursor;
     st->d_ops_cursor += bytes;
-    SPZ_CUDA(cudaMemcpyAsync(slot, ops, sizeof(TileOp) * (size_t)n_ops, cudaMemcpyHostToDevice, st->stream));
+    SPZ_CUDA(cudaMemcpyAsync(slot, prog, sizeof(TileInstr) * (size_t)n_instr, cudaMemcpyHostToDevice, st->stream));
 
     TileArgs a{};
     a.re = st->re; a.im = st->im;
-    a.ops = reinterpret_cast<const TileOp *>(slot);
-    a.n_ops = n_ops;
+    a.prog = reinterpret_cast<const TileInstr *>(slot);
+    a.n_instr = n_instr;
     a.T = plan.tile_bits; a.L = plan.low_bits; a.n_high = plan.n_high;
     for (int k = 0; k < plan.n_high; ++k) a.high[k] = plan.high[k];
     const size_t smem = sizeof(double) * 2u * ((size_t)1 << plan.tile_bits);
     static bool attr_set[64] = {false};
     if (!attr_set[st->device & 63]) {
-        SPZ_CUDA(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sizeof(double) * 2u * ((size_t)1 << kMaxTileBits))));
+        const int max_smem = (int)(sizeof(double) * 2u * ((size_t)1 << kMaxTileBits));
+        SPZ_CUDA(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        SPZ_CUDA(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set[st->device & 63] = true;
     }
     const unsigned grid = (unsigned)((uint64_t)st->len >> plan.tile_bits);
-    k_tile<<<grid, kTileThreads, smem, st->stream>>>(a);
+    const unsigned threads = 1u << (plan.tile_bits - kRegBits);
+    if (exact) k_tile<true><<<grid, threads, smem, st->stream>>>(a);
+    else k_tile<false><<<grid, threads, smem, st->stream>>>(a);
     count_launch();
     SPZ_CUDA(cudaGetLastError());
     return SPZ_OK;
