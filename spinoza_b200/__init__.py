@@ -39,6 +39,8 @@ OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_OOM, ERR_COMM, ERR_NO_DEVICE
 
 def _load() -> C.CDLL:
     """Load the CUDA engine; rebuild it in-tree first when its sources changed.  Never falls back."""
+    # see abi.cu: kernels that spin on peer flags must not meet CUDA's lazy module loading
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
     if os.environ.get("SPINOZA_B200_NO_AUTOBUILD"):
         if not _LIB_PATH.exists():
             raise ImportError(f"{_LIB_PATH} is missing: build it with `python -m spinoza_b200._build` "

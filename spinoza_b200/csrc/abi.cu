@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -12,6 +13,12 @@
 #include "engine.h"
 
 namespace spz {
+
+// Device-side handshakes (dist.cu) spin until a peer's kernel arrives.  With CUDA's default lazy module loading
+// the first launch of a kernel may need a context-wide synchronisation, which can never complete while such a
+// spinning kernel is resident -> load every kernel when the context is created instead.  (Only matters when two
+// shards share a GPU or a process; harmless otherwise.)  Runs at dlopen, before the first CUDA call.
+__attribute__((constructor)) static void spz_force_eager_module_loading() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
@@ -350,7 +357,11 @@ int spz_create(int n_qubits, int device, spz_state **out) {
     if ((e = cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     if ((e = cudaEventCreate(&st->ev0)) != cudaSuccess) return fail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&st->ev1)) != cudaSuccess) return fail(e, "cudaEventCreate");
-    int rc = launch_fill_basis(st, 0);
+    // All scratch is allocated here, never lazily: cudaMalloc synchronises the whole device, which must not
+    // happen while another shard's handshake kernel is spinning on the same GPU.
+    int rc = ensure_scratch(st);
+    if (rc == SPZ_OK) rc = tile_prepare(st);
+    if (rc == SPZ_OK) rc = launch_fill_basis(st, 0);
     if (rc != SPZ_OK) { spz_destroy(st); return rc; }
     *out = st;
     return SPZ_OK;

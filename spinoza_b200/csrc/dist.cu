@@ -20,7 +20,7 @@
 namespace spz {
 
 constexpr int kMaxRanks = 16;
-constexpr unsigned long long kSpinTimeoutNs = 60ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 struct CtrlBlock { // lives in device memory of each rank, mapped by every peer
     unsigned long long ready[kMaxRanks];
@@ -54,6 +54,13 @@ struct DistCtx {
 };
 
 static DistCtx *ctx_of(const spz_state *st) { return static_cast<DistCtx *>(st->dist); }
+
+// device-resident table of peer control blocks (allocated at connect time, never lazily: see spz_create)
+static int upload_peer_table(DistCtx *c) {
+    if (!c->d_table) SPZ_CUDA(cudaMalloc(&c->d_table, sizeof(CtrlBlock *) * kMaxRanks));
+    SPZ_CUDA(cudaMemcpy(c->d_table, c->peer_ctrl, sizeof(CtrlBlock *) * kMaxRanks, cudaMemcpyHostToDevice));
+    return SPZ_OK;
+}
 
 int dist_total_qubits(const spz_state *st) { return ctx_of(st)->plan.n; }
 
@@ -235,10 +242,7 @@ int dist_allreduce(spz_state *st, const double *dev_value, double host_value, do
     if (!c->connected) { set_error("dist state used before spz_dist_connect"); return SPZ_ERR_COMM; }
     SPZ_TRY(ensure_scratch(st));
     const unsigned long long e = ++c->red_epoch;
-    if (!c->d_table) { // device-resident table of peer control blocks
-        SPZ_CUDA(cudaMalloc(&c->d_table, sizeof(CtrlBlock *) * kMaxRanks));
-        SPZ_CUDA(cudaMemcpy(c->d_table, c->peer_ctrl, sizeof(CtrlBlock *) * kMaxRanks, cudaMemcpyHostToDevice));
-    }
+    if (!c->d_table) { set_error("internal: peer table missing"); return SPZ_ERR_COMM; }
     k_allreduce<<<1, 32, 0, st->stream>>>(c->ctrl, c->d_table, c->rank, c->world, e, dev_value, host_value, st->scratch.partials + 0);
     count_launch();
     SPZ_CUDA(cudaGetLastError());
@@ -390,7 +394,7 @@ int spz_dist_create(int n_qubits, int rank, int world, int device, spz_state **o
     if (e == cudaSuccess) e = cudaMemset(c->ctrl, 0, sizeof(CtrlBlock));
     if (e != cudaSuccess) { int rc = cuda_fail(e, "cudaMalloc(ctrl)", __FILE__, __LINE__); spz_destroy(st); return rc; }
     c->peer_ctrl[rank] = c->ctrl; c->peer_re[rank] = st->re; c->peer_im[rank] = st->im;
-    if (world == 1) c->connected = true;
+    if (world == 1) { c->connected = true; if (upload_peer_table(c) != SPZ_OK) { spz_destroy(st); return SPZ_ERR_CUDA; } }
     int rc = dist_fill_basis(st, 0); // |0..0> lives on rank 0 only
     if (rc != SPZ_OK) { spz_destroy(st); return rc; }
     *out = st;
@@ -424,6 +428,7 @@ int spz_dist_connect(spz_state *st, const void *blobs) {
         SPZ_CUDA(cudaIpcOpenMemHandle(&p, b[r].im, cudaIpcMemLazyEnablePeerAccess)); c->peer_im[r] = static_cast<double *>(p);
         SPZ_CUDA(cudaIpcOpenMemHandle(&p, b[r].ctrl, cudaIpcMemLazyEnablePeerAccess)); c->peer_ctrl[r] = static_cast<CtrlBlock *>(p);
     }
+    SPZ_TRY(upload_peer_table(c));
     c->connected = true;
     c->ipc = true;
     return SPZ_OK;
@@ -448,6 +453,7 @@ int spz_dist_connect_local(spz_state **states, int world) {
             }
             c->peer_re[q] = states[q]->re; c->peer_im[q] = states[q]->im; c->peer_ctrl[q] = ctx_of(states[q])->ctrl;
         }
+        SPZ_TRY(upload_peer_table(c));
         c->connected = true;
         c->ipc = false;
     }

@@ -119,6 +119,7 @@ struct TilePlan {
 int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, bool exact);
 int max_tile_bits();
 int min_tile_bits();
+int tile_prepare(spz_state *st); // allocate the program ring buffer, set the kernel's shared-memory limit
 
 // ---- multi-GPU (dist.cu) ----------------------------------------------------------------------------
 int dist_total_qubits(const spz_state *st);

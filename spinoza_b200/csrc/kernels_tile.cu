@@ -262,6 +262,19 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
     }
 }
 
+int tile_prepare(spz_state *st) {
+    if (!st->d_ops) {
+        const size_t cap = (size_t)4 << 20;
+        SPZ_CUDA(cudaMalloc(&st->d_ops, cap));
+        st->d_ops_bytes = cap;
+        st->d_ops_cursor = 0;
+    }
+    const int max_smem = (int)(sizeof(double) * 2u * ((size_t)1 << kMaxTileBits));
+    SPZ_CUDA(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SPZ_CUDA(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    return SPZ_OK;
+}
+
 int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, bool exact) {
     if (n_instr <= 0) return SPZ_OK;
     if (plan.tile_bits > kMaxTileBits || plan.tile_bits < kRegBits || plan.n_high > kMaxHigh || plan.low_bits < 1 ||
@@ -294,13 +307,6 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
     a.T = plan.tile_bits; a.L = plan.low_bits; a.n_high = plan.n_high;
     for (int k = 0; k < plan.n_high; ++k) a.high[k] = plan.high[k];
     const size_t smem = sizeof(double) * 2u * ((size_t)1 << plan.tile_bits);
-    static bool attr_set[64] = {false};
-    if (!attr_set[st->device & 63]) {
-        const int max_smem = (int)(sizeof(double) * 2u * ((size_t)1 << kMaxTileBits));
-        SPZ_CUDA(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        SPZ_CUDA(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_set[st->device & 63] = true;
-    }
     const unsigned grid = (unsigned)((uint64_t)st->len >> plan.tile_bits);
     const unsigned threads = 1u << (plan.tile_bits - kRegBits);
     if (exact) k_tile<true><<<grid, threads, smem, st->stream>>>(a);
