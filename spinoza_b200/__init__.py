@@ -41,6 +41,7 @@ def _load() -> C.CDLL:
     """Load the CUDA engine; rebuild it in-tree first when its sources changed.  Never falls back."""
     # see abi.cu: kernels that spin on peer flags must not meet CUDA's lazy module loading
     os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     if os.environ.get("SPINOZA_B200_NO_AUTOBUILD"):
         if not _LIB_PATH.exists():
             raise ImportError(f"{_LIB_PATH} is missing: build it with `python -m spinoza_b200._build` "

@@ -1,0 +1,258 @@
+// spinoza.hpp -- header-only C++17 mirror of Spinoza's public Rust API for the gate-application path, over the
+// C ABI of libspinoza_b200.so (include/spinoza_b200.h).
+//
+// The reference is Rust and no Rust toolchain exists in this environment, so this is the compiled-language host
+// side above the C ABI (the Rust shim in rust/spinoza-b200 is the same thing in the reference's own language).
+// Names, argument order and semantics follow /root/reference/spinoza/src/{core,gates,circuit,measurement}.rs; each
+// item cites its counterpart.  Where the reference panics (todo!/unimplemented!/assert!) this throws spinoza::Error.
+//
+//   spinoza::State s(3);                              // State::new(3)                      core.rs:32
+//   spinoza::apply(spinoza::Gate::H(), s, 0);         // apply(Gate::H, &mut state, 0)      gates.rs:215
+//   spinoza::c_apply(spinoza::Gate::P(0.5), s, 0, 1); // c_apply(Gate::P(0.5), &mut s, 0, 1) gates.rs:257
+//   spinoza::QuantumRegister q(3); spinoza::QuantumCircuit qc({&q}); qc.h(0); qc.cx(0, 1); qc.execute();
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/spinoza_b200.h"
+
+namespace spinoza {
+
+using Float = double; // math.rs:11-15 (feature "double")
+constexpr Float PI = 3.14159265358979323846;
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int st, const std::string &what) : std::runtime_error(what), status(st) {}
+};
+inline void check(int status) {
+    if (status != SPZ_OK) throw Error(status, std::string(spz_status_string(status)) + ": " + spz_last_error());
+}
+
+// ---- Gate, gates.rs:44-92 -----------------------------------------------------------------------------------
+struct Gate {
+    spz_gate g{};
+    static Gate make(int kind, Float a = 0, Float b = 0, Float c = 0, int t0 = 0, int t1 = 0) {
+        Gate x; x.g.kind = kind; x.g.p[0] = a; x.g.p[1] = b; x.g.p[2] = c; x.g.t0 = t0; x.g.t1 = t1; return x;
+    }
+    static Gate H() { return make(SPZ_GATE_H); }
+    static Gate M() { return make(SPZ_GATE_M); }
+    static Gate X() { return make(SPZ_GATE_X); }
+    static Gate Y() { return make(SPZ_GATE_Y); }
+    static Gate Z() { return make(SPZ_GATE_Z); }
+    static Gate P(Float theta) { return make(SPZ_GATE_P, theta); }
+    static Gate RX(Float theta) { return make(SPZ_GATE_RX, theta); }
+    static Gate RY(Float theta) { return make(SPZ_GATE_RY, theta); }
+    static Gate RZ(Float theta) { return make(SPZ_GATE_RZ, theta); }
+    static Gate SWAP(int t0, int t1) { return make(SPZ_GATE_SWAP, 0, 0, 0, t0, t1); }
+    static Gate U(Float theta, Float phi, Float lambda) { return make(SPZ_GATE_U, theta, phi, lambda); }
+    static Gate BitFlipNoise(Float prob) { return make(SPZ_GATE_BITFLIP, prob); }
+
+    Gate inverse() const { // gates.rs:78-92
+        switch (g.kind) {
+        case SPZ_GATE_H: case SPZ_GATE_X: case SPZ_GATE_Y: case SPZ_GATE_Z: case SPZ_GATE_SWAP: return *this;
+        case SPZ_GATE_P: case SPZ_GATE_RX: case SPZ_GATE_RY: case SPZ_GATE_RZ: return make(g.kind, -g.p[0]);
+        case SPZ_GATE_U: return make(SPZ_GATE_U, -g.p[0], -g.p[2], -g.p[1]);
+        default: throw Error(SPZ_ERR_UNSUPPORTED, "Gate::inverse: unimplemented!() (gates.rs:86)");
+        }
+    }
+};
+
+// ---- State, core.rs:18-51 -----------------------------------------------------------------------------------
+// Device-resident.  `reals()` / `imags()` download (the reference exposes the Vecs directly).
+class State {
+  public:
+    explicit State(std::size_t n, int device = 0) { check(spz_create((int)n, device, &h_)); } // State::new
+    State(const State &o) { check(spz_clone(o.h_, &h_)); }                                    // Clone
+    State(State &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    State &operator=(State o) { std::swap(h_, o.h_); return *this; }
+    ~State() { if (h_) spz_destroy(h_); }
+
+    std::uint8_t n() const { return (std::uint8_t)spz_num_qubits(h_); }
+    std::size_t len() const { return (std::size_t)spz_len(h_); } // core.rs:48
+    std::vector<Float> reals() const { std::vector<Float> v(len()); check(spz_download(h_, v.data(), nullptr, 0, (int64_t)v.size())); return v; }
+    std::vector<Float> imags() const { std::vector<Float> v(len()); check(spz_download(h_, nullptr, v.data(), 0, (int64_t)v.size())); return v; }
+    std::pair<Float, Float> amp(std::size_t i) const { Float r, m; check(spz_download(h_, &r, &m, (int64_t)i, 1)); return {r, m}; }
+    void set(const std::vector<Float> &re, const std::vector<Float> &im) { check(spz_upload(h_, re.data(), im.data(), 0, (int64_t)re.size())); }
+    void set_seed(std::uint64_t seed) { check(spz_set_seed(h_, seed)); }
+    spz_state *handle() const { return h_; }
+
+  private:
+    spz_state *h_ = nullptr;
+};
+
+// ---- gates.rs:215-320 -----------------------------------------------------------------------------------------
+inline void apply(const Gate &gate, State &state, std::size_t target) { check(spz_apply(state.handle(), &gate.g, (int)target)); }
+inline void c_apply(const Gate &gate, State &state, std::size_t control, std::size_t target) {
+    check(spz_c_apply(state.handle(), &gate.g, (int)control, (int)target));
+}
+inline void cc_apply(const Gate &gate, State &state, std::size_t control0, std::size_t control1, std::size_t target) {
+    check(spz_cc_apply(state.handle(), &gate.g, (int)control0, (int)control1, (int)target));
+}
+// mc_apply(gate, state, controls, zeros: Option<HashSet<usize>>, target): pass nullptr for None
+inline void mc_apply(const Gate &gate, State &state, const std::vector<std::size_t> &controls,
+                     const std::set<std::size_t> *zeros, std::size_t target) {
+    std::vector<int32_t> c(controls.begin(), controls.end()), z;
+    if (zeros) z.assign(zeros->begin(), zeros->end());
+    check(spz_mc_apply(state.handle(), &gate.g, c.data(), (int)c.size(), zeros ? z.data() : nullptr, (int)z.size(), (int)target));
+}
+inline void iqft(State &state, const std::vector<std::size_t> &targets) { // core.rs:184
+    std::vector<int32_t> t(targets.begin(), targets.end());
+    check(spz_iqft(state.handle(), t.data(), (int)t.size()));
+}
+
+// ---- measurement.rs:12, core.rs:198-264 ----------------------------------------------------------------------------
+// v: -1 mirrors `None`
+inline std::uint8_t measure_qubit(State &state, std::size_t target, bool reset, int v = -1) {
+    int bit = 0;
+    check(spz_measure_qubit(state.handle(), (int)target, reset ? 1 : 0, v, &bit));
+    return (std::uint8_t)bit;
+}
+inline Float qubit_expectation_value(const State &state, std::size_t target) {
+    Float out = 0;
+    check(spz_qubit_expectation_value(state.handle(), (int)target, &out));
+    return out;
+}
+inline std::vector<Float> xyz_expectation_value(char observable, const State &state, const std::vector<std::size_t> &targets) {
+    std::vector<int32_t> t(targets.begin(), targets.end());
+    std::vector<Float> out(t.size());
+    check(spz_xyz_expectation_value(state.handle(), observable, t.data(), (int)t.size(), out.data()));
+    return out;
+}
+
+// ---- circuit.rs ---------------------------------------------------------------------------------------------------
+struct QuantumRegister { // circuit.rs:13-51
+    std::vector<std::size_t> q;
+    explicit QuantumRegister(std::size_t size) { if (!size) throw Error(SPZ_ERR_INVALID_ARG, "assert!(size > 0)"); for (std::size_t i = 0; i < size; ++i) q.push_back(i); }
+    std::size_t operator[](std::size_t i) const { return q[i]; }
+    std::size_t len() const { return q.size(); }
+    void update_shift(std::size_t shift) { for (auto &x : q) x += shift; }
+    std::size_t get_shift() const { return q[0]; }
+};
+
+struct Controls { // circuit.rs:55-109
+    int kind = SPZ_CTRL_NONE;
+    std::vector<std::size_t> controls;
+    std::set<std::size_t> zeros;
+    static Controls None() { return {}; }
+    static Controls Single(std::size_t c) { Controls x; x.kind = SPZ_CTRL_SINGLE; x.controls = {c}; return x; }
+    static Controls Ones(std::vector<std::size_t> cs) { Controls x; x.kind = SPZ_CTRL_ONES; x.controls = std::move(cs); return x; }
+    static Controls Mixed(std::vector<std::size_t> cs, std::set<std::size_t> zs) { Controls x; x.kind = SPZ_CTRL_MIXED; x.controls = std::move(cs); x.zeros = std::move(zs); return x; }
+    static Controls from(const std::vector<std::size_t> &cs, const std::set<std::size_t> *zs) { // circuit.rs:73-86
+        if (zs) return Mixed(cs, *zs);
+        if (cs.empty()) return None();
+        if (cs.size() == 1) return Single(cs[0]);
+        return Ones(cs);
+    }
+    Controls new_with_control(std::size_t control, std::size_t shift) const { // circuit.rs:97-108
+        std::vector<std::size_t> cs;
+        for (auto c : controls) cs.push_back(c + shift);
+        cs.push_back(control);
+        if (zeros.empty()) return from(cs, nullptr);
+        std::set<std::size_t> zs;
+        for (auto z : zeros) zs.insert(z + shift);
+        return from(cs, &zs);
+    }
+};
+
+struct QuantumTransformation { // circuit.rs:113-120
+    Gate gate;
+    std::size_t target;
+    Controls controls;
+};
+
+class QuantumCircuit { // circuit.rs:168-601
+  public:
+    std::vector<QuantumTransformation> transformations;
+    State state;
+    std::vector<std::size_t> quantum_registers_info;
+    bool fuse = true, exact = false;
+
+    explicit QuantumCircuit(std::vector<QuantumRegister *> registers, int device = 0) : state(shift_all(registers), device) {
+        for (auto *r : registers) quantum_registers_info.push_back(r->len());
+    }
+    explicit QuantumCircuit(State s) : state(std::move(s)) {}
+
+    const State &get_statevector() const { return state; }
+    void inverse() { // circuit.rs:206-211
+        std::vector<QuantumTransformation> r(transformations.rbegin(), transformations.rend());
+        for (auto &t : r) t.gate = t.gate.inverse();
+        transformations = std::move(r);
+    }
+    void add(QuantumTransformation t) { transformations.push_back(std::move(t)); }
+    void measure(std::size_t t) { add({Gate::M(), t, Controls::None()}); }
+    void swap(std::size_t t0, std::size_t t1) { add({Gate::SWAP((int)t0, (int)t1), 0, Controls::None()}); }
+    void x(std::size_t t) { add({Gate::X(), t, Controls::None()}); }
+    void y(std::size_t t) { add({Gate::Y(), t, Controls::None()}); }
+    void z(std::size_t t) { add({Gate::Z(), t, Controls::None()}); }
+    void h(std::size_t t) { add({Gate::H(), t, Controls::None()}); }
+    void p(Float a, std::size_t t) { add({Gate::P(a), t, Controls::None()}); }
+    void rx(Float a, std::size_t t) { add({Gate::RX(a), t, Controls::None()}); }
+    void ry(Float a, std::size_t t) { add({Gate::RY(a), t, Controls::None()}); }
+    void rz(Float a, std::size_t t) { add({Gate::RZ(a), t, Controls::None()}); }
+    void u(Float th, Float ph, Float la, std::size_t t) { add({Gate::U(th, ph, la), t, Controls::None()}); }
+    void cx(std::size_t c, std::size_t t) { add({Gate::X(), t, Controls::Single(c)}); }
+    void ccx(std::size_t c1, std::size_t c2, std::size_t t) { add({Gate::X(), t, Controls::Ones({c1, c2})}); }
+    void ch(std::size_t c, std::size_t t) { add({Gate::H(), t, Controls::Single(c)}); }
+    void cy(std::size_t c, std::size_t t) { add({Gate::Y(), t, Controls::Single(c)}); }
+    void cp(Float a, std::size_t c, std::size_t t) { add({Gate::P(a), t, Controls::Single(c)}); }
+    void crx(Float a, std::size_t c, std::size_t t) { add({Gate::RX(a), t, Controls::Single(c)}); }
+    void cry(Float a, std::size_t c, std::size_t t) { add({Gate::RY(a), t, Controls::Single(c)}); }
+    void crz(Float a, std::size_t c, std::size_t t) { add({Gate::RZ(a), t, Controls::Single(c)}); }
+    void cu(Float th, Float ph, Float la, std::size_t c, std::size_t t) { add({Gate::U(th, ph, la), t, Controls::Single(c)}); }
+    void bit_flip_noise(Float prob, std::size_t t) { add({Gate::BitFlipNoise(prob), t, Controls::None()}); }
+    void iqft(const std::vector<std::size_t> &targets) { // circuit.rs:438-445
+        for (std::size_t j = targets.size(); j-- > 0;) {
+            h(targets[j]);
+            for (std::size_t k = j; k-- > 0;) cp(-PI / std::ldexp(1.0, (int)(j - k)), targets[j], targets[k]);
+        }
+    }
+    void append(const QuantumCircuit &c, const QuantumRegister &reg) { // circuit.rs:448-460
+        for (const auto &t : c.transformations) add({t.gate, reg.get_shift() + t.target, t.controls});
+    }
+    void c_append(const QuantumCircuit &c, std::size_t ctl, const QuantumRegister &reg) { // circuit.rs:463-476
+        if (ctl >= reg.get_shift() && ctl < reg.get_shift() + reg.len()) throw Error(SPZ_ERR_INVALID_ARG, "control inside the register");
+        for (const auto &t : c.transformations) add({t.gate, reg.get_shift() + t.target, t.controls.new_with_control(ctl, reg.get_shift())});
+    }
+    void mc_append(const QuantumCircuit &c, const std::vector<std::size_t> &ctls, const QuantumRegister &reg) { // circuit.rs:479-511
+        for (auto ctl : ctls) {
+            if (ctl >= reg.get_shift() && ctl < reg.get_shift() + reg.len()) throw Error(SPZ_ERR_INVALID_ARG, "control inside the register");
+            for (const auto &t : c.transformations) add({t.gate, reg.get_shift() + t.target, t.controls.new_with_control(ctl, reg.get_shift())});
+        }
+    }
+    bool is_qubit_measured(std::size_t q) const { return (measured_ >> q) & 1; }
+    int get_qubit_measured_val(std::size_t q) const { return is_qubit_measured(q) ? (int)((vals_ >> q) & 1) : -1; }
+
+    void execute() { // circuit.rs:552-600; drains the list
+        std::vector<spz_op> ops(transformations.size());
+        for (std::size_t i = 0; i < ops.size(); ++i) {
+            const auto &t = transformations[i];
+            spz_op &o = ops[i];
+            o = spz_op{};
+            o.kind = t.gate.g.kind; o.target = (int32_t)t.target; o.t0 = t.gate.g.t0; o.t1 = t.gate.g.t1;
+            for (int j = 0; j < 3; ++j) o.p[j] = t.gate.g.p[j];
+            o.ctrl_kind = t.controls.kind;
+            for (auto c : t.controls.controls) o.ctrl_mask |= 1ull << c;
+            for (auto z : t.controls.zeros) o.zeros_mask |= 1ull << z;
+        }
+        transformations.clear();
+        const uint32_t flags = fuse ? (SPZ_EXEC_FUSE | (exact ? SPZ_EXEC_EXACT : 0u)) : SPZ_EXEC_NO_FUSE;
+        check(spz_execute(state.handle(), ops.data(), (int64_t)ops.size(), flags, &measured_, &vals_));
+    }
+
+  private:
+    std::uint64_t measured_ = 0, vals_ = 0; // QubitTracker circuit.rs:122-164
+    static std::size_t shift_all(std::vector<QuantumRegister *> &regs) { // circuit.rs:181-190
+        std::size_t bits = 0;
+        for (auto *r : regs) { r->update_shift(bits); bits += r->len(); }
+        return bits;
+    }
+};
+
+} // namespace spinoza

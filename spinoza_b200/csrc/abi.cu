@@ -18,7 +18,12 @@ namespace spz {
 // the first launch of a kernel may need a context-wide synchronisation, which can never complete while such a
 // spinning kernel is resident -> load every kernel when the context is created instead.  (Only matters when two
 // shards share a GPU or a process; harmless otherwise.)  Runs at dlopen, before the first CUDA call.
-__attribute__((constructor)) static void spz_force_eager_module_loading() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
+// Likewise, streams of different shards must not share a hardware work queue (a queue whose head is a spinning
+// handshake would block the very kernel it waits for): ask for the maximum number of connections (default 8).
+__attribute__((constructor)) static void spz_force_eager_module_loading() {
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+}
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
