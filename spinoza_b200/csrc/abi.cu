@@ -175,7 +175,7 @@ struct Fuser {
     }
 
     // Compile the group into the tile kernel's micro-program (see kernels_tile.cu).
-    int compile(const TilePlan &plan, std::vector<TileInstr> &prog) const {
+    int compile(const TilePlan &plan, std::vector<TileInstr> &prog, std::vector<TileTerm> &terms) const {
         auto tile_bit = [&](int q) -> int {
             if (q < plan.low_bits) return q;
             for (int i = 0; i < plan.n_high; ++i) if (plan.high[i] == q) return plan.low_bits + i;
@@ -194,6 +194,26 @@ struct Fuser {
         }
         int R[4] = {0, 1, 2, 3};
         bool haveR = false;
+        // merged mode: the diagonal gates of the current run, as phase terms bucketed by class
+        // (m = 0, 1, 2, 4, 8, other); diagonal gates commute, so a run may be reordered freely
+        std::vector<TileTerm> bucket[6];
+        auto close_run = [&]() {
+            size_t total = 0;
+            for (auto &b : bucket) total += b.size();
+            if (!total) return;
+            TileInstr r{};
+            r.op = TI_RUN;
+            r.rpos = (int)terms.size();
+            r.rbit[0] = (int)bucket[0].size(); r.rbit[1] = (int)bucket[1].size(); r.rbit[2] = (int)bucket[2].size();
+            r.rbit[3] = (int)bucket[3].size(); r.reg_cmask = (uint32_t)bucket[4].size(); r.thr_cmask = (uint32_t)bucket[5].size();
+            for (auto &b : bucket) { terms.insert(terms.end(), b.begin(), b.end()); b.clear(); }
+            prog.push_back(r);
+        };
+        auto add_term = [&](uint64_t outer, uint32_t thr, uint32_t m, double fr, double fi) {
+            TileTerm t{outer, thr, m, fr, fi};
+            const int cls = m == 0 ? 0 : m == 1 ? 1 : m == 2 ? 2 : m == 4 ? 3 : m == 8 ? 4 : 5;
+            bucket[cls].push_back(t);
+        };
         auto idx_in_R = [&](int b) -> int { for (int i = 0; i < 4; ++i) if (R[i] == b) return i; return -1; };
         auto choose_layout = [&](size_t from, int must) {
             int pick[4], np = 0;
@@ -207,6 +227,7 @@ struct Fuser {
             }
             for (int b = T - 1; b >= 0 && np < 4; --b) add(b);
             std::sort(pick, pick + 4);
+            close_run(); // term masks are relative to the layout
             for (int i = 0; i < 4; ++i) R[i] = pick[i];
             haveR = true;
             TileInstr li{};
@@ -234,6 +255,7 @@ struct Fuser {
             }
             for (int j = 0; j < 7; ++j) t.s[j] = o.g.s[j];
             if (!diag) {
+                close_run(); // the gates of a run commute with each other, not with this butterfly
                 t.rpos = idx_in_R(tb);
             } else {
                 if (o.const_hi >= 0) { t.t_where = 0; t.const_hi = (uint32_t)(o.const_hi + 1); }
@@ -244,9 +266,19 @@ struct Fuser {
                 if (o.kind == SPZ_GATE_Z) { t.f1[0] = -1.0; t.f1[1] = 0.0; }
                 else { t.f1[0] = std::cos(o.theta); t.f1[1] = std::sin(o.theta); } // P and RZ: e^{i theta} on target-bit-1
                 if (o.kind == SPZ_GATE_RZ) { t.has_f0 = 1; t.f0[0] = o.g.s[0]; t.f0[1] = -o.g.s[1]; } // d0 = (cos, -sin)(theta/2)
+                if (!exact) { // fold into the run instead of emitting an instruction
+                    if (t.has_f0) add_term(t.outer_cmask, t.thr_cmask, t.reg_cmask, t.f0[0], t.f0[1]);
+                    if (t.t_where == 0) {
+                        if (t.const_hi == 2) add_term(t.outer_cmask, t.thr_cmask, t.reg_cmask, t.f1[0], t.f1[1]);
+                        else if (t.const_hi == 0) add_term(t.outer_cmask | (1ull << t.outer_target), t.thr_cmask, t.reg_cmask, t.f1[0], t.f1[1]);
+                    } else if (t.t_where == 1) add_term(t.outer_cmask, t.thr_cmask | t.t_mask, t.reg_cmask, t.f1[0], t.f1[1]);
+                    else add_term(t.outer_cmask, t.thr_cmask, t.reg_cmask | t.t_mask, t.f1[0], t.f1[1]);
+                    continue;
+                }
             }
             prog.push_back(t);
         }
+        close_run();
         return SPZ_OK;
     }
 
@@ -267,9 +299,10 @@ struct Fuser {
             int k = 0;
             for (int q = 0; q < 64; ++q) if ((high_set >> q) & 1ull) plan.high[k++] = q;
             std::vector<TileInstr> prog;
+            std::vector<TileTerm> terms;
             prog.reserve(ops.size() + 16);
-            rc = compile(plan, prog);
-            if (rc == SPZ_OK) rc = launch_tile_program(st, plan, prog.data(), (int)prog.size(), exact);
+            rc = compile(plan, prog, terms);
+            if (rc == SPZ_OK) rc = launch_tile_program(st, plan, prog.data(), (int)prog.size(), terms.data(), (int)terms.size(), exact);
         }
         ops.clear();
         high_set = 0;

@@ -92,12 +92,23 @@ int launch_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_
 
 // ---- fused execution (kernels_tile.cu) ------------------------------------------------------------
 // Micro-program of the fused tile kernel (kernels_tile.cu).  128 bytes per instruction.
-enum { TI_LAYOUT = 0, TI_GATE = 1, TI_DIAG = 2 };
+enum { TI_LAYOUT = 0, TI_GATE = 1, TI_DIAG = 2, TI_RUN = 3 };
+
+// One phase term of a merged run of diagonal gates (32 bytes): amplitudes whose tile base contains `outer`,
+// whose thread bits contain `thr` and whose register index contains `m` are multiplied by (fr, fi).
+struct TileTerm {
+    uint64_t outer;
+    uint32_t thr;
+    uint32_t m;
+    double fr, fi;
+};
 struct TileInstr {
     int op;               // TI_*
     int kind;             // spz_gate_kind
     int rbit[4];          // TI_LAYOUT: the 4 register-resident tile bits, ascending
-    int rpos;             // TI_GATE: which register bit (0..3) the target is
+    int rpos;             // TI_GATE: which register bit (0..3) the target is.  TI_RUN: offset of the run's first term
+    // TI_RUN: rbit[0..3], reg_cmask, thr_cmask hold the term counts of classes m = 0, 1, 2, 4, 8, other (in that
+    // order in the term array); diagonal gates commute, so the host sorts a run's terms by class.
     uint32_t reg_cmask;   // controls on register bits (mask over k = 0..15)
     uint32_t thr_cmask;   // controls on thread bits (mask in tile-index space)
     int t_where;          // TI_DIAG target: 0 = outside the tile, 1 = thread bit, 2 = register bit
@@ -116,7 +127,8 @@ struct TilePlan {
     int n_high;          // tile bits L.. are qubits high[0..n_high)
     int high[16];
 };
-int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, bool exact);
+int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, const TileTerm *terms,
+                        int n_terms, bool exact);
 int max_tile_bits();
 int min_tile_bits();
 int tile_prepare(spz_state *st); // allocate the program ring buffer, set the kernel's shared-memory limit

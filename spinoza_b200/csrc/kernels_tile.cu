@@ -42,6 +42,7 @@ struct TileArgs {
     double *re;
     double *im;
     const TileInstr *prog;
+    const TileTerm *terms;
     int n_instr;
     int T, L, n_high;
     int high[kMaxHigh];
@@ -76,6 +77,39 @@ __device__ __forceinline__ void butterfly_pos(int rpos, double (&ar)[16], double
     case 2: butterfly<KIND, 2>(ar, ai, s, creg, ok); break;
     default: butterfly<KIND, 3>(ar, ai, s, creg, ok); break;
     }
+}
+
+// One class of a merged diagonal run: every term multiplies the same accumulator.  Terms are fetched four at a
+// time with warp-uniform 128-bit loads (all loads issued before use) and folded into two independent partial
+// products to halve the dependent-DFMA chain.
+__device__ __forceinline__ void run_class(const TileTerm *__restrict__ t, int cnt, unsigned long long base, unsigned tj,
+                                          double &Fr, double &Fi) {
+    double ar_ = 1.0, ai_ = 0.0, br_ = 1.0, bi_ = 0.0;
+    int i = 0;
+    for (; i + 4 <= cnt; i += 4) {
+        ulonglong2 h[4];
+        double2 f[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            h[u] = __ldg(reinterpret_cast<const ulonglong2 *>(t + i + u));
+            f[u] = __ldg(reinterpret_cast<const double2 *>(&t[i + u].fr));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned thr = (unsigned)(h[u].y & 0xffffffffull);
+            if ((base & h[u].x) == h[u].x && (tj & thr) == thr) {
+                if (u & 1) cmul(br_, bi_, f[u].x, f[u].y); else cmul(ar_, ai_, f[u].x, f[u].y);
+            }
+        }
+    }
+    for (; i < cnt; ++i) {
+        const ulonglong2 h = __ldg(reinterpret_cast<const ulonglong2 *>(t + i));
+        const double2 f = __ldg(reinterpret_cast<const double2 *>(&t[i].fr));
+        const unsigned thr = (unsigned)(h.y & 0xffffffffull);
+        if ((base & h.x) == h.x && (tj & thr) == thr) cmul(ar_, ai_, f.x, f.y);
+    }
+    cmul(ar_, ai_, br_, bi_);
+    cmul(Fr, Fi, ar_, ai_);
 }
 
 template <bool EXACT>
@@ -121,10 +155,12 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
     for (int k = 0; k < 16; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
     bool dirty = false, have_regs = false;
     unsigned tj = 0;                       // this thread's tile index with the register bits cleared
-    int r0 = 0, r1 = 1, r2 = 2, r3 = 3;    // the register-resident tile bits
 
-    auto koff = [&](int k) -> unsigned {
-        return ((k & 1u) << r0) | (((k >> 1) & 1u) << r1) | (((k >> 2) & 1u) << r2) | (((k >> 3) & 1u) << r3);
+    // swz() is linear over XOR, so the swizzled address of amplitude k is swz(tj) ^ (XOR of the swizzled register
+    // bits selected by k): one XOR per access with warp-uniform operands.
+    unsigned stj = 0, sw0 = 1, sw1 = 2, sw2 = 4, sw3 = 8;
+    auto saddr = [&](int k) -> unsigned {
+        return stj ^ ((k & 1) ? sw0 : 0u) ^ ((k & 2) ? sw1 : 0u) ^ ((k & 4) ? sw2 : 0u) ^ ((k & 8) ? sw3 : 0u);
     };
 
     auto flush_diag = [&]() {
@@ -159,7 +195,7 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
     auto store_regs = [&]() {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const unsigned s = swz(tj | koff(k));
+            const unsigned s = saddr(k);
             sre[s] = ar[k]; sim[s] = ai[k];
         }
     };
@@ -191,15 +227,35 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
                 store_regs();
                 __syncthreads();
             }
-            r0 = ins.rbit[0]; r1 = ins.rbit[1]; r2 = ins.rbit[2]; r3 = ins.rbit[3];
+            const int r0 = ins.rbit[0], r1 = ins.rbit[1], r2 = ins.rbit[2], r3 = ins.rbit[3];
             tj = (unsigned)insert_zero(insert_zero(insert_zero(insert_zero(threadIdx.x, r0), r1), r2), r3);
+            stj = swz(tj); sw0 = swz(1u << r0); sw1 = swz(1u << r1); sw2 = swz(1u << r2); sw3 = swz(1u << r3);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                const unsigned s = swz(tj | koff(k));
+                const unsigned s = saddr(k);
                 ar[k] = sre[s]; ai[k] = sim[s];
             }
             have_regs = true;
             __syncthreads(); // everyone has read before anyone's next store_regs
+            continue;
+        }
+        if (op == TI_RUN) {
+            const TileTerm *t = a.terms + ins.rpos;
+            const int c0 = ins.rbit[0], c1 = ins.rbit[1], c2 = ins.rbit[2], c3 = ins.rbit[3];
+            const int c4 = (int)ins.reg_cmask, c5 = (int)ins.thr_cmask;
+            run_class(t, c0, base, tj, f0r, f0i); t += c0;
+            run_class(t, c1, base, tj, f1r, f1i); t += c1;
+            run_class(t, c2, base, tj, f2r, f2i); t += c2;
+            run_class(t, c3, base, tj, f3r, f3i); t += c3;
+            run_class(t, c4, base, tj, f4r, f4i); t += c4;
+            for (int i = 0; i < c5; ++i) { // support with >= 2 register bits: touch the amplitudes directly
+                const TileTerm tt = t[i];
+                const bool ok = (base & tt.outer) == tt.outer && (tj & tt.thr) == tt.thr;
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (ok && ((unsigned)k & tt.m) == tt.m) cmul(ar[k], ai[k], tt.fr, tt.fi);
+            }
+            dirty = true;
             continue;
         }
         const unsigned long long ocm = ins.outer_cmask;
@@ -275,7 +331,8 @@ int tile_prepare(spz_state *st) {
     return SPZ_OK;
 }
 
-int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, bool exact) {
+int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, const TileTerm *terms,
+                        int n_terms, bool exact) {
     if (n_instr <= 0) return SPZ_OK;
     if (plan.tile_bits > kMaxTileBits || plan.tile_bits < kRegBits || plan.n_high > kMaxHigh || plan.low_bits < 1 ||
         plan.tile_bits != plan.low_bits + plan.n_high || plan.tile_bits > st->n) {
@@ -284,7 +341,9 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
     }
     // Programs are staged in a device ring buffer: a group's program must stay intact until its kernel has run,
     // so the cursor only wraps after a stream synchronise.
-    const size_t bytes = (sizeof(TileInstr) * (size_t)n_instr + 255) & ~(size_t)255;
+    const size_t prog_bytes = (sizeof(TileInstr) * (size_t)n_instr + 255) & ~(size_t)255;
+    const size_t term_bytes = (sizeof(TileTerm) * (size_t)n_terms + 255) & ~(size_t)255;
+    const size_t bytes = prog_bytes + term_bytes;
     if (st->d_ops_bytes < bytes || !st->d_ops) {
         if (st->d_ops) { SPZ_CUDA(cudaStreamSynchronize(st->stream)); SPZ_CUDA(cudaFree(st->d_ops)); st->d_ops = nullptr; }
         const size_t cap = std::max<size_t>(bytes * 2, (size_t)4 << 20);
@@ -299,10 +358,13 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
     char *slot = static_cast<char *>(st->d_ops) + st->d_ops_cursor;
     st->d_ops_cursor += bytes;
     SPZ_CUDA(cudaMemcpyAsync(slot, prog, sizeof(TileInstr) * (size_t)n_instr, cudaMemcpyHostToDevice, st->stream));
+    if (n_terms > 0)
+        SPZ_CUDA(cudaMemcpyAsync(slot + prog_bytes, terms, sizeof(TileTerm) * (size_t)n_terms, cudaMemcpyHostToDevice, st->stream));
 
     TileArgs a{};
     a.re = st->re; a.im = st->im;
     a.prog = reinterpret_cast<const TileInstr *>(slot);
+    a.terms = reinterpret_cast<const TileTerm *>(slot + prog_bytes);
     a.n_instr = n_instr;
     a.T = plan.tile_bits; a.L = plan.low_bits; a.n_high = plan.n_high;
     for (int k = 0; k < plan.n_high; ++k) a.high[k] = plan.high[k];

@@ -114,7 +114,8 @@ def test_qft_sharded_closed_form_and_reductions(n, world):
         qc = QuantumCircuit.from_state(s, fuse=True)
         qc.qft()
         qc.execute()
-        out = {"norm": sb.norm2(s), "p0": [sb.prob0(s, t) for t in range(n)],
+        ex = s.stats()["exchanges"]
+        out = {"ex": ex, "norm": sb.norm2(s), "p0": [sb.prob0(s, t) for t in range(n)],
                "x": sb.xyz_expectation_value("x", s, [0, n - 1]), "z": sb.xyz_expectation_value("z", s, [n - 1]),
                "qev": sb.qubit_expectation_value(s, n - 2)}
         s.sync()
@@ -134,7 +135,7 @@ def test_qft_sharded_closed_form_and_reductions(n, world):
         assert abs(res[0]["p0"][t] - orc.prob0(cpu, t)) < 1e-12
     assert np.max(np.abs(np.array(res[0]["x"]) - orc.xyz_expectation_value("x", cpu, [0, n - 1]))) < 1e-12
     assert abs(res[0]["z"][0] - orc.xyz_expectation_value("z", cpu, [n - 1])[0]) < 1e-12
-    assert states[0].stats()["exchanges"] == int(math.log2(world)) + 1  # revolving door: g + 1
+    assert res[0]["ex"] == int(math.log2(world)) + 1  # revolving door: g + 1 exchanges for the whole QFT
 
 
 @pytest.mark.parametrize("n,world", [(7, 4), (11, 2)])
