@@ -312,7 +312,7 @@ def main():
                          "frac_median_of_peak": statistics.median(flat) / peak}
 
     # ---- QFT-n through QuantumCircuit::execute (fused and unfused), sec/gate ----
-    if not args.no_extras:
+    def run_qft():
         qft = {}
         n_gates = n + n * (n - 1) // 2
         for label, fuse in (("fused", True), ("unfused", False)):
@@ -342,7 +342,16 @@ def main():
             ph = ((np.uint64(x) * rev) % np.uint64(1 << n)).astype(np.float64) / float(1 << n)
             want = 2.0 ** (-n / 2) * np.exp(2j * np.pi * ph)
             qft["max_abs_err_vs_closed_form_first_4096"] = float(np.max(np.abs((re + 1j * im) - want)))
-        line["qft"] = qft
+        else:
+            qft["norm2_after"] = sb.norm2(state)
+            qft["exchanges_total_incl_sweep"] = state.stats()["exchanges"]
+        return qft
+
+    if not args.no_extras:
+        try:
+            line["qft"] = run_qft()
+        except Exception as e:  # keep the headline line even if an extra fails
+            line["qft"] = {"error": repr(e)}
 
     # ---- end to end through the C ABI with HOST buffers: upload -> sweep -> download, every step ----
     if not args.no_e2e and dist is None:
