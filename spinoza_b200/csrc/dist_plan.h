@@ -14,9 +14,12 @@
 //   SWAP(a, b)                          -> relabel perm[a] <-> perm[b]; no data moves
 //
 // The plan is identical on every rank (SPMD): `rank` only decides skip / which constant.  The victim local
-// qubit of an EXCHANGE is the resident qubit whose next non-diagonal use is farthest away (from the op list
-// when execute() provides one, else least-recently-used), among physical bits >= kMinExchangeBit so that
-// exchanged runs are long contiguous segments.
+// qubit of an EXCHANGE is the resident qubit whose next non-diagonal use is farthest away when execute()
+// provides the op list (Belady).  Gate-by-gate calls have no look-ahead; there the victim is the MOST recently
+// used resident qubit: circuits sweep over qubits layer by layer (and QFT never touches a qubit non-diagonally
+// again after its H), so the qubit just used is the one needed latest -- LRU would evict exactly the qubit the
+// sweep needs next and thrash (measured: 254 exchanges instead of 12 in the 2-GPU bandwidth sweep).
+// Candidates are physical bits >= kMinExchangeBit so that exchanged runs are long contiguous segments.
 #pragma once
 
 #include <stdint.h>
@@ -61,8 +64,8 @@ struct DistPlan {
             if (best < 0) { best = p; continue; }
             const int bl = inv[best];
             if (next_use) {
-                if (next_use[l] > next_use[bl]) best = p;
-            } else if (last_use[l] < last_use[bl]) best = p;
+                if (next_use[l] > next_use[bl]) best = p; // Belady: farthest next non-diagonal use
+            } else if (last_use[l] > last_use[bl]) best = p; // no look-ahead: MOST recently used (see header)
         }
         if (best < 0) // every candidate is protected: fall back to any unprotected local bit
             for (int p = n_local - 1; p >= 0; --p)
