@@ -1,5 +1,6 @@
 // abi.cu -- the C ABI of libspinoza_b200 (include/spinoza_b200.h): state management, the gate entry points
 // mirroring gates.rs:215-320, and QuantumCircuit::execute (circuit.rs:552-600) with the fusion scheduler.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -175,7 +176,8 @@ struct Fuser {
     }
 
     // Compile the group into the tile kernel's micro-program (see kernels_tile.cu).
-    int compile(const TilePlan &plan, std::vector<TileInstr> &prog, std::vector<TileTerm> &terms) const {
+    int compile(const TilePlan &plan, std::vector<TileInstr> &prog, std::vector<TileGroup> &groups,
+                std::vector<TileTerm> &terms) const {
         auto tile_bit = [&](int q) -> int {
             if (q < plan.low_bits) return q;
             for (int i = 0; i < plan.n_high; ++i) if (plan.high[i] == q) return plan.low_bits + i;
@@ -203,10 +205,28 @@ struct Fuser {
             if (!total) return;
             TileInstr r{};
             r.op = TI_RUN;
-            r.rpos = (int)terms.size();
-            r.rbit[0] = (int)bucket[0].size(); r.rbit[1] = (int)bucket[1].size(); r.rbit[2] = (int)bucket[2].size();
-            r.rbit[3] = (int)bucket[3].size(); r.reg_cmask = (uint32_t)bucket[4].size(); r.thr_cmask = (uint32_t)bucket[5].size();
-            for (auto &b : bucket) { terms.insert(terms.end(), b.begin(), b.end()); b.clear(); }
+            r.rpos = (int)groups.size();
+            int counts[6];
+            for (int c = 0; c < 6; ++c) {
+                auto &b = bucket[c];
+                // terms with the same (thr, m) become one group (their product is a per-tile constant)
+                std::stable_sort(b.begin(), b.end(), [](const TileTerm &x, const TileTerm &y) {
+                    return x.thr != y.thr ? x.thr < y.thr : x.m < y.m;
+                });
+                counts[c] = 0;
+                for (size_t i = 0; i < b.size();) {
+                    size_t j = i;
+                    while (j < b.size() && b[j].thr == b[i].thr && b[j].m == b[i].m) ++j;
+                    TileGroup g{b[i].thr, b[i].m, (int)terms.size(), (int)(j - i)};
+                    groups.push_back(g);
+                    terms.insert(terms.end(), b.begin() + i, b.begin() + j);
+                    ++counts[c];
+                    i = j;
+                }
+                b.clear();
+            }
+            r.rbit[0] = counts[0]; r.rbit[1] = counts[1]; r.rbit[2] = counts[2]; r.rbit[3] = counts[3];
+            r.reg_cmask = (uint32_t)counts[4]; r.thr_cmask = (uint32_t)counts[5];
             prog.push_back(r);
         };
         auto add_term = [&](uint64_t outer, uint32_t thr, uint32_t m, double fr, double fi) {
@@ -299,10 +319,13 @@ struct Fuser {
             int k = 0;
             for (int q = 0; q < 64; ++q) if ((high_set >> q) & 1ull) plan.high[k++] = q;
             std::vector<TileInstr> prog;
+            std::vector<TileGroup> groups;
             std::vector<TileTerm> terms;
             prog.reserve(ops.size() + 16);
-            rc = compile(plan, prog, terms);
-            if (rc == SPZ_OK) rc = launch_tile_program(st, plan, prog.data(), (int)prog.size(), terms.data(), (int)terms.size(), exact);
+            rc = compile(plan, prog, groups, terms);
+            if (rc == SPZ_OK)
+                rc = launch_tile_program(st, plan, prog.data(), (int)prog.size(), groups.data(), (int)groups.size(), terms.data(),
+                                         (int)terms.size(), exact);
         }
         ops.clear();
         high_set = 0;
@@ -312,7 +335,7 @@ struct Fuser {
 
     int add(const ROp &op) {
         uint64_t hs; int ln;
-        if (!fits(op, hs, ln) || ops.size() >= 8192) {
+        if (!fits(op, hs, ln) || ops.size() >= (size_t)kMaxTileGroups / 2) {
             SPZ_TRY(flush());
             if (!fits(op, hs, ln)) { set_error("internal: op does not fit an empty tile"); return SPZ_ERR_INVALID_ARG; }
         }

@@ -102,13 +102,22 @@ struct TileTerm {
     uint32_t m;
     double fr, fi;
 };
+// Terms of one run that share (thr, m) form a group: their product depends only on the tile (through `outer`),
+// so it is computed once per CTA and shared through shared memory.
+struct TileGroup {
+    uint32_t thr;
+    uint32_t m;
+    int first; // first term
+    int count;
+};
+constexpr int kMaxTileGroups = 2048; // shared-memory budget: 20 bytes per group
 struct TileInstr {
     int op;               // TI_*
     int kind;             // spz_gate_kind
     int rbit[4];          // TI_LAYOUT: the 4 register-resident tile bits, ascending
     int rpos;             // TI_GATE: which register bit (0..3) the target is.  TI_RUN: offset of the run's first term
-    // TI_RUN: rbit[0..3], reg_cmask, thr_cmask hold the term counts of classes m = 0, 1, 2, 4, 8, other (in that
-    // order in the term array); diagonal gates commute, so the host sorts a run's terms by class.
+    // TI_RUN: rpos = first group of the run; rbit[0..3], reg_cmask, thr_cmask hold the GROUP counts of classes
+    // m = 0, 1, 2, 4, 8, other (in that order); diagonal gates commute, so the host sorts a run's terms freely.
     uint32_t reg_cmask;   // controls on register bits (mask over k = 0..15)
     uint32_t thr_cmask;   // controls on thread bits (mask in tile-index space)
     int t_where;          // TI_DIAG target: 0 = outside the tile, 1 = thread bit, 2 = register bit
@@ -127,8 +136,8 @@ struct TilePlan {
     int n_high;          // tile bits L.. are qubits high[0..n_high)
     int high[16];
 };
-int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, const TileTerm *terms,
-                        int n_terms, bool exact);
+int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, const TileGroup *groups,
+                        int n_groups, const TileTerm *terms, int n_terms, bool exact);
 int max_tile_bits();
 int min_tile_bits();
 int tile_prepare(spz_state *st); // allocate the program ring buffer, set the kernel's shared-memory limit

@@ -20,8 +20,10 @@
 //                 F0 (all 16 amplitudes) and F1..F4 (amplitudes whose register bit i is 1); only gates whose
 //                 support has >= 2 register bits touch amplitudes directly.  At the end of the run the 16
 //                 per-amplitude factors are expanded from the 5 accumulators (15 complex multiplies) and
-//                 applied once.  A QFT pass with ~280 controlled-phase gates then costs ~1 complex multiply per
-//                 gate per THREAD instead of 16 per gate.  Rounding differs from gate-by-gate application by a few
+//                 applied once.  Terms of a run that share their thread/register masks differ only in which OUTER
+//                 bits they need, so their product is a per-tile constant: it is computed once per CTA
+//                 (cooperatively, before the first barrier) and read from shared memory.  A QFT pass with ~280
+//                 controlled-phase gates then costs ~80 complex multiplies per THREAD instead of 16 per gate.  Rounding differs from gate-by-gate application by a few
 //                 ulp per run (documented in DESIGN.md; tests hold it to 1e-12 absolute).
 // No barrier is needed between gates that act on register bits; barriers only surround LAYOUT changes.
 #include <algorithm>
@@ -42,8 +44,10 @@ struct TileArgs {
     double *re;
     double *im;
     const TileInstr *prog;
+    const TileGroup *groups;
     const TileTerm *terms;
     int n_instr;
+    int n_groups;
     int T, L, n_high;
     int high[kMaxHigh];
 };
@@ -79,34 +83,24 @@ __device__ __forceinline__ void butterfly_pos(int rpos, double (&ar)[16], double
     }
 }
 
-// One class of a merged diagonal run: every term multiplies the same accumulator.  Terms are fetched four at a
-// time with warp-uniform 128-bit loads (all loads issued before use) and folded into two independent partial
-// products to halve the dependent-DFMA chain.
-__device__ __forceinline__ void run_class(const TileTerm *__restrict__ t, int cnt, unsigned long long base, unsigned tj,
-                                          double &Fr, double &Fi) {
+// One class of a merged diagonal run: every group multiplies the same accumulator.  Group factors (already
+// reduced over the tile's outer bits) and thread masks come from shared memory with warp-uniform addresses; two
+// groups are fetched per iteration and folded into two independent partial products.
+__device__ __forceinline__ void run_class(const double2 *__restrict__ gfac, const unsigned *__restrict__ gthr, int cnt,
+                                          unsigned tj, double &Fr, double &Fi) {
+    if (cnt == 0) return;
     double ar_ = 1.0, ai_ = 0.0, br_ = 1.0, bi_ = 0.0;
     int i = 0;
-    for (; i + 4 <= cnt; i += 4) {
-        ulonglong2 h[4];
-        double2 f[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            h[u] = __ldg(reinterpret_cast<const ulonglong2 *>(t + i + u));
-            f[u] = __ldg(reinterpret_cast<const double2 *>(&t[i + u].fr));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const unsigned thr = (unsigned)(h[u].y & 0xffffffffull);
-            if ((base & h[u].x) == h[u].x && (tj & thr) == thr) {
-                if (u & 1) cmul(br_, bi_, f[u].x, f[u].y); else cmul(ar_, ai_, f[u].x, f[u].y);
-            }
-        }
+    for (; i + 2 <= cnt; i += 2) {
+        const unsigned t0 = gthr[i], t1 = gthr[i + 1];
+        const double2 f0 = gfac[i], f1 = gfac[i + 1];
+        if ((tj & t0) == t0) cmul(ar_, ai_, f0.x, f0.y);
+        if ((tj & t1) == t1) cmul(br_, bi_, f1.x, f1.y);
     }
-    for (; i < cnt; ++i) {
-        const ulonglong2 h = __ldg(reinterpret_cast<const ulonglong2 *>(t + i));
-        const double2 f = __ldg(reinterpret_cast<const double2 *>(&t[i].fr));
-        const unsigned thr = (unsigned)(h.y & 0xffffffffull);
-        if ((base & h.x) == h.x && (tj & thr) == thr) cmul(ar_, ai_, f.x, f.y);
+    if (i < cnt) {
+        const unsigned t0 = gthr[i];
+        const double2 f0 = gfac[i];
+        if ((tj & t0) == t0) cmul(ar_, ai_, f0.x, f0.y);
     }
     cmul(ar_, ai_, br_, bi_);
     cmul(Fr, Fi, ar_, ai_);
@@ -120,6 +114,8 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
     const unsigned nthr = blockDim.x;
     double *sre = smem;
     double *sim = smem + tile_len;
+    double2 *gfac = reinterpret_cast<double2 *>(smem + 2 * tile_len); // per-group factor for THIS tile
+    unsigned *gthr = reinterpret_cast<unsigned *>(gfac + a.n_groups);  // per-group thread mask (all ones = never)
     __shared__ unsigned long long seg_off[1 << kMaxHigh];
 
     // absolute index of the tile's first amplitude: CTA id bits go to the non-tile positions
@@ -132,6 +128,18 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
             if ((sgi >> k) & 1) off |= 1ull << a.high[k];
         seg_off[sgi] = off;
     }
+    // per-tile reduction of every group of every diagonal run: product of its terms whose outer bits are set
+    for (int g = threadIdx.x; g < a.n_groups; g += nthr) {
+        const TileGroup gd = a.groups[g];
+        double fr = 1.0, fi = 0.0;
+        bool any = false;
+        for (int i = 0; i < gd.count; ++i) {
+            const TileTerm t = a.terms[gd.first + i];
+            if ((base & t.outer) == t.outer) { cmul(fr, fi, t.fr, t.fi); any = true; }
+        }
+        gfac[g] = make_double2(fr, fi);
+        gthr[g] = any ? gd.thr : 0xffffffffu; // nothing applies to this tile: no thread matches
+    }
     __syncthreads();
 
     // ---- global -> shared (coalesced 128-bit loads; swizzled placement) ----
@@ -142,9 +150,10 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
         const unsigned long long g = base + seg_off[j >> L] + (j & seg_mask);
         const double2 r = *reinterpret_cast<const double2 *>(a.re + g);
         const double2 m = *reinterpret_cast<const double2 *>(a.im + g);
-        const unsigned s0 = swz(j), s1 = swz(j + 1); // s1 == s0 ^ 1
-        sre[s0] = r.x; sre[s1] = r.y;
-        sim[s0] = m.x; sim[s1] = m.y;
+        const unsigned s0 = swz(j); // swz(j + 1) == s0 ^ 1: the pair stays an aligned pair, possibly swapped
+        const bool flip = s0 & 1u;
+        *reinterpret_cast<double2 *>(sre + (s0 & ~1u)) = flip ? make_double2(r.y, r.x) : r;
+        *reinterpret_cast<double2 *>(sim + (s0 & ~1u)) = flip ? make_double2(m.y, m.x) : m;
     }
     __syncthreads();
 
@@ -153,7 +162,8 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
     double f0r = 1.0, f0i = 0.0, f1r = 1.0, f1i = 0.0, f2r = 1.0, f2i = 0.0, f3r = 1.0, f3i = 0.0, f4r = 1.0, f4i = 0.0;
 #pragma unroll
     for (int k = 0; k < 16; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
-    bool dirty = false, have_regs = false;
+    unsigned dirty = 0; // bit c: accumulator of class c is not the identity
+    bool have_regs = false;
     unsigned tj = 0;                       // this thread's tile index with the register bits cleared
 
     // swz() is linear over XOR, so the swizzled address of amplitude k is swz(tj) ^ (XOR of the swizzled register
@@ -165,31 +175,55 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
 
     auto flush_diag = [&]() {
         if (!dirty) return;
-        // expand the 5 accumulators into the 16 per-amplitude factors, depth first (15 + 16 complex multiplies)
+        if (__popc(dirty) <= 2) {
+            // few accumulators: apply each to its amplitudes directly (16 or 8 complex multiplies each)
+            if (dirty & 1u) {
 #pragma unroll
-        for (int b3 = 0; b3 < 2; ++b3) {
-            double g3r = f0r, g3i = f0i;
-            if (b3) cmul(g3r, g3i, f4r, f4i);
+                for (int k = 0; k < 16; ++k) cmul(ar[k], ai[k], f0r, f0i);
+            }
+            if (dirty & 2u) {
 #pragma unroll
-            for (int b2 = 0; b2 < 2; ++b2) {
-                double g2r = g3r, g2i = g3i;
-                if (b2) cmul(g2r, g2i, f3r, f3i);
+                for (int k = 0; k < 16; ++k) if (k & 1) cmul(ar[k], ai[k], f1r, f1i);
+            }
+            if (dirty & 4u) {
 #pragma unroll
-                for (int b1 = 0; b1 < 2; ++b1) {
-                    double g1r = g2r, g1i = g2i;
-                    if (b1) cmul(g1r, g1i, f2r, f2i);
+                for (int k = 0; k < 16; ++k) if (k & 2) cmul(ar[k], ai[k], f2r, f2i);
+            }
+            if (dirty & 8u) {
 #pragma unroll
-                    for (int b0 = 0; b0 < 2; ++b0) {
-                        double gr = g1r, gi = g1i;
-                        if (b0) cmul(gr, gi, f1r, f1i);
-                        cmul(ar[b0 | (b1 << 1) | (b2 << 2) | (b3 << 3)], ai[b0 | (b1 << 1) | (b2 << 2) | (b3 << 3)], gr, gi);
+                for (int k = 0; k < 16; ++k) if (k & 4) cmul(ar[k], ai[k], f3r, f3i);
+            }
+            if (dirty & 16u) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) if (k & 8) cmul(ar[k], ai[k], f4r, f4i);
+            }
+        } else {
+            // expand the 5 accumulators into the 16 per-amplitude factors, depth first (15 + 16 complex multiplies)
+#pragma unroll
+            for (int b3 = 0; b3 < 2; ++b3) {
+                double g3r = f0r, g3i = f0i;
+                if (b3) cmul(g3r, g3i, f4r, f4i);
+#pragma unroll
+                for (int b2 = 0; b2 < 2; ++b2) {
+                    double g2r = g3r, g2i = g3i;
+                    if (b2) cmul(g2r, g2i, f3r, f3i);
+#pragma unroll
+                    for (int b1 = 0; b1 < 2; ++b1) {
+                        double g1r = g2r, g1i = g2i;
+                        if (b1) cmul(g1r, g1i, f2r, f2i);
+#pragma unroll
+                        for (int b0 = 0; b0 < 2; ++b0) {
+                            double gr = g1r, gi = g1i;
+                            if (b0) cmul(gr, gi, f1r, f1i);
+                            cmul(ar[b0 | (b1 << 1) | (b2 << 2) | (b3 << 3)], ai[b0 | (b1 << 1) | (b2 << 2) | (b3 << 3)], gr, gi);
+                        }
                     }
                 }
             }
         }
         f0r = f1r = f2r = f3r = f4r = 1.0;
         f0i = f1i = f2i = f3i = f4i = 0.0;
-        dirty = false;
+        dirty = 0;
     };
 
     auto store_regs = [&]() {
@@ -197,24 +231,6 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
         for (int k = 0; k < 16; ++k) {
             const unsigned s = saddr(k);
             sre[s] = ar[k]; sim[s] = ai[k];
-        }
-    };
-
-    // one merged-mode phase term: amplitudes with (thread bits >= thr) and (k >= m) are multiplied by f
-    auto add_term = [&](unsigned thr, unsigned m, double fr, double fi) {
-        const bool ok = (tj & thr) == thr;
-        dirty = true;
-        switch (m) {
-        case 0: if (ok) cmul(f0r, f0i, fr, fi); break;
-        case 1: if (ok) cmul(f1r, f1i, fr, fi); break;
-        case 2: if (ok) cmul(f2r, f2i, fr, fi); break;
-        case 4: if (ok) cmul(f3r, f3i, fr, fi); break;
-        case 8: if (ok) cmul(f4r, f4i, fr, fi); break;
-        default:
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (ok && ((unsigned)k & m) == m) cmul(ar[k], ai[k], fr, fi);
-            break;
         }
     };
 
@@ -240,22 +256,23 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
             continue;
         }
         if (op == TI_RUN) {
-            const TileTerm *t = a.terms + ins.rpos;
+            int g = ins.rpos;
             const int c0 = ins.rbit[0], c1 = ins.rbit[1], c2 = ins.rbit[2], c3 = ins.rbit[3];
             const int c4 = (int)ins.reg_cmask, c5 = (int)ins.thr_cmask;
-            run_class(t, c0, base, tj, f0r, f0i); t += c0;
-            run_class(t, c1, base, tj, f1r, f1i); t += c1;
-            run_class(t, c2, base, tj, f2r, f2i); t += c2;
-            run_class(t, c3, base, tj, f3r, f3i); t += c3;
-            run_class(t, c4, base, tj, f4r, f4i); t += c4;
+            run_class(gfac + g, gthr + g, c0, tj, f0r, f0i); g += c0;
+            run_class(gfac + g, gthr + g, c1, tj, f1r, f1i); g += c1;
+            run_class(gfac + g, gthr + g, c2, tj, f2r, f2i); g += c2;
+            run_class(gfac + g, gthr + g, c3, tj, f3r, f3i); g += c3;
+            run_class(gfac + g, gthr + g, c4, tj, f4r, f4i); g += c4;
+            dirty |= (c0 ? 1u : 0u) | (c1 ? 2u : 0u) | (c2 ? 4u : 0u) | (c3 ? 8u : 0u) | (c4 ? 16u : 0u);
             for (int i = 0; i < c5; ++i) { // support with >= 2 register bits: touch the amplitudes directly
-                const TileTerm tt = t[i];
-                const bool ok = (base & tt.outer) == tt.outer && (tj & tt.thr) == tt.thr;
+                const unsigned thr = gthr[g + i], m = a.groups[g + i].m;
+                const double2 f = gfac[g + i];
+                const bool ok = (tj & thr) == thr;
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
-                    if (ok && ((unsigned)k & tt.m) == tt.m) cmul(ar[k], ai[k], tt.fr, tt.fi);
+                    if (ok && ((unsigned)k & m) == m) cmul(ar[k], ai[k], f.x, f.y);
             }
-            dirty = true;
             continue;
         }
         const unsigned long long ocm = ins.outer_cmask;
@@ -293,14 +310,8 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
                     diag_update_rt(kind, ins.s, hi, ar[k], ai[k]);
                 }
             }
-        } else {
-            // term A: controls set, any target value (RZ's d0);  term B: controls and target set (e^{i theta}, -1)
-            const unsigned thr = ins.thr_cmask, m = ins.reg_cmask;
-            if (ins.has_f0) add_term(thr, m, ins.f0[0], ins.f0[1]);
-            if (tw == 0) { if (outer_hi) add_term(thr, m, ins.f1[0], ins.f1[1]); }
-            else if (tw == 1) add_term(thr | ins.t_mask, m, ins.f1[0], ins.f1[1]);
-            else add_term(thr, m | ins.t_mask, ins.f1[0], ins.f1[1]);
         }
+        // (merged mode never sees TI_DIAG: the host folds diagonal gates into TI_RUN groups)
     }
     if (have_regs) {
         flush_diag();
@@ -312,9 +323,12 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
     for (unsigned v = threadIdx.x; v < n_vec; v += nthr) {
         const unsigned j = v << 1;
         const unsigned long long g = base + seg_off[j >> L] + (j & seg_mask);
-        const unsigned s0 = swz(j), s1 = swz(j + 1);
-        *reinterpret_cast<double2 *>(a.re + g) = make_double2(sre[s0], sre[s1]);
-        *reinterpret_cast<double2 *>(a.im + g) = make_double2(sim[s0], sim[s1]);
+        const unsigned s0 = swz(j);
+        const bool flip = s0 & 1u;
+        const double2 r = *reinterpret_cast<const double2 *>(sre + (s0 & ~1u));
+        const double2 m = *reinterpret_cast<const double2 *>(sim + (s0 & ~1u));
+        *reinterpret_cast<double2 *>(a.re + g) = flip ? make_double2(r.y, r.x) : r;
+        *reinterpret_cast<double2 *>(a.im + g) = flip ? make_double2(m.y, m.x) : m;
     }
 }
 
@@ -325,14 +339,14 @@ int tile_prepare(spz_state *st) {
         st->d_ops_bytes = cap;
         st->d_ops_cursor = 0;
     }
-    const int max_smem = (int)(sizeof(double) * 2u * ((size_t)1 << kMaxTileBits));
+    const int max_smem = (int)(sizeof(double) * 2u * ((size_t)1 << kMaxTileBits) + kMaxTileGroups * (sizeof(double2) + sizeof(unsigned)));
     SPZ_CUDA(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     SPZ_CUDA(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     return SPZ_OK;
 }
 
-int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, const TileTerm *terms,
-                        int n_terms, bool exact) {
+int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, const TileGroup *groups,
+                        int n_groups, const TileTerm *terms, int n_terms, bool exact) {
     if (n_instr <= 0) return SPZ_OK;
     if (plan.tile_bits > kMaxTileBits || plan.tile_bits < kRegBits || plan.n_high > kMaxHigh || plan.low_bits < 1 ||
         plan.tile_bits != plan.low_bits + plan.n_high || plan.tile_bits > st->n) {
@@ -342,8 +356,10 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
     // Programs are staged in a device ring buffer: a group's program must stay intact until its kernel has run,
     // so the cursor only wraps after a stream synchronise.
     const size_t prog_bytes = (sizeof(TileInstr) * (size_t)n_instr + 255) & ~(size_t)255;
+    const size_t group_bytes = (sizeof(TileGroup) * (size_t)n_groups + 255) & ~(size_t)255;
     const size_t term_bytes = (sizeof(TileTerm) * (size_t)n_terms + 255) & ~(size_t)255;
-    const size_t bytes = prog_bytes + term_bytes;
+    const size_t bytes = prog_bytes + group_bytes + term_bytes;
+    if (n_groups > kMaxTileGroups) { set_error("internal: %d diagonal groups exceed the shared-memory table", n_groups); return SPZ_ERR_INVALID_ARG; }
     if (st->d_ops_bytes < bytes || !st->d_ops) {
         if (st->d_ops) { SPZ_CUDA(cudaStreamSynchronize(st->stream)); SPZ_CUDA(cudaFree(st->d_ops)); st->d_ops = nullptr; }
         const size_t cap = std::max<size_t>(bytes * 2, (size_t)4 << 20);
@@ -358,17 +374,21 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
     char *slot = static_cast<char *>(st->d_ops) + st->d_ops_cursor;
     st->d_ops_cursor += bytes;
     SPZ_CUDA(cudaMemcpyAsync(slot, prog, sizeof(TileInstr) * (size_t)n_instr, cudaMemcpyHostToDevice, st->stream));
+    if (n_groups > 0)
+        SPZ_CUDA(cudaMemcpyAsync(slot + prog_bytes, groups, sizeof(TileGroup) * (size_t)n_groups, cudaMemcpyHostToDevice, st->stream));
     if (n_terms > 0)
-        SPZ_CUDA(cudaMemcpyAsync(slot + prog_bytes, terms, sizeof(TileTerm) * (size_t)n_terms, cudaMemcpyHostToDevice, st->stream));
+        SPZ_CUDA(cudaMemcpyAsync(slot + prog_bytes + group_bytes, terms, sizeof(TileTerm) * (size_t)n_terms, cudaMemcpyHostToDevice, st->stream));
 
     TileArgs a{};
     a.re = st->re; a.im = st->im;
     a.prog = reinterpret_cast<const TileInstr *>(slot);
-    a.terms = reinterpret_cast<const TileTerm *>(slot + prog_bytes);
+    a.groups = reinterpret_cast<const TileGroup *>(slot + prog_bytes);
+    a.terms = reinterpret_cast<const TileTerm *>(slot + prog_bytes + group_bytes);
+    a.n_groups = n_groups;
     a.n_instr = n_instr;
     a.T = plan.tile_bits; a.L = plan.low_bits; a.n_high = plan.n_high;
     for (int k = 0; k < plan.n_high; ++k) a.high[k] = plan.high[k];
-    const size_t smem = sizeof(double) * 2u * ((size_t)1 << plan.tile_bits);
+    const size_t smem = sizeof(double) * 2u * ((size_t)1 << plan.tile_bits) + (size_t)n_groups * (sizeof(double2) + sizeof(unsigned));
     const unsigned grid = (unsigned)((uint64_t)st->len >> plan.tile_bits);
     const unsigned threads = 1u << (plan.tile_bits - kRegBits);
     if (exact) k_tile<true><<<grid, threads, smem, st->stream>>>(a);
