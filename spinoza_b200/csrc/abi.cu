@@ -277,6 +277,8 @@ struct Fuser {
             if (!diag) {
                 close_run(); // the gates of a run commute with each other, not with this butterfly
                 t.rpos = idx_in_R(tb);
+                for (unsigned k = 0; k < 16; ++k) // register indices whose register-bit controls are all set
+                    if ((k & t.reg_cmask) == t.reg_cmask) t.t_mask |= 1u << k;
             } else {
                 if (o.const_hi >= 0) { t.t_where = 0; t.const_hi = (uint32_t)(o.const_hi + 1); }
                 else if (tb < 0) { t.t_where = 0; t.outer_target = o.target; }

@@ -121,7 +121,7 @@ struct TileInstr {
     uint32_t reg_cmask;   // controls on register bits (mask over k = 0..15)
     uint32_t thr_cmask;   // controls on thread bits (mask in tile-index space)
     int t_where;          // TI_DIAG target: 0 = outside the tile, 1 = thread bit, 2 = register bit
-    uint32_t t_mask;      // t_where 1: tile-index mask; t_where 2: mask over k
+    uint32_t t_mask;      // TI_DIAG: t_where 1: tile-index mask; t_where 2: mask over k.  TI_GATE: set of k with controls set
     int outer_target;     // t_where 0: absolute qubit, unless const_hi is set
     uint32_t const_hi;    // t_where 0: 0 = read the bit from the tile base, 1 = bit is 0, 2 = bit is 1 (a rank bit)
     int has_f0;           // merged mode: f0 is not the identity

@@ -62,24 +62,24 @@ __device__ __forceinline__ void cmul(double &xr, double &xi, double fr, double f
 
 // Butterfly of a non-diagonal gate over register bit RPOS: pairs (k, k | 1 << RPOS).
 template <int KIND, int RPOS>
-__device__ __forceinline__ void butterfly(double (&ar)[16], double (&ai)[16], const double *__restrict__ s, unsigned creg,
-                                          bool ok) {
+__device__ __forceinline__ void butterfly(double (&ar)[16], double (&ai)[16], const double *__restrict__ s, unsigned km) {
+    // km: bit k0 set <=> this thread applies the gate to pair (k0, k0 | 1 << RPOS)  (controls already folded in)
 #pragma unroll
     for (int k0 = 0; k0 < 16; ++k0) {
         if (k0 & (1 << RPOS)) continue;
         const int k1 = k0 | (1 << RPOS);
-        if (ok && ((unsigned)k0 & creg) == creg) pair_update<KIND>(s, ar[k0], ai[k0], ar[k1], ai[k1]);
+        if (km & (1u << k0)) pair_update<KIND>(s, ar[k0], ai[k0], ar[k1], ai[k1]);
     }
 }
 
 template <int KIND>
 __device__ __forceinline__ void butterfly_pos(int rpos, double (&ar)[16], double (&ai)[16], const double *__restrict__ s,
-                                              unsigned creg, bool ok) {
+                                              unsigned km) {
     switch (rpos) {
-    case 0: butterfly<KIND, 0>(ar, ai, s, creg, ok); break;
-    case 1: butterfly<KIND, 1>(ar, ai, s, creg, ok); break;
-    case 2: butterfly<KIND, 2>(ar, ai, s, creg, ok); break;
-    default: butterfly<KIND, 3>(ar, ai, s, creg, ok); break;
+    case 0: butterfly<KIND, 0>(ar, ai, s, km); break;
+    case 1: butterfly<KIND, 1>(ar, ai, s, km); break;
+    case 2: butterfly<KIND, 2>(ar, ai, s, km); break;
+    default: butterfly<KIND, 3>(ar, ai, s, km); break;
     }
 }
 
@@ -120,12 +120,15 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
 
     // absolute index of the tile's first amplitude: CTA id bits go to the non-tile positions
     unsigned long long base = (unsigned long long)blockIdx.x << L;
-    for (int k = 0; k < a.n_high; ++k) base = insert_zero(base, a.high[k]);
+#pragma unroll
+    for (int k = 0; k < kMaxHigh; ++k) // compile-time indices keep the kernel parameters in the constant bank
+        if (k < a.n_high) base = insert_zero(base, a.high[k]);
     const int n_seg = 1 << a.n_high;
     for (int sgi = threadIdx.x; sgi < n_seg; sgi += nthr) {
         unsigned long long off = 0;
-        for (int k = 0; k < a.n_high; ++k)
-            if ((sgi >> k) & 1) off |= 1ull << a.high[k];
+#pragma unroll
+        for (int k = 0; k < kMaxHigh; ++k)
+            if (k < a.n_high && ((sgi >> k) & 1)) off |= 1ull << a.high[k];
         seg_off[sgi] = off;
     }
     // per-tile reduction of every group of every diagonal run: product of its terms whose outer bits are set
@@ -143,25 +146,41 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
     __syncthreads();
 
     // ---- global -> shared (coalesced 128-bit loads; swizzled placement) ----
+    // All of a thread's loads (8 per array at T = 12) are issued before the first shared store, staged in the
+    // registers (free at this point), so the HBM latency is paid once per tile, not once per vector.
     const unsigned n_vec = tile_len >> 1;
     const unsigned seg_mask = (1u << L) - 1u;
-    for (unsigned v = threadIdx.x; v < n_vec; v += nthr) {
-        const unsigned j = v << 1;
-        const unsigned long long g = base + seg_off[j >> L] + (j & seg_mask);
-        const double2 r = *reinterpret_cast<const double2 *>(a.re + g);
-        const double2 m = *reinterpret_cast<const double2 *>(a.im + g);
-        const unsigned s0 = swz(j); // swz(j + 1) == s0 ^ 1: the pair stays an aligned pair, possibly swapped
-        const bool flip = s0 & 1u;
-        *reinterpret_cast<double2 *>(sre + (s0 & ~1u)) = flip ? make_double2(r.y, r.x) : r;
-        *reinterpret_cast<double2 *>(sim + (s0 & ~1u)) = flip ? make_double2(m.y, m.x) : m;
+    {
+        double2 tr[8], tm[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const unsigned v = threadIdx.x + it * nthr;
+            tr[it] = make_double2(0.0, 0.0); tm[it] = make_double2(0.0, 0.0);
+            if (v < n_vec) {
+                const unsigned j = v << 1;
+                const unsigned long long g = base + seg_off[j >> L] + (j & seg_mask);
+                tr[it] = *reinterpret_cast<const double2 *>(a.re + g);
+                tm[it] = *reinterpret_cast<const double2 *>(a.im + g);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const unsigned v = threadIdx.x + it * nthr;
+            if (v < n_vec) {
+                const unsigned s0 = swz(v << 1); // swz(j + 1) == s0 ^ 1: the pair stays an aligned pair, possibly swapped
+                const bool flip = s0 & 1u;
+                *reinterpret_cast<double2 *>(sre + (s0 & ~1u)) = flip ? make_double2(tr[it].y, tr[it].x) : tr[it];
+                *reinterpret_cast<double2 *>(sim + (s0 & ~1u)) = flip ? make_double2(tm[it].y, tm[it].x) : tm[it];
+            }
+        }
     }
     __syncthreads();
 
     double ar[16], ai[16];
-    // merged-mode phase accumulators: F0 multiplies all 16 amplitudes, Fi those whose register bit i-1 is set
-    double f0r = 1.0, f0i = 0.0, f1r = 1.0, f1i = 0.0, f2r = 1.0, f2i = 0.0, f3r = 1.0, f3i = 0.0, f4r = 1.0, f4i = 0.0;
 #pragma unroll
     for (int k = 0; k < 16; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
+    // merged-mode phase accumulators: F0 multiplies all 16 amplitudes, Fi those whose register bit i-1 is set
+    double f0r = 1.0, f0i = 0.0, f1r = 1.0, f1i = 0.0, f2r = 1.0, f2i = 0.0, f3r = 1.0, f3i = 0.0, f4r = 1.0, f4i = 0.0;
     unsigned dirty = 0; // bit c: accumulator of class c is not the identity
     bool have_regs = false;
     unsigned tj = 0;                       // this thread's tile index with the register bits cleared
@@ -268,10 +287,23 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
             for (int i = 0; i < c5; ++i) { // support with >= 2 register bits: touch the amplitudes directly
                 const unsigned thr = gthr[g + i], m = a.groups[g + i].m;
                 const double2 f = gfac[g + i];
-                const bool ok = (tj & thr) == thr;
+                if ((tj & thr) != thr) continue;
+                // two register bits (a CP between two register-resident qubits) is the common case: 4 amplitudes
+#define SPZ_M4(A, B, C, D) cmul(ar[A], ai[A], f.x, f.y); cmul(ar[B], ai[B], f.x, f.y); cmul(ar[C], ai[C], f.x, f.y); cmul(ar[D], ai[D], f.x, f.y)
+                switch (m) {
+                case 3: SPZ_M4(3, 7, 11, 15); break;
+                case 5: SPZ_M4(5, 7, 13, 15); break;
+                case 6: SPZ_M4(6, 7, 14, 15); break;
+                case 9: SPZ_M4(9, 11, 13, 15); break;
+                case 10: SPZ_M4(10, 11, 14, 15); break;
+                case 12: SPZ_M4(12, 13, 14, 15); break;
+                default:
 #pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    if (ok && ((unsigned)k & m) == m) cmul(ar[k], ai[k], f.x, f.y);
+                    for (int k = 0; k < 16; ++k)
+                        if (((unsigned)k & m) == m) cmul(ar[k], ai[k], f.x, f.y);
+                    break;
+                }
+#undef SPZ_M4
             }
             continue;
         }
@@ -279,15 +311,15 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
         if ((base & ocm) != ocm) continue; // an outer control is 0 for this whole tile
         if (op == TI_GATE) {
             flush_diag();
-            const bool ok = (tj & ins.thr_cmask) == ins.thr_cmask;
-            const unsigned creg = ins.reg_cmask;
+            // t_mask holds the host-computed set of register indices k whose register-bit controls are all set
+            const unsigned km = ((tj & ins.thr_cmask) == ins.thr_cmask) ? ins.t_mask : 0u;
             switch (ins.kind) {
-            case SPZ_GATE_H: butterfly_pos<SPZ_GATE_H>(ins.rpos, ar, ai, ins.s, creg, ok); break;
-            case SPZ_GATE_X: butterfly_pos<SPZ_GATE_X>(ins.rpos, ar, ai, ins.s, creg, ok); break;
-            case SPZ_GATE_Y: butterfly_pos<SPZ_GATE_Y>(ins.rpos, ar, ai, ins.s, creg, ok); break;
-            case SPZ_GATE_RX: butterfly_pos<SPZ_GATE_RX>(ins.rpos, ar, ai, ins.s, creg, ok); break;
-            case SPZ_GATE_RY: butterfly_pos<SPZ_GATE_RY>(ins.rpos, ar, ai, ins.s, creg, ok); break;
-            case SPZ_GATE_U: butterfly_pos<SPZ_GATE_U>(ins.rpos, ar, ai, ins.s, creg, ok); break;
+            case SPZ_GATE_H: butterfly_pos<SPZ_GATE_H>(ins.rpos, ar, ai, ins.s, km); break;
+            case SPZ_GATE_X: butterfly_pos<SPZ_GATE_X>(ins.rpos, ar, ai, ins.s, km); break;
+            case SPZ_GATE_Y: butterfly_pos<SPZ_GATE_Y>(ins.rpos, ar, ai, ins.s, km); break;
+            case SPZ_GATE_RX: butterfly_pos<SPZ_GATE_RX>(ins.rpos, ar, ai, ins.s, km); break;
+            case SPZ_GATE_RY: butterfly_pos<SPZ_GATE_RY>(ins.rpos, ar, ai, ins.s, km); break;
+            case SPZ_GATE_U: butterfly_pos<SPZ_GATE_U>(ins.rpos, ar, ai, ins.s, km); break;
             default: break;
             }
             continue;
