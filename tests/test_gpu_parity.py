@@ -595,3 +595,18 @@ def test_large_state_properties(n):
     qc.execute()
     assert abs(s.amp(12345) - 1.0) < 1e-12
     assert abs(sb.norm2(s) - 1.0) < 1e-10
+
+
+def test_spynoza_facade_runs():  # spynoza/examples/*.py shape
+    from spinoza_b200 import spynoza as sp
+    q = sp.QuantumRegister(3)
+    qc = sp.QuantumCircuit(q)
+    qc.h(0); qc.cx(0, 1); qc.cx(1, 2)
+    st = sp.run(qc)
+    assert len(st) == 8
+    assert abs(st[0][0] - math.sqrt(0.5)) < 1e-12 and abs(st[7][0] - math.sqrt(0.5)) < 1e-12 and st[3] == (0.0, 0.0)
+    hist = sp.get_samples(st, 2000, 20000, seed=3)
+    assert set(hist) == {0, 7} and sum(hist.values()) == 2000 and abs(hist[0] - 1000) < 150
+    assert "Outcome" in sp.show_table(st) and str(st).count("\n") == 8
+    assert abs(sp.qubit_expectation_value(st.data, 0)) < 1e-12
+    assert abs(sp.xyz_expectation_value("z", st.data, [1])[0]) < 1e-12

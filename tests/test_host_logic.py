@@ -151,3 +151,18 @@ def test_qasm_angle_expressions():
     assert sb.openqasm.eval_angle("2*pi/8 + 0.5") == 2 * PI / 8 + 0.5
     with pytest.raises(ValueError):
         sb.openqasm.eval_angle("__import__('os')")
+
+
+def test_spynoza_facade_surface():  # spynoza/src/lib.rs:411-421
+    from spinoza_b200 import spynoza as sp
+    for name in ("get_samples", "show_table", "run", "qubit_expectation_value", "xyz_expectation_value", "PyState",
+                 "QuantumRegister", "QuantumCircuit", "PyQuantumTransformation"):
+        assert hasattr(sp, name)
+    q = sp.QuantumRegister(3)
+    qc = sp.QuantumCircuit(q)
+    qc.h(0); qc.cp(0.5, 0, 1); qc.ccx(0, 1, 2)
+    assert qc.num_qubits == 3 and qc.register_sizes == [3]
+    t = qc.py_transformations
+    assert (t[0].name, t[0].target, t[0].controls, t[0].arg) == ("h", 0, None, None)
+    assert (t[1].name, t[1].controls, t[1].arg) == ("p", [0], (0.5, 0.0, 0.0))
+    assert t[2].controls == [0, 1]
