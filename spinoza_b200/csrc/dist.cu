@@ -424,9 +424,13 @@ int spz_dist_connect(spz_state *st, const void *blobs) {
         if (r == c->rank) continue;
         if (b[r].rank != r || b[r].len != st->len) { set_error("blob %d does not describe rank %d's shard", r, r); return SPZ_ERR_COMM; }
         void *p = nullptr;
+        // control blocks of every rank (scalar all-reduce); amplitude arrays only of the hypercube partners
+        // rank ^ 2^k -- mapping a 137 GB shard of all 7 peers costs tens of seconds and is never used
+        SPZ_CUDA(cudaIpcOpenMemHandle(&p, b[r].ctrl, cudaIpcMemLazyEnablePeerAccess)); c->peer_ctrl[r] = static_cast<CtrlBlock *>(p);
+        const int diff = r ^ c->rank;
+        if ((diff & (diff - 1)) != 0) continue;
         SPZ_CUDA(cudaIpcOpenMemHandle(&p, b[r].re, cudaIpcMemLazyEnablePeerAccess)); c->peer_re[r] = static_cast<double *>(p);
         SPZ_CUDA(cudaIpcOpenMemHandle(&p, b[r].im, cudaIpcMemLazyEnablePeerAccess)); c->peer_im[r] = static_cast<double *>(p);
-        SPZ_CUDA(cudaIpcOpenMemHandle(&p, b[r].ctrl, cudaIpcMemLazyEnablePeerAccess)); c->peer_ctrl[r] = static_cast<CtrlBlock *>(p);
     }
     SPZ_TRY(upload_peer_table(c));
     c->connected = true;

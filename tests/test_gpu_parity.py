@@ -610,3 +610,36 @@ def test_spynoza_facade_runs():  # spynoza/examples/*.py shape
     assert "Outcome" in sp.show_table(st) and str(st).count("\n") == 8
     assert abs(sp.qubit_expectation_value(st.data, 0)) < 1e-12
     assert abs(sp.xyz_expectation_value("z", st.data, [1])[0]) < 1e-12
+
+
+def test_baseline_size_30_qubits_properties():
+    """BASELINE config 2's register size (2^30 amplitudes, 17 GB): size-independent properties only."""
+    n = 30
+    free, _total = sb.mem_info(0)
+    if free < 40 << 30:
+        pytest.skip("needs ~35 GB of free HBM")
+    s = sb.State(n)
+    x = 0x9E3779B97F4A7C15 % (1 << n)
+    s.set_basis(x)
+    qc = QuantumCircuit.from_state(s, fuse=True)
+    qc.qft()
+    qc.execute()
+    re, im = s.download(0, 1 << 12)
+    k = np.arange(1 << 12, dtype=np.uint64)
+    rev = np.zeros_like(k)
+    for b in range(n):
+        rev |= ((k >> np.uint64(b)) & np.uint64(1)) << np.uint64(n - 1 - b)
+    ph = ((np.uint64(x) * rev) & np.uint64((1 << n) - 1)).astype(np.float64) / float(1 << n)
+    want = 2.0 ** (-n / 2) * np.exp(2j * np.pi * ph)
+    assert np.max(np.abs((re + 1j * im) - want)) < 1e-12
+    assert abs(sb.norm2(s) - 1.0) < 1e-10
+    for t in (0, 1, 2, 15, 28, 29):  # every kernel shape of the bandwidth sweep: G then G^-1
+        for g in (Gate.H, Gate.RX(1.0), Gate.RZ(1.0)):
+            sb.apply(g, s, t)
+            sb.apply(g.inverse(), s, t)
+    re2, im2 = s.download(0, 1 << 12)
+    assert np.max(np.abs(re2 - re)) < 1e-12 and np.max(np.abs(im2 - im)) < 1e-12
+    qc.iqft(list(reversed(range(n))))
+    qc.execute()
+    assert abs(s.amp(x) - 1.0) < 1e-12 and abs(sb.norm2(s) - 1.0) < 1e-10
+    assert abs(sb.prob0(s, 3) - (0.0 if (x >> 3) & 1 else 1.0)) < 1e-10
