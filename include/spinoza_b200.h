@@ -88,6 +88,7 @@ typedef struct {
 #define SPZ_EXEC_NO_FUSE 0u  /* one kernel per gate, arithmetic bit-identical to spz_apply & co. */
 #define SPZ_EXEC_FUSE 1u     /* batch runs of gates into on-chip tiles (one HBM pass per batch); runs of diagonal
                                 gates are merged into phase accumulators (differs from gate-by-gate by a few ulp) */
+#define SPZ_EXEC_KEEP_ORDER 4u /* with SPZ_EXEC_FUSE: do not reorder commuting gates across the op list when packing passes */
 #define SPZ_EXEC_EXACT 2u    /* with SPZ_EXEC_FUSE: apply every gate with the reference arithmetic -> results are
                                 bit-identical to SPZ_EXEC_NO_FUSE (slower on long diagonal runs) */
 

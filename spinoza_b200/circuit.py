@@ -12,6 +12,7 @@ from typing import Iterable, List, Optional, Sequence
 EXEC_NO_FUSE = 0
 EXEC_FUSE = 1   # fused tiles, runs of diagonal gates merged into phase accumulators (few-ulp rounding difference)
 EXEC_EXACT = 2  # with EXEC_FUSE: every gate applied with the reference arithmetic (bit-identical to unfused)
+EXEC_KEEP_ORDER = 4  # with EXEC_FUSE: pack passes in strict program order (no commutation-aware reordering)
 
 
 class QuantumRegister:
@@ -107,7 +108,8 @@ class QuantumTransformation:
 class QuantumCircuit:
     """circuit.rs:168-601"""
 
-    def __init__(self, *registers: QuantumRegister, device: int = 0, state=None, fuse: bool = True, exact: bool = False):
+    def __init__(self, *registers: QuantumRegister, device: int = 0, state=None, fuse: bool = True, exact: bool = False,
+                 reorder: bool = True):
         bits = 0
         self.quantum_registers_info: List[int] = []
         for r in registers:  # circuit.rs:186-190
@@ -125,6 +127,7 @@ class QuantumCircuit:
         self._measured_qubits_vals = 0
         self.fuse = fuse
         self.exact = exact
+        self.reorder = reorder
 
     @property
     def state(self):
@@ -139,9 +142,9 @@ class QuantumCircuit:
         self.n_qubits = value.n
 
     @classmethod
-    def from_state(cls, state, fuse: bool = True, exact: bool = False) -> "QuantumCircuit":
+    def from_state(cls, state, fuse: bool = True, exact: bool = False, reorder: bool = True) -> "QuantumCircuit":
         """The tests' `QuantumCircuit { state, transformations: Vec::new(), .. }` literal (circuit.rs:839-844)."""
-        return cls(state=state, fuse=fuse, exact=exact)
+        return cls(state=state, fuse=fuse, exact=exact, reorder=reorder)
 
     def get_statevector(self):  # circuit.rs:200-202
         return self.state
@@ -308,7 +311,7 @@ class QuantumCircuit:
         arr, n = self._encode()
         m = C.c_uint64(self._measured_qubits)
         v = C.c_uint64(self._measured_qubits_vals)
-        flags = (EXEC_FUSE | (EXEC_EXACT if self.exact else 0)) if self.fuse else EXEC_NO_FUSE
+        flags = (EXEC_FUSE | (EXEC_EXACT if self.exact else 0) | (0 if self.reorder else EXEC_KEEP_ORDER)) if self.fuse else EXEC_NO_FUSE
         self.transformations = []  # drain(..): the list is consumed even if a gate "panics"
         _check(_lib.spz_execute(self.state._h, arr, n, flags, C.byref(m), C.byref(v)))
         self._measured_qubits, self._measured_qubits_vals = m.value, v.value

@@ -304,7 +304,8 @@ struct Fuser {
         return SPZ_OK;
     }
 
-    int flush() {
+    // Launch the current group (ops / high_set / low_need) and reset it.
+    int emit_group() {
         if (ops.empty()) return SPZ_OK;
         int rc = SPZ_OK;
         if (ops.size() == 1 && ops[0].const_hi >= 0) {
@@ -335,14 +336,97 @@ struct Fuser {
         return rc;
     }
 
+    // Append to the current group, closing it first when the op does not fit (order-preserving greedy).
     int add(const ROp &op) {
         uint64_t hs; int ln;
         if (!fits(op, hs, ln) || ops.size() >= (size_t)kMaxTileGroups / 2) {
-            SPZ_TRY(flush());
+            SPZ_TRY(emit_group());
             if (!fits(op, hs, ln)) { set_error("internal: op does not fit an empty tile"); return SPZ_ERR_INVALID_ARG; }
         }
         high_set = hs; low_need = ln;
         ops.push_back(op);
+        return SPZ_OK;
+    }
+
+    // ---- scheduling window ---------------------------------------------------------------------------------
+    // Ops are buffered and grouped at flush points (end of the list, a measurement, an exchange).  In the default
+    // fused mode the window is scheduled as a dependency DAG: two ops need their program order only if they share
+    // a qubit on which at least one of them is not "Z-like" (diagonal gates and controls are Z-like: block diagonal
+    // in that qubit's computational basis).  Ready ops are packed into the current tile in program order, so e.g.
+    // the rotations of the next layer on qubits the tile already holds join the pass instead of opening a new one.
+    // Reordering commuting gates is exact mathematically but changes rounding in the last place, so EXACT mode
+    // (bit-identical to unfused) keeps strict program order.
+    std::vector<ROp> pending;
+    bool reorder = true;
+
+    int push(const ROp &op) {
+        pending.push_back(op);
+        if (pending.size() >= 4096) return flush();
+        return SPZ_OK;
+    }
+
+    int flush() {
+        int rc = (exact || !reorder || pending.size() < 3) ? schedule_in_order() : schedule_dag();
+        pending.clear();
+        return rc;
+    }
+
+    int schedule_in_order() {
+        for (const ROp &op : pending) SPZ_TRY(add(op));
+        return emit_group();
+    }
+
+    int schedule_dag() {
+        const int N = (int)pending.size();
+        std::vector<int> npred(N, 0), stamp(N, -1);
+        std::vector<std::vector<int>> succ(N);
+        int last_w[64];
+        std::vector<int> zl[64]; // Z-like ops on the qubit since its last writer
+        for (int &w : last_w) w = -1;
+        for (int i = 0; i < N; ++i) {
+            const ROp &op = pending[i];
+            const bool diag = is_diagonal_kind(op.kind);
+            uint64_t xmask = 0, zmask = op.cmask;
+            if (op.kind == SPZ_GATE_SWAP) xmask = (1ull << op.target) | (1ull << op.t2);
+            else if (!diag) xmask = 1ull << op.target;
+            else if (op.const_hi < 0) zmask |= 1ull << op.target;
+            auto dep = [&](int j) {
+                if (stamp[j] == i) return;
+                stamp[j] = i;
+                succ[j].push_back(i);
+                ++npred[i];
+            };
+            for (int q = 0; q < 64; ++q) {
+                if ((xmask >> q) & 1ull) {
+                    if (last_w[q] >= 0) dep(last_w[q]);
+                    for (int r : zl[q]) dep(r);
+                } else if ((zmask >> q) & 1ull) {
+                    if (last_w[q] >= 0) dep(last_w[q]);
+                }
+            }
+            for (int q = 0; q < 64; ++q) {
+                if ((xmask >> q) & 1ull) { last_w[q] = i; zl[q].clear(); }
+                else if ((zmask >> q) & 1ull) zl[q].push_back(i);
+            }
+        }
+        std::vector<char> done(N, 0);
+        int remaining = N;
+        while (remaining > 0) {
+            // one ascending scan per group: successors always have larger indices, and tile capacity only shrinks
+            for (int i = 0; i < N; ++i) {
+                if (done[i] || npred[i] != 0) continue;
+                if (ops.size() >= (size_t)kMaxTileGroups / 2) break;
+                uint64_t hs; int ln;
+                if (!fits(pending[i], hs, ln)) continue;
+                high_set = hs; low_need = ln;
+                ops.push_back(pending[i]);
+                done[i] = 1;
+                --remaining;
+                for (int sidx : succ[i]) --npred[sidx];
+            }
+            if (ops.empty()) { set_error("internal: scheduler made no progress"); return SPZ_ERR_INVALID_ARG; }
+            SPZ_TRY(emit_group());
+        }
         return SPZ_OK;
     }
 };
@@ -600,6 +684,7 @@ int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags,
     const bool fuse = (flags & SPZ_EXEC_FUSE) != 0 && st->n >= min_tile_bits();
     Fuser fuser(st);
     fuser.exact = (flags & SPZ_EXEC_EXACT) != 0;
+    fuser.reorder = (flags & SPZ_EXEC_KEEP_ORDER) == 0;
 
     const int nq = total_qubits(st);
     int64_t cur = 0; // index of the op being emitted (for the exchange look-ahead)
@@ -626,7 +711,7 @@ int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags,
         r.theta = p ? p[0] : 0.0;
         if (kind == SPZ_GATE_SWAP) { if (target == t2) return SPZ_OK; r.g.kind = kind; }
         else SPZ_TRY(resolve_gate(kind, p, &r.g));
-        return fuser.add(r);
+        return fuser.push(r);
     };
 
     auto emit = [&](int kind, const double *p, uint64_t cmask, int target, int t2) -> int {

@@ -12,7 +12,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 depth = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 s = sb.State(n)
 out = {"workload": f"random layered circuit, n={n}, depth={depth}, seed 42"}
-for label, kw in (("fused", dict(fuse=True)), ("fused_exact", dict(fuse=True, exact=True)), ("unfused", dict(fuse=False))):
+for label, kw in (("fused", dict(fuse=True)), ("fused_keep_order", dict(fuse=True, reorder=False)),
+                  ("fused_exact", dict(fuse=True, exact=True)), ("unfused", dict(fuse=False))):
     s.init_random(42)
     qc = QuantumCircuit.from_state(s, **kw)
     gates = workloads.random_layered_circuit(qc, depth=depth, seed=42)
