@@ -412,17 +412,37 @@ struct Fuser {
         std::vector<char> done(N, 0);
         int remaining = N;
         while (remaining > 0) {
-            // one ascending scan per group: successors always have larger indices, and tile capacity only shrinks
-            for (int i = 0; i < N; ++i) {
-                if (done[i] || npred[i] != 0) continue;
-                if (ops.size() >= (size_t)kMaxTileGroups / 2) break;
-                uint64_t hs; int ln;
-                if (!fits(pending[i], hs, ln)) continue;
-                high_set = hs; low_need = ln;
-                ops.push_back(pending[i]);
-                done[i] = 1;
-                --remaining;
-                for (int sidx : succ[i]) --npred[sidx];
+            // Fill one group.  Ready ops are taken in ascending scans (successors always have larger indices, and
+            // tile capacity only shrinks).  Non-diagonal targets are taken in CLUSTERS of at most 4 distinct qubits
+            // -- the register layout of the tile kernel -- so that the compiled program changes layout once per
+            // cluster instead of once per gate; a scan that takes nothing opens the next cluster, and a fresh
+            // cluster that still takes nothing closes the group.
+            uint64_t cluster = 0;
+            bool fresh_cluster = true;
+            for (;;) {
+                bool progress = false;
+                for (int i = 0; i < N; ++i) {
+                    if (done[i] || npred[i] != 0) continue;
+                    if (ops.size() >= (size_t)kMaxTileGroups / 2) break;
+                    const ROp &op = pending[i];
+                    uint64_t want = 0; // non-diagonal targets this op needs register-resident
+                    if (op.kind == SPZ_GATE_SWAP) want = (1ull << op.target) | (1ull << op.t2);
+                    else if (!is_diagonal_kind(op.kind)) want = 1ull << op.target;
+                    if (want && __builtin_popcountll(cluster | want) > 4) continue;
+                    uint64_t hs; int ln;
+                    if (!fits(op, hs, ln)) continue;
+                    high_set = hs; low_need = ln;
+                    cluster |= want;
+                    ops.push_back(op);
+                    done[i] = 1;
+                    --remaining;
+                    for (int sidx : succ[i]) --npred[sidx];
+                    progress = true;
+                }
+                if (progress) { fresh_cluster = false; continue; }
+                if (fresh_cluster || ops.size() >= (size_t)kMaxTileGroups / 2 || remaining == 0) break;
+                cluster = 0;
+                fresh_cluster = true;
             }
             if (ops.empty()) { set_error("internal: scheduler made no progress"); return SPZ_ERR_INVALID_ARG; }
             SPZ_TRY(emit_group());
