@@ -287,7 +287,10 @@ def main():
                      "frac_of_nominal_8000": achieved_gpu / 8000.0, "peak_source": peak_src,
                      "kernel": "k_pair_vec / k_pair_low (kernels_direct.cuh)",
                      "algorithmic_bytes_per_launch": bytes_per_gate_gpu, "avg_launch_ms": per_gate_ms,
-                     "traffic": None},
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one k_pair_vec launch at n = 30, from the committed
+                     # ncu --set full capture (profiles/round1_k_pair_vec_ncu_full_raw.csv); only valid for 30 local qubits
+                     "traffic": 34.30e9 if n_local == 30 else None,
+                     "traffic_source": "profiles/round1_k_pair_vec_ncu_full_raw.csv (17.18 GB read + 17.12 GB written)"},
         "clocks": clocks, "gpu_launches": int(launches),
     }
     if nvlink is not None:

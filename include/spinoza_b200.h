@@ -135,6 +135,11 @@ SPZ_API int spz_iqft(spz_state *st, const int32_t *targets, int n_targets);     
 SPZ_API int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags, uint64_t *measured_mask,
                 uint64_t *measured_vals);
 SPZ_API int spz_set_seed(spz_state *st, uint64_t seed);
+/* Planning only (pure host code, no CUDA): how spz_execute would schedule the list.  out_order[k] = index of the op
+   executed k-th, out_pass[k] = the HBM pass (kernel launch) it belongs to; entries past the number of scheduled ops
+   are -1 (e.g. a BitFlipNoise that did not fire).  Used by the CPU tests of the scheduler. */
+SPZ_API int spz_plan_fusion(int n_qubits, const spz_op *ops, int64_t n_ops, uint32_t flags, int32_t *out_order,
+                            int32_t *out_pass, int32_t *out_n_passes);
 
 /* ---- reductions: measurement.rs:12-92, core.rs:65-129,198-264 --------------------------------- */
 SPZ_API int spz_prob0(spz_state *st, int target, double *out);   /* measurement.rs:16-29 */

@@ -305,13 +305,26 @@ class QuantumCircuit:
             op.zeros_mask = tr.controls.zeros_mask()
         return arr, n
 
+    def _flags(self) -> int:
+        return (EXEC_FUSE | (EXEC_EXACT if self.exact else 0) | (0 if self.reorder else EXEC_KEEP_ORDER)) if self.fuse else EXEC_NO_FUSE
+
+    def plan(self):
+        """How `execute` would schedule the current list (no GPU needed): [(op index, pass number)] in execution order."""
+        from . import _lib, _check
+        arr, n = self._encode()
+        order = (C.c_int32 * max(n, 1))()
+        passes = (C.c_int32 * max(n, 1))()
+        n_pass = C.c_int32()
+        _check(_lib.spz_plan_fusion(self.n_qubits, arr, n, self._flags(), order, passes, C.byref(n_pass)))
+        return [(order[i], passes[i]) for i in range(n) if order[i] >= 0], n_pass.value
+
     def execute(self):
         """circuit.rs:552-600.  Drains the transformation list (re-entrant on the same state)."""
         from . import _lib, _check
         arr, n = self._encode()
         m = C.c_uint64(self._measured_qubits)
         v = C.c_uint64(self._measured_qubits_vals)
-        flags = (EXEC_FUSE | (EXEC_EXACT if self.exact else 0) | (0 if self.reorder else EXEC_KEEP_ORDER)) if self.fuse else EXEC_NO_FUSE
+        flags = self._flags()
         self.transformations = []  # drain(..): the list is consumed even if a gate "panics"
         _check(_lib.spz_execute(self.state._h, arr, n, flags, C.byref(m), C.byref(v)))
         self._measured_qubits, self._measured_qubits_vals = m.value, v.value

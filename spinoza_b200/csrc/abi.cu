@@ -140,6 +140,17 @@ struct ROp { // an op resolved to what the kernels need (physical qubits of this
     GateK g;
     int const_hi = -1; // >= 0: diagonal gate whose target is a rank bit of a sharded register; value of that bit
     double theta = 0.0; // first gate parameter (merged diagonal factors are computed from the angle itself)
+    int src = -1;       // index of the originating op in the caller's list (planning output)
+};
+
+// Dry-run sink: instead of launching kernels, record which pass every op ends up in (spz_plan_fusion).
+struct PlanSink {
+    std::vector<int32_t> order, group;
+    int n_groups = 0;
+    void take(const std::vector<ROp> &ops) {
+        for (const ROp &o : ops) { order.push_back(o.src); group.push_back(n_groups); }
+        ++n_groups;
+    }
 };
 
 struct Fuser {
@@ -150,6 +161,7 @@ struct Fuser {
     uint64_t high_set = 0;
     int low_need = 0;
     bool exact = false;
+    PlanSink *sink = nullptr;
 
     Fuser(spz_state *s) : st(s) {
         T = std::min(max_tile_bits(), s->n);
@@ -307,6 +319,7 @@ struct Fuser {
     // Launch the current group (ops / high_set / low_need) and reset it.
     int emit_group() {
         if (ops.empty()) return SPZ_OK;
+        if (sink) { sink->take(ops); ops.clear(); high_set = 0; low_need = 0; return SPZ_OK; }
         int rc = SPZ_OK;
         if (ops.size() == 1 && ops[0].const_hi >= 0) {
             rc = dist_diag_const(st, ops[0].g, ops[0].cmask, ops[0].const_hi);
@@ -694,9 +707,8 @@ int spz_iqft(spz_state *st, const int32_t *targets, int m) {
 }
 
 // ---- execute -------------------------------------------------------------------------------------------
-int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags, uint64_t *measured_mask,
-                uint64_t *measured_vals) {
-    SPZ_CHECK_STATE(st);
+static int execute_impl(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags, uint64_t *measured_mask,
+                        uint64_t *measured_vals, PlanSink *sink) {
     if (n_ops < 0 || (n_ops && !ops)) { set_error("bad op list"); return SPZ_ERR_INVALID_ARG; }
     uint64_t local_m = 0, local_v = 0;
     uint64_t *mm = measured_mask ? measured_mask : &local_m;
@@ -705,6 +717,7 @@ int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags,
     Fuser fuser(st);
     fuser.exact = (flags & SPZ_EXEC_EXACT) != 0;
     fuser.reorder = (flags & SPZ_EXEC_KEEP_ORDER) == 0;
+    fuser.sink = sink;
 
     const int nq = total_qubits(st);
     int64_t cur = 0; // index of the op being emitted (for the exchange look-ahead)
@@ -719,7 +732,7 @@ int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags,
     };
 
     auto emit_local = [&](int kind, const double *p, uint64_t cmask, int target, int t2, int const_hi) -> int {
-        if (!fuse) {
+        if (!fuse && !sink) {
             if (kind == SPZ_GATE_SWAP) return launch_swap(st, target, t2);
             GateK g;
             SPZ_TRY(resolve_gate(kind, p, &g));
@@ -729,6 +742,12 @@ int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags,
         ROp r{};
         r.kind = kind; r.target = target; r.t2 = t2; r.cmask = cmask; r.const_hi = const_hi;
         r.theta = p ? p[0] : 0.0;
+        r.src = (int)cur;
+        if (!fuse) { // dry run of the unfused path: one pass per op
+            if (kind != SPZ_GATE_SWAP) SPZ_TRY(resolve_gate(kind, p, &r.g));
+            sink->take(std::vector<ROp>{r});
+            return SPZ_OK;
+        }
         if (kind == SPZ_GATE_SWAP) { if (target == t2) return SPZ_OK; r.g.kind = kind; }
         else SPZ_TRY(resolve_gate(kind, p, &r.g));
         return fuser.push(r);
@@ -775,6 +794,7 @@ int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags,
                 if (op.target < 0 || op.target >= total_qubits(st)) { set_error("target %d out of range", op.target); return SPZ_ERR_INVALID_ARG; }
                 if (!((*mm >> op.target) & 1ull)) {
                     SPZ_TRY(fuser.flush());
+                    if (sink) { ROp m{}; m.kind = SPZ_GATE_M; m.target = op.target; m.src = (int)i; sink->take(std::vector<ROp>{m}); continue; }
                     int bit = 0;
                     SPZ_TRY(measure_impl(st, op.target, 1, -1, &bit));
                     *mm |= 1ull << op.target;
@@ -813,6 +833,26 @@ int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags,
         }
     }
     return fuser.flush();
+}
+
+int spz_execute(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags, uint64_t *measured_mask,
+                uint64_t *measured_vals) {
+    SPZ_CHECK_STATE(st);
+    return execute_impl(st, ops, n_ops, flags, measured_mask, measured_vals, nullptr);
+}
+
+int spz_plan_fusion(int n_qubits, const spz_op *ops, int64_t n_ops, uint32_t flags, int32_t *out_order, int32_t *out_pass,
+                    int32_t *out_n_passes) {
+    if (n_qubits < 1 || n_qubits > 40 || !out_order || !out_pass || !out_n_passes) { set_error("bad arguments"); return SPZ_ERR_INVALID_ARG; }
+    spz_state dummy; // never touches a device: only the qubit count and the seeded generator are read
+    dummy.n = n_qubits;
+    dummy.len = (int64_t)1 << n_qubits;
+    PlanSink sink;
+    SPZ_TRY(execute_impl(&dummy, ops, n_ops, flags, nullptr, nullptr, &sink));
+    for (size_t i = 0; i < sink.order.size(); ++i) { out_order[i] = sink.order[i]; out_pass[i] = sink.group[i]; }
+    for (size_t i = sink.order.size(); i < (size_t)n_ops; ++i) { out_order[i] = -1; out_pass[i] = -1; }
+    *out_n_passes = sink.n_groups;
+    return SPZ_OK;
 }
 
 // ---- reductions --------------------------------------------------------------------------------------------
