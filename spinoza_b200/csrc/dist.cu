@@ -205,6 +205,21 @@ int dist_exchange(spz_state *st, int gbit, int lq) {
     const int my_bit = (c->rank >> gbit) & 1;
     const unsigned long long e = ++c->epoch;
     k_handshake<<<1, 1, 0, st->stream>>>(&c->peer_ctrl[partner]->ready[c->rank], &c->ctrl->ready[partner], e, &c->ctrl->error);
+    // recycle the timing events of exchanges that have already finished (keeps the pool bounded on long runs)
+    if (c->pending.size() >= 32) {
+        size_t keep = 0;
+        for (auto &e : c->pending) {
+            float ms = 0.f;
+            if (cudaEventQuery(e.second) == cudaSuccess && cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) {
+                c->ms_accum += ms;
+                c->free_events.push_back(e);
+            } else {
+                c->pending[keep++] = e;
+            }
+        }
+        c->pending.resize(keep);
+        cudaGetLastError(); // cudaErrorNotReady from the query is not an error
+    }
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!c->free_events.empty()) { ev = c->free_events.back(); c->free_events.pop_back(); }
     else { SPZ_CUDA(cudaEventCreate(&ev.first)); SPZ_CUDA(cudaEventCreate(&ev.second)); }

@@ -112,24 +112,32 @@ struct TileGroup {
 };
 constexpr int kMaxTileGroups = 2048; // shared-memory budget: 20 bytes per group
 struct TileInstr {
+    // ---- chunk 0 (16 B): read for every instruction ----
     int op;               // TI_*
     int kind;             // spz_gate_kind
-    int rbit[4];          // TI_LAYOUT: the 4 register-resident tile bits, ascending
-    int rpos;             // TI_GATE: which register bit (0..3) the target is.  TI_RUN: offset of the run's first term
-    // TI_RUN: rpos = first group of the run; rbit[0..3], reg_cmask, thr_cmask hold the GROUP counts of classes
-    // m = 0, 1, 2, 4, 8, other (in that order); diagonal gates commute, so the host sorts a run's terms freely.
+    int rpos;             // TI_GATE: which register bit (0..3) the target is.  TI_RUN: first group of the run
+    uint32_t t_mask;      // TI_DIAG: t_where 1: tile-index mask; t_where 2: mask over k.  TI_GATE: set of k with controls set
+    // ---- chunk 1 (16 B) ----
     uint32_t reg_cmask;   // controls on register bits (mask over k = 0..15)
     uint32_t thr_cmask;   // controls on thread bits (mask in tile-index space)
     int t_where;          // TI_DIAG target: 0 = outside the tile, 1 = thread bit, 2 = register bit
-    uint32_t t_mask;      // TI_DIAG: t_where 1: tile-index mask; t_where 2: mask over k.  TI_GATE: set of k with controls set
     int outer_target;     // t_where 0: absolute qubit, unless const_hi is set
+    // ---- chunk 2 (16 B) ----
+    // TI_LAYOUT: the 4 register-resident tile bits, ascending.
+    // TI_RUN: rbit[0..3], reg_cmask, thr_cmask hold the GROUP counts of classes m = 0, 1, 2, 4, 8, other (in that
+    // order); diagonal gates commute, so the host sorts a run's terms freely.
+    int rbit[4];
+    // ---- chunk 3 (16 B) ----
+    uint64_t outer_cmask; // controls outside the tile (absolute positions)
     uint32_t const_hi;    // t_where 0: 0 = read the bit from the tile base, 1 = bit is 0, 2 = bit is 1 (a rank bit)
     int has_f0;           // merged mode: f0 is not the identity
-    uint64_t outer_cmask; // controls outside the tile (absolute positions)
+    // ---- payload ----
     double s[7];          // gate scalars for the exact arithmetic (gate_math.cuh)
     double f0[2];         // merged mode: factor when all controls are set (RZ's d0)
     double f1[2];         // merged mode: extra factor when the target bit is set too (e^{i theta}, -1)
+    double pad_;          // keeps the size a multiple of 16 bytes (staged with 128-bit copies)
 };
+static_assert(sizeof(TileInstr) % 16 == 0, "TileInstr is copied to shared memory in 16-byte units");
 struct TilePlan {
     int tile_bits;       // T
     int low_bits;        // L: tile bits 0..L-1 are qubits 0..L-1

@@ -36,6 +36,7 @@ namespace spz {
 constexpr int kMaxTileBits = 12;
 constexpr int kMaxHigh = 8;
 constexpr int kRegBits = 4; // 16 amplitudes per thread
+constexpr int kMaxSmemInstr = 96; // programs up to this many instructions (12 KB) are staged in shared memory
 
 int max_tile_bits() { return kMaxTileBits; }
 int min_tile_bits() { return kRegBits; }
@@ -48,6 +49,8 @@ struct TileArgs {
     const TileTerm *terms;
     int n_instr;
     int n_groups;
+    int prog_in_smem; // 1: the program is staged in shared memory (it fits the budget)
+    unsigned prog_off; // byte offset of the staged program inside dynamic shared memory
     int T, L, n_high;
     int high[kMaxHigh];
 };
@@ -92,13 +95,13 @@ __device__ __forceinline__ void run_class(const double2 *__restrict__ gfac, cons
     double ar_ = 1.0, ai_ = 0.0, br_ = 1.0, bi_ = 0.0;
     int i = 0;
     for (; i + 2 <= cnt; i += 2) {
-        const unsigned t0 = gthr[i], t1 = gthr[i + 1];
+        const unsigned t0 = gthr[i] & 0xffffu, t1 = gthr[i + 1] & 0xffffu;
         const double2 f0 = gfac[i], f1 = gfac[i + 1];
         if ((tj & t0) == t0) cmul(ar_, ai_, f0.x, f0.y);
         if ((tj & t1) == t1) cmul(br_, bi_, f1.x, f1.y);
     }
     if (i < cnt) {
-        const unsigned t0 = gthr[i];
+        const unsigned t0 = gthr[i] & 0xffffu;
         const double2 f0 = gfac[i];
         if ((tj & t0) == t0) cmul(ar_, ai_, f0.x, f0.y);
     }
@@ -116,6 +119,8 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
     double *sim = smem + tile_len;
     double2 *gfac = reinterpret_cast<double2 *>(smem + 2 * tile_len); // per-group factor for THIS tile
     unsigned *gthr = reinterpret_cast<unsigned *>(gfac + a.n_groups);  // per-group thread mask (all ones = never)
+    // the micro-program itself, staged once per CTA so that decoding reads shared memory with uniform addresses
+    TileInstr *sprog = reinterpret_cast<TileInstr *>(reinterpret_cast<char *>(smem) + a.prog_off);
     __shared__ unsigned long long seg_off[1 << kMaxHigh];
 
     // absolute index of the tile's first amplitude: CTA id bits go to the non-tile positions
@@ -131,6 +136,12 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
             if (k < a.n_high && ((sgi >> k) & 1)) off |= 1ull << a.high[k];
         seg_off[sgi] = off;
     }
+    if (a.prog_in_smem) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.prog);
+        uint4 *dst = reinterpret_cast<uint4 *>(sprog);
+        const int n16 = a.n_instr * (int)(sizeof(TileInstr) / sizeof(uint4));
+        for (int i = threadIdx.x; i < n16; i += nthr) dst[i] = src[i];
+    }
     // per-tile reduction of every group of every diagonal run: product of its terms whose outer bits are set
     for (int g = threadIdx.x; g < a.n_groups; g += nthr) {
         const TileGroup gd = a.groups[g];
@@ -141,7 +152,8 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
             if ((base & t.outer) == t.outer) { cmul(fr, fi, t.fr, t.fi); any = true; }
         }
         gfac[g] = make_double2(fr, fi);
-        gthr[g] = any ? gd.thr : 0xffffffffu; // nothing applies to this tile: no thread matches
+        // low 16 bits: thread mask (all ones = nothing applies to this tile, no thread matches); high bits: register mask m
+        gthr[g] = (any ? gd.thr : 0xffffu) | (gd.m << 16);
     }
     __syncthreads();
 
@@ -254,7 +266,7 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
     };
 
     for (int pc = 0; pc < a.n_instr; ++pc) {
-        const TileInstr &ins = a.prog[pc];
+        const TileInstr &ins = a.prog_in_smem ? sprog[pc] : a.prog[pc];
         const int op = ins.op;
         if (op == TI_LAYOUT) {
             if (have_regs) {
@@ -285,7 +297,7 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
             run_class(gfac + g, gthr + g, c4, tj, f4r, f4i); g += c4;
             dirty |= (c0 ? 1u : 0u) | (c1 ? 2u : 0u) | (c2 ? 4u : 0u) | (c3 ? 8u : 0u) | (c4 ? 16u : 0u);
             for (int i = 0; i < c5; ++i) { // support with >= 2 register bits: touch the amplitudes directly
-                const unsigned thr = gthr[g + i], m = a.groups[g + i].m;
+                const unsigned packed = gthr[g + i], thr = packed & 0xffffu, m = packed >> 16;
                 const double2 f = gfac[g + i];
                 if ((tj & thr) != thr) continue;
                 // two register bits (a CP between two register-resident qubits) is the common case: 4 amplitudes
@@ -371,7 +383,8 @@ int tile_prepare(spz_state *st) {
         st->d_ops_bytes = cap;
         st->d_ops_cursor = 0;
     }
-    const int max_smem = (int)(sizeof(double) * 2u * ((size_t)1 << kMaxTileBits) + kMaxTileGroups * (sizeof(double2) + sizeof(unsigned)));
+    const int max_smem = (int)(sizeof(double) * 2u * ((size_t)1 << kMaxTileBits) + kMaxTileGroups * (sizeof(double2) + sizeof(unsigned)) + 16 +
+                               kMaxSmemInstr * sizeof(TileInstr));
     SPZ_CUDA(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     SPZ_CUDA(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     return SPZ_OK;
@@ -420,7 +433,11 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
     a.n_instr = n_instr;
     a.T = plan.tile_bits; a.L = plan.low_bits; a.n_high = plan.n_high;
     for (int k = 0; k < plan.n_high; ++k) a.high[k] = plan.high[k];
-    const size_t smem = sizeof(double) * 2u * ((size_t)1 << plan.tile_bits) + (size_t)n_groups * (sizeof(double2) + sizeof(unsigned));
+    size_t smem = sizeof(double) * 2u * ((size_t)1 << plan.tile_bits) + (size_t)n_groups * (sizeof(double2) + sizeof(unsigned));
+    smem = (smem + 15) & ~(size_t)15;
+    a.prog_off = (unsigned)smem;
+    a.prog_in_smem = n_instr <= kMaxSmemInstr ? 1 : 0;
+    if (a.prog_in_smem) smem += sizeof(TileInstr) * (size_t)n_instr;
     const unsigned grid = (unsigned)((uint64_t)st->len >> plan.tile_bits);
     const unsigned threads = 1u << (plan.tile_bits - kRegBits);
     if (exact) k_tile<true><<<grid, threads, smem, st->stream>>>(a);
