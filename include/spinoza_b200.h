@@ -152,7 +152,8 @@ SPZ_API int spz_qubit_expectation_value(spz_state *st, int target, double *out);
 SPZ_API int spz_xyz_expectation_value(spz_state *st, char observable, const int32_t *targets, int n_targets, double *out);
 /* Sampling (replaces reservoir_sampling core.rs:125): `shots` exact inverse-CDF draws; u01[k] in [0,1)
    supplied by the caller (so results are reproducible and checkable); out_index[k] = smallest i with
-   cdf(i) > u01[k] * norm2. */
+   cdf(i) > u01[k] * norm2.  On a sharded register every rank passes the same u01; a shot is answered by the rank
+   that owns it (logical basis index) and comes back as -1 on the others (combine with a max). */
 SPZ_API int spz_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_index);
 
 /* ---- multi-GPU: one process per GPU, amplitudes sharded by the top log2(world) index bits ------ */

@@ -904,7 +904,7 @@ int spz_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_ind
     SPZ_CHECK_STATE(st);
     if (shots < 0 || (shots && (!u01 || !out_index))) return SPZ_ERR_INVALID_ARG;
     static_assert(sizeof(long long) == sizeof(int64_t), "int64_t layout");
-    if (st->dist) { set_error("sampling a sharded register is not implemented yet"); return SPZ_ERR_UNSUPPORTED; }
+    if (st->dist) return dist_sample(st, u01, shots, out_index); // shots owned by other ranks come back as -1
     return launch_sample(st, u01, shots, out_index);
 }
 

@@ -363,6 +363,49 @@ int dist_init_random(spz_state *st, uint64_t seed) {
     return launch_rand_finish(st, seed, (long long)c->rank * st->len, total_len, d_total);
 }
 
+// Sampling a sharded register: rank masses are all-gathered (one scalar all-reduce per rank, so every rank holds the
+// bitwise-identical table), each shot is routed to the rank whose mass interval contains u * total, and that rank
+// runs the single-GPU sampler on its shard with the rescaled uniform.  The CDF therefore walks PHYSICAL index order
+// (rank-major); the outcome is reported as a logical basis index.  Shots owned by other ranks are returned as -1.
+int dist_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_index) {
+    DistCtx *c = ctx_of(st);
+    double mine = 0.0;
+    SPZ_TRY(reduce_scalar(st, 1, 0, &mine));
+    double mass[kMaxRanks];
+    for (int r = 0; r < c->world; ++r) SPZ_TRY(dist_allreduce(st, nullptr, r == c->rank ? mine : 0.0, &mass[r], nullptr));
+    double cum[kMaxRanks + 1];
+    cum[0] = 0.0;
+    for (int r = 0; r < c->world; ++r) cum[r + 1] = cum[r] + mass[r];
+    const double total = cum[c->world];
+    std::vector<double> lu;
+    std::vector<int64_t> where;
+    for (int64_t k = 0; k < shots; ++k) {
+        double u = u01[k];
+        if (!(u >= 0.0)) u = 0.0;
+        if (u >= 1.0) u = 0x1.fffffffffffffp-1;
+        const double x = u * total;
+        int owner = 0;
+        while (owner + 1 < c->world && x >= cum[owner + 1]) ++owner;
+        out_index[k] = -1;
+        if (owner != c->rank || mass[owner] <= 0.0) continue;
+        double v = (x - cum[owner]) / mass[owner];
+        if (!(v >= 0.0)) v = 0.0;
+        if (v >= 1.0) v = 0x1.fffffffffffffp-1;
+        lu.push_back(v);
+        where.push_back(k);
+    }
+    if (lu.empty()) return SPZ_OK;
+    std::vector<int64_t> local(lu.size());
+    SPZ_TRY(launch_sample(st, lu.data(), (int64_t)lu.size(), local.data()));
+    for (size_t i = 0; i < lu.size(); ++i) {
+        const uint64_t phys = ((uint64_t)c->rank << c->plan.n_local) | (uint64_t)local[i];
+        uint64_t logical = 0;
+        for (int q = 0; q < c->plan.n; ++q) logical |= ((phys >> c->plan.perm[q]) & 1ull) << q;
+        out_index[where[i]] = (int64_t)logical;
+    }
+    return SPZ_OK;
+}
+
 void dist_destroy(spz_state *st) {
     DistCtx *c = ctx_of(st);
     if (!c) return;

@@ -159,6 +159,7 @@ int dist_reduce_scalar(spz_state *st, int mode, int target, double *out);
 int dist_collapse(spz_state *st, int target, int outcome, double scale);
 int dist_fill_basis(spz_state *st, uint64_t logical_index);
 int dist_init_random(spz_state *st, uint64_t seed);
+int dist_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_index);
 void dist_destroy(spz_state *st);
 
 } // namespace spz

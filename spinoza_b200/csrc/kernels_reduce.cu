@@ -352,15 +352,18 @@ int launch_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_
     int rc = SPZ_OK;
     std::vector<double> l2((size_t)n_l2), resid((size_t)shots);
     std::vector<long long> group((size_t)shots);
+    // stream-ordered allocations: cudaMalloc/cudaFree would synchronise the whole device (see spz_create)
     auto cleanup = [&]() {
-        cudaFree(d_l1); cudaFree(d_l2); cudaFree(d_resid); cudaFree(d_group); cudaFree(d_out);
+        cudaFreeAsync(d_l1, st->stream); cudaFreeAsync(d_l2, st->stream); cudaFreeAsync(d_resid, st->stream);
+        cudaFreeAsync(d_group, st->stream); cudaFreeAsync(d_out, st->stream);
+        cudaStreamSynchronize(st->stream);
     };
 #define SPZ_S(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = cuda_fail(e__, #call, __FILE__, __LINE__); cleanup(); return rc; } } while (0)
-    SPZ_S(cudaMalloc(&d_l1, sizeof(double) * (size_t)n_l1));
-    SPZ_S(cudaMalloc(&d_l2, sizeof(double) * (size_t)n_l2));
-    SPZ_S(cudaMalloc(&d_resid, sizeof(double) * (size_t)shots));
-    SPZ_S(cudaMalloc(&d_group, sizeof(long long) * (size_t)shots));
-    SPZ_S(cudaMalloc(&d_out, sizeof(long long) * (size_t)shots));
+    SPZ_S(cudaMallocAsync(&d_l1, sizeof(double) * (size_t)n_l1, st->stream));
+    SPZ_S(cudaMallocAsync(&d_l2, sizeof(double) * (size_t)n_l2, st->stream));
+    SPZ_S(cudaMallocAsync(&d_resid, sizeof(double) * (size_t)shots, st->stream));
+    SPZ_S(cudaMallocAsync(&d_group, sizeof(long long) * (size_t)shots, st->stream));
+    SPZ_S(cudaMallocAsync(&d_out, sizeof(long long) * (size_t)shots, st->stream));
     k_block_prob<<<(unsigned)n_l1, 256, 0, st->stream>>>(st->re, st->im, len, d_l1);
     k_group_sum<<<(unsigned)n_l2, 256, 0, st->stream>>>(d_l1, n_l1, d_l2);
     count_launch(2);

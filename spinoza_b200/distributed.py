@@ -121,6 +121,19 @@ class DistState(State):
     def clone(self):
         raise NotImplementedError("clone of a sharded register")
 
+    def sample(self, shots: int, seed: int = 0, u01: Optional[np.ndarray] = None) -> np.ndarray:
+        """Exact sampling of the whole sharded register: every rank passes the same uniforms, the owning rank answers
+        each shot, and the answers are combined with a max all-reduce (gloo)."""
+        from . import sample as _sample
+        local = _sample(self, shots, seed=seed, u01=u01)
+        if self.env.world == 1:
+            return local
+        import torch
+        import torch.distributed as td
+        t = torch.from_numpy(local.copy())
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return t.numpy()
+
     def gather_logical(self):
         """Rank 0: the full state in LOGICAL index order (re, im); other ranks: None.  Small registers only."""
         re, im = self.download()

@@ -189,3 +189,29 @@ def test_two_gpus_ipc_nvlink():
                        capture_output=True, text=True, env=env, timeout=600, cwd=str(ROOT))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "GPU_DIST_OK" in r.stdout
+
+
+@pytest.mark.parametrize("n,world", [(8, 4), (12, 2)])
+def test_sample_sharded(n, world):
+    cpu = orc.gen_random_state(n, 77 + n)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, cpu)
+    # move a qubit around first so that the permutation is not the identity
+    run_group(states, lambda r, s: (sb.apply(Gate.H, s, n - 1), sb.apply(Gate.H, s, n - 1), s.sync()))
+    shots = 1 << 15
+    u = orc.uniforms(7, shots)
+    outs = run_group(states, lambda r, s: sb.sample(s, shots, u01=u))
+    merged = np.max(np.stack(outs), axis=0)
+    owners = np.sum(np.stack(outs) >= 0, axis=0)
+    assert np.all(owners == 1) and merged.min() >= 0 and merged.max() < (1 << n)   # every shot answered exactly once
+    re, im = gather(states)
+    p = re ** 2 + im ** 2
+    counts = np.bincount(merged, minlength=1 << n)
+    keep = p * shots > 5
+    chi2 = np.sum((counts[keep] - shots * p[keep]) ** 2 / (shots * p[keep]))
+    dof = int(np.count_nonzero(keep))
+    assert chi2 < dof + 6 * math.sqrt(2 * dof)
+    # basis state: exact (core.rs:272-291)
+    run_group(states, lambda r, s: (s.set_basis(5), s.sync()))
+    outs = run_group(states, lambda r, s: sb.sample(s, 64, seed=1))
+    assert np.all(np.max(np.stack(outs), axis=0) == 5)
