@@ -550,6 +550,7 @@ int spz_create(int n_qubits, int device, spz_state **out) {
 int spz_destroy(spz_state *st) {
     if (!st) return SPZ_OK;
     cudaSetDevice(st->device);
+    if (st->dist) dist_join(st);
     if (st->stream) cudaStreamSynchronize(st->stream);
     if (st->dist) dist_destroy(st);
     cudaFree(st->re);
@@ -590,6 +591,7 @@ int spz_set_seed(spz_state *st, uint64_t seed) { if (!st) return SPZ_ERR_INVALID
 int spz_upload(spz_state *st, const double *re, const double *im, int64_t offset, int64_t count) {
     SPZ_CHECK_STATE(st);
     if (offset < 0 || count < 0 || offset + count > st->len) { set_error("upload range [%lld, +%lld) outside the state", (long long)offset, (long long)count); return SPZ_ERR_INVALID_ARG; }
+    SPZ_TRY(join_pending(st));
     const size_t bytes = sizeof(double) * (size_t)count;
     if (re) SPZ_CUDA(cudaMemcpyAsync(st->re + offset, re, bytes, cudaMemcpyHostToDevice, st->stream));
     if (im) SPZ_CUDA(cudaMemcpyAsync(st->im + offset, im, bytes, cudaMemcpyHostToDevice, st->stream));
@@ -600,6 +602,7 @@ int spz_upload(spz_state *st, const double *re, const double *im, int64_t offset
 int spz_download(const spz_state *st, double *re, double *im, int64_t offset, int64_t count) {
     SPZ_CHECK_STATE(st);
     if (offset < 0 || count < 0 || offset + count > st->len) { set_error("download range [%lld, +%lld) outside the state", (long long)offset, (long long)count); return SPZ_ERR_INVALID_ARG; }
+    SPZ_TRY(join_pending(const_cast<spz_state *>(st)));
     const size_t bytes = sizeof(double) * (size_t)count;
     if (re) SPZ_CUDA(cudaMemcpyAsync(re, st->re + offset, bytes, cudaMemcpyDeviceToHost, st->stream));
     if (im) SPZ_CUDA(cudaMemcpyAsync(im, st->im + offset, bytes, cudaMemcpyDeviceToHost, st->stream));
@@ -609,6 +612,7 @@ int spz_download(const spz_state *st, double *re, double *im, int64_t offset, in
 
 int spz_sync(spz_state *st) {
     SPZ_CHECK_STATE(st);
+    SPZ_TRY(join_pending(st));
     SPZ_CUDA(cudaStreamSynchronize(st->stream));
     return SPZ_OK;
 }
@@ -911,12 +915,14 @@ int spz_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_ind
 // ---- instrumentation -----------------------------------------------------------------------------------------
 int spz_timer_start(spz_state *st) {
     SPZ_CHECK_STATE(st);
+    SPZ_TRY(join_pending(st));
     SPZ_CUDA(cudaEventRecord(st->ev0, st->stream));
     return SPZ_OK;
 }
 
 int spz_timer_stop(spz_state *st, double *out_ms) {
     SPZ_CHECK_STATE(st);
+    SPZ_TRY(join_pending(st));
     SPZ_CUDA(cudaEventRecord(st->ev1, st->stream));
     SPZ_CUDA(cudaEventSynchronize(st->ev1));
     float ms = 0.f;

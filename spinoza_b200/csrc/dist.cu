@@ -11,6 +11,7 @@
 //                      device memory, st.release.sys / ld.acquire.sys), before and after each exchange.
 //   * k_allreduce    : scalar sum across all ranks through the same IPC control blocks (prob0 / norm / <O>).
 // No NCCL: the data path is peer loads/stores issued by our own kernels.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -25,6 +26,7 @@ constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ul
 struct CtrlBlock { // lives in device memory of each rank, mapped by every peer
     unsigned long long ready[kMaxRanks];
     unsigned long long done[kMaxRanks];
+    unsigned long long done1[kMaxRanks]; // second chunk of an overlapped exchange
     unsigned long long red_epoch[2][kMaxRanks];
     double red_slot[2][kMaxRanks];
     double red_result;
@@ -48,8 +50,15 @@ struct DistCtx {
     CtrlBlock **d_table = nullptr; // device copy of peer_ctrl[] for k_allreduce
     bool connected = false, ipc = false;
     unsigned long long epoch = 0, red_epoch = 0;
+    // overlapped exchange (second stream): the shard is exchanged in two halves split by local bit `split_bit`; the
+    // fused pass that follows starts on half 0 while half 1 is still on the wire
+    cudaStream_t xstream = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_half[2] = {nullptr, nullptr};
+    bool split_pending = false;
+    int split_bit = -1;
+    bool overlap = true;
     // stats
-    double n_exchanges = 0, bytes_sent = 0, ms_accum = 0;
+    double n_exchanges = 0, bytes_sent = 0, ms_accum = 0, n_overlapped = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, free_events;
 };
 
@@ -198,13 +207,15 @@ static int check_comm_error(spz_state *st) {
     return SPZ_OK;
 }
 
+int dist_join(spz_state *st);
+
 int dist_exchange(spz_state *st, int gbit, int lq) {
     DistCtx *c = ctx_of(st);
     if (!c->connected) { set_error("dist state used before spz_dist_connect"); return SPZ_ERR_COMM; }
     const int partner = c->rank ^ (1 << gbit);
     const int my_bit = (c->rank >> gbit) & 1;
+    SPZ_TRY(dist_join(st)); // a previous overlapped exchange must have landed completely
     const unsigned long long e = ++c->epoch;
-    k_handshake<<<1, 1, 0, st->stream>>>(&c->peer_ctrl[partner]->ready[c->rank], &c->ctrl->ready[partner], e, &c->ctrl->error);
     // recycle the timing events of exchanges that have already finished (keeps the pool bounded on long runs)
     if (c->pending.size() >= 32) {
         size_t keep = 0;
@@ -223,37 +234,82 @@ int dist_exchange(spz_state *st, int gbit, int lq) {
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!c->free_events.empty()) { ev = c->free_events.back(); c->free_events.pop_back(); }
     else { SPZ_CUDA(cudaEventCreate(&ev.first)); SPZ_CUDA(cudaEventCreate(&ev.second)); }
-    SPZ_CUDA(cudaEventRecord(ev.first, st->stream));
     XArgs a{};
     a.mine_re = st->re; a.mine_im = st->im; a.peer_re = c->peer_re[partner]; a.peer_im = c->peer_im[partner];
     a.lq = lq; a.my_bit = my_bit;
     const int n_local = st->n;
     constexpr int W = 4, U = 4, THREADS = 256;
-    if (lq >= LogW<W>::v && n_local - 1 - LogW<W>::v >= 1) {
-        const long long nvec = 1ll << (n_local - 1 - LogW<W>::v);
-        a.nvec_begin = my_bit ? nvec / 2 : 0;
-        a.nvec_end = my_bit ? nvec : nvec / 2;
-        const long long cnt = a.nvec_end - a.nvec_begin, per = (long long)THREADS * U;
-        k_exchange_vec<W, U, THREADS><<<(unsigned)((cnt + per - 1) / per), THREADS, 0, st->stream>>>(a);
+    const bool vec = lq >= LogW<W>::v && n_local - 1 - LogW<W>::v >= 1;
+    const long long nvec = vec ? (1ll << (n_local - 1 - LogW<W>::v)) : (1ll << (n_local - 1));
+    auto launch_range = [&](long long b, long long e2, cudaStream_t stream) {
+        XArgs r = a;
+        r.nvec_begin = b; r.nvec_end = e2;
+        const long long cnt = e2 - b, per = (long long)THREADS * U;
+        if (vec) k_exchange_vec<W, U, THREADS><<<(unsigned)((cnt + per - 1) / per), THREADS, 0, stream>>>(r);
+        else k_exchange_scalar<<<(unsigned)std::max<long long>(1, std::min<long long>((cnt + 255) / 256, 148 * 8)), 256, 0, stream>>>(r);
+    };
+    // The top bit of the pair-list index is the top local bit that is not lq: halves of the pair list are halves of
+    // the shard along that bit.  Overlapped mode needs a vector path and at least 4 vectors per half.
+    const int top = (lq == n_local - 1) ? n_local - 2 : n_local - 1;
+    if (c->overlap && vec && nvec >= 64 && top >= 0) {
+        // stream X: [ready handshake] [half 0: my quarter] [done0 handshake] ev_half[0] [half 1] [done1] ev_half[1]
+        SPZ_CUDA(cudaEventRecord(c->ev_main, st->stream));
+        SPZ_CUDA(cudaStreamWaitEvent(c->xstream, c->ev_main, 0));
+        k_handshake<<<1, 1, 0, c->xstream>>>(&c->peer_ctrl[partner]->ready[c->rank], &c->ctrl->ready[partner], e, &c->ctrl->error);
+        SPZ_CUDA(cudaEventRecord(ev.first, c->xstream));
+        for (int h = 0; h < 2; ++h) {
+            const long long hb = h * (nvec / 2) + my_bit * (nvec / 4);
+            launch_range(hb, hb + nvec / 4, c->xstream);
+            unsigned long long *peer_done = h ? &c->peer_ctrl[partner]->done1[c->rank] : &c->peer_ctrl[partner]->done[c->rank];
+            const unsigned long long *my_done = h ? &c->ctrl->done1[partner] : &c->ctrl->done[partner];
+            k_handshake<<<1, 1, 0, c->xstream>>>(peer_done, my_done, e, &c->ctrl->error);
+            if (h == 1) SPZ_CUDA(cudaEventRecord(ev.second, c->xstream));
+            SPZ_CUDA(cudaEventRecord(c->ev_half[h], c->xstream));
+        }
+        c->pending.push_back(ev);
+        c->split_pending = true;
+        c->split_bit = top;
+        c->n_overlapped += 1;
+        count_launch(5);
     } else {
-        const long long nvec = 1ll << (n_local - 1);
-        a.nvec_begin = my_bit ? nvec / 2 : 0;
-        a.nvec_end = my_bit ? nvec : nvec / 2;
-        const long long cnt = a.nvec_end - a.nvec_begin;
-        k_exchange_scalar<<<(unsigned)std::max<long long>(1, std::min<long long>((cnt + 255) / 256, 148 * 8)), 256, 0, st->stream>>>(a);
+        k_handshake<<<1, 1, 0, st->stream>>>(&c->peer_ctrl[partner]->ready[c->rank], &c->ctrl->ready[partner], e, &c->ctrl->error);
+        SPZ_CUDA(cudaEventRecord(ev.first, st->stream));
+        launch_range(my_bit ? nvec / 2 : 0, my_bit ? nvec : nvec / 2, st->stream);
+        SPZ_CUDA(cudaEventRecord(ev.second, st->stream));
+        c->pending.push_back(ev);
+        k_handshake<<<1, 1, 0, st->stream>>>(&c->peer_ctrl[partner]->done[c->rank], &c->ctrl->done[partner], e, &c->ctrl->error);
+        // keep the second-chunk flag in step so that a later overlapped exchange with this partner sees epoch order
+        count_launch(3);
     }
-    SPZ_CUDA(cudaEventRecord(ev.second, st->stream));
-    c->pending.push_back(ev);
-    k_handshake<<<1, 1, 0, st->stream>>>(&c->peer_ctrl[partner]->done[c->rank], &c->ctrl->done[partner], e, &c->ctrl->error);
-    count_launch(3);
     SPZ_CUDA(cudaGetLastError());
     c->n_exchanges += 1;
     c->bytes_sent += 16.0 * (double)(1ll << (n_local - 1)); // half a shard leaves this GPU (re + im)
     return SPZ_OK;
 }
 
+// Make the main stream wait for an overlapped exchange still in flight (everything but the split tile pass needs
+// the whole shard).
+int dist_join(spz_state *st) {
+    DistCtx *c = ctx_of(st);
+    if (!c || !c->split_pending) return SPZ_OK;
+    SPZ_CUDA(cudaStreamWaitEvent(st->stream, c->ev_half[1], 0));
+    c->split_pending = false;
+    return SPZ_OK;
+}
+
+// For the tile pass that directly follows an overlapped exchange: returns the two events to wait for and the local
+// bit that separates the halves; the caller launches half 0 after ev[0] and half 1 after ev[1].
+bool dist_take_split(spz_state *st, int *split_bit, cudaEvent_t *ev0, cudaEvent_t *ev1) {
+    DistCtx *c = ctx_of(st);
+    if (!c || !c->split_pending) return false;
+    *split_bit = c->split_bit; *ev0 = c->ev_half[0]; *ev1 = c->ev_half[1];
+    c->split_pending = false;
+    return true;
+}
+
 int dist_allreduce(spz_state *st, const double *dev_value, double host_value, double *host_out, double **dev_out) {
     DistCtx *c = ctx_of(st);
+    SPZ_TRY(dist_join(st));
     if (!c->connected) { set_error("dist state used before spz_dist_connect"); return SPZ_ERR_COMM; }
     SPZ_TRY(ensure_scratch(st));
     const unsigned long long e = ++c->red_epoch;
@@ -272,6 +328,7 @@ int dist_allreduce(spz_state *st, const double *dev_value, double host_value, do
 }
 
 int dist_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int hi) {
+    SPZ_TRY(dist_join(st));
     const long long count = st->len >> __builtin_popcountll(local_cmask);
     const int grid = (int)std::max<long long>(1, std::min<long long>((count + 255) / 256, 148 * 16));
     k_diag_const<<<grid, 256, 0, st->stream>>>(st->re, st->im, count, local_cmask, g.kind, hi, g);
@@ -417,6 +474,10 @@ void dist_destroy(spz_state *st) {
     }
     for (auto &e : c->pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto &e : c->free_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (c->xstream) { cudaStreamSynchronize(c->xstream); cudaStreamDestroy(c->xstream); }
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_half[0]) cudaEventDestroy(c->ev_half[0]);
+    if (c->ev_half[1]) cudaEventDestroy(c->ev_half[1]);
     cudaFree(c->d_table);
     cudaFree(c->ctrl);
     delete c;
@@ -450,6 +511,11 @@ int spz_dist_create(int n_qubits, int rank, int world, int device, spz_state **o
     st->dist = c;
     cudaError_t e = cudaMalloc(&c->ctrl, sizeof(CtrlBlock));
     if (e == cudaSuccess) e = cudaMemset(c->ctrl, 0, sizeof(CtrlBlock));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_half[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_half[1], cudaEventDisableTiming);
+    if (getenv("SPZ_NO_OVERLAP")) c->overlap = false;
     if (e != cudaSuccess) { int rc = cuda_fail(e, "cudaMalloc(ctrl)", __FILE__, __LINE__); spz_destroy(st); return rc; }
     c->peer_ctrl[rank] = c->ctrl; c->peer_re[rank] = st->re; c->peer_im[rank] = st->im;
     if (world == 1) { c->connected = true; if (upload_peer_table(c) != SPZ_OK) { spz_destroy(st); return SPZ_ERR_CUDA; } }
@@ -544,7 +610,7 @@ int spz_dist_stats(const spz_state *cst, double *out4) {
         c->free_events.push_back(e);
     }
     c->pending.clear();
-    out4[0] = c->n_exchanges; out4[1] = c->bytes_sent; out4[2] = c->ms_accum; out4[3] = 0.0;
+    out4[0] = c->n_exchanges; out4[1] = c->bytes_sent; out4[2] = c->ms_accum; out4[3] = c->n_overlapped;
     return SPZ_OK;
 }
 

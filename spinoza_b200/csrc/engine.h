@@ -154,6 +154,9 @@ int tile_prepare(spz_state *st); // allocate the program ring buffer, set the ke
 int dist_total_qubits(const spz_state *st);
 int dist_apply_masked(spz_state *st, int kind, const double *p, int t0, int t1, uint64_t cmask, int target);
 int dist_exchange(spz_state *st, int gbit, int lq);
+int dist_join(spz_state *st); // main stream waits for an overlapped exchange still in flight
+bool dist_take_split(spz_state *st, int *split_bit, cudaEvent_t *ev0, cudaEvent_t *ev1);
+inline int join_pending(spz_state *st) { return st->dist ? dist_join(st) : SPZ_OK; }
 int dist_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int hi);
 int dist_reduce_scalar(spz_state *st, int mode, int target, double *out);
 int dist_collapse(spz_state *st, int target, int outcome, double scale);

@@ -54,6 +54,7 @@ static void dispatch_kind(bool low, const PairArgs &a, cudaStream_t s) {
 }
 
 int launch_gate(spz_state *st, const GateK &g, uint64_t ctrl_mask, int target) {
+    SPZ_TRY(join_pending(st));
     const int n = st->n;
     if (target < 0 || target >= n) { set_error("target %d out of range for %d qubits", target, n); return SPZ_ERR_INVALID_ARG; }
     if ((ctrl_mask >> target) & 1ull) { set_error("target %d is also a control", target); return SPZ_ERR_INVALID_ARG; }
@@ -112,6 +113,7 @@ int launch_gate(spz_state *st, const GateK &g, uint64_t ctrl_mask, int target) {
 }
 
 int launch_swap(spz_state *st, int t0, int t1) {
+    SPZ_TRY(join_pending(st));
     const int n = st->n;
     // assert!(state.n > t0 && state.n > t1) gates.rs:1377
     if (t0 < 0 || t1 < 0 || t0 >= n || t1 >= n) { set_error("swap operands (%d,%d) out of range for %d qubits", t0, t1, n); return SPZ_ERR_INVALID_ARG; }

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kRedThreads) k_final_sum(const double *__restr
 }
 
 int reduce_scalar(spz_state *st, int mode, int target, double *out) {
+    SPZ_TRY(join_pending(st));
     SPZ_TRY(ensure_scratch(st));
     const long long len = st->len;
     long long work = mode == 1 ? (len >= 2 ? len / 2 : 0) : len / 2;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(256) k_collapse(double *__restrict__ re, doubl
 }
 
 int launch_collapse(spz_state *st, int target, int outcome, int reset, double scale) {
+    SPZ_TRY(join_pending(st));
     const long long npairs = st->len / 2;
     const int grid = (int)std::max<long long>(1, std::min<long long>((npairs + 255) / 256, 148 * 16));
     k_collapse<<<grid, 256, 0, st->stream>>>(st->re, st->im, npairs, target, outcome, reset, scale);
@@ -154,6 +156,7 @@ int launch_collapse(spz_state *st, int target, int outcome, int reset, double sc
 __global__ void k_set_one(double *re, unsigned long long index) { re[index] = 1.0; }
 
 int launch_fill_basis(spz_state *st, uint64_t index) {
+    SPZ_TRY(join_pending(st));
     if (index >= (uint64_t)st->len) { set_error("basis index out of range"); return SPZ_ERR_INVALID_ARG; }
     SPZ_CUDA(cudaMemsetAsync(st->re, 0, sizeof(double) * (size_t)st->len, st->stream));
     SPZ_CUDA(cudaMemsetAsync(st->im, 0, sizeof(double) * (size_t)st->len, st->stream));
@@ -204,6 +207,7 @@ __global__ void __launch_bounds__(256) k_rand_finish(double *__restrict__ re, do
 }
 
 int launch_rand_probs(spz_state *st, uint64_t seed, long long index_offset, double **d_local_total) {
+    SPZ_TRY(join_pending(st));
     SPZ_TRY(ensure_scratch(st));
     const int grid = (int)std::max<long long>(1, std::min<long long>((st->len + 255) / 256, kRedBlocks));
     double *part = st->scratch.partials;
@@ -238,6 +242,7 @@ __global__ void __launch_bounds__(256) k_scale_all(double *__restrict__ re, doub
 }
 
 int launch_scale(spz_state *st, double scale) {
+    SPZ_TRY(join_pending(st));
     const int grid = (int)std::max<long long>(1, std::min<long long>((st->len + 255) / 256, 148 * 16));
     k_scale_all<<<grid, 256, 0, st->stream>>>(st->re, st->im, st->len, scale);
     count_launch();
@@ -344,6 +349,7 @@ __global__ void __launch_bounds__(256) k_sample(const double *__restrict__ re, c
 
 int launch_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_index) {
     if (shots <= 0) return SPZ_OK;
+    SPZ_TRY(join_pending(st));
     const long long len = st->len;
     const long long n_l1 = (len + kB - 1) / kB;
     const long long n_l2 = (n_l1 + kB - 1) / kB;

@@ -49,6 +49,7 @@ struct TileArgs {
     const TileTerm *terms;
     int n_instr;
     int n_groups;
+    unsigned tile_offset; // first tile of this launch (a pass may be launched in two halves, see dist.cu)
     int prog_in_smem; // 1: the program is staged in shared memory (it fits the budget)
     unsigned prog_off; // byte offset of the staged program inside dynamic shared memory
     int T, L, n_high;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
     __shared__ unsigned long long seg_off[1 << kMaxHigh];
 
     // absolute index of the tile's first amplitude: CTA id bits go to the non-tile positions
-    unsigned long long base = (unsigned long long)blockIdx.x << L;
+    unsigned long long base = (unsigned long long)(blockIdx.x + a.tile_offset) << L;
 #pragma unroll
     for (int k = 0; k < kMaxHigh; ++k) // compile-time indices keep the kernel parameters in the constant bank
         if (k < a.n_high) base = insert_zero(base, a.high[k]);
@@ -440,8 +441,37 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
     if (a.prog_in_smem) smem += sizeof(TileInstr) * (size_t)n_instr;
     const unsigned grid = (unsigned)((uint64_t)st->len >> plan.tile_bits);
     const unsigned threads = 1u << (plan.tile_bits - kRegBits);
-    if (exact) k_tile<true><<<grid, threads, smem, st->stream>>>(a);
-    else k_tile<false><<<grid, threads, smem, st->stream>>>(a);
+    auto launch = [&](unsigned first, unsigned count) {
+        a.tile_offset = first;
+        if (exact) k_tile<true><<<count, threads, smem, st->stream>>>(a);
+        else k_tile<false><<<count, threads, smem, st->stream>>>(a);
+    };
+    // Directly after an overlapped exchange (dist.cu) the shard arrives in two halves along local bit `sb`.  If sb is
+    // the highest bit outside the tile, the halves are the two halves of the grid: start on the first while the second
+    // is still on the wire.
+    int sb = -1;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (st->dist && dist_take_split(st, &sb, &e0, &e1)) {
+        bool top_outer = grid >= 2 && sb >= plan.low_bits;
+        for (int k = 0; k < plan.n_high; ++k) if (plan.high[k] == sb) top_outer = false;
+        for (int q = sb + 1; q < st->n && top_outer; ++q) { // every higher local bit must be a tile bit
+            bool is_tile = false;
+            for (int k = 0; k < plan.n_high; ++k) if (plan.high[k] == q) is_tile = true;
+            if (!is_tile) top_outer = false;
+        }
+        if (top_outer) {
+            SPZ_CUDA(cudaStreamWaitEvent(st->stream, e0, 0));
+            launch(0, grid / 2);
+            SPZ_CUDA(cudaStreamWaitEvent(st->stream, e1, 0));
+            launch(grid / 2, grid - grid / 2);
+            count_launch();
+        } else {
+            SPZ_CUDA(cudaStreamWaitEvent(st->stream, e1, 0));
+            launch(0, grid);
+        }
+    } else {
+        launch(0, grid);
+    }
     count_launch();
     SPZ_CUDA(cudaGetLastError());
     return SPZ_OK;

@@ -115,7 +115,7 @@ class DistState(State):
         out = (C.c_double * 4)()
         _check(_lib.spz_dist_stats(self._h, out))
         ex, sent, ms = out[0], out[1], out[2]
-        return {"exchanges": int(ex), "bytes_sent": sent, "exchange_ms": ms,
+        return {"exchanges": int(ex), "overlapped": int(out[3]), "bytes_sent": sent, "exchange_ms": ms,
                 "nvlink_GBps_per_direction": (sent / (ms * 1e-3) / 1e9) if ms > 0 else None}
 
     def clone(self):

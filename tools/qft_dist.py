@@ -79,7 +79,7 @@ def main():
         print(json.dumps({
             "workload": f"QFT-{n} on {env.world} GPU(s), 2^{s.n_local} amplitudes per GPU, {'unfused' if args.unfused else 'fused'}",
             "gates": n_gates, "seconds": ms * 1e-3, "sec_per_gate": ms * 1e-3 / n_gates, "launches": int(launches),
-            "exchanges": stats["exchanges"], "nvlink_GBps_per_direction": stats["nvlink_GBps_per_direction"],
+            "exchanges": stats["exchanges"], "overlapped_exchanges": stats["overlapped"], "nvlink_GBps_per_direction": stats["nvlink_GBps_per_direction"],
             "exchange_ms_total": stats["exchange_ms"], "max_abs_err_vs_closed_form": err, "norm2": nrm,
             "iqft_seconds": ms_inv * 1e-3, "roundtrip_abs_err_at_x": back, "norm2_after_roundtrip": nrm2,
             "exchanges_incl_roundtrip": stats2["exchanges"], "alloc_seconds": alloc_s,
