@@ -57,6 +57,7 @@ struct DistCtx {
     bool split_pending = false;
     int split_bit = -1;
     bool overlap = true;
+    int xchg_ctas = 40; // CTAs of the persistent exchange kernel in overlapped mode (SPZ_XCHG_CTAS)
     // stats
     double n_exchanges = 0, bytes_sent = 0, ms_accum = 0, n_overlapped = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, free_events;
@@ -171,6 +172,41 @@ __global__ void __launch_bounds__(THREADS) k_exchange_vec(const XArgs a) {
     }
 }
 
+// Persistent variant for the overlapped mode: a small fixed grid walks the range in blocks of THREADS * U vectors, so the
+// exchange keeps only a few SMs busy (enough bytes in flight to fill the link) and leaves the rest to the fused pass.
+template <int W, int U, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_exchange_vec_persistent(const XArgs a) {
+    const unsigned long long lbit = 1ull << a.lq;
+    const long long per = (long long)THREADS * U;
+    for (long long blk = a.nvec_begin + (long long)blockIdx.x * per; blk < a.nvec_end; blk += (long long)gridDim.x * per) {
+        unsigned long long im_[U], ip_[U];
+        Vec<W> mr[U], mi[U], pr[U], pi[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long v = blk + threadIdx.x + (long long)u * THREADS;
+            if (v < a.nvec_end) {
+                const unsigned long long base = insert_zero((unsigned long long)v << LogW<W>::v, a.lq);
+                im_[u] = a.my_bit ? base : (base | lbit);
+                ip_[u] = a.my_bit ? (base | lbit) : base;
+                pr[u] = ldv<W, 0>(a.peer_re + ip_[u]);
+                pi[u] = ldv<W, 0>(a.peer_im + ip_[u]);
+                mr[u] = ldv<W, 0>(a.mine_re + im_[u]);
+                mi[u] = ldv<W, 0>(a.mine_im + im_[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long v = blk + threadIdx.x + (long long)u * THREADS;
+            if (v < a.nvec_end) {
+                stv<W, 0>(a.peer_re + ip_[u], mr[u]);
+                stv<W, 0>(a.peer_im + ip_[u], mi[u]);
+                stv<W, 0>(a.mine_re + im_[u], pr[u]);
+                stv<W, 0>(a.mine_im + im_[u], pi[u]);
+            }
+        }
+    }
+}
+
 __global__ void k_exchange_scalar(const XArgs a) {
     const unsigned long long lbit = 1ull << a.lq;
     for (long long v = a.nvec_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; v < a.nvec_end;
@@ -259,7 +295,9 @@ int dist_exchange(spz_state *st, int gbit, int lq) {
         SPZ_CUDA(cudaEventRecord(ev.first, c->xstream));
         for (int h = 0; h < 2; ++h) {
             const long long hb = h * (nvec / 2) + my_bit * (nvec / 4);
-            launch_range(hb, hb + nvec / 4, c->xstream);
+            XArgs r = a;
+            r.nvec_begin = hb; r.nvec_end = hb + nvec / 4;
+            k_exchange_vec_persistent<W, U, THREADS><<<(unsigned)c->xchg_ctas, THREADS, 0, c->xstream>>>(r);
             unsigned long long *peer_done = h ? &c->peer_ctrl[partner]->done1[c->rank] : &c->peer_ctrl[partner]->done[c->rank];
             const unsigned long long *my_done = h ? &c->ctrl->done1[partner] : &c->ctrl->done[partner];
             k_handshake<<<1, 1, 0, c->xstream>>>(peer_done, my_done, e, &c->ctrl->error);
@@ -511,11 +549,16 @@ int spz_dist_create(int n_qubits, int rank, int world, int device, spz_state **o
     st->dist = c;
     cudaError_t e = cudaMalloc(&c->ctrl, sizeof(CtrlBlock));
     if (e == cudaSuccess) e = cudaMemset(c->ctrl, 0, sizeof(CtrlBlock));
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) { // the exchange stream outranks the compute stream: its few CTAs are placed first
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, hi);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_half[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_half[1], cudaEventDisableTiming);
     if (getenv("SPZ_NO_OVERLAP")) c->overlap = false;
+    if (const char *v = getenv("SPZ_XCHG_CTAS")) { const int k = atoi(v); if (k >= 1 && k <= 1024) c->xchg_ctas = k; }
     if (e != cudaSuccess) { int rc = cuda_fail(e, "cudaMalloc(ctrl)", __FILE__, __LINE__); spz_destroy(st); return rc; }
     c->peer_ctrl[rank] = c->ctrl; c->peer_re[rank] = st->re; c->peer_im[rank] = st->im;
     if (world == 1) { c->connected = true; if (upload_peer_table(c) != SPZ_OK) { spz_destroy(st); return SPZ_ERR_CUDA; } }
