@@ -316,7 +316,6 @@ int dist_exchange(spz_state *st, int gbit, int lq) {
         SPZ_CUDA(cudaEventRecord(ev.second, st->stream));
         c->pending.push_back(ev);
         k_handshake<<<1, 1, 0, st->stream>>>(&c->peer_ctrl[partner]->done[c->rank], &c->ctrl->done[partner], e, &c->ctrl->error);
-        // keep the second-chunk flag in step so that a later overlapped exchange with this partner sees epoch order
         count_launch(3);
     }
     SPZ_CUDA(cudaGetLastError());
@@ -645,6 +644,7 @@ int spz_dist_stats(const spz_state *cst, double *out4) {
     spz_state *st = const_cast<spz_state *>(cst);
     DistCtx *c = ctx_of(st);
     SPZ_CUDA(cudaSetDevice(st->device));
+    SPZ_TRY(dist_join(st)); // an overlapped exchange may still be running on the second stream
     SPZ_CUDA(cudaStreamSynchronize(st->stream));
     for (auto &e : c->pending) {
         float ms = 0.f;
