@@ -151,7 +151,7 @@ def run_reference(args, rank: int, world: int):
     import oracle as orc
     threads = orc.max_threads()
     n_total = 30 + int(math.log2(max(args.gpus, 1)))
-    n = pick_cpu_n(min(n_total, 30))
+    n = pick_cpu_n(min(n_total, args.cpu_qubits or 30))
     targets = cpu_targets(n)
     sample = (f"oracle port (C + OpenMP mirroring rayon chunking, gates.rs:361-372) of H/RX(1.0)/RZ(1.0) on targets "
               f"{targets} of a {n}-qubit state = {3 * len(targets)} unfused passes per step; full workload is all "
@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip per-target table and QFT")
+    ap.add_argument("--cpu-qubits", type=int, default=0, help="cap the qubit count of the CPU (reference / cpu_baseline) sample")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -401,7 +402,7 @@ def main():
         del state
         import oracle as orc
         threads = orc.max_threads()
-        cn = pick_cpu_n(min(n, 30))
+        cn = pick_cpu_n(min(n, args.cpu_qubits or 30))
         tg = cpu_targets(cn)
         v, dt, gcount = cpu_sweep_sample(cn, threads, tg)
         v1, dt1, _ = cpu_sweep_sample(min(cn, 26), 1, cpu_targets(min(cn, 26)))
