@@ -140,6 +140,10 @@ SPZ_API int spz_set_seed(spz_state *st, uint64_t seed);
    are -1 (e.g. a BitFlipNoise that did not fire).  Used by the CPU tests of the scheduler. */
 SPZ_API int spz_plan_fusion(int n_qubits, const spz_op *ops, int64_t n_ops, uint32_t flags, int32_t *out_order,
                             int32_t *out_pass, int32_t *out_n_passes);
+/* Test hook (pure host code): the tile micro-program spz_execute would launch for pass `pass_index`, serialised into
+   `out` (layout documented at the definition in csrc/abi.cu).  tests/test_tile_program.py interprets it in NumPy. */
+SPZ_API int spz_debug_compile_pass(int n_qubits, const spz_op *ops, int64_t n_ops, uint32_t flags, int pass_index, void *out,
+                                   int64_t out_bytes, int64_t *out_used);
 
 /* ---- reductions: measurement.rs:12-92, core.rs:65-129,198-264 --------------------------------- */
 SPZ_API int spz_prob0(spz_state *st, int target, double *out);   /* measurement.rs:16-29 */

@@ -147,6 +147,13 @@ struct ROp { // an op resolved to what the kernels need (physical qubits of this
 struct PlanSink {
     std::vector<int32_t> order, group;
     int n_groups = 0;
+    // optional: the compiled micro-program of pass `capture_pass` (spz_debug_compile_pass)
+    int capture_pass = -1;
+    bool captured = false, captured_direct = false;
+    TilePlan cap_plan{};
+    std::vector<TileInstr> cap_prog;
+    std::vector<TileGroup> cap_groups;
+    std::vector<TileTerm> cap_terms;
     void take(const std::vector<ROp> &ops) {
         for (const ROp &o : ops) { order.push_back(o.src); group.push_back(n_groups); }
         ++n_groups;
@@ -319,7 +326,24 @@ struct Fuser {
     // Launch the current group (ops / high_set / low_need) and reset it.
     int emit_group() {
         if (ops.empty()) return SPZ_OK;
-        if (sink) { sink->take(ops); ops.clear(); high_set = 0; low_need = 0; return SPZ_OK; }
+        if (sink) {
+            if (sink->capture_pass == sink->n_groups) { // compile exactly as the launch path below would
+                sink->captured = true;
+                if (ops.size() == 1) {
+                    sink->captured_direct = true; // a single op goes to the direct kernel: no micro-program
+                } else {
+                    TilePlan plan{};
+                    plan.n_high = n_high();
+                    plan.tile_bits = T;
+                    plan.low_bits = T - plan.n_high;
+                    int k = 0;
+                    for (int q = 0; q < 64; ++q) if ((high_set >> q) & 1ull) plan.high[k++] = q;
+                    sink->cap_plan = plan;
+                    SPZ_TRY(compile(plan, sink->cap_prog, sink->cap_groups, sink->cap_terms));
+                }
+            }
+            sink->take(ops); ops.clear(); high_set = 0; low_need = 0; return SPZ_OK;
+        }
         int rc = SPZ_OK;
         if (ops.size() == 1 && ops[0].const_hi >= 0) {
             rc = dist_diag_const(st, ops[0].g, ops[0].cmask, ops[0].const_hi);
@@ -856,6 +880,38 @@ int spz_plan_fusion(int n_qubits, const spz_op *ops, int64_t n_ops, uint32_t fla
     for (size_t i = 0; i < sink.order.size(); ++i) { out_order[i] = sink.order[i]; out_pass[i] = sink.group[i]; }
     for (size_t i = sink.order.size(); i < (size_t)n_ops; ++i) { out_order[i] = -1; out_pass[i] = -1; }
     *out_n_passes = sink.n_groups;
+    return SPZ_OK;
+}
+
+// Debug / test hook (pure host code): the micro-program spz_execute would launch for pass `pass_index` of the list.
+// Layout of `out` (int32 header then raw structs, all host-endian):
+//   [0] status: 0 = tile program, 1 = single op on the direct kernel, 2 = no such pass
+//   [1] tile_bits [2] low_bits [3] n_high [4..11] high[8] [12] n_instr [13] n_groups [14] n_terms [15] sizeof(TileInstr)
+//   then n_instr TileInstr, n_groups TileGroup (16 B), n_terms TileTerm (32 B).
+int spz_debug_compile_pass(int n_qubits, const spz_op *ops, int64_t n_ops, uint32_t flags, int pass_index, void *out,
+                           int64_t out_bytes, int64_t *out_used) {
+    if (n_qubits < 1 || n_qubits > 40 || !out || !out_used || pass_index < 0) { set_error("bad arguments"); return SPZ_ERR_INVALID_ARG; }
+    spz_state dummy;
+    dummy.n = n_qubits;
+    dummy.len = (int64_t)1 << n_qubits;
+    PlanSink sink;
+    sink.capture_pass = pass_index;
+    SPZ_TRY(execute_impl(&dummy, ops, n_ops, flags, nullptr, nullptr, &sink));
+    const size_t need = 16 * sizeof(int32_t) + sizeof(TileInstr) * sink.cap_prog.size() + sizeof(TileGroup) * sink.cap_groups.size() +
+                        sizeof(TileTerm) * sink.cap_terms.size();
+    if ((int64_t)need > out_bytes) { set_error("output buffer too small: need %zu bytes", need); return SPZ_ERR_INVALID_ARG; }
+    int32_t hdr[16] = {0};
+    hdr[0] = !sink.captured ? 2 : sink.captured_direct ? 1 : 0;
+    hdr[1] = sink.cap_plan.tile_bits; hdr[2] = sink.cap_plan.low_bits; hdr[3] = sink.cap_plan.n_high;
+    for (int k = 0; k < 8; ++k) hdr[4 + k] = sink.cap_plan.high[k];
+    hdr[12] = (int32_t)sink.cap_prog.size(); hdr[13] = (int32_t)sink.cap_groups.size(); hdr[14] = (int32_t)sink.cap_terms.size();
+    hdr[15] = (int32_t)sizeof(TileInstr);
+    char *w = static_cast<char *>(out);
+    std::memcpy(w, hdr, sizeof hdr); w += sizeof hdr;
+    if (!sink.cap_prog.empty()) { std::memcpy(w, sink.cap_prog.data(), sizeof(TileInstr) * sink.cap_prog.size()); w += sizeof(TileInstr) * sink.cap_prog.size(); }
+    if (!sink.cap_groups.empty()) { std::memcpy(w, sink.cap_groups.data(), sizeof(TileGroup) * sink.cap_groups.size()); w += sizeof(TileGroup) * sink.cap_groups.size(); }
+    if (!sink.cap_terms.empty()) { std::memcpy(w, sink.cap_terms.data(), sizeof(TileTerm) * sink.cap_terms.size()); w += sizeof(TileTerm) * sink.cap_terms.size(); }
+    *out_used = (int64_t)need;
     return SPZ_OK;
 }
 
