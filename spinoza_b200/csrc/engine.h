@@ -149,6 +149,11 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
 int max_tile_bits();
 int min_tile_bits();
 int tile_prepare(spz_state *st); // allocate the program ring buffer, set the kernel's shared-memory limit
+// kernels_tile2.cu: opt-in (SPZ_TILE_V2=1) second-generation tile kernel behind the same program format
+bool tile2_enabled();
+bool tile2_eligible(const spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, int n_groups);
+int launch_tile2(spz_state *st, const TilePlan &plan, const TileInstr *h_prog, int n_instr, const TileInstr *d_prog,
+                 const TileGroup *d_groups, int n_groups, const TileTerm *d_terms, bool exact, unsigned first, unsigned count);
 
 // ---- multi-GPU (dist.cu) ----------------------------------------------------------------------------
 int dist_total_qubits(const spz_state *st);

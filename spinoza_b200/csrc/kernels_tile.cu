@@ -441,7 +441,13 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
     if (a.prog_in_smem) smem += sizeof(TileInstr) * (size_t)n_instr;
     const unsigned grid = (unsigned)((uint64_t)st->len >> plan.tile_bits);
     const unsigned threads = 1u << (plan.tile_bits - kRegBits);
+    // opt-in second-generation kernel (kernels_tile2.cu): same program, same staging, fewer instructions per tile
+    const bool v2 = tile2_enabled() && tile2_eligible(st, plan, prog, n_instr, n_groups);
     auto launch = [&](unsigned first, unsigned count) {
+        if (v2) {
+            launch_tile2(st, plan, prog, n_instr, a.prog, a.groups, n_groups, a.terms, exact, first, count);
+            return;
+        }
         a.tile_offset = first;
         if (exact) k_tile<true><<<count, threads, smem, st->stream>>>(a);
         else k_tile<false><<<count, threads, smem, st->stream>>>(a);

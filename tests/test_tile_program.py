@@ -75,9 +75,10 @@ def gate_matrix_from_scalars(kind, s):
 class TileMachine:
     """All tiles at once: every per-thread quantity of k_tile becomes an array over the 2^n absolute indices."""
 
-    def __init__(self, n, plan, groups, terms, exact):
+    def __init__(self, n, plan, groups, terms, exact, lazy=False):
         self.n, self.T, self.L, self.high = n, plan["T"], plan["L"], plan["high"]
         self.exact = exact
+        self.lazy = lazy  # k_tile2: a butterfly on register bit r flushes accumulator F_{r+1} only
         idx = np.arange(1 << n, dtype=np.uint64)
         self.qubit_of_bit = list(range(self.L)) + self.high
         assert len(self.qubit_of_bit) == self.T and len(set(self.qubit_of_bit)) == self.T
@@ -152,8 +153,12 @@ class TileMachine:
         return psi
 
     def gate(self, psi, ins):
-        psi = self.flush(psi)
         rpos = int(ins["rpos"])
+        if self.lazy:
+            psi = np.where((self.k >> rpos) & 1 == 1, psi * self.F[rpos + 1], psi)
+            self.F[rpos + 1] = np.ones(1 << self.n, dtype=complex)
+        else:
+            psi = self.flush(psi)
         q = self.qubit_of_bit[self.R[rpos]]
         idx = np.arange(1 << self.n, dtype=np.uint64)
         ocm = ins["outer_cmask"]
@@ -193,12 +198,12 @@ class TileMachine:
         return np.where(ok, psi * np.where(hi, f_hi, f_lo), psi)
 
 
-def interpret(n, psi, compiled, exact):
+def interpret(n, psi, compiled, exact, lazy=False):
     _, plan, instrs, groups, terms = compiled
     assert plan["T"] == plan["L"] + len(plan["high"]) and plan["T"] <= 12 and len(plan["high"]) <= 8
     assert len(groups) <= 2048
     assert instrs[0]["op"] == TI_LAYOUT, "a program starts by choosing a register layout"
-    tm = TileMachine(n, plan, groups, terms, exact)
+    tm = TileMachine(n, plan, groups, terms, exact, lazy)
     seen_groups = 0
     for ins in instrs:
         op = int(ins["op"])
@@ -218,7 +223,7 @@ def interpret(n, psi, compiled, exact):
     return tm.flush(psi)
 
 
-def run_plan(qc, psi):
+def run_plan(qc, psi, lazy=False):
     """Execute the circuit the way spz_execute schedules it, interpreting every fused pass."""
     n = qc.n_qubits
     trs = list(qc.transformations)
@@ -235,19 +240,20 @@ def run_plan(qc, psi):
             psi = run_dense_order(n, psi, trs, by_pass[p])
         else:
             assert len(by_pass[p]) > 1
-            psi = interpret(n, psi, comp, qc.exact)
+            psi = interpret(n, psi, comp, qc.exact, lazy)
             n_tile += 1
     assert compile_pass(qc, n_pass) is None
     return psi, n_tile
 
 
+@pytest.mark.parametrize("lazy", [False, True], ids=["k_tile", "k_tile2-lazy-flush"])
 @pytest.mark.parametrize("exact", [False, True])
 @pytest.mark.parametrize("n,count,seed", [(13, 150, 11), (14, 200, 12), (15, 250, 13), (16, 120, 14)])
-def test_compiled_passes_equal_the_dense_statement(n, count, seed, exact):
+def test_compiled_passes_equal_the_dense_statement(n, count, seed, exact, lazy):
     qc = random_circuit(n, count, seed, exact=exact)
     trs = list(qc.transformations)
     psi0 = D.random_state(n, seed)
-    got, n_tile = run_plan(qc, psi0.copy())
+    got, n_tile = run_plan(qc, psi0.copy(), lazy)
     want = run_dense_order(n, psi0.copy(), trs, range(len(trs)))
     assert n_tile >= 1
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
@@ -271,9 +277,10 @@ def test_qft_passes_fold_every_controlled_phase_into_runs():
     n_cp = sum(1 for t in trs if t.gate.kind == Gate.KIND_P)
     assert total_terms == n_cp  # one phase term per controlled-phase gate (P has no f0 term)
     psi0 = D.random_state(n, 5)
-    got, _ = run_plan(qc, psi0.copy())
     want = run_dense_order(n, psi0.copy(), trs, range(len(trs)))
-    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+    for lazy in (False, True):
+        got, _ = run_plan(qc, psi0.copy(), lazy)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
 
 
 def test_layered_rotation_circuit_and_swaps():
