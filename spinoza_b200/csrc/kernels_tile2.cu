@@ -25,6 +25,15 @@
 
 #include "gate_math.cuh"
 
+// tests/emu/ compiles this file with g++ (SPZ_CPU_EMULATION, one OS thread per CUDA thread, a pthread barrier for
+// __syncthreads) so that the kernel body itself -- not a restatement of it -- is checked on the CPU; only the way the
+// dynamic shared-memory window is named differs between the two builds.
+#ifdef SPZ_CPU_EMULATION
+#define SPZ_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(spz_emu::dyn_smem)
+#else
+#define SPZ_DYN_SMEM(T, name) extern __shared__ T name[]
+#endif
+
 namespace spz {
 
 namespace {
@@ -100,7 +109,7 @@ __device__ __forceinline__ void run_class2(const double2 *__restrict__ gfac, con
 
 template <bool EXACT, bool CTRL>
 __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
-    extern __shared__ double smem[];
+    SPZ_DYN_SMEM(double, smem);
     constexpr unsigned tile_len = 1u << kT2;
     constexpr unsigned nthr = kThreads2;
     const int L = a.L;
@@ -252,7 +261,9 @@ __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
         }
         __syncthreads();
         load_regs();
-        __syncthreads(); // everyone has read before anyone's next store_regs
+        // No barrier here (k_tile has one): the next shared-memory access of this thread is store_regs() under the SAME
+        // layout, i.e. to exactly the cells it has just read, which no other thread touches in between.  Checked with
+        // ThreadSanitizer on the CPU emulation (tests/test_tile2_cpu_emulation.py).
     }
 
     for (int pc = 1; pc < a.n_instr; ++pc) {
@@ -263,8 +274,7 @@ __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
             store_regs();
             __syncthreads();
             set_layout(ins.rbit[0], ins.rbit[1], ins.rbit[2], ins.rbit[3]);
-            load_regs();
-            __syncthreads();
+            load_regs(); // one barrier per layout change is enough, see above
             continue;
         }
         if (op == TI_RUN) {
@@ -385,41 +395,13 @@ size_t tile2_max_smem() {
     return sizeof(double) * 2u * ((size_t)1 << kT2) + kMaxTileGroups * (sizeof(double2) + sizeof(unsigned)) + 16 + kMaxInstr2 * sizeof(TileInstr);
 }
 
-} // namespace
-
-// 0 = off (default), 1 = on.  Read per call so that tests can toggle it inside one process.
-bool tile2_enabled() {
-    const char *e = std::getenv("SPZ_TILE_V2");
-    return e && e[0] == '1';
-}
-
-int tile2_prepare() {
-    const int max_smem = (int)tile2_max_smem();
-    SPZ_CUDA(cudaFuncSetAttribute(k_tile2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    SPZ_CUDA(cudaFuncSetAttribute(k_tile2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    SPZ_CUDA(cudaFuncSetAttribute(k_tile2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    return SPZ_OK;
-}
-
-// Can this pass run on k_tile2?  (full 12-bit tile, program short enough for shared memory, starts with a LAYOUT)
-bool tile2_eligible(const spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, int n_groups) {
-    if (plan.tile_bits != kT2 || plan.n_high > kMaxHigh2 || plan.low_bits < 4 || st->n < kT2) return false;
-    if (n_instr < 1 || n_instr > kMaxInstr2 || n_groups > kMaxTileGroups) return false;
-    return prog[0].op == TI_LAYOUT;
-}
-
-// `slot`: device copy of prog | groups | terms laid out by launch_tile_program (kernels_tile.cu), which also owns the
-// ring buffer and the split launch after an overlapped exchange; this function only picks the instantiation and launches
-// tiles [first, first + count).
-int launch_tile2(spz_state *st, const TilePlan &plan, const TileInstr *h_prog, int n_instr, const TileInstr *d_prog,
-                 const TileGroup *d_groups, int n_groups, const TileTerm *d_terms, bool exact, unsigned first, unsigned count) {
-    static bool prepared[64] = {false};
-    if (st->device >= 0 && st->device < 64 && !prepared[st->device]) {
-        SPZ_TRY(tile2_prepare());
-        prepared[st->device] = true;
-    }
+// Kernel arguments, dynamic shared-memory size and instantiation for tiles [first, ...) of one pass.  Pure host code,
+// shared by the launcher below and by the CPU emulation harness.
+Tile2Args tile2_make_args(double *re, double *im, const TilePlan &plan, const TileInstr *h_prog, int n_instr, const TileInstr *d_prog,
+                          const TileGroup *d_groups, int n_groups, const TileTerm *d_terms, unsigned first, size_t *smem_bytes,
+                          bool *ctrl) {
     Tile2Args a{};
-    a.re = st->re; a.im = st->im;
+    a.re = re; a.im = im;
     a.prog = d_prog; a.groups = d_groups; a.terms = d_terms;
     a.n_instr = n_instr; a.n_groups = n_groups;
     a.tile_offset = first;
@@ -429,19 +411,65 @@ int launch_tile2(spz_state *st, const TilePlan &plan, const TileInstr *h_prog, i
     smem = (smem + 15) & ~(size_t)15;
     a.prog_off = (unsigned)smem;
     smem += sizeof(TileInstr) * (size_t)n_instr;
-    bool ctrl = false;
+    *smem_bytes = smem;
+    *ctrl = false;
     int last_layout = 0;
     for (int i = 0; i < n_instr; ++i) {
         if (h_prog[i].op == TI_LAYOUT) last_layout = i;
-        if (h_prog[i].op == TI_GATE && (h_prog[i].thr_cmask || h_prog[i].reg_cmask)) ctrl = true;
+        if (h_prog[i].op == TI_GATE && (h_prog[i].thr_cmask || h_prog[i].reg_cmask)) *ctrl = true;
     }
     auto high_layout = [&](const TileInstr &l) { return l.rbit[0] >= 4; }; // rbit is ascending
     a.first_direct = high_layout(h_prog[0]) ? 1 : 0;
     a.last_direct = high_layout(h_prog[last_layout]) ? 1 : 0;
+    return a;
+}
+
+bool tile2_shape_ok(int n_qubits, const TilePlan &plan, const TileInstr *prog, int n_instr, int n_groups) {
+    if (plan.tile_bits != kT2 || plan.n_high > kMaxHigh2 || plan.low_bits < 4 || n_qubits < kT2) return false;
+    if (n_instr < 1 || n_instr > kMaxInstr2 || n_groups > kMaxTileGroups) return false;
+    return prog[0].op == TI_LAYOUT;
+}
+
+} // namespace
+
+#ifndef SPZ_CPU_EMULATION
+// 0 = off (default), 1 = on.  Read per call so that tests can toggle it inside one process.
+bool tile2_enabled() {
+    const char *e = std::getenv("SPZ_TILE_V2");
+    return e && e[0] == '1';
+}
+
+static int tile2_prepare() {
+    const int max_smem = (int)tile2_max_smem();
+    SPZ_CUDA(cudaFuncSetAttribute(k_tile2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SPZ_CUDA(cudaFuncSetAttribute(k_tile2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SPZ_CUDA(cudaFuncSetAttribute(k_tile2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    return SPZ_OK;
+}
+
+// Can this pass run on k_tile2?  (full 12-bit tile, program short enough for shared memory, starts with a LAYOUT)
+bool tile2_eligible(const spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, int n_groups) {
+    return tile2_shape_ok(st->n, plan, prog, n_instr, n_groups);
+}
+
+// d_prog / d_groups / d_terms: the device copies staged by launch_tile_program (kernels_tile.cu), which also owns the
+// ring buffer and the split launch after an overlapped exchange; this function only picks the instantiation and launches
+// tiles [first, first + count).
+int launch_tile2(spz_state *st, const TilePlan &plan, const TileInstr *h_prog, int n_instr, const TileInstr *d_prog,
+                 const TileGroup *d_groups, int n_groups, const TileTerm *d_terms, bool exact, unsigned first, unsigned count) {
+    static bool prepared[64] = {false};
+    if (st->device >= 0 && st->device < 64 && !prepared[st->device]) {
+        SPZ_TRY(tile2_prepare());
+        prepared[st->device] = true;
+    }
+    size_t smem = 0;
+    bool ctrl = false;
+    const Tile2Args a = tile2_make_args(st->re, st->im, plan, h_prog, n_instr, d_prog, d_groups, n_groups, d_terms, first, &smem, &ctrl);
     if (exact) k_tile2<true, true><<<count, kThreads2, smem, st->stream>>>(a);
     else if (ctrl) k_tile2<false, true><<<count, kThreads2, smem, st->stream>>>(a);
     else k_tile2<false, false><<<count, kThreads2, smem, st->stream>>>(a);
     return SPZ_OK;
 }
+#endif // !SPZ_CPU_EMULATION
 
 } // namespace spz
