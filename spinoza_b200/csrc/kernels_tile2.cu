@@ -54,8 +54,10 @@ struct Tile2Args {
     unsigned tile_offset;
     unsigned prog_off;   // byte offset of the staged program inside dynamic shared memory
     int L, n_high;
-    int first_direct;    // first layout: all register bits >= 4 -> global -> registers
-    int last_direct;     // last layout: all register bits >= 4 -> registers -> global
+    int first_direct;    // first layout is loaded global -> registers (host decides, see tile2_make_args)
+    int last_direct;     // last layout is stored registers -> global
+    unsigned first_rbits; // the first layout's register bits, one byte each (= prog[0].rbit, known before the program is staged)
+    unsigned last_rbits;  // the last layout's
     int high[kMaxHigh2];
 };
 
@@ -120,10 +122,16 @@ __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
     TileInstr *sprog = reinterpret_cast<TileInstr *>(reinterpret_cast<char *>(smem) + a.prog_off);
     __shared__ unsigned long long seg_off[1 << kMaxHigh2];
 
-    unsigned long long base = (unsigned long long)(blockIdx.x + a.tile_offset) << L;
+    // absolute index of the tile's first amplitude: CTA id bits go to the non-tile positions.  Recomputed for the
+    // write-back instead of being kept alive through the interpreter loop (the loop reads per-instruction flags instead).
+    auto tile_base = [&]() -> unsigned long long {
+        unsigned long long b = (unsigned long long)(blockIdx.x + a.tile_offset) << L;
 #pragma unroll
-    for (int k = 0; k < kMaxHigh2; ++k)
-        if (k < a.n_high) base = insert_zero(base, a.high[k]);
+        for (int k = 0; k < kMaxHigh2; ++k)
+            if (k < a.n_high) b = insert_zero(b, a.high[k]);
+        return b;
+    };
+    __shared__ unsigned char iflag[kMaxInstr2]; // bit 0: skip (an outer control is 0 for this tile); bit 1: outer target bit is 1
     const int n_seg = 1 << a.n_high;
     for (int sgi = threadIdx.x; sgi < n_seg; sgi += nthr) {
         unsigned long long off = 0;
@@ -131,6 +139,67 @@ __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
         for (int k = 0; k < kMaxHigh2; ++k)
             if (k < a.n_high && ((sgi >> k) & 1)) off |= 1ull << a.high[k];
         seg_off[sgi] = off;
+    }
+    __syncthreads(); // seg_off is needed to address the tile
+
+    const unsigned seg_mask = (1u << L) - 1u;
+    constexpr unsigned n_vec = tile_len >> 1;
+
+    double ar[16], ai[16];
+    double f0r = 1.0, f0i = 0.0, f1r = 1.0, f1i = 0.0, f2r = 1.0, f2i = 0.0, f3r = 1.0, f3i = 0.0, f4r = 1.0, f4i = 0.0;
+    unsigned dirty = 0;
+    unsigned tj = 0;
+    unsigned stj = 0, sw0 = 1, sw1 = 2, sw2 = 4, sw3 = 8;
+    auto saddr = [&](int k) -> unsigned {
+        return stj ^ ((k & 1) ? sw0 : 0u) ^ ((k & 2) ? sw1 : 0u) ^ ((k & 4) ? sw2 : 0u) ^ ((k & 8) ? sw3 : 0u);
+    };
+    auto set_layout = [&](int r0, int r1, int r2, int r3) {
+        tj = (unsigned)insert_zero(insert_zero(insert_zero(insert_zero(threadIdx.x, r0), r1), r2), r3);
+        stj = swz2(tj); sw0 = swz2(1u << r0); sw1 = swz2(1u << r1); sw2 = swz2(1u << r2); sw3 = swz2(1u << r3);
+    };
+    // absolute offset of tile bit b (a power of two: low bits map to themselves, the others to high[b - L])
+    auto bit_off = [&](unsigned b) -> unsigned long long { return b < (unsigned)L ? (1ull << b) : seg_off[1u << (b - L)]; };
+
+    // ---- issue the tile's global loads FIRST, under the first register layout (passed in the kernel arguments), so
+    // that staging the program and reducing the phase groups below run while the amplitudes are in flight ----
+    set_layout((int)(a.first_rbits & 255u), (int)((a.first_rbits >> 8) & 255u), (int)((a.first_rbits >> 16) & 255u), (int)(a.first_rbits >> 24));
+    {
+    const unsigned long long base = tile_base();
+    if (a.first_direct) {
+        const unsigned rpack = a.first_rbits;
+        const unsigned long long g0 = base + seg_off[tj >> L] + (tj & seg_mask);
+        const unsigned long long o0 = bit_off(rpack & 255u), o1 = bit_off((rpack >> 8) & 255u);
+        const unsigned long long o2 = bit_off((rpack >> 16) & 255u), o3 = bit_off(rpack >> 24);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const unsigned long long g = g0 + ((k & 1) ? o0 : 0ull) + ((k & 2) ? o1 : 0ull) + ((k & 4) ? o2 : 0ull) + ((k & 8) ? o3 : 0ull);
+            ar[k] = a.re[g];
+            ai[k] = a.im[g];
+        }
+    } else {
+        // coalesced 128-bit loads, parked in the amplitude registers (pairs 2*it, 2*it+1) until the staging stores below
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const unsigned v = threadIdx.x + it * nthr;
+            const unsigned j = v << 1;
+            const unsigned long long g = base + seg_off[j >> L] + (j & seg_mask);
+            const double2 r = *reinterpret_cast<const double2 *>(a.re + g);
+            const double2 m = *reinterpret_cast<const double2 *>(a.im + g);
+            ar[2 * it] = r.x; ar[2 * it + 1] = r.y;
+            ai[2 * it] = m.x; ai[2 * it + 1] = m.y;
+        }
+    }
+
+    // ---- stage the program; per-instruction tile flags; reduce every phase group over this tile's outer bits ----
+    if ((int)threadIdx.x < a.n_instr) {
+        const TileInstr *gi = a.prog + threadIdx.x; // straight from global memory: independent of the staging copy below
+        const unsigned long long ocm = gi->outer_cmask;
+        unsigned f = ((base & ocm) != ocm) ? 1u : 0u;
+        if (gi->op == TI_DIAG && gi->t_where == 0) {
+            const bool hi = gi->const_hi ? (gi->const_hi == 2u) : (bool)((base >> gi->outer_target) & 1ull);
+            f |= hi ? 2u : 0u;
+        }
+        iflag[threadIdx.x] = (unsigned char)f;
     }
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.prog);
@@ -149,27 +218,7 @@ __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
         gfac[g] = make_double2(fr, fi);
         gthr[g] = (any ? gd.thr : 0xffffu) | (gd.m << 16);
     }
-    __syncthreads();
-
-    const unsigned seg_mask = (1u << L) - 1u;
-    constexpr unsigned n_vec = tile_len >> 1;
-
-    double ar[16], ai[16];
-    double f0r = 1.0, f0i = 0.0, f1r = 1.0, f1i = 0.0, f2r = 1.0, f2i = 0.0, f3r = 1.0, f3i = 0.0, f4r = 1.0, f4i = 0.0;
-    unsigned dirty = 0;
-    unsigned tj = 0;
-    unsigned rpack = 0; // the current layout's register bits, one byte each
-    unsigned stj = 0, sw0 = 1, sw1 = 2, sw2 = 4, sw3 = 8;
-    auto saddr = [&](int k) -> unsigned {
-        return stj ^ ((k & 1) ? sw0 : 0u) ^ ((k & 2) ? sw1 : 0u) ^ ((k & 4) ? sw2 : 0u) ^ ((k & 8) ? sw3 : 0u);
-    };
-    auto set_layout = [&](int r0, int r1, int r2, int r3) {
-        tj = (unsigned)insert_zero(insert_zero(insert_zero(insert_zero(threadIdx.x, r0), r1), r2), r3);
-        stj = swz2(tj); sw0 = swz2(1u << r0); sw1 = swz2(1u << r1); sw2 = swz2(1u << r2); sw3 = swz2(1u << r3);
-        rpack = (unsigned)r0 | ((unsigned)r1 << 8) | ((unsigned)r2 << 16) | ((unsigned)r3 << 24);
-    };
-    // absolute offset of tile bit b (a power of two: low bits map to themselves, the others to high[b - L])
-    auto bit_off = [&](unsigned b) -> unsigned long long { return b < (unsigned)L ? (1ull << b) : seg_off[1u << (b - L)]; };
+    } // base
 
     // expand all five accumulators into the 16 per-amplitude factors (layout changes and the end of the program)
     auto flush_all = [&]() {
@@ -225,41 +274,19 @@ __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
         }
     };
 
-    // ---- the program starts with a LAYOUT (Fuser::compile); fill the registers under it ----
-    {
-        const TileInstr &l0 = sprog[0];
-        set_layout(l0.rbit[0], l0.rbit[1], l0.rbit[2], l0.rbit[3]);
-    }
-    if (a.first_direct) {
-        const unsigned long long g0 = base + seg_off[tj >> L] + (tj & seg_mask);
-        const unsigned long long o0 = bit_off(rpack & 255u), o1 = bit_off((rpack >> 8) & 255u);
-        const unsigned long long o2 = bit_off((rpack >> 16) & 255u), o3 = bit_off(rpack >> 24);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const unsigned long long g = g0 + ((k & 1) ? o0 : 0ull) + ((k & 2) ? o1 : 0ull) + ((k & 4) ? o2 : 0ull) + ((k & 8) ? o3 : 0ull);
-            ar[k] = a.re[g];
-            ai[k] = a.im[g];
-        }
-    } else {
-        // global -> shared (coalesced 128-bit loads, swizzled placement), as in k_tile
-        double2 tr[8], tm[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const unsigned v = threadIdx.x + it * nthr;
-            const unsigned j = v << 1;
-            const unsigned long long g = base + seg_off[j >> L] + (j & seg_mask);
-            tr[it] = *reinterpret_cast<const double2 *>(a.re + g);
-            tm[it] = *reinterpret_cast<const double2 *>(a.im + g);
-        }
+    if (!a.first_direct) {
+        // swizzled placement in shared memory, then re-read under the register layout
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const unsigned v = threadIdx.x + it * nthr;
             const unsigned s0 = swz2(v << 1);
             const bool flip = s0 & 1u;
-            *reinterpret_cast<double2 *>(sre + (s0 & ~1u)) = flip ? make_double2(tr[it].y, tr[it].x) : tr[it];
-            *reinterpret_cast<double2 *>(sim + (s0 & ~1u)) = flip ? make_double2(tm[it].y, tm[it].x) : tm[it];
+            *reinterpret_cast<double2 *>(sre + (s0 & ~1u)) = flip ? make_double2(ar[2 * it + 1], ar[2 * it]) : make_double2(ar[2 * it], ar[2 * it + 1]);
+            *reinterpret_cast<double2 *>(sim + (s0 & ~1u)) = flip ? make_double2(ai[2 * it + 1], ai[2 * it]) : make_double2(ai[2 * it], ai[2 * it + 1]);
         }
-        __syncthreads();
+    }
+    __syncthreads(); // program and group tables staged (and, on the staged path, the tile)
+    if (!a.first_direct) {
         load_regs();
         // No barrier here (k_tile has one): the next shared-memory access of this thread is store_regs() under the SAME
         // layout, i.e. to exactly the cells it has just read, which no other thread touches in between.  Checked with
@@ -309,8 +336,8 @@ __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
             }
             continue;
         }
-        const unsigned long long ocm = ins.outer_cmask;
-        if ((base & ocm) != ocm) continue; // an outer control is 0 for this whole tile
+        const unsigned fl = iflag[pc];
+        if (fl & 1u) continue; // an outer control is 0 for this whole tile
         if (op == TI_GATE) {
             // CTRL = false: no in-tile controls anywhere in the program, so the pair mask is the same for every thread
             // (0xffff, read from shared memory with a uniform address): the per-pair guards become uniform branches,
@@ -347,7 +374,7 @@ __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
             const int kind = ins.kind;
             const int tw = ins.t_where;
             bool outer_hi = false;
-            if (tw == 0) outer_hi = ins.const_hi ? (ins.const_hi == 2) : (bool)((base >> ins.outer_target) & 1ull);
+            if (tw == 0) outer_hi = (fl & 2u) != 0u;
             if (tw == 0 && !outer_hi && kind != SPZ_GATE_RZ) continue;
             const bool ok = (tj & ins.thr_cmask) == ins.thr_cmask;
             const bool thr_hi = tw == 1 ? ((tj & ins.t_mask) != 0) : outer_hi;
@@ -364,8 +391,10 @@ __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
     }
 
     flush_all();
+    const unsigned long long base = tile_base();
     if (a.last_direct) {
-        // registers -> global under the final layout (tj and rpack describe it)
+        // registers -> global under the final layout (tj is current; its register bits come with the arguments)
+        const unsigned rpack = a.last_rbits;
         const unsigned long long g0 = base + seg_off[tj >> L] + (tj & seg_mask);
         const unsigned long long o0 = bit_off(rpack & 255u), o1 = bit_off((rpack >> 8) & 255u);
         const unsigned long long o2 = bit_off((rpack >> 16) & 255u), o3 = bit_off(rpack >> 24);
@@ -398,8 +427,8 @@ size_t tile2_max_smem() {
 // Kernel arguments, dynamic shared-memory size and instantiation for tiles [first, ...) of one pass.  Pure host code,
 // shared by the launcher below and by the CPU emulation harness.
 Tile2Args tile2_make_args(double *re, double *im, const TilePlan &plan, const TileInstr *h_prog, int n_instr, const TileInstr *d_prog,
-                          const TileGroup *d_groups, int n_groups, const TileTerm *d_terms, unsigned first, size_t *smem_bytes,
-                          bool *ctrl) {
+                          const TileGroup *d_groups, int n_groups, const TileTerm *d_terms, unsigned first, int direct_level,
+                          size_t *smem_bytes, bool *ctrl) {
     Tile2Args a{};
     a.re = re; a.im = im;
     a.prog = d_prog; a.groups = d_groups; a.terms = d_terms;
@@ -418,9 +447,19 @@ Tile2Args tile2_make_args(double *re, double *im, const TilePlan &plan, const Ti
         if (h_prog[i].op == TI_LAYOUT) last_layout = i;
         if (h_prog[i].op == TI_GATE && (h_prog[i].thr_cmask || h_prog[i].reg_cmask)) *ctrl = true;
     }
-    auto high_layout = [&](const TileInstr &l) { return l.rbit[0] >= 4; }; // rbit is ascending
-    a.first_direct = high_layout(h_prog[0]) ? 1 : 0;
-    a.last_direct = high_layout(h_prog[last_layout]) ? 1 : 0;
+    // When may a layout be transferred global <-> registers directly?  level 1 (default): all register bits >= 4, so 16
+    // consecutive lanes own one 128-byte line.  2: no register bit below 2 (4 lanes own one 32-byte sector).  3: always.
+    // 0: never (always stage through shared memory).  The kernel is correct at every level; only coalescing differs.
+    auto direct_ok = [&](const TileInstr &l) { // rbit is ascending
+        return direct_level >= 3 || (direct_level == 2 && l.rbit[0] >= 2) || (direct_level == 1 && l.rbit[0] >= 4);
+    };
+    a.first_direct = direct_ok(h_prog[0]) ? 1 : 0;
+    a.last_direct = direct_ok(h_prog[last_layout]) ? 1 : 0;
+    auto pack = [](const TileInstr &l) {
+        return (unsigned)l.rbit[0] | ((unsigned)l.rbit[1] << 8) | ((unsigned)l.rbit[2] << 16) | ((unsigned)l.rbit[3] << 24);
+    };
+    a.first_rbits = pack(h_prog[0]);
+    a.last_rbits = pack(h_prog[last_layout]);
     return a;
 }
 
@@ -464,7 +503,10 @@ int launch_tile2(spz_state *st, const TilePlan &plan, const TileInstr *h_prog, i
     }
     size_t smem = 0;
     bool ctrl = false;
-    const Tile2Args a = tile2_make_args(st->re, st->im, plan, h_prog, n_instr, d_prog, d_groups, n_groups, d_terms, first, &smem, &ctrl);
+    int direct_level = 1; // SPZ_TILE_V2_DIRECT = 0..3, see tile2_make_args
+    if (const char *e = std::getenv("SPZ_TILE_V2_DIRECT")) if (e[0] >= '0' && e[0] <= '3') direct_level = e[0] - '0';
+    const Tile2Args a = tile2_make_args(st->re, st->im, plan, h_prog, n_instr, d_prog, d_groups, n_groups, d_terms, first, direct_level,
+                                        &smem, &ctrl);
     if (exact) k_tile2<true, true><<<count, kThreads2, smem, st->stream>>>(a);
     else if (ctrl) k_tile2<false, true><<<count, kThreads2, smem, st->stream>>>(a);
     else k_tile2<false, false><<<count, kThreads2, smem, st->stream>>>(a);

@@ -46,7 +46,8 @@ void run_blocks(const spz::Tile2Args &a, unsigned n_blocks) {
 
 // blob: the serialisation produced by spz_debug_compile_pass (layout documented in csrc/abi.cu).
 // info[0..3] <- {ctrl instantiation, first_direct, last_direct, eligible}
-extern "C" int emu_tile2_run(int n_qubits, double *re, double *im, const void *blob, long long blob_bytes, int exact, int *info) {
+extern "C" int emu_tile2_run(int n_qubits, double *re, double *im, const void *blob, long long blob_bytes, int exact, int direct_level,
+                             int *info) {
     const char *p = static_cast<const char *>(blob);
     int32_t hdr[16];
     if (blob_bytes < (long long)sizeof hdr) return -1;
@@ -68,7 +69,7 @@ extern "C" int emu_tile2_run(int n_qubits, double *re, double *im, const void *b
     if (!info[3]) return 1; // the launcher would fall back to k_tile
     size_t smem = 0;
     bool ctrl = false;
-    const spz::Tile2Args a = spz::tile2_make_args(re, im, plan, prog.data(), ni, prog.data(), groups.data(), ng, terms.data(), 0u, &smem, &ctrl);
+    const spz::Tile2Args a = spz::tile2_make_args(re, im, plan, prog.data(), ni, prog.data(), groups.data(), ng, terms.data(), 0u, direct_level, &smem, &ctrl);
     info[0] = ctrl ? 1 : 0; info[1] = a.first_direct; info[2] = a.last_direct;
     std::vector<unsigned char> window(smem + 64);
     spz_emu::dyn_smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(window.data()) + 63) & ~(uintptr_t)63);
@@ -89,11 +90,12 @@ extern "C" int emu_tile2_run(int n_qubits, double *re, double *im, const void *b
 
 #ifdef SPZ_EMU_MAIN
 // Stand-alone driver (used for the ThreadSanitizer run: a sanitised shared object cannot be loaded into CPython):
-//   tile2_emu <n_qubits> <exact 0|1> <state.bin: re[2^n] then im[2^n], f64> <blob.bin> ; the state file is rewritten.
+//   tile2_emu <n_qubits> <exact 0|1> <state.bin: re[2^n] then im[2^n], f64> <blob.bin> <direct level 0..3>
+// the state file is rewritten.
 #include <cstdio>
 #include <cstdlib>
 int main(int argc, char **argv) {
-    if (argc != 5) return 64;
+    if (argc != 6) return 64;
     const int n = std::atoi(argv[1]), exact = std::atoi(argv[2]);
     const size_t len = (size_t)1 << n;
     std::vector<double> st(2 * len);
@@ -108,7 +110,7 @@ int main(int argc, char **argv) {
     while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) blob.insert(blob.end(), buf, buf + got);
     std::fclose(f);
     int info[4] = {0, 0, 0, 0};
-    const int rc = emu_tile2_run(n, st.data(), st.data() + len, blob.data(), (long long)blob.size(), exact, info);
+    const int rc = emu_tile2_run(n, st.data(), st.data() + len, blob.data(), (long long)blob.size(), exact, std::atoi(argv[5]), info);
     if (rc != 0) return 70 + rc;
     f = std::fopen(argv[3], "wb");
     if (!f || std::fwrite(st.data(), sizeof(double), 2 * len, f) != 2 * len) return 65;

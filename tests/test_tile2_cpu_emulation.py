@@ -41,7 +41,7 @@ def emu():
     subprocess.run(cmd, check=True, cwd=ROOT)
     h = C.CDLL(str(lib))
     h.emu_tile2_run.restype = C.c_int
-    h.emu_tile2_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_longlong, C.c_int, C.POINTER(C.c_int)]
+    h.emu_tile2_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_int)]
     return h
 
 
@@ -53,7 +53,7 @@ def raw_pass(qc, pass_index):
     return bytes(buf[: used.value])
 
 
-def run_emulated(emu, qc, re, im, stats):
+def run_emulated(emu, qc, re, im, stats, direct_level=1):
     """Every fused pass through the emulated kernel; single-op passes through the dense statement."""
     n = qc.n_qubits
     trs = list(qc.transformations)
@@ -70,8 +70,13 @@ def run_emulated(emu, qc, re, im, stats):
             stats["direct"] = stats.get("direct", 0) + 1
             continue
         info = (C.c_int * 4)()
-        rc = emu.emu_tile2_run(n, re.ctypes.data, im.ctypes.data, blob, len(blob), 1 if qc.exact else 0, info)
-        assert rc == 0, f"pass {p}: emulation refused the program (rc={rc}, eligible={info[3]})"
+        rc = emu.emu_tile2_run(n, re.ctypes.data, im.ctypes.data, blob, len(blob), 1 if qc.exact else 0, direct_level, info)
+        if rc == 1:  # too long for k_tile2's shared-memory budget: the launcher falls back to k_tile
+            psi = run_dense_order(n, re + 1j * im, trs, by_pass[p])
+            re[:], im[:] = psi.real, psi.imag
+            stats["fallback"] = stats.get("fallback", 0) + 1
+            continue
+        assert rc == 0, f"pass {p}: emulation failed (rc={rc})"
         key = ("ctrl" if info[0] else "noctrl", "ld-direct" if info[1] else "ld-staged", "st-direct" if info[2] else "st-staged")
         stats[key] = stats.get(key, 0) + 1
     return re, im
@@ -136,6 +141,22 @@ def test_random_circuits_merged_mode(emu, n, count, seed):
     assert any(k[0] == "ctrl" for k in stats if isinstance(k, tuple)), stats
 
 
+@pytest.mark.parametrize("level", [0, 2, 3])
+def test_every_direct_transfer_level_is_correct(emu, level):
+    """SPZ_TILE_V2_DIRECT only moves the coalescing trade-off; results must not depend on it."""
+    n = 13
+    qc = random_circuit(n, 160, 35)
+    psi0, re, im = start(n, 35)
+    stats = {}
+    run_emulated(emu, qc, re, im, stats, direct_level=level)
+    np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
+    tiles = [k for k in stats if isinstance(k, tuple)]
+    if level == 0:
+        assert all(k[1:] == ("ld-staged", "st-staged") for k in tiles), stats
+    if level == 3:
+        assert all(k[1:] == ("ld-direct", "st-direct") for k in tiles), stats
+
+
 @pytest.mark.parametrize("n,count,seed", [(13, 60, 41), (14, 80, 42)])
 def test_exact_mode_is_bit_identical_to_the_oracle(emu, n, count, seed):
     """EXACT programs replay the reference arithmetic operation by operation; the emulation is built with
@@ -160,7 +181,7 @@ def test_exact_mode_is_bit_identical_to_the_oracle(emu, n, count, seed):
             re, im = s.reals.copy(), s.imags.copy()
             continue
         info = (C.c_int * 4)()
-        rc = emu.emu_tile2_run(n, re.ctypes.data, im.ctypes.data, blob, len(blob), 1, info)
+        rc = emu.emu_tile2_run(n, re.ctypes.data, im.ctypes.data, blob, len(blob), 1, 1, info)
         if rc == 1:   # program too long for k_tile2's shared-memory budget: the launcher falls back to k_tile
             s = orc.State(n)
             s.reals[:], s.imags[:] = re, im
@@ -243,11 +264,11 @@ def emu_tsan():
     return exe
 
 
-def tsan_run(exe, tmp_path, n, exact, re, im, blob):
+def tsan_run(exe, tmp_path, n, exact, re, im, blob, direct_level=1):
     state = tmp_path / "state.bin"
     np.concatenate([re, im]).tofile(state)
     (tmp_path / "blob.bin").write_bytes(blob)
-    r = subprocess.run([str(exe), str(n), "1" if exact else "0", str(state), str(tmp_path / "blob.bin")], capture_output=True, text=True,
+    r = subprocess.run([str(exe), str(n), "1" if exact else "0", str(state), str(tmp_path / "blob.bin"), str(direct_level)], capture_output=True, text=True,
                        env={"TSAN_OPTIONS": "halt_on_error=0 exitcode=0"}, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "ThreadSanitizer" not in r.stderr, r.stderr[:4000]
@@ -273,10 +294,11 @@ def test_no_shared_memory_race_in_any_pass(emu, emu_tsan, tmp_path, case):
             continue
         info = (C.c_int * 4)()
         r2, i2 = re.copy(), im.copy()
-        rc = emu.emu_tile2_run(n, r2.ctypes.data, i2.ctypes.data, blob, len(blob), 1 if qc.exact else 0, info)
+        level = p % 4  # cycle through the transfer variants as well
+        rc = emu.emu_tile2_run(n, r2.ctypes.data, i2.ctypes.data, blob, len(blob), 1 if qc.exact else 0, level, info)
         if rc == 1:
             continue  # not eligible for k_tile2
-        rt, it, out = tsan_run(emu_tsan, tmp_path, n, qc.exact, re, im, blob)
+        rt, it, out = tsan_run(emu_tsan, tmp_path, n, qc.exact, re, im, blob, level)
         assert np.array_equal(rt, r2) and np.array_equal(it, i2)  # same code, same arithmetic, with and without the sanitizer
         seen.add(out.strip())
         re, im = r2, i2  # feed the next pass with this pass's output, as execute would
