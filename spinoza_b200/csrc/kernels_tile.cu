@@ -31,6 +31,14 @@
 
 #include "gate_math.cuh"
 
+// tests/emu/ compiles the kernel body with g++ (SPZ_CPU_EMULATION: one OS thread per CUDA thread) to check it on the CPU;
+// only the name of the dynamic shared-memory window differs between the two builds.
+#ifdef SPZ_CPU_EMULATION
+#define SPZ_TILE_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(spz_emu::dyn_smem)
+#else
+#define SPZ_TILE_DYN_SMEM(T, name) extern __shared__ T name[]
+#endif
+
 namespace spz {
 
 constexpr int kMaxTileBits = 12;
@@ -112,7 +120,7 @@ __device__ __forceinline__ void run_class(const double2 *__restrict__ gfac, cons
 
 template <bool EXACT>
 __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
-    extern __shared__ double smem[];
+    SPZ_TILE_DYN_SMEM(double, smem);
     const int T = a.T, L = a.L;
     const unsigned tile_len = 1u << T;
     const unsigned nthr = blockDim.x;
@@ -377,6 +385,7 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
     }
 }
 
+#ifndef SPZ_CPU_EMULATION
 int tile_prepare(spz_state *st) {
     if (!st->d_ops) {
         const size_t cap = (size_t)4 << 20;
@@ -482,5 +491,7 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
     SPZ_CUDA(cudaGetLastError());
     return SPZ_OK;
 }
+
+#endif // !SPZ_CPU_EMULATION
 
 } // namespace spz

@@ -1,6 +1,6 @@
 // cuda_cpu_shim.h -- just enough of the CUDA execution model to run one thread block of a kernel on the CPU.
 //
-// Test infrastructure only (tests/test_tile2_cpu_emulation.py builds tests/emu/tile2_emu.cpp with g++ and this header
+// Test infrastructure only (tests/test_tile_cpu_emulation.py builds tests/emu/tile_emu.cpp with g++ and this header
 // force-included).  A block is executed by blockDim.x OS threads; __syncthreads() is a pthread barrier; `__shared__`
 // variables become function-local statics (blocks run one after another, so one copy is enough); the dynamic shared-memory
 // window is a heap buffer.  Nothing here models warps, memory ordering or timing: the emulation checks indexing, control
@@ -61,6 +61,7 @@ inline void barrier() { pthread_barrier_wait(&block_barrier); }
 
 static thread_local uint3 threadIdx;
 static thread_local uint3 blockIdx;
+static thread_local uint3 blockDim;
 
 static inline void __syncthreads() { spz_emu::barrier(); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }

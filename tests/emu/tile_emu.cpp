@@ -1,0 +1,168 @@
+// tile_emu.cpp -- runs the bodies of the fused tile kernels k_tile (spinoza_b200/csrc/kernels_tile.cu) and k_tile2
+// (kernels_tile2.cu) on the CPU, block by block.
+//
+// Test infrastructure only: built by tests/test_tile_cpu_emulation.py with
+//   g++ -O1 -std=c++17 -ffp-contract=off -shared -fPIC -pthread -I/usr/local/cuda/include -include tests/emu/cuda_cpu_shim.h
+// The kernel sources are #included unchanged; see cuda_cpu_shim.h for what the emulation does and does not model.
+#define SPZ_CPU_EMULATION 1
+#include "cuda_cpu_shim.h"
+
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../spinoza_b200/csrc/kernels_tile.cu"
+#include "../../spinoza_b200/csrc/kernels_tile2.cu"
+
+namespace spz_emu {
+unsigned char *dyn_smem = nullptr;
+unsigned block_threads = 0;
+#ifdef SPZ_EMU_TSAN
+std::atomic<unsigned> bar_count{0}, bar_gen{0};
+char bar_tags[4096];
+#else
+pthread_barrier_t block_barrier;
+#endif
+} // namespace spz_emu
+
+namespace {
+
+// One OS thread per CUDA thread; the blocks of the grid run one after another.
+template <class Kernel>
+void run_grid(unsigned n_blocks, unsigned n_threads, size_t smem_bytes, Kernel kernel) {
+    std::vector<unsigned char> window(smem_bytes + 64);
+    spz_emu::dyn_smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(window.data()) + 63) & ~(uintptr_t)63);
+    spz_emu::block_threads = n_threads;
+#ifndef SPZ_EMU_TSAN
+    pthread_barrier_init(&spz_emu::block_barrier, nullptr, n_threads);
+#endif
+    std::vector<std::thread> pool;
+    pool.reserve(n_threads);
+    for (unsigned t = 0; t < n_threads; ++t) {
+        pool.emplace_back([&, t]() {
+            threadIdx.x = t; threadIdx.y = 0; threadIdx.z = 0;
+            blockDim.x = n_threads; blockDim.y = 1; blockDim.z = 1;
+            for (unsigned b = 0; b < n_blocks; ++b) {
+                blockIdx.x = b; blockIdx.y = 0; blockIdx.z = 0;
+                kernel();
+                spz_emu::barrier(); // the next block reuses the shared-memory statics
+            }
+        });
+    }
+    for (auto &th : pool) th.join();
+#ifndef SPZ_EMU_TSAN
+    pthread_barrier_destroy(&spz_emu::block_barrier);
+#endif
+    spz_emu::dyn_smem = nullptr;
+}
+
+struct Program {
+    spz::TilePlan plan{};
+    std::vector<spz::TileInstr> prog;
+    std::vector<spz::TileGroup> groups;
+    std::vector<spz::TileTerm> terms;
+    int ni = 0, ng = 0, nt = 0;
+};
+
+// blob: the serialisation produced by spz_debug_compile_pass (layout documented in csrc/abi.cu)
+int parse(const void *blob, long long blob_bytes, Program &P) {
+    const char *p = static_cast<const char *>(blob);
+    int32_t hdr[16];
+    if (blob_bytes < (long long)sizeof hdr) return -1;
+    std::memcpy(hdr, p, sizeof hdr);
+    if (hdr[0] != 0 || hdr[15] != (int32_t)sizeof(spz::TileInstr)) return -2;
+    P.plan.tile_bits = hdr[1]; P.plan.low_bits = hdr[2]; P.plan.n_high = hdr[3];
+    for (int k = 0; k < 8; ++k) P.plan.high[k] = hdr[4 + k];
+    P.ni = hdr[12]; P.ng = hdr[13]; P.nt = hdr[14];
+    P.prog.resize(P.ni);
+    P.groups.resize(P.ng > 0 ? P.ng : 1);
+    P.terms.resize(P.nt > 0 ? P.nt : 1);
+    p += sizeof hdr;
+    std::memcpy(P.prog.data(), p, sizeof(spz::TileInstr) * P.ni); p += sizeof(spz::TileInstr) * P.ni;
+    if (P.ng) std::memcpy(P.groups.data(), p, sizeof(spz::TileGroup) * P.ng);
+    p += sizeof(spz::TileGroup) * P.ng;
+    if (P.nt) std::memcpy(P.terms.data(), p, sizeof(spz::TileTerm) * P.nt);
+    return 0;
+}
+
+} // namespace
+
+// k_tile2.  info[0..3] <- {ctrl instantiation, first_direct, last_direct, eligible}; returns 1 when the launcher would fall
+// back to k_tile.
+extern "C" int emu_tile2_run(int n_qubits, double *re, double *im, const void *blob, long long blob_bytes, int exact, int direct_level,
+                             int *info) {
+    Program P;
+    if (int rc = parse(blob, blob_bytes, P)) return rc;
+    info[3] = spz::tile2_shape_ok(n_qubits, P.plan, P.prog.data(), P.ni, P.ng) ? 1 : 0;
+    if (!info[3]) return 1;
+    size_t smem = 0;
+    bool ctrl = false;
+    const spz::Tile2Args a = spz::tile2_make_args(re, im, P.plan, P.prog.data(), P.ni, P.prog.data(), P.groups.data(), P.ng, P.terms.data(), 0u,
+                                                  direct_level, &smem, &ctrl);
+    info[0] = ctrl ? 1 : 0; info[1] = a.first_direct; info[2] = a.last_direct;
+    const unsigned n_blocks = (unsigned)(((uint64_t)1 << n_qubits) >> P.plan.tile_bits);
+    if (exact) run_grid(n_blocks, spz::kThreads2, smem, [&]() { spz::k_tile2<true, true>(a); });
+    else if (ctrl) run_grid(n_blocks, spz::kThreads2, smem, [&]() { spz::k_tile2<false, true>(a); });
+    else run_grid(n_blocks, spz::kThreads2, smem, [&]() { spz::k_tile2<false, false>(a); });
+    return 0;
+}
+
+// k_tile, with the arguments launch_tile_program (kernels_tile.cu) builds.  prog_in_smem: 0 decodes from "global" memory.
+extern "C" int emu_tile1_run(int n_qubits, double *re, double *im, const void *blob, long long blob_bytes, int exact, int prog_in_smem) {
+    Program P;
+    if (int rc = parse(blob, blob_bytes, P)) return rc;
+    const spz::TilePlan &plan = P.plan;
+    if (plan.tile_bits > spz::kMaxTileBits || plan.tile_bits < spz::kRegBits || plan.n_high > spz::kMaxHigh || plan.low_bits < 1 ||
+        plan.tile_bits != plan.low_bits + plan.n_high || plan.tile_bits > n_qubits)
+        return -3;
+    spz::TileArgs a{};
+    a.re = re; a.im = im;
+    a.prog = P.prog.data(); a.groups = P.groups.data(); a.terms = P.terms.data();
+    a.n_groups = P.ng; a.n_instr = P.ni;
+    a.T = plan.tile_bits; a.L = plan.low_bits; a.n_high = plan.n_high;
+    for (int k = 0; k < plan.n_high; ++k) a.high[k] = plan.high[k];
+    size_t smem = sizeof(double) * 2u * ((size_t)1 << plan.tile_bits) + (size_t)P.ng * (sizeof(double2) + sizeof(unsigned));
+    smem = (smem + 15) & ~(size_t)15;
+    a.prog_off = (unsigned)smem;
+    a.prog_in_smem = (prog_in_smem && P.ni <= spz::kMaxSmemInstr) ? 1 : 0;
+    if (a.prog_in_smem) smem += sizeof(spz::TileInstr) * (size_t)P.ni;
+    a.tile_offset = 0;
+    const unsigned n_blocks = (unsigned)(((uint64_t)1 << n_qubits) >> plan.tile_bits);
+    const unsigned threads = 1u << (plan.tile_bits - spz::kRegBits);
+    if (exact) run_grid(n_blocks, threads, smem, [&]() { spz::k_tile<true>(a); });
+    else run_grid(n_blocks, threads, smem, [&]() { spz::k_tile<false>(a); });
+    return 0;
+}
+
+#ifdef SPZ_EMU_MAIN
+// Stand-alone driver (used for the ThreadSanitizer run: a sanitised shared object cannot be loaded into CPython):
+//   tile_emu <kernel 1|2> <n_qubits> <exact 0|1> <state.bin: re[2^n] then im[2^n], f64> <blob.bin> <option>
+// option: k_tile2 = direct level 0..3, k_tile = prog_in_smem 0|1.  The state file is rewritten.
+#include <cstdio>
+#include <cstdlib>
+int main(int argc, char **argv) {
+    if (argc != 7) return 64;
+    const int kernel = std::atoi(argv[1]), n = std::atoi(argv[2]), exact = std::atoi(argv[3]), option = std::atoi(argv[6]);
+    const size_t len = (size_t)1 << n;
+    std::vector<double> st(2 * len);
+    FILE *f = std::fopen(argv[4], "rb");
+    if (!f || std::fread(st.data(), sizeof(double), 2 * len, f) != 2 * len) return 65;
+    std::fclose(f);
+    f = std::fopen(argv[5], "rb");
+    if (!f) return 65;
+    std::vector<char> blob;
+    char buf[1 << 16];
+    size_t got;
+    while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) blob.insert(blob.end(), buf, buf + got);
+    std::fclose(f);
+    int info[4] = {0, 0, 0, 0};
+    const int rc = kernel == 2 ? emu_tile2_run(n, st.data(), st.data() + len, blob.data(), (long long)blob.size(), exact, option, info)
+                               : emu_tile1_run(n, st.data(), st.data() + len, blob.data(), (long long)blob.size(), exact, option);
+    if (rc != 0) return 70 + rc;
+    f = std::fopen(argv[4], "wb");
+    if (!f || std::fwrite(st.data(), sizeof(double), 2 * len, f) != 2 * len) return 65;
+    std::fclose(f);
+    std::printf("kernel=%d ctrl=%d first_direct=%d last_direct=%d\n", kernel, info[0], info[1], info[2]);
+    return 0;
+}
+#endif

@@ -1,11 +1,12 @@
-"""The body of k_tile2 (csrc/kernels_tile2.cu) executed on the CPU: tests/emu/ compiles the kernel source itself with g++
-(one OS thread per CUDA thread, a pthread barrier for __syncthreads) and runs it block by block on the micro-programs that
-spz_execute would upload (spz_debug_compile_pass).  Unlike tests/test_tile_program.py -- an independent NumPy statement of
-the execution model -- this exercises the real indexing code: direct global<->register transfers, swizzled staging, lazy
-phase flush, the CTRL=false instantiation, exact-mode diagonal arithmetic.
+"""The bodies of the fused tile kernels -- k_tile (csrc/kernels_tile.cu, the default) and k_tile2 (csrc/kernels_tile2.cu,
+opt-in) -- executed on the CPU: tests/emu/ compiles the kernel sources themselves with g++ (one OS thread per CUDA thread, a
+barrier for __syncthreads) and runs them block by block on the micro-programs that spz_execute would upload
+(spz_debug_compile_pass).  Unlike tests/test_tile_program.py -- an independent NumPy statement of the execution model -- this
+exercises the real indexing code: swizzled staging, register layouts, merged phase runs, exact-mode diagonal arithmetic, and
+for k_tile2 the direct global<->register transfers, the lazy phase flush and the CTRL=false instantiation.
 
-It does not replace the GPU parity tests (no warps, no memory model, no timing); it exists because k_tile2 was written
-when no GPU time was left, and it keeps guarding the kernel's logic in the CPU suite afterwards.
+It does not replace the GPU parity tests (no warps, no memory model, no timing).  It exists because k_tile2 was written when
+no GPU time was left, and it lets the CPU suite (-m "not gpu") guard the logic of both kernels.
 """
 import ctypes as C
 import shutil
@@ -35,13 +36,15 @@ def emu():
         pytest.skip("needs g++ and the CUDA headers")
     out = EMU_DIR / "_build"
     out.mkdir(exist_ok=True)
-    lib = out / "libtile2_emu.so"
+    lib = out / "libtile_emu.so"
     cmd = [gxx, "-O1", "-std=c++17", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-pthread", f"-I{CUDA_INC}",
-           "-include", str(EMU_DIR / "cuda_cpu_shim.h"), "-x", "c++", str(EMU_DIR / "tile2_emu.cpp"), "-o", str(lib)]
+           "-include", str(EMU_DIR / "cuda_cpu_shim.h"), "-x", "c++", str(EMU_DIR / "tile_emu.cpp"), "-o", str(lib)]
     subprocess.run(cmd, check=True, cwd=ROOT)
     h = C.CDLL(str(lib))
     h.emu_tile2_run.restype = C.c_int
     h.emu_tile2_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    h.emu_tile1_run.restype = C.c_int
+    h.emu_tile1_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_longlong, C.c_int, C.c_int]
     return h
 
 
@@ -53,7 +56,16 @@ def raw_pass(qc, pass_index):
     return bytes(buf[: used.value])
 
 
-def run_emulated(emu, qc, re, im, stats, direct_level=1):
+def emu_pass(emu, kernel, n, re, im, blob, exact, option, info=None):
+    """One fused pass through the emulated kernel.  kernel 1 = k_tile (option: program decoded from shared memory 1 / global
+    memory 0), kernel 2 = k_tile2 (option: direct-transfer level 0..3).  Returns 1 when k_tile2 is not eligible."""
+    if kernel == 1:
+        return emu.emu_tile1_run(n, re.ctypes.data, im.ctypes.data, blob, len(blob), 1 if exact else 0, option)
+    info = info if info is not None else (C.c_int * 4)()
+    return emu.emu_tile2_run(n, re.ctypes.data, im.ctypes.data, blob, len(blob), 1 if exact else 0, option, info)
+
+
+def run_emulated(emu, qc, re, im, stats, direct_level=1, kernel=2):
     """Every fused pass through the emulated kernel; single-op passes through the dense statement."""
     n = qc.n_qubits
     trs = list(qc.transformations)
@@ -70,7 +82,11 @@ def run_emulated(emu, qc, re, im, stats, direct_level=1):
             stats["direct"] = stats.get("direct", 0) + 1
             continue
         info = (C.c_int * 4)()
-        rc = emu.emu_tile2_run(n, re.ctypes.data, im.ctypes.data, blob, len(blob), 1 if qc.exact else 0, direct_level, info)
+        rc = emu_pass(emu, kernel, n, re, im, blob, qc.exact, direct_level if kernel == 2 else (p & 1), info)
+        if kernel == 1:
+            assert rc == 0, f"pass {p}: emulation failed (rc={rc})"
+            stats["k_tile"] = stats.get("k_tile", 0) + 1
+            continue
         if rc == 1:  # too long for k_tile2's shared-memory budget: the launcher falls back to k_tile
             psi = run_dense_order(n, re + 1j * im, trs, by_pass[p])
             re[:], im[:] = psi.real, psi.imag
@@ -131,14 +147,38 @@ def test_qft_merged_mode_uses_every_transfer_path(emu):
     assert stats.get(("noctrl", "ld-direct", "st-staged"), 0) >= 1, stats
 
 
+@pytest.mark.parametrize("kernel", [1, 2], ids=["k_tile", "k_tile2"])
 @pytest.mark.parametrize("n,count,seed", [(13, 160, 31), (14, 220, 32), (15, 120, 33)])
-def test_random_circuits_merged_mode(emu, n, count, seed):
+def test_random_circuits_merged_mode(emu, n, count, seed, kernel):
     qc = random_circuit(n, count, seed)
     psi0, re, im = start(n, seed)
     stats = {}
-    run_emulated(emu, qc, re, im, stats)
+    run_emulated(emu, qc, re, im, stats, kernel=kernel)
     np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
-    assert any(k[0] == "ctrl" for k in stats if isinstance(k, tuple)), stats
+    if kernel == 2:
+        assert any(k[0] == "ctrl" for k in stats if isinstance(k, tuple)), stats
+    else:
+        assert stats.get("k_tile", 0) >= 1
+
+
+@pytest.mark.parametrize("n", [5, 8, 11])
+def test_k_tile_small_registers_use_partial_tiles(emu, n):
+    """n < 12: the tile is the whole register and the block has 2^(n-4) threads (k_tile only; k_tile2 needs full tiles)."""
+    qc = random_circuit(n, 80, 60 + n)
+    psi0, re, im = start(n, n)
+    stats = {}
+    run_emulated(emu, qc, re, im, stats, kernel=1)
+    np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
+    assert stats.get("k_tile", 0) >= 1
+
+
+def test_qft_k_tile(emu):
+    n = 14
+    qc = QuantumCircuit(QuantumRegister(n))
+    qc.qft()
+    psi0, re, im = start(n, 4)
+    run_emulated(emu, qc, re, im, {}, kernel=1)
+    np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
 
 
 @pytest.mark.parametrize("level", [0, 2, 3])
@@ -157,8 +197,9 @@ def test_every_direct_transfer_level_is_correct(emu, level):
         assert all(k[1:] == ("ld-direct", "st-direct") for k in tiles), stats
 
 
+@pytest.mark.parametrize("kernel", [1, 2], ids=["k_tile", "k_tile2"])
 @pytest.mark.parametrize("n,count,seed", [(13, 60, 41), (14, 80, 42)])
-def test_exact_mode_is_bit_identical_to_the_oracle(emu, n, count, seed):
+def test_exact_mode_is_bit_identical_to_the_oracle(emu, n, count, seed, kernel):
     """EXACT programs replay the reference arithmetic operation by operation; the emulation is built with
     -ffp-contract=off like the oracle, so even on the CPU the two must agree in every bit."""
     qc = reference_cells_circuit(n, count, seed, exact=True)
@@ -181,7 +222,7 @@ def test_exact_mode_is_bit_identical_to_the_oracle(emu, n, count, seed):
             re, im = s.reals.copy(), s.imags.copy()
             continue
         info = (C.c_int * 4)()
-        rc = emu.emu_tile2_run(n, re.ctypes.data, im.ctypes.data, blob, len(blob), 1, 1, info)
+        rc = emu_pass(emu, kernel, n, re, im, blob, True, 1, info)
         if rc == 1:   # program too long for k_tile2's shared-memory budget: the launcher falls back to k_tile
             s = orc.State(n)
             s.reals[:], s.imags[:] = re, im
@@ -252,9 +293,9 @@ def emu_tsan():
         pytest.skip("needs g++ and the CUDA headers")
     out = EMU_DIR / "_build"
     out.mkdir(exist_ok=True)
-    exe = out / "tile2_emu_tsan"
+    exe = out / "tile_emu_tsan"
     cmd = [gxx, "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-w", "-fsanitize=thread", "-DSPZ_EMU_TSAN", "-DSPZ_EMU_MAIN", "-pthread",
-           f"-I{CUDA_INC}", "-include", str(EMU_DIR / "cuda_cpu_shim.h"), "-x", "c++", str(EMU_DIR / "tile2_emu.cpp"), "-o", str(exe)]
+           f"-I{CUDA_INC}", "-include", str(EMU_DIR / "cuda_cpu_shim.h"), "-x", "c++", str(EMU_DIR / "tile_emu.cpp"), "-o", str(exe)]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
     if r.returncode != 0:
         pytest.skip("ThreadSanitizer runtime not available: " + r.stderr[-200:])
@@ -264,11 +305,12 @@ def emu_tsan():
     return exe
 
 
-def tsan_run(exe, tmp_path, n, exact, re, im, blob, direct_level=1):
+def tsan_run(exe, tmp_path, kernel, n, exact, re, im, blob, option=1):
     state = tmp_path / "state.bin"
     np.concatenate([re, im]).tofile(state)
     (tmp_path / "blob.bin").write_bytes(blob)
-    r = subprocess.run([str(exe), str(n), "1" if exact else "0", str(state), str(tmp_path / "blob.bin"), str(direct_level)], capture_output=True, text=True,
+    r = subprocess.run([str(exe), str(kernel), str(n), "1" if exact else "0", str(state), str(tmp_path / "blob.bin"), str(option)],
+                       capture_output=True, text=True,
                        env={"TSAN_OPTIONS": "halt_on_error=0 exitcode=0"}, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "ThreadSanitizer" not in r.stderr, r.stderr[:4000]
@@ -276,8 +318,9 @@ def tsan_run(exe, tmp_path, n, exact, re, im, blob, direct_level=1):
     return out[: 1 << n].copy(), out[1 << n:].copy(), r.stdout
 
 
+@pytest.mark.parametrize("kernel", [1, 2], ids=["k_tile", "k_tile2"])
 @pytest.mark.parametrize("case", ["qft", "random", "random-exact"])
-def test_no_shared_memory_race_in_any_pass(emu, emu_tsan, tmp_path, case):
+def test_no_shared_memory_race_in_any_pass(emu, emu_tsan, tmp_path, case, kernel):
     n = 13
     if case == "qft":
         qc = QuantumCircuit(QuantumRegister(n)); qc.qft()
@@ -294,11 +337,11 @@ def test_no_shared_memory_race_in_any_pass(emu, emu_tsan, tmp_path, case):
             continue
         info = (C.c_int * 4)()
         r2, i2 = re.copy(), im.copy()
-        level = p % 4  # cycle through the transfer variants as well
-        rc = emu.emu_tile2_run(n, r2.ctypes.data, i2.ctypes.data, blob, len(blob), 1 if qc.exact else 0, level, info)
+        option = p % 4 if kernel == 2 else p % 2  # cycle through the transfer / decode variants as well
+        rc = emu_pass(emu, kernel, n, r2, i2, blob, qc.exact, option, info)
         if rc == 1:
             continue  # not eligible for k_tile2
-        rt, it, out = tsan_run(emu_tsan, tmp_path, n, qc.exact, re, im, blob, level)
+        rt, it, out = tsan_run(emu_tsan, tmp_path, kernel, n, qc.exact, re, im, blob, option)
         assert np.array_equal(rt, r2) and np.array_equal(it, i2)  # same code, same arithmetic, with and without the sanitizer
         seen.add(out.strip())
         re, im = r2, i2  # feed the next pass with this pass's output, as execute would
