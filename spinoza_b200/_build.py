@@ -37,7 +37,7 @@ STAMP = LIBDIR / ".source_hash"
 def _source_hash() -> str:
     import hashlib
     h = hashlib.sha256()
-    deps = sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")))
+    deps = sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.inl")))
     deps.append(PKG.parent / "include" / "spinoza_b200.h")
     for d in deps:
         h.update(d.name.encode())

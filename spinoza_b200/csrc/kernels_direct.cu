@@ -22,17 +22,27 @@ namespace spz {
 constexpr int W = SPZ_W, U = SPZ_U, THREADS = SPZ_THREADS, POL = SPZ_POL;
 constexpr int LOGW = LogW<W>::v;
 
+// Every launch of this file goes through SPZ_LAUNCH so that tests/emu/ can run the dispatch code below -- not a copy of
+// it -- on the CPU (these kernels have no barriers: the emulation simply loops over blocks and threads).
+#ifdef SPZ_CPU_EMULATION
+#define SPZ_LAUNCH(kern, grid, threads, stream, args) spz_emu::run_flat((grid), (threads), [&]() { kern(args); })
+#else
+#define SPZ_LAUNCH(kern, grid, threads, stream, args) kern<<<(grid), (threads), 0, (stream)>>>(args)
+#endif
+
 template <int KIND, int NINS>
 static void launch_vec(const PairArgs &a, cudaStream_t s) {
     const long long per_block = (long long)THREADS * U;
     const unsigned grid = (unsigned)((a.nvec + per_block - 1) / per_block);
-    k_pair_vec<KIND, NINS, W, U, THREADS, POL><<<grid, THREADS, 0, s>>>(a);
+    auto kern = k_pair_vec<KIND, NINS, W, U, THREADS, POL>;
+    SPZ_LAUNCH(kern, grid, THREADS, s, a);
 }
 template <int KIND, int NINS>
 static void launch_low(const PairArgs &a, cudaStream_t s) {
     const long long per_block = (long long)THREADS * U;
     const unsigned grid = (unsigned)((a.nvec + per_block - 1) / per_block);
-    k_pair_low<KIND, NINS, W, U, THREADS, POL><<<grid, THREADS, 0, s>>>(a);
+    auto kern = k_pair_low<KIND, NINS, W, U, THREADS, POL>;
+    SPZ_LAUNCH(kern, grid, THREADS, s, a);
 }
 
 template <int KIND>
@@ -105,7 +115,7 @@ int launch_gate(spz_state *st, const GateK &g, uint64_t ctrl_mask, int target) {
         a.nins = k;
         for (int i = 0; i < 7; ++i) a.s[i] = g.s[i];
         const unsigned grid = (unsigned)std::min<long long>((a.npairs + 255) / 256, 148 * 8);
-        k_pair_scalar<<<grid, 256, 0, st->stream>>>(a);
+        SPZ_LAUNCH(k_pair_scalar, grid, 256, st->stream, a);
     }
     count_launch();
     SPZ_CUDA(cudaGetLastError());
@@ -124,11 +134,12 @@ int launch_swap(spz_state *st, int t0, int t1) {
     if (a.lo >= LOGW && n - 2 - LOGW >= 0) {
         a.nvec = 1ll << (n - 2 - LOGW);
         const unsigned grid = (unsigned)((a.nvec + THREADS - 1) / THREADS);
-        k_swap_vec<W, THREADS><<<grid, THREADS, 0, st->stream>>>(a);
+        auto kern = k_swap_vec<W, THREADS>;
+        SPZ_LAUNCH(kern, grid, THREADS, st->stream, a);
     } else {
         a.nvec = 1ll << (n - 2);
         const unsigned grid = (unsigned)std::min<long long>((a.nvec + 255) / 256, 148 * 16);
-        k_swap_scalar<<<grid, 256, 0, st->stream>>>(a);
+        SPZ_LAUNCH(k_swap_scalar, grid, 256, st->stream, a);
     }
     count_launch();
     SPZ_CUDA(cudaGetLastError());

@@ -46,6 +46,9 @@ struct Vec {
 template <int W, int POL>
 __device__ __forceinline__ Vec<W> ldv(const double *p) {
     Vec<W> r;
+#ifdef SPZ_CPU_EMULATION // tests/emu/: the same kernel bodies compiled with g++; cache policies mean nothing there
+    for (int l = 0; l < W; ++l) r.v[l] = p[l];
+#else
     if constexpr (W == 4) {
         if constexpr (POL == 1)
             asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];"
@@ -65,11 +68,15 @@ __device__ __forceinline__ Vec<W> ldv(const double *p) {
     } else {
         r.v[0] = *p;
     }
+#endif
     return r;
 }
 
 template <int W, int POL>
 __device__ __forceinline__ void stv(double *p, const Vec<W> &r) {
+#ifdef SPZ_CPU_EMULATION
+    for (int l = 0; l < W; ++l) p[l] = r.v[l];
+#else
     if constexpr (W == 4) {
         if constexpr (POL == 1)
             asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};"
@@ -88,6 +95,7 @@ __device__ __forceinline__ void stv(double *p, const Vec<W> &r) {
     } else {
         *p = r.v[0];
     }
+#endif
 }
 
 template <int W> struct LogW;

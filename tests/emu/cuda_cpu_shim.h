@@ -62,6 +62,31 @@ inline void barrier() { pthread_barrier_wait(&block_barrier); }
 static thread_local uint3 threadIdx;
 static thread_local uint3 blockIdx;
 static thread_local uint3 blockDim;
+static thread_local uint3 gridDim;
+
+namespace spz_emu {
+// Kernels without barriers: no OS threads needed, just the two loops of the grid.
+template <class F>
+inline void run_flat(unsigned grid, unsigned threads, F f) {
+    gridDim.x = grid; gridDim.y = 1; gridDim.z = 1;
+    blockDim.x = threads; blockDim.y = 1; blockDim.z = 1;
+    for (unsigned b = 0; b < grid; ++b)
+        for (unsigned t = 0; t < threads; ++t) {
+            blockIdx.x = b; blockIdx.y = 0; blockIdx.z = 0;
+            threadIdx.x = t; threadIdx.y = 0; threadIdx.z = 0;
+            f();
+        }
+}
+} // namespace spz_emu
+
+// cache-policy loads/stores: plain accesses
+static inline double2 __ldcs(const double2 *p) { return *p; }
+static inline double2 __ldcg(const double2 *p) { return *p; }
+static inline void __stcs(double2 *p, double2 v) { *p = v; }
+static inline void __stcg(double2 *p, double2 v) { *p = v; }
+
+// the dispatch code checks for launch errors; there is nothing to fail here
+#define cudaGetLastError() cudaSuccess
 
 static inline void __syncthreads() { spz_emu::barrier(); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
