@@ -54,8 +54,11 @@ struct Tile2Args {
     unsigned tile_offset;
     unsigned prog_off;   // byte offset of the staged program inside dynamic shared memory
     int L, n_high;
-    int first_direct;    // first layout is loaded global -> registers (host decides, see tile2_make_args)
-    int last_direct;     // last layout is stored registers -> global
+    // how the first layout is loaded / the last one stored: 0 = staged through shared memory; direct global <-> registers
+    // with 1 = one amplitude, 2 = two (register bit 0 is tile bit 0), 4 = four (register bits 0,1 are tile bits 0,1) per
+    // access.  The host decides (tile2_make_args).
+    int first_direct;
+    int last_direct;
     unsigned first_rbits; // the first layout's register bits, one byte each (= prog[0].rbit, known before the program is staged)
     unsigned last_rbits;  // the last layout's
     int high[kMaxHigh2];
@@ -67,6 +70,22 @@ __device__ __forceinline__ void cmul2(double &xr, double &xi, double fr, double 
     const double nr = xr * fr - xi * fi;
     const double ni = xr * fi + xi * fr;
     xr = nr; xi = ni;
+}
+
+// 256-bit global access (one full 32-byte sector per lane); plain loads in the CPU emulation build.
+__device__ __forceinline__ void ld4(const double *p, double &x0, double &x1, double &x2, double &x3) {
+#ifdef SPZ_CPU_EMULATION
+    x0 = p[0]; x1 = p[1]; x2 = p[2]; x3 = p[3];
+#else
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x0), "=d"(x1), "=d"(x2), "=d"(x3) : "l"(p));
+#endif
+}
+__device__ __forceinline__ void st4(double *p, double x0, double x1, double x2, double x3) {
+#ifdef SPZ_CPU_EMULATION
+    p[0] = x0; p[1] = x1; p[2] = x2; p[3] = x3;
+#else
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(x0), "d"(x1), "d"(x2), "d"(x3) : "memory");
+#endif
 }
 
 // Butterfly over register bit RPOS.  CTRL: bit k0 of km says whether pair (k0, k0 | 1 << RPOS) is updated.
@@ -170,11 +189,29 @@ __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
         const unsigned long long g0 = base + seg_off[tj >> L] + (tj & seg_mask);
         const unsigned long long o0 = bit_off(rpack & 255u), o1 = bit_off((rpack >> 8) & 255u);
         const unsigned long long o2 = bit_off((rpack >> 16) & 255u), o3 = bit_off(rpack >> 24);
+        if (a.first_direct == 4) { // amplitudes k = 4q .. 4q+3 are consecutive in memory
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const unsigned long long g = g0 + ((k & 1) ? o0 : 0ull) + ((k & 2) ? o1 : 0ull) + ((k & 4) ? o2 : 0ull) + ((k & 8) ? o3 : 0ull);
-            ar[k] = a.re[g];
-            ai[k] = a.im[g];
+            for (int q = 0; q < 4; ++q) {
+                const unsigned long long g = g0 + ((q & 1) ? o2 : 0ull) + ((q & 2) ? o3 : 0ull);
+                ld4(a.re + g, ar[4 * q], ar[4 * q + 1], ar[4 * q + 2], ar[4 * q + 3]);
+                ld4(a.im + g, ai[4 * q], ai[4 * q + 1], ai[4 * q + 2], ai[4 * q + 3]);
+            }
+        } else if (a.first_direct == 2) { // pairs k = 2p, 2p+1
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const unsigned long long g = g0 + ((q & 1) ? o1 : 0ull) + ((q & 2) ? o2 : 0ull) + ((q & 4) ? o3 : 0ull);
+                const double2 r = *reinterpret_cast<const double2 *>(a.re + g);
+                const double2 m = *reinterpret_cast<const double2 *>(a.im + g);
+                ar[2 * q] = r.x; ar[2 * q + 1] = r.y;
+                ai[2 * q] = m.x; ai[2 * q + 1] = m.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const unsigned long long g = g0 + ((k & 1) ? o0 : 0ull) + ((k & 2) ? o1 : 0ull) + ((k & 4) ? o2 : 0ull) + ((k & 8) ? o3 : 0ull);
+                ar[k] = a.re[g];
+                ai[k] = a.im[g];
+            }
         }
     } else {
         // coalesced 128-bit loads, parked in the amplitude registers (pairs 2*it, 2*it+1) until the staging stores below
@@ -398,11 +435,27 @@ __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
         const unsigned long long g0 = base + seg_off[tj >> L] + (tj & seg_mask);
         const unsigned long long o0 = bit_off(rpack & 255u), o1 = bit_off((rpack >> 8) & 255u);
         const unsigned long long o2 = bit_off((rpack >> 16) & 255u), o3 = bit_off(rpack >> 24);
+        if (a.last_direct == 4) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const unsigned long long g = g0 + ((k & 1) ? o0 : 0ull) + ((k & 2) ? o1 : 0ull) + ((k & 4) ? o2 : 0ull) + ((k & 8) ? o3 : 0ull);
-            a.re[g] = ar[k];
-            a.im[g] = ai[k];
+            for (int q = 0; q < 4; ++q) {
+                const unsigned long long g = g0 + ((q & 1) ? o2 : 0ull) + ((q & 2) ? o3 : 0ull);
+                st4(a.re + g, ar[4 * q], ar[4 * q + 1], ar[4 * q + 2], ar[4 * q + 3]);
+                st4(a.im + g, ai[4 * q], ai[4 * q + 1], ai[4 * q + 2], ai[4 * q + 3]);
+            }
+        } else if (a.last_direct == 2) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const unsigned long long g = g0 + ((q & 1) ? o1 : 0ull) + ((q & 2) ? o2 : 0ull) + ((q & 4) ? o3 : 0ull);
+                *reinterpret_cast<double2 *>(a.re + g) = make_double2(ar[2 * q], ar[2 * q + 1]);
+                *reinterpret_cast<double2 *>(a.im + g) = make_double2(ai[2 * q], ai[2 * q + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const unsigned long long g = g0 + ((k & 1) ? o0 : 0ull) + ((k & 2) ? o1 : 0ull) + ((k & 4) ? o2 : 0ull) + ((k & 8) ? o3 : 0ull);
+                a.re[g] = ar[k];
+                a.im[g] = ai[k];
+            }
         }
         return;
     }
@@ -447,14 +500,25 @@ Tile2Args tile2_make_args(double *re, double *im, const TilePlan &plan, const Ti
         if (h_prog[i].op == TI_LAYOUT) last_layout = i;
         if (h_prog[i].op == TI_GATE && (h_prog[i].thr_cmask || h_prog[i].reg_cmask)) *ctrl = true;
     }
-    // When may a layout be transferred global <-> registers directly?  level 1 (default): all register bits >= 4, so 16
-    // consecutive lanes own one 128-byte line.  2: no register bit below 2 (4 lanes own one 32-byte sector).  3: always.
-    // 0: never (always stage through shared memory).  The kernel is correct at every level; only coalescing differs.
-    auto direct_ok = [&](const TileInstr &l) { // rbit is ascending
-        return direct_level >= 3 || (direct_level == 2 && l.rbit[0] >= 2) || (direct_level == 1 && l.rbit[0] >= 4);
+    // How is a layout transferred?  (rbit is ascending.)  The kernel is correct for every choice; only coalescing differs,
+    // which is what SPZ_TILE_V2_DIRECT lets a GPU run explore:
+    //   level 0: always staged through shared memory (as k_tile).
+    //   level 1 (default): direct, one amplitude per access, when all register bits are >= 4 -- 16 consecutive lanes own one
+    //            128-byte line, the best case; staged otherwise.
+    //   level 2: additionally direct with 256-bit accesses when register bits 0,1 are tile bits 0,1 (each lane owns full
+    //            32-byte sectors, lanes 128 bytes or more apart).
+    //   level 3: always direct: 256-bit if possible, else 128-bit when register bit 0 is tile bit 0, else one amplitude.
+    auto mode = [&](const TileInstr &l) -> int {
+        const bool quad = l.rbit[0] == 0 && l.rbit[1] == 1, pair = l.rbit[0] == 0;
+        if (direct_level <= 0) return 0;
+        if (l.rbit[0] >= 4) return 1;
+        if (direct_level == 1) return 0;
+        if (quad) return 4;
+        if (direct_level == 2) return 0;
+        return pair ? 2 : 1;
     };
-    a.first_direct = direct_ok(h_prog[0]) ? 1 : 0;
-    a.last_direct = direct_ok(h_prog[last_layout]) ? 1 : 0;
+    a.first_direct = mode(h_prog[0]);
+    a.last_direct = mode(h_prog[last_layout]);
     auto pack = [](const TileInstr &l) {
         return (unsigned)l.rbit[0] | ((unsigned)l.rbit[1] << 8) | ((unsigned)l.rbit[2] << 16) | ((unsigned)l.rbit[3] << 24);
     };

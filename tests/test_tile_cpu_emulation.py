@@ -197,6 +197,36 @@ def test_every_direct_transfer_level_is_correct(emu, level):
         assert all(k[1:] == ("ld-direct", "st-direct") for k in tiles), stats
 
 
+def test_vector_direct_transfers(emu):
+    """Level 3 picks 256-bit accesses when register bits 0,1 are tile bits 0,1, 128-bit when only bit 0 is, one amplitude
+    otherwise; build one pass of each shape at both ends and check the modes were really taken."""
+    n = 13
+    modes = set()
+    for first, last in (((0, 1, 2, 3), (0, 1, 6, 7)), ((0, 2, 4, 6), (0, 3, 5, 9)), ((2, 3, 4, 5), (1, 2, 10, 11)), ((0, 1, 10, 11), (5, 6, 7, 8))):
+        qc = QuantumCircuit(QuantumRegister(n))
+        for t in first:
+            qc.h(t)
+        qc.cp(0.3, first[0], 12)
+        for t in last:
+            if t in first:
+                qc.h(8)       # force a layout change: 8 is in neither cluster's first half
+            qc.ry(0.2 + 0.1 * t, t)
+        psi0, re, im = start(n, sum(first) + 7 * sum(last))
+        plan, n_pass = qc.plan()
+        for p in range(n_pass):
+            blob = raw_pass(qc, p)
+            if int(np.frombuffer(blob, dtype="<i4", count=1)[0]) != 0:
+                trs = list(qc.transformations)
+                psi = run_dense_order(n, re + 1j * im, trs, [i for i, pp in plan if pp == p])
+                re[:], im[:] = psi.real, psi.imag
+                continue
+            info = (C.c_int * 4)()
+            assert emu_pass(emu, 2, n, re, im, blob, False, 3, info) == 0
+            modes.add(info[1]); modes.add(info[2])
+        np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
+    assert {1, 2, 4} <= modes, modes
+
+
 @pytest.mark.parametrize("kernel", [1, 2], ids=["k_tile", "k_tile2"])
 @pytest.mark.parametrize("n,count,seed", [(13, 60, 41), (14, 80, 42)])
 def test_exact_mode_is_bit_identical_to_the_oracle(emu, n, count, seed, kernel):

@@ -22,7 +22,7 @@ from spinoza_b200 import QuantumCircuit, workloads
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 VARIANTS = [("k_tile", {"SPZ_TILE_V2": "0"})] + [
-    (f"k_tile2/direct{lv}", {"SPZ_TILE_V2": "1", "SPZ_TILE_V2_DIRECT": str(lv)}) for lv in (1, 0, 2, 3)]
+    (f"k_tile2/direct{lv}", {"SPZ_TILE_V2": "1", "SPZ_TILE_V2_DIRECT": str(lv)}) for lv in (1, 0, 2, 3)]  # 1 = default policy; see tile2_make_args for the levels
 
 
 def set_env(env):
