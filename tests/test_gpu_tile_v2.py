@@ -26,26 +26,32 @@ pytestmark = [pytest.mark.gpu,
 
 
 class tile_v2:
-    def __init__(self, on):
-        self.on = on
+    """Environment for one execute(): the library reads SPZ_TILE_V2 / SPZ_TILE_V2_DIRECT at every launch."""
+
+    def __init__(self, on, direct=None):
+        self.new = {"SPZ_TILE_V2": "1" if on else "0"}
+        if direct is not None:
+            self.new["SPZ_TILE_V2_DIRECT"] = str(direct)
 
     def __enter__(self):
-        self.old = os.environ.get("SPZ_TILE_V2")
-        os.environ["SPZ_TILE_V2"] = "1" if self.on else "0"
+        self.old = {k: os.environ.get(k) for k in ("SPZ_TILE_V2", "SPZ_TILE_V2_DIRECT")}
+        os.environ.pop("SPZ_TILE_V2_DIRECT", None)
+        os.environ.update(self.new)
 
     def __exit__(self, *exc):
-        if self.old is None:
-            os.environ.pop("SPZ_TILE_V2", None)
-        else:
-            os.environ["SPZ_TILE_V2"] = self.old
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
-def run(init, build, v2, **kw):
+def run(init, build, v2, direct=None, **kw):
     st = to_gpu(init)
     qc = QuantumCircuit.from_state(st, **kw)
     build(qc)
     ops = oracle_ops_from(qc)
-    with tile_v2(v2):
+    with tile_v2(v2, direct):
         qc.execute()
         st.sync()
     return st.download(), ops
@@ -105,6 +111,17 @@ def test_merged_mode_within_tolerance_of_the_oracle(n, name):
     orc.execute(cpu, ops)
     for r, i in ((r1, i1), (r2, i2)):
         assert np.max(np.abs(r - cpu.reals)) <= 1e-12 and np.max(np.abs(i - cpu.imags)) <= 1e-12
+
+
+@pytest.mark.parametrize("level", [0, 2, 3])
+@pytest.mark.parametrize("name", ["qft", "layered", "low_high", "high_low"])
+def test_every_transfer_level_is_bit_identical_in_exact_mode(name, level):
+    n = 18
+    init = orc.gen_random_state(n, 300 + level)
+    build = builders(n)[name]
+    (r1, i1), _ = run(init, build, False, fuse=True, exact=True)
+    (r2, i2), _ = run(init, build, True, direct=level, fuse=True, exact=True)
+    assert np.array_equal(r1, r2) and np.array_equal(i1, i2)
 
 
 def test_v2_is_actually_selected_and_counts_one_launch_per_pass():
