@@ -19,7 +19,7 @@ import oracle as orc
 import spinoza_b200 as sb
 from spinoza_b200 import QuantumCircuit, workloads
 from tests.test_gpu_parity import oracle_ops_from, to_gpu
-from tests.test_scheduler_plan import random_circuit
+from tests.test_tile_cpu_emulation import reference_cells_circuit
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("SPZ_TEST_TILE_V2") != "1", reason="opt-in: SPZ_TEST_TILE_V2=1")]
@@ -65,7 +65,7 @@ def builders(n):
         workloads.random_layered_circuit(qc, depth=8, seed=7)
 
     def rand(qc):
-        src = random_circuit(n, 300, 21)
+        src = reference_cells_circuit(n, 300, 21)  # only gate x control cells the oracle (= the reference) supports
         for t in src.transformations:
             qc.add(t)
 
