@@ -1,24 +1,30 @@
 // kernels_tile2.cu -- second generation of the fused tile kernel (see kernels_tile.cu for the execution model).
 //
 // STATUS: opt-in (environment SPZ_TILE_V2=1).  Written at the end of round 1 from the ncu / SASS analysis of k_tile
-// (profiles/round1_summary.md section 3 and 10) when no GPU time was left: it compiles for sm_100a and its instruction
-// semantics are covered by the NumPy interpreter in tests/test_tile_program.py, but it has NOT run on a B200 yet, so the
-// default path stays k_tile until tests/test_gpu_tile_v2.py has been green on hardware.
+// (profiles/round1_summary.md sections 3 and 10) when no GPU time was left.  It compiles for sm_100a without spills, and its
+// body runs correctly -- bit-identical to the oracle in exact mode, race-free under ThreadSanitizer -- on the CPU emulation
+// of tests/emu/ (tests/test_tile_cpu_emulation.py); it has NOT run on a B200 yet, so the default stays k_tile until
+// tools/round2_first_call.sh (tests/test_gpu_tile_v2.py + A/B timing) has been run on hardware.
 //
 // Same micro-program (TileInstr / TileGroup / TileTerm, engine.h), same results as k_tile up to the documented merged
-// rounding.  What changes is the instruction count per tile (k_tile: ~5 200 warp instructions per warp for a 27-gate
-// QFT pass, ~7 900 for the 276-gate one, against ~1 000 of irreducible work):
+// rounding.  What changes is the instruction count per tile (k_tile: ~5 200 warp instructions per warp for a 27-gate QFT
+// pass, ~7 900 for the 276-gate one, against ~1 000 of irreducible work):
 //   1. Lazy phase flush.  A butterfly on register bit r only needs accumulator F_{r+1} applied first: F0 and the other
 //      F_i multiply both members of every pair (k, k | 1 << r) by the same factor, which commutes with any (controlled)
 //      2x2 gate on the pair.  k_tile expands all five accumulators before every butterfly (up to 31 complex multiplies);
 //      here a butterfly costs at most 8, and the full expansion happens once per register layout.
-//   2. Direct global <-> register transfers.  When the first (last) register layout has all four register bits >= 4,
-//      consecutive lanes own consecutive amplitudes, so the tile is loaded (stored) straight into (from) the registers
-//      with fully used 128-byte lines: no staging store, no barrier, no swizzled re-read.
-//   3. The program is always decoded from shared memory (typed LDS instead of generic loads); longer programs fall back
-//      to k_tile.
-//   4. CTRL = false instantiation for passes whose butterflies have no in-tile controls (every QFT pass): straight-line
-//      butterflies without per-pair predicates and convergence barriers.
+//   2. Direct global <-> register transfers.  When the first (last) register layout keeps consecutive lanes on consecutive
+//      amplitudes (all register bits >= 4), the tile is loaded (stored) straight into (from) the registers: no staging
+//      store, no barrier, no swizzled re-read.  Layouts holding tile bits 0,1 can use 256/128-bit accesses instead
+//      (SPZ_TILE_V2_DIRECT, see tile2_make_args).
+//   3. The tile's loads are issued first; staging the program and reducing the phase groups run under the HBM latency.
+//   4. The program is always decoded from shared memory (typed LDS instead of generic loads; longer programs fall back to
+//      k_tile), and per-instruction flags computed once per tile replace the 64-bit tile base in the interpreter loop.
+//   5. CTRL = false instantiation for passes whose butterflies have no in-tile controls (every QFT pass): the pair mask is
+//      then the same for every thread, the per-pair guards compile to uniform branches (no convergence barriers) and the
+//      pair updates stay in place.
+//   6. One barrier per layout change and none after a register load: a thread's next shared-memory access after
+//      load_regs() is store_regs() under the same layout, i.e. to the cells it has just read.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
