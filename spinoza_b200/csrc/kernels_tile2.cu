@@ -47,7 +47,10 @@ namespace {
 constexpr int kT2 = 12;          // full tiles only (registers of >= 12 qubits)
 constexpr int kThreads2 = 256;   // 2^(kT2 - 4)
 constexpr int kMaxHigh2 = 8;
-constexpr int kMaxInstr2 = 96;   // 15 KB of shared memory
+constexpr int kMaxInstr2 = 256;  // one flag per instruction is computed by thread pc; the real limit is kSmemBudget2
+// Two CTAs per SM (228 KB of shared memory, 1 KB reserved per CTA, ~2.3 KB static here): a pass whose tile + group table +
+// program need more than this falls back to k_tile.
+constexpr size_t kSmemBudget2 = 110 * 1024;
 
 struct Tile2Args {
     double *re;
@@ -479,8 +482,11 @@ __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
     }
 }
 
-size_t tile2_max_smem() {
-    return sizeof(double) * 2u * ((size_t)1 << kT2) + kMaxTileGroups * (sizeof(double2) + sizeof(unsigned)) + 16 + kMaxInstr2 * sizeof(TileInstr);
+size_t tile2_smem_bytes(int n_instr, int n_groups, unsigned *prog_off) {
+    size_t smem = sizeof(double) * 2u * ((size_t)1 << kT2) + (size_t)n_groups * (sizeof(double2) + sizeof(unsigned));
+    smem = (smem + 15) & ~(size_t)15;
+    if (prog_off) *prog_off = (unsigned)smem;
+    return smem + sizeof(TileInstr) * (size_t)n_instr;
 }
 
 // Kernel arguments, dynamic shared-memory size and instantiation for tiles [first, ...) of one pass.  Pure host code,
@@ -495,11 +501,7 @@ Tile2Args tile2_make_args(double *re, double *im, const TilePlan &plan, const Ti
     a.tile_offset = first;
     a.L = plan.low_bits; a.n_high = plan.n_high;
     for (int k = 0; k < plan.n_high; ++k) a.high[k] = plan.high[k];
-    size_t smem = sizeof(double) * 2u * ((size_t)1 << kT2) + (size_t)n_groups * (sizeof(double2) + sizeof(unsigned));
-    smem = (smem + 15) & ~(size_t)15;
-    a.prog_off = (unsigned)smem;
-    smem += sizeof(TileInstr) * (size_t)n_instr;
-    *smem_bytes = smem;
+    *smem_bytes = tile2_smem_bytes(n_instr, n_groups, &a.prog_off);
     *ctrl = false;
     int last_layout = 0;
     for (int i = 0; i < n_instr; ++i) {
@@ -536,6 +538,7 @@ Tile2Args tile2_make_args(double *re, double *im, const TilePlan &plan, const Ti
 bool tile2_shape_ok(int n_qubits, const TilePlan &plan, const TileInstr *prog, int n_instr, int n_groups) {
     if (plan.tile_bits != kT2 || plan.n_high > kMaxHigh2 || plan.low_bits < 4 || n_qubits < kT2) return false;
     if (n_instr < 1 || n_instr > kMaxInstr2 || n_groups > kMaxTileGroups) return false;
+    if (tile2_smem_bytes(n_instr, n_groups, nullptr) > kSmemBudget2) return false;
     return prog[0].op == TI_LAYOUT;
 }
 
@@ -549,7 +552,7 @@ bool tile2_enabled() {
 }
 
 static int tile2_prepare() {
-    const int max_smem = (int)tile2_max_smem();
+    const int max_smem = (int)kSmemBudget2;
     SPZ_CUDA(cudaFuncSetAttribute(k_tile2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     SPZ_CUDA(cudaFuncSetAttribute(k_tile2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     SPZ_CUDA(cudaFuncSetAttribute(k_tile2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
