@@ -147,7 +147,12 @@ struct Fuser {
 
     Fuser(spz_state *s) : st(s) {
         T = std::min(max_tile_bits(), s->n);
-        Lmin = std::min(6, T);
+        // 2^Lmin contiguous amplitudes per tile segment: 6 (512 bytes per array) keeps every access a run of full 128-byte
+        // lines.  SPZ_TILE_LMIN=4|5 trades segment length for up to 8 (7) arbitrary high qubits per pass instead of 6 --
+        // an experiment knob: the kernels are correct for any L >= 4, only coalescing changes.
+        int lmin = 6;
+        if (const char *e = std::getenv("SPZ_TILE_LMIN")) if (e[0] >= '4' && e[0] <= '6' && !e[1]) lmin = e[0] - '0';
+        Lmin = std::min(lmin, T);
     }
     int n_high() const { return __builtin_popcountll(high_set); }
 

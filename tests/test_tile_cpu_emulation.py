@@ -197,6 +197,29 @@ def test_every_direct_transfer_level_is_correct(emu, level):
         assert all(k[1:] == ("ld-direct", "st-direct") for k in tiles), stats
 
 
+@pytest.mark.parametrize("kernel", [1, 2], ids=["k_tile", "k_tile2"])
+@pytest.mark.parametrize("lmin", ["4", "5"])
+def test_shorter_tile_segments(emu, monkeypatch, lmin, kernel):
+    """SPZ_TILE_LMIN = 4 / 5: up to 8 / 7 arbitrary high qubits per pass, segments of 16 / 32 amplitudes."""
+    monkeypatch.setenv("SPZ_TILE_LMIN", lmin)
+    n = 15
+    qc = QuantumCircuit(QuantumRegister(n))
+    workloads.random_layered_circuit(qc, depth=6, seed=11)
+    for t in range(n - 1, 6, -1):   # a run of high targets so that one pass really takes more than 6 high qubits
+        qc.h(t)
+    widest = 0
+    _, n_pass = qc.plan()
+    for p in range(n_pass):
+        c = compile_pass(qc, p)
+        if c[0] == "tile":
+            assert c[1]["L"] >= int(lmin)
+            widest = max(widest, len(c[1]["high"]))
+    assert widest == 12 - int(lmin)
+    psi0, re, im = start(n, 21)
+    run_emulated(emu, qc, re, im, {}, kernel=kernel)
+    np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
+
+
 def test_vector_direct_transfers(emu):
     """Level 3 picks 256-bit accesses when register bits 0,1 are tile bits 0,1, 128-bit when only bit 0 is, one amplitude
     otherwise; build one pass of each shape at both ends and check the modes were really taken."""
