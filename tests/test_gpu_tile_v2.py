@@ -28,14 +28,17 @@ pytestmark = [pytest.mark.gpu,
 class tile_v2:
     """Environment for one execute(): the library reads SPZ_TILE_V2 / SPZ_TILE_V2_DIRECT at every launch."""
 
-    def __init__(self, on, direct=None):
+    def __init__(self, on, direct=None, lmin=None):
         self.new = {"SPZ_TILE_V2": "1" if on else "0"}
         if direct is not None:
             self.new["SPZ_TILE_V2_DIRECT"] = str(direct)
+        if lmin is not None:
+            self.new["SPZ_TILE_LMIN"] = str(lmin)
 
     def __enter__(self):
-        self.old = {k: os.environ.get(k) for k in ("SPZ_TILE_V2", "SPZ_TILE_V2_DIRECT")}
+        self.old = {k: os.environ.get(k) for k in ("SPZ_TILE_V2", "SPZ_TILE_V2_DIRECT", "SPZ_TILE_LMIN")}
         os.environ.pop("SPZ_TILE_V2_DIRECT", None)
+        os.environ.pop("SPZ_TILE_LMIN", None)
         os.environ.update(self.new)
 
     def __exit__(self, *exc):
@@ -46,12 +49,12 @@ class tile_v2:
                 os.environ[k] = v
 
 
-def run(init, build, v2, direct=None, **kw):
+def run(init, build, v2, direct=None, lmin=None, **kw):
     st = to_gpu(init)
     qc = QuantumCircuit.from_state(st, **kw)
     build(qc)
     ops = oracle_ops_from(qc)
-    with tile_v2(v2, direct):
+    with tile_v2(v2, direct, lmin):
         qc.execute()
         st.sync()
     return st.download(), ops
@@ -121,6 +124,19 @@ def test_every_transfer_level_is_bit_identical_in_exact_mode(name, level):
     build = builders(n)[name]
     (r1, i1), _ = run(init, build, False, fuse=True, exact=True)
     (r2, i2), _ = run(init, build, True, direct=level, fuse=True, exact=True)
+    assert np.array_equal(r1, r2) and np.array_equal(i1, i2)
+
+
+@pytest.mark.parametrize("v2", [False, True], ids=["k_tile", "k_tile2"])
+@pytest.mark.parametrize("lmin", [4, 5])
+@pytest.mark.parametrize("name", ["qft", "layered"])
+def test_shorter_tile_segments_are_bit_identical_in_exact_mode(name, lmin, v2):
+    """SPZ_TILE_LMIN: passes with 7 / 8 arbitrary high qubits (never run on hardware in round 1, where the maximum was 6)."""
+    n = 20
+    init = orc.gen_random_state(n, 400 + lmin)
+    build = builders(n)[name]
+    (r1, i1), _ = run(init, build, False, fuse=True, exact=True)
+    (r2, i2), _ = run(init, build, v2, lmin=lmin, fuse=True, exact=True)
     assert np.array_equal(r1, r2) and np.array_equal(i1, i2)
 
 
