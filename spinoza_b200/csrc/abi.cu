@@ -156,10 +156,14 @@ struct Fuser {
     }
     int n_high() const { return __builtin_popcountll(high_set); }
 
+    // schedule_dag() chooses the pass's tile qubits before filling it: high_set is then final and must not grow
+    bool tile_fixed = false;
+
     bool try_add_target(int q, uint64_t &hs, int &ln) const {
         const int Lcur = T - __builtin_popcountll(hs);
         if (q < Lcur) { ln = std::max(ln, q + 1); return true; }
         if ((hs >> q) & 1ull) return true;
+        if (tile_fixed) return false;
         const int Lnew = Lcur - 1;
         if (Lnew < std::max(ln, Lmin) || __builtin_popcountll(hs) + 1 > 8) return false;
         hs |= 1ull << q;
@@ -169,7 +173,13 @@ struct Fuser {
     bool fits(const ROp &op, uint64_t &hs, int &ln) const {
         hs = high_set; ln = low_need;
         // low_need records every target accepted as a low tile bit, so L can never shrink below it
-        if (op.kind == SPZ_GATE_SWAP) return try_add_target(op.target, hs, ln) && try_add_target(op.t2, hs, ln);
+        if (op.kind == SPZ_GATE_SWAP) {
+            // Either operand may have to become a high tile bit, and taking the larger one first can make room that the
+            // other order does not (SWAP(11, 13) in an empty 12-bit tile: 11 is low only while there is no high bit).
+            if (try_add_target(op.target, hs, ln) && try_add_target(op.t2, hs, ln)) return true;
+            hs = high_set; ln = low_need;
+            return try_add_target(op.t2, hs, ln) && try_add_target(op.target, hs, ln);
+        }
         if (is_diagonal_kind(op.kind)) return true; // includes const_hi ops
         return try_add_target(op.target, hs, ln);
     }
@@ -428,7 +438,87 @@ struct Fuser {
         }
         std::vector<char> done(N, 0);
         int remaining = N;
+        // ---- choice of the tile for one pass ----
+        // For a candidate tile (low qubits 0..L-1 plus a high set) one forward scan over the window counts the ops that
+        // could run in it: an op runs if its non-diagonal targets are tile qubits and all its predecessors run (or have
+        // run).  The tile is grown greedily for every admissible L -- add the high qubit with the largest gain -- and the
+        // best (L, high set) wins; ties go to the longer contiguous segment.  Without this the first ready ops in program
+        // order fix the tile, which on layered circuits strands most passes with a dozen gates.
+        const int n_local = 63 - __builtin_clzll((unsigned long long)st->len); // qubits held by this handle (a shard holds fewer than st->n)
+        std::vector<std::vector<int>> pred(N);
+        for (int j = 0; j < N; ++j) for (int i : succ[j]) pred[i].push_back(j);
+        std::vector<uint64_t> xm(N, 0);
+        for (int i = 0; i < N; ++i) {
+            const ROp &op = pending[i];
+            if (op.kind == SPZ_GATE_SWAP) xm[i] = (1ull << op.target) | (1ull << op.t2);
+            else if (!is_diagonal_kind(op.kind)) xm[i] = 1ull << op.target;
+        }
+        std::vector<char> runs(N, 0);
+        int first_undone = 0;
+        // Choosing costs ~0.1-0.2 ms of host time per pass (hidden behind the previous pass's kernel on large registers, but
+        // more than a whole pass on small ones), so by default it is used from 24 local qubits up.  SPZ_TILE_SELECT=0|1
+        // forces it off / on.
+        bool select_tiles = n_local >= 24;
+        if (const char *e = std::getenv("SPZ_TILE_SELECT")) select_tiles = e[0] != '0';
+        const int kScan = 512; // evaluation horizon in ops (the rest of the window waits for a later pass)
+        const int lstep = 3;   // candidate segment lengths: L = T, T-3, ... and Lmin
+        auto count_tile = [&](uint64_t tile) -> int {
+            int c = 0;
+            const int end = std::min(N, first_undone + kScan);
+            for (int i = first_undone; i < end; ++i) {
+                runs[i] = 0;
+                if (done[i]) continue;
+                if (xm[i] & ~tile) continue;
+                bool ok = true;
+                for (int p : pred[i]) if (!done[p] && !(p >= first_undone && runs[p])) { ok = false; break; }
+                if (!ok) continue;
+                runs[i] = 1;
+                ++c;
+            }
+            return c;
+        };
+        auto choose_tile = [&](uint64_t &best_high) -> int {
+            while (first_undone < N && done[first_undone]) ++first_undone;
+            uint64_t cand = 0; // qubits some undone non-diagonal op within the horizon targets
+            const int end = std::min(N, first_undone + kScan);
+            for (int i = first_undone; i < end; ++i) if (!done[i]) cand |= xm[i];
+            int best_count = -1, best_L = T;
+            best_high = 0;
+            for (int L = T; L >= Lmin; L -= (L - lstep >= Lmin || L == Lmin ? lstep : L - Lmin)) {
+                const uint64_t low = L >= 64 ? ~0ull : ((1ull << L) - 1ull);
+                uint64_t high = 0;
+                int cur = count_tile(low);
+                for (int h = 0; h < T - L; ++h) {
+                    int gain_best = -1, q_best = -1;
+                    for (int q = L; q < n_local; ++q) {
+                        if (!((cand >> q) & 1ull) || ((high >> q) & 1ull)) continue;
+                        const int c = count_tile(low | high | (1ull << q));
+                        if (c > gain_best) { gain_best = c; q_best = q; }
+                    }
+                    if (q_best < 0) { // no useful qubit left: pad (the kernel derives L from the number of high qubits)
+                        for (int q = n_local - 1; q >= L; --q) if (!((high >> q) & 1ull)) { q_best = q; break; }
+                        if (q_best < 0) break;
+                        gain_best = cur;
+                    }
+                    high |= 1ull << q_best;
+                    cur = gain_best;
+                }
+                if (__builtin_popcountll(high) != T - L) continue;
+                if (cur > best_count) { best_count = cur; best_L = L; best_high = high; }
+            }
+            (void)best_L;
+            return best_count;
+        };
         while (remaining > 0) {
+            {
+                // One-qubit growth cannot see an op that needs two new high qubits at once (a SWAP between them); if no
+                // tile admits any op, fall back to letting the first ready ops claim their qubits, which always progresses.
+                uint64_t h = 0;
+                const bool chosen = select_tiles && choose_tile(h) > 0;
+                high_set = chosen ? h : 0;
+                low_need = 0;
+                tile_fixed = chosen;
+            }
             // Fill one group.  Ready ops are taken in ascending scans (successors always have larger indices, and
             // tile capacity only shrinks).  Non-diagonal targets are taken in CLUSTERS of at most 4 distinct qubits
             // -- the register layout of the tile kernel -- so that the compiled program changes layout once per
@@ -461,7 +551,9 @@ struct Fuser {
                 cluster = 0;
                 fresh_cluster = true;
             }
-            if (ops.empty()) { set_error("internal: scheduler made no progress"); return SPZ_ERR_INVALID_ARG; }
+            tile_fixed = false;
+            if (ops.empty()) {
+                set_error("internal: scheduler made no progress"); return SPZ_ERR_INVALID_ARG; }
             SPZ_TRY(emit_group());
         }
         return SPZ_OK;

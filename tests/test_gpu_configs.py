@@ -39,6 +39,30 @@ def test_config3_random_layered_circuit(n):
     assert abs(sb.norm2(fused) - 1.0) < 1e-10
 
 
+@pytest.mark.parametrize("n", [16, 20, 22])
+def test_config3_with_chosen_tiles(n, monkeypatch):
+    """From 24 qubits up the scheduler chooses each pass's tile qubits by how many ops they admit (abi.cu: choose_tile); force
+    that mode at sizes the oracle can check.  Merged mode within 1e-12 of the oracle, and the plan must really be shorter."""
+    init = orc.gen_random_state(n, 44)
+    passes = {}
+    for select in ("0", "1"):
+        monkeypatch.setenv("SPZ_TILE_SELECT", select)
+        gpu = to_gpu(init)
+        qc = QuantumCircuit.from_state(gpu, fuse=True)
+        workloads.random_layered_circuit(qc, depth=20, seed=42)
+        ops = oracle_ops_from(qc)
+        passes[select] = qc.plan()[1]
+        before = sb.launch_count()
+        qc.execute()
+        gpu.sync()
+        assert sb.launch_count() - before == passes[select]
+        cpu = init.clone()
+        orc.execute(cpu, ops)
+        re, im = gpu.download()
+        assert np.max(np.abs(re - cpu.reals)) <= 1e-12 and np.max(np.abs(im - cpu.imags)) <= 1e-12
+    assert passes["1"] <= passes["0"]
+
+
 @pytest.mark.parametrize("n,world", [(14, 2), (16, 4)])
 def test_config3_two_shards_equal_one_shard(n, world):
     init = orc.gen_random_state(n, 43)

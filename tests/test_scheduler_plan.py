@@ -66,8 +66,11 @@ def check_pass_capacity(trs, plan):
         assert ok, f"pass {p}: non-diagonal targets {sorted(targets)} do not fit a 12-bit tile with >= {L_MIN} low bits"
 
 
+@pytest.mark.parametrize("select", ["0", "1"], ids=["first-come-tile", "chosen-tile"])
 @pytest.mark.parametrize("n,count,seed", [(13, 120, 1), (14, 200, 2), (15, 200, 3), (16, 150, 4), (14, 300, 5)])
-def test_plan_is_a_valid_semantics_preserving_reordering(n, count, seed):
+def test_plan_is_a_valid_semantics_preserving_reordering(n, count, seed, select, monkeypatch):
+    # tile selection (abi.cu: choose_tile) is on by default only from 24 qubits up; force both variants at test sizes
+    monkeypatch.setenv("SPZ_TILE_SELECT", select)
     qc = random_circuit(n, count, seed)
     trs = list(qc.transformations)
     plan, n_pass = qc.plan()
@@ -147,3 +150,34 @@ def test_sequences_on_one_qubit_stay_in_order():
     for q in range(n):
         assert pos[3 * q] < pos[3 * q + 1] < pos[3 * q + 2]
     assert n_pass == 2
+
+
+@pytest.mark.parametrize("a,b", [(11, 13), (13, 11), (11, 12), (10, 13), (5, 13), (12, 13)])
+def test_swap_between_a_boundary_qubit_and_a_high_qubit_fits_an_empty_tile(a, b):
+    """Regression: SWAP(11, b >= 12) was rejected by an empty 12-bit tile when its operands were tried in the given order
+    (qubit 11 is a low tile bit only while the tile has no high bit)."""
+    n = 14
+    for extra in (0, 1, 4):           # alone (in-order path), and inside a window that takes the DAG path
+        qc = QuantumCircuit(QuantumRegister(n))
+        qc.swap(a, b)
+        for k in range(extra):
+            qc.h(k)
+            qc.swap(a, b)
+        trs = list(qc.transformations)
+        plan, n_pass = qc.plan()
+        assert sorted(i for i, _ in plan) == list(range(len(trs))) and n_pass >= 1
+        psi = D.random_state(n, a * 16 + b)
+        got = run_dense_order(n, psi.copy(), trs, [i for i, _ in plan])
+        want = run_dense_order(n, psi.copy(), trs, range(len(trs)))
+        assert np.max(np.abs(got - want)) < 1e-12
+
+
+def test_tile_selection_keeps_layered_circuits_in_few_passes():
+    """The scheduler picks each pass's tile qubits by how many ops they admit (abi.cu: choose_tile).  BASELINE config 3 at 30
+    qubits (890 gates): 88 passes with the order-preserving greedy, 30 when the first ready ops claimed the tile, 17 now."""
+    qc = QuantumCircuit(QuantumRegister(30))
+    workloads.random_layered_circuit(qc, depth=20, seed=42)
+    plan, n_pass = qc.plan()
+    assert len(plan) == len(qc.transformations) == 890
+    assert n_pass <= 20
+    check_pass_capacity(list(qc.transformations), plan)

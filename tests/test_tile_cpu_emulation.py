@@ -147,9 +147,11 @@ def test_qft_merged_mode_uses_every_transfer_path(emu):
     assert stats.get(("noctrl", "ld-direct", "st-staged"), 0) >= 1, stats
 
 
+@pytest.mark.parametrize("select", ["0", "1"], ids=["first-come-tile", "chosen-tile"])
 @pytest.mark.parametrize("kernel", [1, 2], ids=["k_tile", "k_tile2"])
 @pytest.mark.parametrize("n,count,seed", [(13, 160, 31), (14, 220, 32), (15, 120, 33)])
-def test_random_circuits_merged_mode(emu, n, count, seed, kernel):
+def test_random_circuits_merged_mode(emu, n, count, seed, kernel, select, monkeypatch):
+    monkeypatch.setenv("SPZ_TILE_SELECT", select)  # both ways of choosing a pass's tile qubits (default: chosen from 24 qubits up)
     qc = random_circuit(n, count, seed)
     psi0, re, im = start(n, seed)
     stats = {}

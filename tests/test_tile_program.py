@@ -246,10 +246,12 @@ def run_plan(qc, psi, lazy=False):
     return psi, n_tile
 
 
+@pytest.mark.parametrize("select", ["0", "1"], ids=["first-come-tile", "chosen-tile"])
 @pytest.mark.parametrize("lazy", [False, True], ids=["k_tile", "k_tile2-lazy-flush"])
 @pytest.mark.parametrize("exact", [False, True])
 @pytest.mark.parametrize("n,count,seed", [(13, 150, 11), (14, 200, 12), (15, 250, 13), (16, 120, 14)])
-def test_compiled_passes_equal_the_dense_statement(n, count, seed, exact, lazy):
+def test_compiled_passes_equal_the_dense_statement(n, count, seed, exact, lazy, select, monkeypatch):
+    monkeypatch.setenv("SPZ_TILE_SELECT", select)
     qc = random_circuit(n, count, seed, exact=exact)
     trs = list(qc.transformations)
     psi0 = D.random_state(n, seed)

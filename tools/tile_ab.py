@@ -21,7 +21,9 @@ from spinoza_b200 import QuantumCircuit, workloads
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-VARIANTS = [("k_tile", {"SPZ_TILE_V2": "0"})] + [
+VARIANTS = [("k_tile", {"SPZ_TILE_V2": "0"}),
+            # the round-1 scheduler (first ready ops claim the tile): the 0.82-0.92 s / 30 passes of profiles section 6
+            ("k_tile/first-come-tile", {"SPZ_TILE_V2": "0", "SPZ_TILE_SELECT": "0"})] + [
     (f"k_tile2/direct{lv}", {"SPZ_TILE_V2": "1", "SPZ_TILE_V2_DIRECT": str(lv)}) for lv in (1, 0, 2, 3)] + [  # 1 = default policy
     # shorter tile segments: more arbitrary high qubits per pass (config 3: 30 passes -> 21 at L >= 4), worse coalescing
     ("k_tile/lmin4", {"SPZ_TILE_V2": "0", "SPZ_TILE_LMIN": "4"}), ("k_tile/lmin5", {"SPZ_TILE_V2": "0", "SPZ_TILE_LMIN": "5"}),
@@ -29,7 +31,7 @@ VARIANTS = [("k_tile", {"SPZ_TILE_V2": "0"})] + [
 
 
 def set_env(env):
-    for k in ("SPZ_TILE_V2", "SPZ_TILE_V2_DIRECT", "SPZ_TILE_LMIN"):
+    for k in ("SPZ_TILE_V2", "SPZ_TILE_V2_DIRECT", "SPZ_TILE_LMIN", "SPZ_TILE_SELECT"):
         os.environ.pop(k, None)
     os.environ.update(env)
 
