@@ -482,7 +482,7 @@ struct Fuser {
             uint64_t cand = 0; // qubits some undone non-diagonal op within the horizon targets
             const int end = std::min(N, first_undone + kScan);
             for (int i = first_undone; i < end; ++i) if (!done[i]) cand |= xm[i];
-            int best_count = -1, best_L = T;
+            int best_count = -1;
             best_high = 0;
             for (int L = T; L >= Lmin; L -= (L - lstep >= Lmin || L == Lmin ? lstep : L - Lmin)) {
                 const uint64_t low = L >= 64 ? ~0ull : ((1ull << L) - 1ull);
@@ -504,9 +504,8 @@ struct Fuser {
                     cur = gain_best;
                 }
                 if (__builtin_popcountll(high) != T - L) continue;
-                if (cur > best_count) { best_count = cur; best_L = L; best_high = high; }
+                if (cur > best_count) { best_count = cur; best_high = high; } // strict: ties keep the longer segment
             }
-            (void)best_L;
             return best_count;
         };
         while (remaining > 0) {
