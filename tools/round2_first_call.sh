@@ -2,7 +2,8 @@
 # First GPU call of round 2: validate and measure the opt-in tile kernel k_tile2 (csrc/kernels_tile2.cu), which was written
 # and checked on the CPU emulation only (tests/test_tile_cpu_emulation.py) after round 1's GPU budget was spent.
 #
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'            # ~15 min
+#   /usr/local/graft/bin/gpurun --timeout 3000 -- 'bash tools/round2_first_call.sh --full-suite' # + the whole GPU suite under k_tile2
 #
 # Outputs (all under gpurun_out/):
 #   v2_tests.log            parity of k_tile2 against k_tile and the oracle (tests/test_gpu_tile_v2.py)
@@ -26,6 +27,11 @@ try:
 except Exception as e:
     print("no A/B result:", e)
 PY
+if [ "${1:-}" = "--full-suite" ]; then
+  # the whole GPU suite with k_tile2 as the fused kernel (tests/conftest.py pins the tuning switches unless told otherwise)
+  SPZ_TEST_KEEP_ENV=1 SPZ_TILE_V2=1 timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/gpu_suite_under_v2.log 2>&1
+  echo "GPU suite under SPZ_TILE_V2=1: rc=$?"; tail -3 gpurun_out/gpu_suite_under_v2.log
+fi
 for v in 0 1; do
   SPZ_TILE_V2=$v timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active \
       --clock-control none -k regex:k_tile --csv --log-file gpurun_out/k_tile_v${v}_qft30.csv python tools/profile_qft.py 30 > gpurun_out/ncu_v${v}.log 2>&1
