@@ -444,7 +444,7 @@ struct Fuser {
         // run).  The tile is grown greedily for every admissible L -- add the high qubit with the largest gain -- and the
         // best (L, high set) wins; ties go to the longer contiguous segment.  Without this the first ready ops in program
         // order fix the tile, which on layered circuits strands most passes with a dozen gates.
-        const int n_local = 63 - __builtin_clzll((unsigned long long)st->len); // qubits held by this handle (a shard holds fewer than st->n)
+        const int n_local = st->n; // qubits held by this handle (for a shard: its local qubits)
         std::vector<std::vector<int>> pred(N);
         for (int j = 0; j < N; ++j) for (int i : succ[j]) pred[i].push_back(j);
         std::vector<uint64_t> xm(N, 0);

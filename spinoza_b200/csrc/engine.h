@@ -53,7 +53,7 @@ struct Scratch {
 } // namespace spz
 
 struct spz_state {
-    int n = 0;           // total qubits of the register
+    int n = 0;           // qubits held by this handle: the whole register, or the local qubits of a shard (len == 1 << n)
     int device = 0;
     int64_t len = 0;     // amplitudes held by this handle (2^n single-GPU)
     double *re = nullptr;

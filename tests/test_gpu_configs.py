@@ -84,6 +84,31 @@ def test_config3_two_shards_equal_one_shard(n, world):
     assert np.array_equal(re, r1) and np.array_equal(im, i1)
 
 
+@pytest.mark.parametrize("select", ["0", "1"])
+@pytest.mark.parametrize("n,world", [(15, 2), (16, 4)])
+def test_config3_sharded_dag_schedule_matches_the_oracle(n, world, select, monkeypatch):
+    """Merged (DAG-scheduled) execution on shards, with both ways of choosing a pass's tile: the windows between exchanges
+    hold rank-constant diagonal ops (const_hi) next to local ones, which only the sharded path produces."""
+    monkeypatch.setenv("SPZ_TILE_SELECT", select)
+    init = orc.gen_random_state(n, 45)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, init)
+    ops_box = {}
+
+    def body(rank, s):
+        q = QuantumCircuit.from_state(s, fuse=True)
+        workloads.random_layered_circuit(q, depth=12, seed=42)
+        if rank == 0:
+            ops_box["ops"] = oracle_ops_from(q)
+        q.execute()
+        s.sync()
+    run_group(states, body)
+    re, im = gather(states)
+    cpu = init.clone()
+    orc.execute(cpu, ops_box["ops"])
+    assert np.max(np.abs(re - cpu.reals)) <= 1e-12 and np.max(np.abs(im - cpu.imags)) <= 1e-12
+
+
 @pytest.mark.parametrize("n", [8, 12, 16, 20])
 def test_config5_tiled_qasm_mc_gates_and_sampling(n):
     for name in ("quantum_lstm.qasm", "iqft.qasm"):
