@@ -142,6 +142,10 @@ SPZ_API int spz_plan_fusion(int n_qubits, const spz_op *ops, int64_t n_ops, uint
                             int32_t *out_pass, int32_t *out_n_passes);
 /* Test hook (pure host code): the tile micro-program spz_execute would launch for pass `pass_index`, serialised into
    `out` (layout documented at the definition in csrc/abi.cu).  tests/test_tile_program.py interprets it in NumPy. */
+/* Test hook (pure host code): every step rank `rank` of `world` would execute for the list -- fused passes, single ops,
+   exchanges -- serialised (layout at the definition in csrc/abi.cu).  tests/test_dist_fused_cpu.py replays it in NumPy. */
+SPZ_API int spz_debug_compile_sharded(int n_total, int world, int rank, const spz_op *ops, int64_t n_ops, uint32_t flags, void *out,
+                                      int64_t out_bytes, int64_t *out_used);
 SPZ_API int spz_debug_compile_pass(int n_qubits, const spz_op *ops, int64_t n_ops, uint32_t flags, int pass_index, void *out,
                                    int64_t out_bytes, int64_t *out_used);
 

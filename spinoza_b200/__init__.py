@@ -108,6 +108,8 @@ _SIGNATURES = {
     "spz_execute": (C.c_int, [_vp, C.POINTER(_Op), C.c_int64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "spz_set_seed": (C.c_int, [_vp, C.c_uint64]),
     "spz_plan_fusion": (C.c_int, [C.c_int, C.POINTER(_Op), C.c_int64, C.c_uint32, _i32p, _i32p, _i32p]),
+    "spz_debug_compile_sharded": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_Op), C.c_int64, C.c_uint32, C.c_void_p, C.c_int64,
+                                            C.POINTER(C.c_int64)]),
     "spz_debug_compile_pass": (C.c_int, [C.c_int, C.POINTER(_Op), C.c_int64, C.c_uint32, C.c_int, C.c_void_p, C.c_int64,
                                          C.POINTER(C.c_int64)]),
     "spz_prob0": (C.c_int, [_vp, C.c_int, _dp]),

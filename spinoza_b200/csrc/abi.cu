@@ -129,9 +129,33 @@ struct PlanSink {
     std::vector<TileInstr> cap_prog;
     std::vector<TileGroup> cap_groups;
     std::vector<TileTerm> cap_terms;
+    // optional: everything a (sharded) execute would do, in order (spz_debug_compile_sharded)
+    struct Step {
+        int type = 0; // 0 = tile program, 1 = single op, 2 = exchange, 3 = measurement
+        TilePlan plan{};
+        std::vector<TileInstr> prog;
+        std::vector<TileGroup> groups;
+        std::vector<TileTerm> terms;
+        ROp op{};
+        int gbit = 0, lq = 0;
+    };
+    bool capture_all = false;
+    std::vector<Step> steps;
     void take(const std::vector<ROp> &ops) {
         for (const ROp &o : ops) { order.push_back(o.src); group.push_back(n_groups); }
         ++n_groups;
+        if (capture_all && ops.size() == 1) {
+            Step st;
+            st.type = ops[0].kind == SPZ_GATE_M ? 3 : 1;
+            st.op = ops[0];
+            steps.push_back(std::move(st));
+        }
+    }
+    void exchange(int gbit, int lq) {
+        if (!capture_all) return;
+        Step st;
+        st.type = 2; st.gbit = gbit; st.lq = lq;
+        steps.push_back(std::move(st));
     }
 };
 
@@ -331,6 +355,17 @@ struct Fuser {
                     sink->cap_plan = plan;
                     SPZ_TRY(compile(plan, sink->cap_prog, sink->cap_groups, sink->cap_terms));
                 }
+            }
+            if (sink->capture_all && ops.size() > 1) {
+                PlanSink::Step step;
+                step.type = 0;
+                step.plan.n_high = n_high();
+                step.plan.tile_bits = T;
+                step.plan.low_bits = T - step.plan.n_high;
+                int k = 0;
+                for (int q = 0; q < 64; ++q) if ((high_set >> q) & 1ull) step.plan.high[k++] = q;
+                SPZ_TRY(compile(step.plan, step.prog, step.groups, step.terms));
+                sink->steps.push_back(std::move(step));
             }
             sink->take(ops); ops.clear(); high_set = 0; low_need = 0; return SPZ_OK;
         }
@@ -871,7 +906,11 @@ static int execute_impl(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_
         for (const spz_dist_action &a : acts) {
             switch (a.type) {
             case ACT_SKIP: break;
-            case ACT_EXCHANGE: SPZ_TRY(fuser.flush()); SPZ_TRY(dist_exchange(st, a.gbit, a.lq)); break;
+            case ACT_EXCHANGE:
+                SPZ_TRY(fuser.flush());
+                if (sink) sink->exchange(a.gbit, a.lq); // dry run: the plan's permutation has already been updated
+                else SPZ_TRY(dist_exchange(st, a.gbit, a.lq));
+                break;
             case ACT_LOCAL_GATE: SPZ_TRY(emit_local(a.kind, a.p, a.cmask, a.target, 0, -1)); break;
             case ACT_DIAG_CONST: SPZ_TRY(emit_local(a.kind, a.p, a.cmask, 0, 0, a.hi)); break;
             default: return SPZ_ERR_INVALID_ARG;
@@ -983,6 +1022,72 @@ int spz_debug_compile_pass(int n_qubits, const spz_op *ops, int64_t n_ops, uint3
     if (!sink.cap_groups.empty()) { std::memcpy(w, sink.cap_groups.data(), sizeof(TileGroup) * sink.cap_groups.size()); w += sizeof(TileGroup) * sink.cap_groups.size(); }
     if (!sink.cap_terms.empty()) { std::memcpy(w, sink.cap_terms.data(), sizeof(TileTerm) * sink.cap_terms.size()); w += sizeof(TileTerm) * sink.cap_terms.size(); }
     *out_used = (int64_t)need;
+    return SPZ_OK;
+}
+
+// Debug / test hook (pure host code): everything spz_execute would do on rank `rank` of a register of n_total qubits
+// sharded over `world` ranks -- fused passes as micro-programs, single ops, exchanges -- in order.  Serialisation:
+//   int64 n_steps, then per step an int32 header h[20] and a payload of h[16] bytes:
+//     h[0] = 0 tile program : h[1..3] = tile_bits, low_bits, n_high; h[4..11] = high[8]; h[12..14] = #instr, #groups, #terms;
+//                             h[15] = sizeof(TileInstr); payload = instr | groups | terms
+//     h[0] = 1 single op    : h[1..4] = kind, target, t2, const_hi; payload = u64 cmask, double s[7]
+//     h[0] = 2 exchange     : h[1] = bit of the rank, h[2] = local physical bit it trades places with
+//     h[0] = 3 measurement  : h[1] = target
+//   then int32 perm[64] (logical -> physical after the last op).  world = 1 describes an unsharded register.
+int spz_debug_compile_sharded(int n_total, int world, int rank, const spz_op *ops, int64_t n_ops, uint32_t flags, void *out,
+                              int64_t out_bytes, int64_t *out_used) {
+    if (n_total < 1 || n_total > 40 || world < 1 || (world & (world - 1)) || rank < 0 || rank >= world || !out || !out_used) {
+        set_error("bad arguments"); return SPZ_ERR_INVALID_ARG;
+    }
+    int g = 0;
+    while ((1 << g) < world) ++g;
+    if (n_total - g < 1) { set_error("more ranks than amplitudes"); return SPZ_ERR_INVALID_ARG; }
+    spz_state dummy;
+    dummy.n = n_total - g;
+    dummy.len = (int64_t)1 << dummy.n;
+    if (world > 1) dist_debug_attach(&dummy, n_total, world, rank);
+    PlanSink sink;
+    sink.capture_all = true;
+    int rc = execute_impl(&dummy, ops, n_ops, flags, nullptr, nullptr, &sink);
+    int32_t perm[64];
+    for (int q = 0; q < 64; ++q) perm[q] = q;
+    if (world > 1) { spz_dist_perm(&dummy, perm); dist_debug_detach(&dummy); }
+    SPZ_TRY(rc);
+    char *w = static_cast<char *>(out), *end = w + out_bytes;
+    auto put = [&](const void *src, size_t bytes) -> bool {
+        if (w + bytes > end) return false;
+        std::memcpy(w, src, bytes);
+        w += bytes;
+        return true;
+    };
+    const int64_t n_steps = (int64_t)sink.steps.size();
+    bool ok = put(&n_steps, sizeof n_steps);
+    for (const PlanSink::Step &st : sink.steps) {
+        int32_t h[20] = {0};
+        h[0] = st.type;
+        if (st.type == 0) {
+            h[1] = st.plan.tile_bits; h[2] = st.plan.low_bits; h[3] = st.plan.n_high;
+            for (int k = 0; k < 8; ++k) h[4 + k] = st.plan.high[k];
+            h[12] = (int32_t)st.prog.size(); h[13] = (int32_t)st.groups.size(); h[14] = (int32_t)st.terms.size();
+            h[15] = (int32_t)sizeof(TileInstr);
+            h[16] = (int32_t)(sizeof(TileInstr) * st.prog.size() + sizeof(TileGroup) * st.groups.size() + sizeof(TileTerm) * st.terms.size());
+            ok = ok && put(h, sizeof h);
+            if (!st.prog.empty()) ok = ok && put(st.prog.data(), sizeof(TileInstr) * st.prog.size());
+            if (!st.groups.empty()) ok = ok && put(st.groups.data(), sizeof(TileGroup) * st.groups.size());
+            if (!st.terms.empty()) ok = ok && put(st.terms.data(), sizeof(TileTerm) * st.terms.size());
+        } else if (st.type == 1) {
+            h[1] = st.op.kind; h[2] = st.op.target; h[3] = st.op.t2; h[4] = st.op.const_hi;
+            h[16] = (int32_t)(sizeof(uint64_t) + 7 * sizeof(double));
+            ok = ok && put(h, sizeof h) && put(&st.op.cmask, sizeof(uint64_t)) && put(st.op.g.s, 7 * sizeof(double));
+        } else {
+            h[1] = st.type == 2 ? st.gbit : st.op.target;
+            h[2] = st.lq;
+            ok = ok && put(h, sizeof h);
+        }
+    }
+    ok = ok && put(perm, sizeof perm);
+    if (!ok) { set_error("output buffer too small"); return SPZ_ERR_INVALID_ARG; }
+    *out_used = (int64_t)(w - static_cast<char *>(out));
     return SPZ_OK;
 }
 

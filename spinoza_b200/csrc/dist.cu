@@ -74,6 +74,19 @@ static int upload_peer_table(DistCtx *c) {
 
 int dist_total_qubits(const spz_state *st) { return ctx_of(st)->plan.n; }
 
+// Dry-run support (spz_debug_compile_sharded, pure host code): a context that only knows the plan and the rank.
+void dist_debug_attach(spz_state *st, int n_total, int world, int rank) {
+    DistCtx *c = new DistCtx();
+    c->plan.init(n_total, world);
+    c->rank = rank;
+    c->world = world;
+    st->dist = c;
+}
+void dist_debug_detach(spz_state *st) {
+    delete ctx_of(st);
+    st->dist = nullptr;
+}
+
 // ---- device helpers ---------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;

@@ -169,5 +169,7 @@ int dist_fill_basis(spz_state *st, uint64_t logical_index);
 int dist_init_random(spz_state *st, uint64_t seed);
 int dist_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_index);
 void dist_destroy(spz_state *st);
+void dist_debug_attach(spz_state *st, int n_total, int world, int rank); // host-only plan context for dry runs
+void dist_debug_detach(spz_state *st);
 
 } // namespace spz

@@ -1,0 +1,199 @@
+"""Sharded execute() replayed on the CPU -- pure host code on the library side, NumPy on this side, no GPU.
+
+`spz_debug_compile_sharded` returns, for one rank, every step `spz_execute` would take on a register sharded over `world`
+ranks: fused passes as tile micro-programs, single ops (with rank-constant diagonal ops already resolved), exchanges.  This
+file replays all ranks in lockstep -- the interpreter of tests/test_tile_program.py for the programs, a bit swap of the
+physical index for the exchanges -- and compares the un-permuted result with the dense gate-by-gate statement.
+
+It covers what only the sharded path produces and no single-GPU test can reach: ops skipped on ranks whose global control
+bit is 0, diagonal gates on rank bits folded into tile programs as constants (const_hi), windows closed by exchanges,
+Belady victim choice from the execute look-ahead, and the scheduler (both ways of choosing a tile) inside those windows.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import spinoza_b200 as sb
+from spinoza_b200 import Gate, QuantumCircuit, QuantumRegister, workloads
+from tests import _dense as D
+from tests.test_scheduler_plan import random_circuit, run_dense_order
+from tests.test_tile_program import GROUP, INSTR, TERM, gate_matrix_from_scalars, interpret
+
+DIAG = {Gate.KIND_Z, Gate.KIND_P, Gate.KIND_RZ}
+
+
+def steps_of_rank(qc, world, rank):
+    arr, n_ops = qc._encode()
+    buf = (C.c_char * (32 << 20))()
+    used = C.c_int64()
+    sb._check(sb._lib.spz_debug_compile_sharded(qc.n_qubits, world, rank, arr, n_ops, qc._flags(), buf, len(buf), C.byref(used)))
+    raw = bytes(buf[: used.value])
+    n_steps = int(np.frombuffer(raw, dtype="<i8", count=1)[0])
+    off = 8
+    steps = []
+    for _ in range(n_steps):
+        h = np.frombuffer(raw, dtype="<i4", count=20, offset=off)
+        off += 80
+        kind = int(h[0])
+        if kind == 0:
+            assert h[15] == INSTR.itemsize
+            ni, ng, nt = int(h[12]), int(h[13]), int(h[14])
+            instrs = np.frombuffer(raw, dtype=INSTR, count=ni, offset=off); off += ni * INSTR.itemsize
+            groups = np.frombuffer(raw, dtype=GROUP, count=ng, offset=off); off += ng * GROUP.itemsize
+            terms = np.frombuffer(raw, dtype=TERM, count=nt, offset=off); off += nt * TERM.itemsize
+            plan = {"T": int(h[1]), "L": int(h[2]), "high": [int(x) for x in h[4:4 + int(h[3])]]}
+            steps.append(("tile", plan, instrs, groups, terms))
+        elif kind == 1:
+            cmask = int(np.frombuffer(raw, dtype="<u8", count=1, offset=off)[0])
+            s = np.frombuffer(raw, dtype="<f8", count=7, offset=off + 8).copy()
+            off += 64
+            steps.append(("op", int(h[1]), int(h[2]), int(h[3]), int(h[4]), cmask, s))
+        elif kind == 2:
+            steps.append(("exchange", int(h[1]), int(h[2])))
+        else:
+            raise AssertionError("measurement steps are not replayed here")
+    perm = [int(x) for x in np.frombuffer(raw, dtype="<i4", count=64, offset=off)]
+    assert off + 256 == used.value
+    return steps, perm
+
+
+def apply_single(n_local, psi, step):
+    _, kind, target, t2, const_hi, cmask, s = step
+    if kind == Gate.KIND_SWAP:
+        return D.apply_swap(psi, n_local, target, t2)
+    if kind in DIAG:
+        if kind == Gate.KIND_Z:
+            f_lo, f_hi = 1.0, -1.0
+        elif kind == Gate.KIND_P:
+            f_lo, f_hi = 1.0, complex(s[0], s[1])
+        else:
+            f_lo, f_hi = complex(s[0], -s[1]), complex(s[0], s[1])
+        idx = np.arange(1 << n_local, dtype=np.int64)
+        ctrl = (idx & cmask) == cmask
+        if const_hi >= 0:                                   # target is a bit of the rank: one constant for the whole shard
+            return np.where(ctrl, psi * (f_hi if const_hi else f_lo), psi)
+        hi = ((idx >> target) & 1) == 1
+        return np.where(ctrl, psi * np.where(hi, f_hi, f_lo), psi)
+    assert const_hi < 0
+    return D.apply_matrix(psi, n_local, gate_matrix_from_scalars(kind, s), target, cmask)
+
+
+def replay(qc, world, psi0):
+    """-> logical state vector after the sharded execution."""
+    n = qc.n_qubits
+    g = world.bit_length() - 1
+    n_local = n - g
+    per_rank = [steps_of_rank(qc, world, r) for r in range(world)]
+    perms = [p for _, p in per_rank]
+    assert all(p == perms[0] for p in perms), "the plan must evolve identically on every rank"
+    shards = [psi0[r << n_local:(r + 1) << n_local].copy() for r in range(world)]
+    cursors = [0] * world
+    stats = {"tile": 0, "op": 0, "exchange": 0}
+    while True:
+        pending = []
+        for r in range(world):
+            steps = per_rank[r][0]
+            while cursors[r] < len(steps) and steps[cursors[r]][0] != "exchange":
+                st = steps[cursors[r]]
+                if st[0] == "tile":
+                    shards[r] = interpret(n_local, shards[r], st, qc.exact, allow_rank_constants=True)
+                    stats["tile"] += 1
+                else:
+                    shards[r] = apply_single(n_local, shards[r], st)
+                    stats["op"] += 1
+                cursors[r] += 1
+            pending.append(steps[cursors[r]] if cursors[r] < len(steps) else None)
+        if all(p is None for p in pending):
+            break
+        assert all(p is not None and p == pending[0] for p in pending), "every rank must reach the same exchange"
+        _, gbit, lq = pending[0]
+        phys = np.concatenate(shards)                        # physical index = rank << n_local | local index
+        phys = D.apply_swap(phys, n, n_local + gbit, lq)      # the exchange swaps a rank bit with a local bit
+        shards = [phys[r << n_local:(r + 1) << n_local].copy() for r in range(world)]
+        stats["exchange"] += 1
+        cursors = [c + 1 for c in cursors]
+    phys = np.concatenate(shards)
+    # logical amplitude at index i sits at the physical index whose bit perm[q] is bit q of i
+    perm = perms[0][:n]
+    i = np.arange(1 << n, dtype=np.int64)
+    p_idx = np.zeros_like(i)
+    for q in range(n):
+        p_idx |= ((i >> q) & 1) << perm[q]
+    return phys[p_idx], stats
+
+
+def dense(qc, psi0):
+    trs = list(qc.transformations)
+    return run_dense_order(qc.n_qubits, psi0.copy(), trs, range(len(trs)))
+
+
+def layered(n, depth, seed, **kw):
+    qc = QuantumCircuit(QuantumRegister(n), **kw)
+    workloads.random_layered_circuit(qc, depth=depth, seed=seed)
+    return qc
+
+
+def qft(n, **kw):
+    qc = QuantumCircuit(QuantumRegister(n), **kw)
+    qc.qft()
+    return qc
+
+
+@pytest.mark.parametrize("select", ["0", "1"], ids=["first-come-tile", "chosen-tile"])
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("name", ["qft", "layered", "random"])
+def test_sharded_fused_execution_equals_the_dense_statement(name, exact, world, select, monkeypatch):
+    monkeypatch.setenv("SPZ_TILE_SELECT", select)
+    n = 14 + (world.bit_length() - 1) - 1          # 13 local qubits: real 12-bit tiles on every shard
+    qc = {"qft": lambda: qft(n, exact=exact), "layered": lambda: layered(n, 8, 3, exact=exact),
+          "random": lambda: random_circuit(n, 180, 17, exact=exact)}[name]()
+    psi0 = D.random_state(n, 9)
+    got, stats = replay(qc, world, psi0)
+    np.testing.assert_allclose(got, dense(qc, psi0), rtol=0, atol=1e-12)
+    assert stats["tile"] >= world and stats["exchange"] >= 1, stats
+
+
+def test_eight_ranks_qft_with_chosen_tiles(monkeypatch):
+    monkeypatch.setenv("SPZ_TILE_SELECT", "1")
+    n, world = 16, 8
+    qc = qft(n)
+    psi0 = D.random_state(n, 12)
+    got, stats = replay(qc, world, psi0)
+    np.testing.assert_allclose(got, dense(qc, psi0), rtol=0, atol=1e-12)
+    assert stats["exchange"] == 3, stats          # one per global qubit: QFT never returns to a qubit after its H
+
+
+def test_unfused_sharded_execution(monkeypatch):
+    n, world = 10, 4
+    qc = random_circuit(n, 120, 23, fuse=False)
+    psi0 = D.random_state(n, 4)
+    got, stats = replay(qc, world, psi0)
+    np.testing.assert_allclose(got, dense(qc, psi0), rtol=0, atol=1e-12)
+    assert stats["tile"] == 0 and stats["op"] > 0
+
+
+def test_world_of_one_is_the_unsharded_plan():
+    n = 13
+    qc = layered(n, 6, 5)
+    psi0 = D.random_state(n, 6)
+    got, stats = replay(qc, 1, psi0)
+    np.testing.assert_allclose(got, dense(qc, psi0), rtol=0, atol=1e-12)
+    assert stats["exchange"] == 0
+
+
+def test_diagonal_gates_on_rank_bits_never_exchange():
+    """QFT's controlled phases touch global qubits long before their H: they must all be rank constants."""
+    n, world = 15, 4
+    qc = QuantumCircuit(QuantumRegister(n))
+    for t in range(n):
+        qc.rz(0.1 * (t + 1), t)
+    for c in range(n - 2):
+        qc.cp(0.3 + 0.01 * c, c, n - 1)       # target: a global qubit
+        qc.cp(0.2, n - 2, c)                  # control: a global qubit
+    psi0 = D.random_state(n, 8)
+    got, stats = replay(qc, world, psi0)
+    np.testing.assert_allclose(got, dense(qc, psi0), rtol=0, atol=1e-12)
+    assert stats["exchange"] == 0

@@ -75,10 +75,11 @@ def gate_matrix_from_scalars(kind, s):
 class TileMachine:
     """All tiles at once: every per-thread quantity of k_tile becomes an array over the 2^n absolute indices."""
 
-    def __init__(self, n, plan, groups, terms, exact, lazy=False):
+    def __init__(self, n, plan, groups, terms, exact, lazy=False, allow_rank_constants=False):
         self.n, self.T, self.L, self.high = n, plan["T"], plan["L"], plan["high"]
         self.exact = exact
         self.lazy = lazy  # k_tile2: a butterfly on register bit r flushes accumulator F_{r+1} only
+        self.allow_rank_constants = allow_rank_constants  # sharded registers: diagonal target on a bit of the rank
         idx = np.arange(1 << n, dtype=np.uint64)
         self.qubit_of_bit = list(range(self.L)) + self.high
         assert len(self.qubit_of_bit) == self.T and len(set(self.qubit_of_bit)) == self.T
@@ -181,8 +182,10 @@ class TileMachine:
         kind, tw, s = int(ins["kind"]), int(ins["t_where"]), ins["s"]
         ocm = ins["outer_cmask"]
         ok = ((self.base & ocm) == ocm) & ((self.tj & ins["thr_cmask"]) == ins["thr_cmask"]) & ((self.k & ins["reg_cmask"]) == ins["reg_cmask"])
-        if tw == 0:
-            assert ins["const_hi"] == 0  # rank-bit targets only exist in sharded lowering
+        if tw == 0 and ins["const_hi"] != 0:
+            assert self.allow_rank_constants  # rank-bit targets only exist in sharded lowering
+            hi = np.full(1 << self.n, ins["const_hi"] == 2)
+        elif tw == 0:
             hi = ((self.base >> np.uint64(ins["outer_target"])) & np.uint64(1)) == 1
         elif tw == 1:
             hi = (self.tj & ins["t_mask"]) != 0
@@ -198,12 +201,12 @@ class TileMachine:
         return np.where(ok, psi * np.where(hi, f_hi, f_lo), psi)
 
 
-def interpret(n, psi, compiled, exact, lazy=False):
+def interpret(n, psi, compiled, exact, lazy=False, allow_rank_constants=False):
     _, plan, instrs, groups, terms = compiled
     assert plan["T"] == plan["L"] + len(plan["high"]) and plan["T"] <= 12 and len(plan["high"]) <= 8
     assert len(groups) <= 2048
     assert instrs[0]["op"] == TI_LAYOUT, "a program starts by choosing a register layout"
-    tm = TileMachine(n, plan, groups, terms, exact, lazy)
+    tm = TileMachine(n, plan, groups, terms, exact, lazy, allow_rank_constants)
     seen_groups = 0
     for ins in instrs:
         op = int(ins["op"])
