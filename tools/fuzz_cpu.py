@@ -3,10 +3,12 @@ gate-by-gate statement.
 
     python tools/fuzz_cpu.py [iterations=200] [seed=1]
 
-Two engines per case, chosen at random: the NumPy interpreter of the micro-program (tests/test_tile_program.py) and the
-kernels' own code on the CPU emulation (tests/emu/, k_tile or k_tile2 at a random transfer level).  Knobs drawn per case:
+Three engines, chosen at random per case: the NumPy interpreter of the micro-program (tests/test_tile_program.py), the
+kernels' own code on the CPU emulation (tests/emu/, k_tile or k_tile2 at a random transfer level), and the lockstep replay
+of a register sharded over 2 / 4 / 8 ranks (tests/test_dist_fused_cpu.py).  Knobs drawn per case:
 exact / merged, SPZ_TILE_SELECT, SPZ_TILE_LMIN, lazy flush.  Round-1 record: 400 + 300 + 160 cases, no failure
-(the SWAP(11, high) bug fixed in abi.cu: Fuser::fits was found by the unit tests of the tile selection, not by fuzzing).
+plus 120 sharded ones (the SWAP(11, high) bug fixed in abi.cu: Fuser::fits was found by the unit tests of the tile selection,
+not by fuzzing).
 """
 import ctypes as C
 import math
@@ -23,6 +25,7 @@ from spinoza_b200 import Controls, Gate, QuantumCircuit, QuantumRegister, Quantu
 from tests import _dense as D
 from tests.test_scheduler_plan import KINDS, random_circuit, run_dense_order
 from tests.test_tile_cpu_emulation import CUDA_INC, EMU_DIR, run_emulated
+from tests.test_dist_fused_cpu import replay
 from tests.test_tile_program import run_plan
 
 
@@ -72,7 +75,8 @@ def main():
         os.environ["SPZ_TILE_SELECT"] = str(int(rng.integers(2)))
         os.environ["SPZ_TILE_LMIN"] = str(int(rng.integers(4, 7)))
         gen = swap_heavy if rng.random() < 0.3 else random_circuit
-        engine = "emu" if rng.random() < 0.4 and n <= 14 else "numpy"
+        x = rng.random()
+        engine = "emu" if x < 0.35 and n <= 14 else "sharded" if x > 0.75 else "numpy"
         desc = dict(it=it, n=n, count=count, seed=seed, exact=exact, gen=gen.__name__, engine=engine,
                     select=os.environ["SPZ_TILE_SELECT"], lmin=os.environ["SPZ_TILE_LMIN"])
         try:
@@ -82,6 +86,10 @@ def main():
             want = run_dense_order(n, psi0.copy(), trs, range(len(trs)))
             if engine == "numpy":
                 got, _ = run_plan(qc, psi0.copy(), lazy=bool(rng.integers(2)))
+            elif engine == "sharded":
+                world = int(2 ** rng.integers(1, min(4, n - 3)))
+                desc["world"] = world
+                got, _ = replay(qc, world, psi0)
             else:
                 kernel = 2 if n >= 12 and rng.random() < 0.6 else 1
                 re, im = np.ascontiguousarray(psi0.real), np.ascontiguousarray(psi0.imag)
