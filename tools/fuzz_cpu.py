@@ -87,7 +87,7 @@ def main():
             if engine == "numpy":
                 got, _ = run_plan(qc, psi0.copy(), lazy=bool(rng.integers(2)))
             elif engine == "sharded":
-                world = int(2 ** rng.integers(1, min(4, n - 3)))
+                world = int(2 ** rng.integers(1, max(2, min(4, n - 3))))  # at least 4 local qubits per rank
                 desc["world"] = world
                 got, _ = replay(qc, world, psi0)
             else:
