@@ -178,7 +178,7 @@ typedef struct {
     int32_t gbit;    /* type 3: which bit of the rank is exchanged */
     int32_t lq;      /* type 3: local physical bit it trades places with */
     int32_t partner; /* type 3: rank ^ (1 << gbit) */
-    int32_t reserved;
+    int32_t grefs;   /* types 0,1,2: mask of the rank bits the lowering consulted (global controls / global diagonal target) */
     double p[3];
 } spz_dist_action;
 

@@ -67,7 +67,7 @@ class _Gate(C.Structure):
 class _DistAction(C.Structure):
     _fields_ = [("type", C.c_int32), ("kind", C.c_int32), ("target", C.c_int32), ("hi", C.c_int32),
                 ("cmask", C.c_uint64), ("gbit", C.c_int32), ("lq", C.c_int32), ("partner", C.c_int32),
-                ("reserved", C.c_int32), ("p", C.c_double * 3)]
+                ("grefs", C.c_int32), ("p", C.c_double * 3)]
 
 
 class _Op(C.Structure):

@@ -116,7 +116,12 @@ struct ROp { // an op resolved to what the kernels need (physical qubits of this
     int const_hi = -1; // >= 0: diagonal gate whose target is a rank bit of a sharded register; value of that bit
     double theta = 0.0; // first gate parameter (merged diagonal factors are computed from the angle itself)
     int src = -1;       // index of the originating op in the caller's list (planning output)
+    // sharded registers, exchange-spanning windows (SPZ_DIST_WINDOW): see Fuser::schedule_dag
+    bool skip = false;  // placeholder of an op this rank skips (a global control is 0 here): scheduled like the real op so
+                        // that every rank forms the same passes, compiled to nothing
+    uint32_t grefs = 0; // rank bits the lowering of this op consulted
 };
+constexpr int kRopExchange = 100; // ROp::kind of an exchange inside a window: target = local physical bit, t2 = rank bit
 
 // Dry-run sink: instead of launching kernels, record which pass every op ends up in (spz_plan_fusion).
 struct PlanSink {
@@ -339,7 +344,9 @@ struct Fuser {
 
     // Launch the current group (ops / high_set / low_need) and reset it.
     int emit_group() {
-        if (ops.empty()) return SPZ_OK;
+        // placeholders (ops another rank applies and this one skips) took part in the scheduling only
+        ops.erase(std::remove_if(ops.begin(), ops.end(), [](const ROp &o) { return o.skip; }), ops.end());
+        if (ops.empty()) { high_set = 0; low_need = 0; return SPZ_OK; }
         if (sink) {
             if (sink->capture_pass == sink->n_groups) { // compile exactly as the launch path below would
                 sink->captured = true;
@@ -433,8 +440,18 @@ struct Fuser {
         return rc;
     }
 
+    // an exchange queued in the window (sharded registers): everything scheduled so far must be on the device first
+    int run_exchange(const ROp &x) {
+        SPZ_TRY(emit_group());
+        if (sink) { sink->exchange(x.t2, x.target); return SPZ_OK; }
+        return dist_exchange(st, x.t2, x.target);
+    }
+
     int schedule_in_order() {
-        for (const ROp &op : pending) SPZ_TRY(add(op));
+        for (const ROp &op : pending) {
+            if (op.kind == kRopExchange) SPZ_TRY(run_exchange(op));
+            else SPZ_TRY(add(op));
+        }
         return emit_group();
     }
 
@@ -443,15 +460,27 @@ struct Fuser {
         std::vector<int> npred(N, 0), stamp(N, -1);
         std::vector<std::vector<int>> succ(N);
         int last_w[64];
+        int last_exchange = -1;
         std::vector<int> zl[64]; // Z-like ops on the qubit since its last writer
         for (int &w : last_w) w = -1;
         for (int i = 0; i < N; ++i) {
             const ROp &op = pending[i];
             const bool diag = is_diagonal_kind(op.kind);
-            uint64_t xmask = 0, zmask = op.cmask;
-            if (op.kind == SPZ_GATE_SWAP) xmask = (1ull << op.target) | (1ull << op.t2);
+            // Index bits 56.. stand for the bits of the rank: an op whose lowering consulted rank bit b (a global control, a
+            // diagonal target on a global qubit) is Z-like on 56 + b, and an exchange, which moves a local bit into that
+            // rank bit, writes both.  So an op may cross an exchange exactly when it touches neither -- and because
+            // skipped ops stay in the window as placeholders, every rank builds the same graph and takes the same
+            // decisions, which is what keeps the two partners of an exchange consistent.  Exchanges keep their order.
+            uint64_t xmask = 0, zmask = op.cmask | ((uint64_t)op.grefs << 56);
+            if (op.kind == kRopExchange) {
+                xmask = (1ull << op.target) | (1ull << (56 + op.t2));
+                zmask = 0;
+                if (last_exchange >= 0 && stamp[last_exchange] != i) { stamp[last_exchange] = i; succ[last_exchange].push_back(i); ++npred[i]; }
+                last_exchange = i;
+            }
+            else if (op.kind == SPZ_GATE_SWAP) xmask = (1ull << op.target) | (1ull << op.t2);
             else if (!diag) xmask = 1ull << op.target;
-            else if (op.const_hi < 0) zmask |= 1ull << op.target;
+            else if (op.const_hi < 0 && op.target >= 0) zmask |= 1ull << op.target;
             auto dep = [&](int j) {
                 if (stamp[j] == i) return;
                 stamp[j] = i;
@@ -485,7 +514,8 @@ struct Fuser {
         std::vector<uint64_t> xm(N, 0);
         for (int i = 0; i < N; ++i) {
             const ROp &op = pending[i];
-            if (op.kind == SPZ_GATE_SWAP) xm[i] = (1ull << op.target) | (1ull << op.t2);
+            if (op.kind == kRopExchange) xm[i] = ~0ull; // never part of a pass: its successors wait for it
+            else if (op.kind == SPZ_GATE_SWAP) xm[i] = (1ull << op.target) | (1ull << op.t2);
             else if (!is_diagonal_kind(op.kind)) xm[i] = 1ull << op.target;
         }
         std::vector<char> runs(N, 0);
@@ -516,7 +546,7 @@ struct Fuser {
             while (first_undone < N && done[first_undone]) ++first_undone;
             uint64_t cand = 0; // qubits some undone non-diagonal op within the horizon targets
             const int end = std::min(N, first_undone + kScan);
-            for (int i = first_undone; i < end; ++i) if (!done[i]) cand |= xm[i];
+            for (int i = first_undone; i < end; ++i) if (!done[i] && pending[i].kind != kRopExchange) cand |= xm[i];
             int best_count = -1;
             best_high = 0;
             for (int L = T; L >= Lmin; L -= (L - lstep >= Lmin || L == Lmin ? lstep : L - Lmin)) {
@@ -543,7 +573,17 @@ struct Fuser {
             }
             return best_count;
         };
+        int next_exchange = 0; // exchanges run in window order, as soon as everything they depend on has run: the ops that
+                               // remain commute with them and can only gain company from what the exchange unlocks
         while (remaining > 0) {
+            while (next_exchange < N && (pending[next_exchange].kind != kRopExchange || done[next_exchange])) ++next_exchange;
+            if (next_exchange < N && npred[next_exchange] == 0) {
+                SPZ_TRY(run_exchange(pending[next_exchange]));
+                done[next_exchange] = 1;
+                --remaining;
+                for (int sidx : succ[next_exchange]) --npred[sidx];
+                continue;
+            }
             {
                 // One-qubit growth cannot see an op that needs two new high qubits at once (a SWAP between them); if no
                 // tile admits any op, fall back to letting the first ready ops claim their qubits, which always progresses.
@@ -563,7 +603,7 @@ struct Fuser {
             for (;;) {
                 bool progress = false;
                 for (int i = 0; i < N; ++i) {
-                    if (done[i] || npred[i] != 0) continue;
+                    if (done[i] || npred[i] != 0 || pending[i].kind == kRopExchange) continue;
                     if (ops.size() >= (size_t)kMaxTileGroups / 2) break;
                     const ROp &op = pending[i];
                     uint64_t want = 0; // non-diagonal targets this op needs register-resident
@@ -865,7 +905,15 @@ static int execute_impl(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_
         }
     };
 
-    auto emit_local = [&](int kind, const double *p, uint64_t cmask, int target, int t2, int const_hi) -> int {
+    // Sharded registers: keep exchanges (and the ops this rank skips, as placeholders) inside the scheduling window instead
+    // of closing the window at every exchange.  Opt-in (SPZ_DIST_WINDOW=1) until it has run on hardware; checked on the
+    // CPU by tests/test_dist_fused_cpu.py.
+    bool window_exchanges = false;
+    if (fuse && st->dist && fuser.reorder && !fuser.exact)
+        if (const char *e = std::getenv("SPZ_DIST_WINDOW")) window_exchanges = e[0] == '1';
+
+    auto emit_local = [&](int kind, const double *p, uint64_t cmask, int target, int t2, int const_hi, bool skip = false,
+                          uint32_t grefs = 0) -> int {
         if (!fuse && !sink) {
             if (kind == SPZ_GATE_SWAP) return launch_swap(st, target, t2);
             GateK g;
@@ -877,6 +925,7 @@ static int execute_impl(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_
         r.kind = kind; r.target = target; r.t2 = t2; r.cmask = cmask; r.const_hi = const_hi;
         r.theta = p ? p[0] : 0.0;
         r.src = (int)cur;
+        r.skip = skip; r.grefs = grefs;
         if (!fuse) { // dry run of the unfused path: one pass per op
             if (kind != SPZ_GATE_SWAP) SPZ_TRY(resolve_gate(kind, p, &r.g));
             sink->take(std::vector<ROp>{r});
@@ -905,14 +954,23 @@ static int execute_impl(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_
         if (rc != SPZ_OK) { set_error("cannot lower gate kind %d onto the sharded register", kind); return rc; }
         for (const spz_dist_action &a : acts) {
             switch (a.type) {
-            case ACT_SKIP: break;
+            case ACT_SKIP:
+                if (window_exchanges) // placeholder with the real op's shape
+                    SPZ_TRY(emit_local(a.kind, a.p, a.cmask, a.target < 0 ? 0 : a.target, 0, a.target < 0 ? a.hi : -1, true, (uint32_t)a.grefs));
+                break;
             case ACT_EXCHANGE:
+                if (window_exchanges) {
+                    ROp x{};
+                    x.kind = kRopExchange; x.target = a.lq; x.t2 = a.gbit; x.src = (int)cur;
+                    SPZ_TRY(fuser.push(x));
+                    break;
+                }
                 SPZ_TRY(fuser.flush());
                 if (sink) sink->exchange(a.gbit, a.lq); // dry run: the plan's permutation has already been updated
                 else SPZ_TRY(dist_exchange(st, a.gbit, a.lq));
                 break;
-            case ACT_LOCAL_GATE: SPZ_TRY(emit_local(a.kind, a.p, a.cmask, a.target, 0, -1)); break;
-            case ACT_DIAG_CONST: SPZ_TRY(emit_local(a.kind, a.p, a.cmask, 0, 0, a.hi)); break;
+            case ACT_LOCAL_GATE: SPZ_TRY(emit_local(a.kind, a.p, a.cmask, a.target, 0, -1, false, (uint32_t)a.grefs)); break;
+            case ACT_DIAG_CONST: SPZ_TRY(emit_local(a.kind, a.p, a.cmask, 0, 0, a.hi, false, (uint32_t)a.grefs)); break;
             default: return SPZ_ERR_INVALID_ARG;
             }
         }

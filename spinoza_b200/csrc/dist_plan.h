@@ -111,10 +111,11 @@ struct DistPlan {
         // resolve controls: local -> mask bit, global -> per-rank constant
         uint64_t local_cmask = 0;
         bool skip = false;
+        int grefs = 0; // rank bits this lowering depends on (the same on every rank, whatever their values)
         for (int c = 0; c < n; ++c) {
             if (!((cmask >> c) & 1ull)) continue;
             const int pc = perm[c];
-            if (is_global_phys(pc)) { if (!((rank >> (pc - n_local)) & 1)) skip = true; }
+            if (is_global_phys(pc)) { grefs |= 1 << (pc - n_local); if (!((rank >> (pc - n_local)) & 1)) skip = true; }
             else local_cmask |= 1ull << pc;
         }
         spz_dist_action a{};
@@ -122,13 +123,17 @@ struct DistPlan {
         if (params) { a.p[0] = params[0]; a.p[1] = params[1]; a.p[2] = params[2]; }
         a.cmask = local_cmask;
         const int pt = perm[target];
-        if (skip) { a.type = ACT_SKIP; out.push_back(a); return SPZ_OK; }
+        // A skipped op is still described completely (target, controls, grefs): a scheduler that wants the same pass
+        // structure on every rank treats it as a placeholder with the dependencies of the real op.
         if (!is_global_phys(pt)) {
             a.type = ACT_LOCAL_GATE; a.target = pt;
         } else { // diagonal gate on a global target: constant per rank
+            grefs |= 1 << (pt - n_local);
             a.type = ACT_DIAG_CONST; a.target = -1; a.hi = (rank >> (pt - n_local)) & 1;
-            if (!a.hi && kind != SPZ_GATE_RZ) a.type = ACT_SKIP; // Z / P leave target-bit-0 amplitudes alone
+            if (!a.hi && kind != SPZ_GATE_RZ) skip = true; // Z / P leave target-bit-0 amplitudes alone
         }
+        a.grefs = grefs;
+        if (skip) a.type = ACT_SKIP;
         out.push_back(a);
         return SPZ_OK;
     }

@@ -141,12 +141,14 @@ def qft(n, **kw):
     return qc
 
 
+@pytest.mark.parametrize("window", ["0", "1"], ids=["window-closes-at-exchange", "window-spans-exchanges"])
 @pytest.mark.parametrize("select", ["0", "1"], ids=["first-come-tile", "chosen-tile"])
 @pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("exact", [False, True])
 @pytest.mark.parametrize("name", ["qft", "layered", "random"])
-def test_sharded_fused_execution_equals_the_dense_statement(name, exact, world, select, monkeypatch):
+def test_sharded_fused_execution_equals_the_dense_statement(name, exact, world, select, window, monkeypatch):
     monkeypatch.setenv("SPZ_TILE_SELECT", select)
+    monkeypatch.setenv("SPZ_DIST_WINDOW", window)
     n = 14 + (world.bit_length() - 1) - 1          # 13 local qubits: real 12-bit tiles on every shard
     qc = {"qft": lambda: qft(n, exact=exact), "layered": lambda: layered(n, 8, 3, exact=exact),
           "random": lambda: random_circuit(n, 180, 17, exact=exact)}[name]()
