@@ -152,3 +152,34 @@ def test_v2_is_actually_selected_and_counts_one_launch_per_pass():
         qc.execute()
         st.sync()
     assert sb.launch_count() - before == n_pass
+
+
+# ---- exchange-spanning windows on sharded registers (SPZ_DIST_WINDOW=1, also opt-in until run on hardware) ----------------
+
+@pytest.mark.parametrize("select", ["0", "1"])
+@pytest.mark.parametrize("n,world", [(15, 2), (16, 4), (17, 8)])
+def test_windows_spanning_exchanges_match_the_oracle(n, world, select, monkeypatch):
+    from spinoza_b200.distributed import DistState
+    from tests.test_gpu_dist import gather, run_group, upload_shards
+    monkeypatch.setenv("SPZ_DIST_WINDOW", "1")
+    monkeypatch.setenv("SPZ_TILE_SELECT", select)
+    init = orc.gen_random_state(n, 46)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, init)
+    box = {}
+
+    def body(rank, s):
+        q = QuantumCircuit.from_state(s, fuse=True)
+        workloads.random_layered_circuit(q, depth=12, seed=42)
+        q.qft()
+        if rank == 0:
+            box["ops"] = oracle_ops_from(q)
+        q.execute()
+        s.sync()
+        box[rank] = s.stats()["exchanges"]
+    run_group(states, body)
+    re, im = gather(states)
+    cpu = init.clone()
+    orc.execute(cpu, box["ops"])
+    assert np.max(np.abs(re - cpu.reals)) <= 1e-12 and np.max(np.abs(im - cpu.imags)) <= 1e-12
+    assert len({box[r] for r in range(world)}) == 1   # every rank ran the same exchanges

@@ -6,7 +6,8 @@
 #   /usr/local/graft/bin/gpurun --timeout 3000 -- 'bash tools/round2_first_call.sh --full-suite' # + the whole GPU suite under k_tile2
 #
 # Outputs (all under gpurun_out/):
-#   v2_tests.log            parity of k_tile2 against k_tile and the oracle (tests/test_gpu_tile_v2.py)
+#   v2_tests.log            parity of k_tile2 against k_tile and the oracle, the tile-segment knob, and exchange-spanning
+#                           windows on sharded registers (tests/test_gpu_tile_v2.py: everything that is opt-in)
 #   tile_ab_n30.json        QFT-30 and config-3 timings, k_tile vs k_tile2 at every direct-transfer level
 #   k_tile_v{0,1}_qft30.csv ncu per-launch duration / instructions / issue utilisation of the four QFT-30 passes
 # Every step runs under its own timeout so a hang cannot hold the box.
