@@ -377,12 +377,18 @@ struct Fuser {
             sink->take(ops); ops.clear(); high_set = 0; low_need = 0; return SPZ_OK;
         }
         int rc = SPZ_OK;
-        if (ops.size() == 1 && ops[0].const_hi >= 0) {
-            rc = dist_diag_const(st, ops[0].g, ops[0].cmask, ops[0].const_hi);
-        } else if (ops.size() == 1 && ops[0].kind != SPZ_GATE_SWAP) {
-            rc = launch_gate(st, ops[0].g, ops[0].cmask, ops[0].target);
-        } else if (ops.size() == 1) {
-            rc = launch_swap(st, ops[0].target, ops[0].t2);
+        // A group of one op goes to the one-gate-per-pass kernels, which run at the HBM roofline.  SPZ_TILE_MIN_OPS=k
+        // (default 2) sends groups of fewer than k ops the same way, one launch each in group order: a knob for tuning
+        // against the tile kernel's fixed cost per pass (results are identical either way).
+        size_t min_tile_ops = 2;
+        if (const char *e = std::getenv("SPZ_TILE_MIN_OPS")) { const int v = std::atoi(e); if (v >= 2 && v <= 16) min_tile_ops = (size_t)v; }
+        if (ops.size() < min_tile_ops) {
+            for (size_t i = 0; i < ops.size() && rc == SPZ_OK; ++i) {
+                const ROp &o = ops[i];
+                if (o.const_hi >= 0) rc = dist_diag_const(st, o.g, o.cmask, o.const_hi);
+                else if (o.kind != SPZ_GATE_SWAP) rc = launch_gate(st, o.g, o.cmask, o.target);
+                else rc = launch_swap(st, o.target, o.t2);
+            }
         } else {
             TilePlan plan{};
             plan.n_high = n_high();

@@ -27,11 +27,13 @@ VARIANTS = [("k_tile", {"SPZ_TILE_V2": "0"}),
     (f"k_tile2/direct{lv}", {"SPZ_TILE_V2": "1", "SPZ_TILE_V2_DIRECT": str(lv)}) for lv in (1, 0, 2, 3)] + [  # 1 = default policy
     # shorter tile segments: more arbitrary high qubits per pass (config 3: 30 passes -> 21 at L >= 4), worse coalescing
     ("k_tile/lmin4", {"SPZ_TILE_V2": "0", "SPZ_TILE_LMIN": "4"}), ("k_tile/lmin5", {"SPZ_TILE_V2": "0", "SPZ_TILE_LMIN": "5"}),
-    ("k_tile2/lmin4", {"SPZ_TILE_V2": "1", "SPZ_TILE_LMIN": "4"}), ("k_tile2/lmin5", {"SPZ_TILE_V2": "1", "SPZ_TILE_LMIN": "5"})]
+    ("k_tile2/lmin4", {"SPZ_TILE_V2": "1", "SPZ_TILE_LMIN": "4"}), ("k_tile2/lmin5", {"SPZ_TILE_V2": "1", "SPZ_TILE_LMIN": "5"}),
+    # groups of fewer than k ops as k-1 roofline passes instead of one tile pass
+    ("k_tile/minops3", {"SPZ_TILE_V2": "0", "SPZ_TILE_MIN_OPS": "3"}), ("k_tile/minops4", {"SPZ_TILE_V2": "0", "SPZ_TILE_MIN_OPS": "4"})]
 
 
 def set_env(env):
-    for k in ("SPZ_TILE_V2", "SPZ_TILE_V2_DIRECT", "SPZ_TILE_LMIN", "SPZ_TILE_SELECT"):
+    for k in ("SPZ_TILE_V2", "SPZ_TILE_V2_DIRECT", "SPZ_TILE_LMIN", "SPZ_TILE_SELECT", "SPZ_TILE_MIN_OPS"):
         os.environ.pop(k, None)
     os.environ.update(env)
 
