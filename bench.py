@@ -359,6 +359,43 @@ def main():
         except Exception as e:  # keep the headline line even if an extra fails
             line["qft"] = {"error": repr(e)}
 
+    # ---- BASELINE config 3 through QuantumCircuit::execute (single GPU): random layered circuit, depth 20 ----
+    # Timed twice: with the scheduler choosing each pass's tile qubits (default from 24 qubits up) and with the round-1 rule
+    # (first ready ops claim the tile, SPZ_TILE_SELECT=0), so that one bench line shows what the shorter plan is worth.
+    def run_config3():
+        from spinoza_b200 import workloads
+        out = {"qubits": n, "depth": 20}
+        saved = os.environ.get("SPZ_TILE_SELECT")
+        try:
+            for label, select in (("chosen_tile", None), ("first_come_tile", "0")):
+                if select is None:
+                    os.environ.pop("SPZ_TILE_SELECT", None)
+                else:
+                    os.environ["SPZ_TILE_SELECT"] = select
+                state.init_random(42)
+                qc = QuantumCircuit.from_state(state, fuse=True)
+                out["gates"] = workloads.random_layered_circuit(qc, depth=20, seed=42)
+                passes = qc.plan()[1]
+                state.sync()
+                l1 = sb.launch_count()
+                state.timer_start()
+                qc.execute()
+                t_ms = state.timer_stop()
+                out[label] = {"seconds": t_ms * 1e-3, "passes": passes, "launches": int(sb.launch_count() - l1),
+                              "sec_per_gate": t_ms * 1e-3 / out["gates"], "norm2_after": sb.norm2(state)}
+        finally:
+            if saved is None:
+                os.environ.pop("SPZ_TILE_SELECT", None)
+            else:
+                os.environ["SPZ_TILE_SELECT"] = saved
+        return out
+
+    if rank == 0 and dist is None and not args.no_extras:
+        try:
+            line["config3"] = run_config3()
+        except Exception as e:
+            line["config3"] = {"error": repr(e)}
+
     # ---- end to end through the C ABI with HOST buffers: upload -> sweep -> download, every step ----
     # (sharded: every rank moves its own shard between its pinned host buffers and its GPU; max over ranks)
     def mem_available():
