@@ -153,7 +153,8 @@ int tile_prepare(spz_state *st); // allocate the program ring buffer, set the ke
 bool tile2_enabled();
 bool tile2_eligible(const spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, int n_groups);
 int launch_tile2(spz_state *st, const TilePlan &plan, const TileInstr *h_prog, int n_instr, const TileInstr *d_prog,
-                 const TileGroup *d_groups, int n_groups, const TileTerm *d_terms, bool exact, unsigned first, unsigned count);
+                 const TileGroup *d_groups, int n_groups, const TileTerm *d_terms, int n_terms, bool exact, unsigned first,
+                 unsigned count);
 
 // ---- multi-GPU (dist.cu) ----------------------------------------------------------------------------
 int dist_total_qubits(const spz_state *st);

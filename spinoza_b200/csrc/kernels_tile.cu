@@ -454,7 +454,7 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
     const bool v2 = tile2_enabled() && tile2_eligible(st, plan, prog, n_instr, n_groups);
     auto launch = [&](unsigned first, unsigned count) {
         if (v2) {
-            launch_tile2(st, plan, prog, n_instr, a.prog, a.groups, n_groups, a.terms, exact, first, count);
+            launch_tile2(st, plan, prog, n_instr, a.prog, a.groups, n_groups, a.terms, n_terms, exact, first, count);
             return;
         }
         a.tile_offset = first;

@@ -60,6 +60,7 @@ struct Tile2Args {
     const TileTerm *terms;
     int n_instr;
     int n_groups;
+    int n_terms;
     unsigned tile_offset;
     unsigned prog_off;   // byte offset of the staged program inside dynamic shared memory
     int L, n_high;
@@ -253,17 +254,43 @@ __global__ void __launch_bounds__(kThreads2, 2) k_tile2(const Tile2Args a) {
         const int n16 = a.n_instr * (int)(sizeof(TileInstr) / sizeof(uint4));
         for (int i = threadIdx.x; i < n16; i += nthr) dst[i] = src[i];
     }
+    // Phase factors: every group's product over the terms whose outer bits are set in this tile.  Term-parallel when the
+    // terms fit the (still unused) tile region as scratch: one L2 round trip for all terms at once instead of one per term
+    // in series per group -- a QFT pass has groups of ~20 terms, i.e. microseconds at the head of every tile otherwise.
+    constexpr int kScratchTerms = 2048; // 32 KB of factors + 2 KB of hit flags inside the 64 KB tile region
+    const bool term_parallel = a.n_terms <= kScratchTerms;
+    double2 *scr = reinterpret_cast<double2 *>(sre);
+    unsigned char *scr_hit = reinterpret_cast<unsigned char *>(scr + kScratchTerms);
+    if (term_parallel) {
+        for (int t = threadIdx.x; t < a.n_terms; t += nthr) {
+            const TileTerm tm = a.terms[t];
+            const bool hit = (base & tm.outer) == tm.outer;
+            scr[t] = hit ? make_double2(tm.fr, tm.fi) : make_double2(1.0, 0.0);
+            scr_hit[t] = hit ? 1 : 0;
+        }
+        __syncthreads();
+    }
     for (int g = threadIdx.x; g < a.n_groups; g += nthr) {
         const TileGroup gd = a.groups[g];
         double fr = 1.0, fi = 0.0;
         bool any = false;
-        for (int i = 0; i < gd.count; ++i) {
-            const TileTerm t = a.terms[gd.first + i];
-            if ((base & t.outer) == t.outer) { cmul2(fr, fi, t.fr, t.fi); any = true; }
+        if (term_parallel) {
+            for (int i = 0; i < gd.count; ++i) {
+                if (!scr_hit[gd.first + i]) continue;
+                const double2 f = scr[gd.first + i];
+                cmul2(fr, fi, f.x, f.y);
+                any = true;
+            }
+        } else {
+            for (int i = 0; i < gd.count; ++i) {
+                const TileTerm t = a.terms[gd.first + i];
+                if ((base & t.outer) == t.outer) { cmul2(fr, fi, t.fr, t.fi); any = true; }
+            }
         }
         gfac[g] = make_double2(fr, fi);
         gthr[g] = (any ? gd.thr : 0xffffu) | (gd.m << 16);
     }
+    if (term_parallel && !a.first_direct) __syncthreads(); // the staged tile is about to overwrite the scratch
     } // base
 
     // expand all five accumulators into the 16 per-amplitude factors (layout changes and the end of the program)
@@ -492,12 +519,12 @@ size_t tile2_smem_bytes(int n_instr, int n_groups, unsigned *prog_off) {
 // Kernel arguments, dynamic shared-memory size and instantiation for tiles [first, ...) of one pass.  Pure host code,
 // shared by the launcher below and by the CPU emulation harness.
 Tile2Args tile2_make_args(double *re, double *im, const TilePlan &plan, const TileInstr *h_prog, int n_instr, const TileInstr *d_prog,
-                          const TileGroup *d_groups, int n_groups, const TileTerm *d_terms, unsigned first, int direct_level,
-                          size_t *smem_bytes, bool *ctrl) {
+                          const TileGroup *d_groups, int n_groups, const TileTerm *d_terms, int n_terms, unsigned first,
+                          int direct_level, size_t *smem_bytes, bool *ctrl) {
     Tile2Args a{};
     a.re = re; a.im = im;
     a.prog = d_prog; a.groups = d_groups; a.terms = d_terms;
-    a.n_instr = n_instr; a.n_groups = n_groups;
+    a.n_instr = n_instr; a.n_groups = n_groups; a.n_terms = n_terms;
     a.tile_offset = first;
     a.L = plan.low_bits; a.n_high = plan.n_high;
     for (int k = 0; k < plan.n_high; ++k) a.high[k] = plan.high[k];
@@ -568,7 +595,8 @@ bool tile2_eligible(const spz_state *st, const TilePlan &plan, const TileInstr *
 // ring buffer and the split launch after an overlapped exchange; this function only picks the instantiation and launches
 // tiles [first, first + count).
 int launch_tile2(spz_state *st, const TilePlan &plan, const TileInstr *h_prog, int n_instr, const TileInstr *d_prog,
-                 const TileGroup *d_groups, int n_groups, const TileTerm *d_terms, bool exact, unsigned first, unsigned count) {
+                 const TileGroup *d_groups, int n_groups, const TileTerm *d_terms, int n_terms, bool exact, unsigned first,
+                 unsigned count) {
     static bool prepared[64] = {false};
     if (st->device >= 0 && st->device < 64 && !prepared[st->device]) {
         SPZ_TRY(tile2_prepare());
@@ -578,8 +606,8 @@ int launch_tile2(spz_state *st, const TilePlan &plan, const TileInstr *h_prog, i
     bool ctrl = false;
     int direct_level = 1; // SPZ_TILE_V2_DIRECT = 0..3, see tile2_make_args
     if (const char *e = std::getenv("SPZ_TILE_V2_DIRECT")) if (e[0] >= '0' && e[0] <= '3') direct_level = e[0] - '0';
-    const Tile2Args a = tile2_make_args(st->re, st->im, plan, h_prog, n_instr, d_prog, d_groups, n_groups, d_terms, first, direct_level,
-                                        &smem, &ctrl);
+    const Tile2Args a = tile2_make_args(st->re, st->im, plan, h_prog, n_instr, d_prog, d_groups, n_groups, d_terms, n_terms, first,
+                                        direct_level, &smem, &ctrl);
     if (exact) k_tile2<true, true><<<count, kThreads2, smem, st->stream>>>(a);
     else if (ctrl) k_tile2<false, true><<<count, kThreads2, smem, st->stream>>>(a);
     else k_tile2<false, false><<<count, kThreads2, smem, st->stream>>>(a);

@@ -97,7 +97,7 @@ extern "C" int emu_tile2_run(int n_qubits, double *re, double *im, const void *b
     if (!info[3]) return 1;
     size_t smem = 0;
     bool ctrl = false;
-    const spz::Tile2Args a = spz::tile2_make_args(re, im, P.plan, P.prog.data(), P.ni, P.prog.data(), P.groups.data(), P.ng, P.terms.data(), 0u,
+    const spz::Tile2Args a = spz::tile2_make_args(re, im, P.plan, P.prog.data(), P.ni, P.prog.data(), P.groups.data(), P.ng, P.terms.data(), P.nt, 0u,
                                                   direct_level, &smem, &ctrl);
     info[0] = ctrl ? 1 : 0; info[1] = a.first_direct; info[2] = a.last_direct;
     const unsigned n_blocks = (unsigned)(((uint64_t)1 << n_qubits) >> P.plan.tile_bits);

@@ -335,11 +335,12 @@ def test_layered_circuit(emu):
 # ---- shared-memory protocol under ThreadSanitizer ------------------------------------------------------------------
 # The emulation's barrier is annotated per generation (tests/emu/cuda_cpu_shim.h), so a missing __syncthreads() between a
 # shared-memory store and a load by another thread is a happens-before race that TSan reports deterministically.
-# Mutation check done by hand when this test was written (QFT-13, remove one barrier at a time): each of the four barriers
-# k_tile2 has now (after the tables are staged; between the staged store and the first register load; between store_regs and
-# load_regs of a LAYOUT; before the final copy-out) is reported when deleted, and the two further barriers inherited from
-# k_tile ("everyone has read before anyone's next store_regs") were reported as unnecessary -- a thread's next store goes to
-# the cells it has just read -- and were removed from k_tile2.
+# Mutation check (QFT-15, replace one __syncthreads() at a time by a no-op, both transfer modes): each of the six barriers
+# k_tile2 has -- after seg_off; after the per-term scratch is written; before the staged tile overwrites that scratch; after
+# the tables (and the staged tile) are in place; between store_regs and load_regs of a LAYOUT; before the final copy-out -- is
+# reported when deleted.  The two further barriers k_tile carries per layout change ("everyone has read before anyone's next
+# store_regs") were reported as unnecessary -- a thread's next store goes to the cells it has just read -- and are not in
+# k_tile2.
 
 @pytest.fixture(scope="module")
 def emu_tsan():
@@ -376,7 +377,7 @@ def tsan_run(exe, tmp_path, kernel, n, exact, re, im, blob, option=1):
 @pytest.mark.parametrize("kernel", [1, 2], ids=["k_tile", "k_tile2"])
 @pytest.mark.parametrize("case", ["qft", "random", "random-exact"])
 def test_no_shared_memory_race_in_any_pass(emu, emu_tsan, tmp_path, case, kernel):
-    n = 13
+    n = 15 if case == "qft" else 13   # QFT-15: groups of several outer terms, so the term-parallel reduction of k_tile2 shares scratch
     if case == "qft":
         qc = QuantumCircuit(QuantumRegister(n)); qc.qft()
     elif case == "random":
