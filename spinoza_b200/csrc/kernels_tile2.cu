@@ -25,6 +25,8 @@
 //      pair updates stay in place.
 //   6. One barrier per layout change and none after a register load: a thread's next shared-memory access after
 //      load_regs() is store_regs() under the same layout, i.e. to the cells it has just read.
+//   7. The per-tile reduction of the phase groups is parallel over TERMS (factors parked in the still unused tile region),
+//      one L2 round trip for all of them instead of one per term in series inside each group.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
