@@ -26,37 +26,59 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 
+#include <atomic>
+#include <sched.h>
+#ifdef SPZ_EMU_TSAN
+#include <sanitizer/tsan_interface.h>
+#endif
+
 namespace spz_emu {
 extern unsigned char *dyn_smem;
-extern unsigned block_threads;
+
+// The barrier of one thread block.  Plain build: a pthread barrier.  ThreadSanitizer build (race check of the shared-memory
+// protocol, i.e. "is a __syncthreads() missing?"): pthread_barrier_wait is useless for that -- TSan models it as
+// release/acquire on ONE sync object, so a fast thread that has already arrived at the NEXT barrier publishes its later
+// writes to slow threads still leaving the previous one, and the race disappears from the happens-before graph.  The TSan
+// barrier synchronises through relaxed atomics (no happens-before edges of their own) and annotates each GENERATION with
+// its own tag, which makes the graph exact.
+struct CtaBarrier {
+    unsigned n = 0;
+    std::atomic<int> or_acc{0};
 #ifdef SPZ_EMU_TSAN
-// ThreadSanitizer build (race check of the shared-memory protocol, i.e. "is a __syncthreads() missing?").
-// pthread_barrier_wait is useless for that: TSan models it as release/acquire on ONE sync object, so a fast thread that has
-// already arrived at the NEXT barrier publishes its later writes to slow threads still leaving the previous one, and the
-// race disappears from the happens-before graph.  This barrier synchronises through relaxed atomics (no happens-before
-// edges of their own) and annotates each GENERATION with its own tag, which makes the graph exact.
-} // namespace spz_emu
-#include <atomic>
-#include <sanitizer/tsan_interface.h>
-#include <sched.h>
-namespace spz_emu {
-extern std::atomic<unsigned> bar_count, bar_gen;
-extern char bar_tags[4096];
-inline void barrier() {
-    const unsigned g = bar_gen.load(std::memory_order_relaxed);
-    __tsan_release(&bar_tags[g & 4095u]);
-    if (bar_count.fetch_add(1u, std::memory_order_relaxed) + 1u == block_threads) {
-        bar_count.store(0u, std::memory_order_relaxed);
-        bar_gen.store(g + 1u, std::memory_order_relaxed);
-    } else {
-        while (bar_gen.load(std::memory_order_relaxed) == g) sched_yield();
+    std::atomic<unsigned> count{0}, gen{0};
+    char tags[4096];
+    void init(unsigned threads) { n = threads; count.store(0); gen.store(0); }
+    void destroy() {}
+    void wait() {
+        const unsigned g = gen.load(std::memory_order_relaxed);
+        __tsan_release(&tags[g & 4095u]);
+        if (count.fetch_add(1u, std::memory_order_relaxed) + 1u == n) {
+            count.store(0u, std::memory_order_relaxed);
+            gen.store(g + 1u, std::memory_order_relaxed);
+        } else {
+            while (gen.load(std::memory_order_relaxed) == g) sched_yield();
+        }
+        __tsan_acquire(&tags[g & 4095u]);
     }
-    __tsan_acquire(&bar_tags[g & 4095u]);
-}
 #else
-extern pthread_barrier_t block_barrier;
-inline void barrier() { pthread_barrier_wait(&block_barrier); }
+    pthread_barrier_t b;
+    void init(unsigned threads) { n = threads; pthread_barrier_init(&b, nullptr, threads); }
+    void destroy() { pthread_barrier_destroy(&b); }
+    void wait() { pthread_barrier_wait(&b); }
 #endif
+    // __syncthreads_or: two barriers keep it simple (nobody can start the next round before everyone has read this one)
+    int sync_or(int pred) {
+        if (pred) or_acc.store(1, std::memory_order_relaxed);
+        wait();
+        const int r = or_acc.load(std::memory_order_relaxed);
+        wait();
+        or_acc.store(0, std::memory_order_relaxed);
+        return r;
+    }
+};
+extern CtaBarrier default_cta;                 // harnesses that run one block at a time
+static thread_local CtaBarrier *cta = nullptr;  // harnesses with concurrent blocks point every thread at its block's barrier
+inline void barrier() { (cta ? cta : &default_cta)->wait(); }
 } // namespace spz_emu
 
 static thread_local uint3 threadIdx;
@@ -89,6 +111,7 @@ static inline void __stcg(double2 *p, double2 v) { *p = v; }
 #define cudaGetLastError() cudaSuccess
 
 static inline void __syncthreads() { spz_emu::barrier(); }
+static inline int __syncthreads_or(int pred) { return (spz_emu::cta ? spz_emu::cta : &spz_emu::default_cta)->sync_or(pred); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 // round-to-nearest intrinsics: plain IEEE operations (the emulation is compiled with -ffp-contract=off)
 static inline double __dmul_rn(double a, double b) { return a * b; }

@@ -16,13 +16,7 @@
 
 namespace spz_emu {
 unsigned char *dyn_smem = nullptr;
-unsigned block_threads = 0;
-#ifdef SPZ_EMU_TSAN
-std::atomic<unsigned> bar_count{0}, bar_gen{0};
-char bar_tags[4096];
-#else
-pthread_barrier_t block_barrier;
-#endif
+CtaBarrier default_cta;
 } // namespace spz_emu
 
 namespace {
@@ -32,10 +26,7 @@ template <class Kernel>
 void run_grid(unsigned n_blocks, unsigned n_threads, size_t smem_bytes, Kernel kernel) {
     std::vector<unsigned char> window(smem_bytes + 64);
     spz_emu::dyn_smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(window.data()) + 63) & ~(uintptr_t)63);
-    spz_emu::block_threads = n_threads;
-#ifndef SPZ_EMU_TSAN
-    pthread_barrier_init(&spz_emu::block_barrier, nullptr, n_threads);
-#endif
+    spz_emu::default_cta.init(n_threads);
     std::vector<std::thread> pool;
     pool.reserve(n_threads);
     for (unsigned t = 0; t < n_threads; ++t) {
@@ -50,9 +41,7 @@ void run_grid(unsigned n_blocks, unsigned n_threads, size_t smem_bytes, Kernel k
         });
     }
     for (auto &th : pool) th.join();
-#ifndef SPZ_EMU_TSAN
-    pthread_barrier_destroy(&spz_emu::block_barrier);
-#endif
+    spz_emu::default_cta.destroy();
     spz_emu::dyn_smem = nullptr;
 }
 
