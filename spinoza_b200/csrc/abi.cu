@@ -958,7 +958,19 @@ static int execute_impl(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_
         std::vector<spz_dist_action> acts;
         int rc = dist_lower(st, kind, p, target, t2, cmask, target, nu, acts);
         if (rc != SPZ_OK) { set_error("cannot lower gate kind %d onto the sharded register", kind); return rc; }
-        for (const spz_dist_action &a : acts) {
+        for (size_t ai = 0; ai < acts.size(); ++ai) {
+            const spz_dist_action &a = acts[ai];
+            // exchange + the uncontrolled gate that asked for it as one kernel (opt-in; not inside exchange-spanning windows,
+            // where the exchange is a node of the scheduling graph)
+            if (!sink && !window_exchanges && a.type == ACT_EXCHANGE && ai + 1 < acts.size() && acts[ai + 1].type == ACT_LOCAL_GATE &&
+                dist_can_fuse_gate(st, acts[ai + 1].kind, cmask, acts[ai + 1].target, a.lq)) {
+                GateK g;
+                SPZ_TRY(resolve_gate(acts[ai + 1].kind, acts[ai + 1].p, &g));
+                SPZ_TRY(fuser.flush());
+                SPZ_TRY(dist_exchange_gate(st, a.gbit, a.lq, g));
+                ++ai;
+                continue;
+            }
             switch (a.type) {
             case ACT_SKIP:
                 if (window_exchanges) // placeholder with the real op's shape

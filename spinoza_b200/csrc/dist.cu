@@ -18,6 +18,8 @@
 #include "dist_plan.h"
 #include "kernels_direct.cuh"
 
+#include "kernels_xgate.cuh"
+
 namespace spz {
 
 constexpr int kMaxRanks = 16;
@@ -31,6 +33,7 @@ struct CtrlBlock { // lives in device memory of each rank, mapped by every peer
     double red_slot[2][kMaxRanks];
     double red_result;
     unsigned long long error;
+    unsigned long long xg_flag[kMaxXgCtas]; // fused exchange + gate: "partner CTA b has read step i" (kernels_xgate.cuh)
 };
 
 struct IpcBlob {
@@ -58,6 +61,9 @@ struct DistCtx {
     int split_bit = -1;
     bool overlap = true;
     int xchg_ctas = 40; // CTAs of the persistent exchange kernel in overlapped mode (SPZ_XCHG_CTAS)
+    // fused exchange + gate (opt-in, SPZ_DIST_FUSE_GATE=1): flag values already used, and the size of its persistent grid
+    unsigned long long xg_base = 0;
+    int xg_ctas = 96;   // SPZ_XG_CTAS; every CTA must be resident at once, so <= the number of SMs
     // stats
     double n_exchanges = 0, bytes_sent = 0, ms_accum = 0, n_overlapped = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, free_events;
@@ -337,6 +343,66 @@ int dist_exchange(spz_state *st, int gbit, int lq) {
     return SPZ_OK;
 }
 
+// Exchange fused with the uncontrolled non-diagonal gate that asked for it (kernels_xgate.cuh).  Same bracket as the
+// sequential exchange: ready handshake, one kernel, done handshake, all on the main stream.
+bool dist_fuse_gate_enabled() {
+    const char *e = std::getenv("SPZ_DIST_FUSE_GATE");
+    return e && e[0] == '1';
+}
+
+int dist_exchange_gate(spz_state *st, int gbit, int lq, const GateK &g) {
+    DistCtx *c = ctx_of(st);
+    if (!c->connected) { set_error("dist state used before spz_dist_connect"); return SPZ_ERR_COMM; }
+    constexpr int W = 4, U = 2, THREADS = 256;
+    const int n_local = st->n;
+    if (lq < LogW<W>::v || n_local - 1 - LogW<W>::v < 0) { set_error("internal: fused exchange needs a vector path"); return SPZ_ERR_INVALID_ARG; }
+    const int partner = c->rank ^ (1 << gbit);
+    SPZ_TRY(dist_join(st));
+    const unsigned long long e = ++c->epoch;
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!c->free_events.empty()) { ev = c->free_events.back(); c->free_events.pop_back(); }
+    else { SPZ_CUDA(cudaEventCreate(&ev.first)); SPZ_CUDA(cudaEventCreate(&ev.second)); }
+    XGArgs a{};
+    a.mine_re = st->re; a.mine_im = st->im; a.peer_re = c->peer_re[partner]; a.peer_im = c->peer_im[partner];
+    a.nvec = 1ll << (n_local - 1 - LogW<W>::v);
+    a.lq = lq; a.my_bit = (c->rank >> gbit) & 1;
+    a.peer_flag = c->peer_ctrl[partner]->xg_flag; a.my_flag = c->ctrl->xg_flag;
+    a.flag_base = c->xg_base;
+    a.err = &c->ctrl->error;
+    a.timeout_ns = kSpinTimeoutNs;
+    for (int k = 0; k < 7; ++k) a.s[k] = g.s[k];
+    const long long per = (long long)THREADS * U;
+    const int ctas = (int)std::max<long long>(1, std::min<long long>(std::min(c->xg_ctas, kMaxXgCtas), (a.nvec + per - 1) / per));
+    c->xg_base += (unsigned long long)((a.nvec + per * ctas - 1) / (per * ctas)); // steps of the busiest CTA, the same on both ranks
+    k_handshake<<<1, 1, 0, st->stream>>>(&c->peer_ctrl[partner]->ready[c->rank], &c->ctrl->ready[partner], e, &c->ctrl->error);
+    SPZ_CUDA(cudaEventRecord(ev.first, st->stream));
+    switch (g.kind) {
+    case SPZ_GATE_H: k_exchange_gate<SPZ_GATE_H, W, U, THREADS><<<ctas, THREADS, 0, st->stream>>>(a); break;
+    case SPZ_GATE_X: k_exchange_gate<SPZ_GATE_X, W, U, THREADS><<<ctas, THREADS, 0, st->stream>>>(a); break;
+    case SPZ_GATE_Y: k_exchange_gate<SPZ_GATE_Y, W, U, THREADS><<<ctas, THREADS, 0, st->stream>>>(a); break;
+    case SPZ_GATE_RX: k_exchange_gate<SPZ_GATE_RX, W, U, THREADS><<<ctas, THREADS, 0, st->stream>>>(a); break;
+    case SPZ_GATE_RY: k_exchange_gate<SPZ_GATE_RY, W, U, THREADS><<<ctas, THREADS, 0, st->stream>>>(a); break;
+    case SPZ_GATE_U: k_exchange_gate<SPZ_GATE_U, W, U, THREADS><<<ctas, THREADS, 0, st->stream>>>(a); break;
+    default: set_error("internal: gate kind %d cannot be fused into an exchange", g.kind); return SPZ_ERR_INVALID_ARG;
+    }
+    SPZ_CUDA(cudaEventRecord(ev.second, st->stream));
+    c->pending.push_back(ev);
+    k_handshake<<<1, 1, 0, st->stream>>>(&c->peer_ctrl[partner]->done[c->rank], &c->ctrl->done[partner], e, &c->ctrl->error);
+    count_launch(3);
+    SPZ_CUDA(cudaGetLastError());
+    c->n_exchanges += 1;
+    c->bytes_sent += 16.0 * (double)(1ll << (n_local - 1)); // half a shard crosses the link in each direction, here as reads
+    return SPZ_OK;
+}
+
+// May the gate be fused into the exchange that fetches its target?  Opted in, non-diagonal, vector path, and NO control at
+// all in the logical op: a control that happened to be the evicted qubit would sit on the exchanged rank bit afterwards, one
+// partner would skip the gate and the other apply it, and the two would run different kernels against each other.
+bool dist_can_fuse_gate(const spz_state *st, int kind, uint64_t logical_cmask, int target, int lq) {
+    if (!dist_fuse_gate_enabled() || logical_cmask != 0 || target != lq || lq < 2 || st->n < 3) return false;
+    return kind == SPZ_GATE_H || kind == SPZ_GATE_X || kind == SPZ_GATE_Y || kind == SPZ_GATE_RX || kind == SPZ_GATE_RY || kind == SPZ_GATE_U;
+}
+
 // Make the main stream wait for an overlapped exchange still in flight (everything but the split tile pass needs
 // the whole shard).
 int dist_join(spz_state *st) {
@@ -393,7 +459,17 @@ int dist_apply_masked(spz_state *st, int kind, const double *p, int t0, int t1, 
     std::vector<spz_dist_action> acts;
     int rc = c->plan.lower(c->rank, kind, p, t0, t1, cmask, target, nullptr, acts);
     if (rc != SPZ_OK) { set_error("cannot lower gate kind %d target %d onto the sharded register", kind, target); return rc; }
-    for (const spz_dist_action &a : acts) {
+    for (size_t ai = 0; ai < acts.size(); ++ai) {
+        const spz_dist_action &a = acts[ai];
+        // exchange immediately followed by the uncontrolled gate that asked for it: one fused kernel (opt-in)
+        if (a.type == ACT_EXCHANGE && ai + 1 < acts.size() && acts[ai + 1].type == ACT_LOCAL_GATE &&
+            dist_can_fuse_gate(st, acts[ai + 1].kind, cmask, acts[ai + 1].target, a.lq)) {
+            GateK g;
+            SPZ_TRY(resolve_gate(acts[ai + 1].kind, acts[ai + 1].p, &g));
+            SPZ_TRY(dist_exchange_gate(st, a.gbit, a.lq, g));
+            ++ai;
+            continue;
+        }
         switch (a.type) {
         case ACT_SKIP: break;
         case ACT_EXCHANGE: SPZ_TRY(dist_exchange(st, a.gbit, a.lq)); break;
@@ -571,6 +647,7 @@ int spz_dist_create(int n_qubits, int rank, int world, int device, spz_state **o
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_half[1], cudaEventDisableTiming);
     if (getenv("SPZ_NO_OVERLAP")) c->overlap = false;
     if (const char *v = getenv("SPZ_XCHG_CTAS")) { const int k = atoi(v); if (k >= 1 && k <= 1024) c->xchg_ctas = k; }
+    if (const char *v = getenv("SPZ_XG_CTAS")) { const int k = atoi(v); if (k >= 1 && k <= kMaxXgCtas) c->xg_ctas = k; }
     if (e != cudaSuccess) { int rc = cuda_fail(e, "cudaMalloc(ctrl)", __FILE__, __LINE__); spz_destroy(st); return rc; }
     c->peer_ctrl[rank] = c->ctrl; c->peer_re[rank] = st->re; c->peer_im[rank] = st->im;
     if (world == 1) { c->connected = true; if (upload_peer_table(c) != SPZ_OK) { spz_destroy(st); return SPZ_ERR_CUDA; } }

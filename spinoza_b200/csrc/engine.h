@@ -160,6 +160,9 @@ int launch_tile2(spz_state *st, const TilePlan &plan, const TileInstr *h_prog, i
 int dist_total_qubits(const spz_state *st);
 int dist_apply_masked(spz_state *st, int kind, const double *p, int t0, int t1, uint64_t cmask, int target);
 int dist_exchange(spz_state *st, int gbit, int lq);
+// opt-in (SPZ_DIST_FUSE_GATE=1): the exchange and the uncontrolled non-diagonal gate on the arriving qubit in one kernel
+bool dist_can_fuse_gate(const spz_state *st, int kind, uint64_t logical_cmask, int target, int lq);
+int dist_exchange_gate(spz_state *st, int gbit, int lq, const GateK &g);
 int dist_join(spz_state *st); // main stream waits for an overlapped exchange still in flight
 bool dist_take_split(spz_state *st, int *split_bit, cudaEvent_t *ev0, cudaEvent_t *ev1);
 inline int join_pending(spz_state *st) { return st->dist ? dist_join(st) : SPZ_OK; }

@@ -33,7 +33,7 @@ def pytest_collection_modifyitems(config, items):
 
 # Tuning switches of the engine change how a circuit is scheduled or which kernel variant runs, never
 # what it computes; the suite pins them to their defaults so that shape-specific assertions do not depend on the caller's shell.
-TUNING_ENV = ("SPZ_TILE_V2", "SPZ_TILE_V2_DIRECT", "SPZ_TILE_LMIN", "SPZ_TILE_SELECT", "SPZ_DIST_WINDOW", "SPZ_TILE_MIN_OPS")
+TUNING_ENV = ("SPZ_TILE_V2", "SPZ_TILE_V2_DIRECT", "SPZ_TILE_LMIN", "SPZ_TILE_SELECT", "SPZ_DIST_WINDOW", "SPZ_TILE_MIN_OPS", "SPZ_DIST_FUSE_GATE", "SPZ_XG_CTAS")
 
 
 @pytest.fixture(autouse=True)

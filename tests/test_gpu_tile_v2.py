@@ -183,3 +183,57 @@ def test_windows_spanning_exchanges_match_the_oracle(n, world, select, monkeypat
     orc.execute(cpu, box["ops"])
     assert np.max(np.abs(re - cpu.reals)) <= 1e-12 and np.max(np.abs(im - cpu.imags)) <= 1e-12
     assert len({box[r] for r in range(world)}) == 1   # every rank ran the same exchanges
+
+
+# ---- exchange fused with the gate that asked for it (SPZ_DIST_FUSE_GATE=1, kernels_xgate.cuh; opt-in) --------------------
+
+@pytest.mark.parametrize("n,world", [(12, 2), (14, 4)])
+def test_fused_exchange_gate_is_bit_identical_gate_by_gate(n, world, monkeypatch):
+    """The 1-qubit sweep of the bench on shards: every non-diagonal gate on a global qubit takes the fused kernel."""
+    from spinoza_b200.distributed import DistState
+    from tests.test_gpu_dist import gather, run_group, upload_shards
+    monkeypatch.setenv("SPZ_DIST_FUSE_GATE", "1")
+    monkeypatch.setenv("SPZ_XG_CTAS", "8")   # several shards share one GPU here: every CTA of every shard must be resident
+    init = orc.gen_random_state(n, 47)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, init)
+    seq = [(orc.H, ()), (orc.RX, (1.0,)), (orc.RY, (0.4,)), (orc.X, ()), (orc.Y, ()), (orc.U, (0.1, 0.2, 0.3)), (orc.RZ, (1.0,))]
+    cpu = init.clone()
+    for kind, p in seq:
+        for t in range(n):
+            orc.apply(kind, cpu, t, p)
+
+    def body(rank, s):
+        for kind, p in seq:
+            for t in range(n):
+                sb.apply(sb.Gate(kind, p), s, t)
+        s.sync()
+    run_group(states, body)
+    re, im = gather(states)
+    assert np.array_equal(re, cpu.reals) and np.array_equal(im, cpu.imags)
+
+
+@pytest.mark.parametrize("n,world", [(15, 2), (16, 4)])
+def test_fused_exchange_gate_inside_execute(n, world, monkeypatch):
+    from spinoza_b200.distributed import DistState
+    from tests.test_gpu_dist import gather, run_group, upload_shards
+    monkeypatch.setenv("SPZ_DIST_FUSE_GATE", "1")
+    monkeypatch.setenv("SPZ_XG_CTAS", "8")
+    init = orc.gen_random_state(n, 48)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, init)
+    box = {}
+
+    def body(rank, s):
+        q = QuantumCircuit.from_state(s, fuse=True)
+        q.qft()
+        workloads.random_layered_circuit(q, depth=6, seed=42)
+        if rank == 0:
+            box["ops"] = oracle_ops_from(q)
+        q.execute()
+        s.sync()
+    run_group(states, body)
+    re, im = gather(states)
+    cpu = init.clone()
+    orc.execute(cpu, box["ops"])
+    assert np.max(np.abs(re - cpu.reals)) <= 1e-12 and np.max(np.abs(im - cpu.imags)) <= 1e-12
