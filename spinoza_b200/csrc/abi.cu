@@ -424,7 +424,8 @@ struct Fuser {
     }
 
     // ---- scheduling window ---------------------------------------------------------------------------------
-    // Ops are buffered and grouped at flush points (end of the list, a measurement, an exchange).  In the default
+    // Ops are buffered and grouped at flush points (end of the list, a measurement, an exchange -- unless the window is
+    // allowed to span exchanges, SPZ_DIST_WINDOW).  In the default
     // fused mode the window is scheduled as a dependency DAG: two ops need their program order only if they share
     // a qubit on which at least one of them is not "Z-like" (diagonal gates and controls are Z-like: block diagonal
     // in that qubit's computational basis).  Ready ops are packed into the current tile in program order, so e.g.
@@ -962,12 +963,19 @@ static int execute_impl(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_
             const spz_dist_action &a = acts[ai];
             // exchange + the uncontrolled gate that asked for it as one kernel (opt-in; not inside exchange-spanning windows,
             // where the exchange is a node of the scheduling graph)
-            if (!sink && !window_exchanges && a.type == ACT_EXCHANGE && ai + 1 < acts.size() && acts[ai + 1].type == ACT_LOCAL_GATE &&
+            if (!window_exchanges && a.type == ACT_EXCHANGE && ai + 1 < acts.size() && acts[ai + 1].type == ACT_LOCAL_GATE &&
                 dist_can_fuse_gate(st, acts[ai + 1].kind, cmask, acts[ai + 1].target, a.lq)) {
                 GateK g;
                 SPZ_TRY(resolve_gate(acts[ai + 1].kind, acts[ai + 1].p, &g));
                 SPZ_TRY(fuser.flush());
-                SPZ_TRY(dist_exchange_gate(st, a.gbit, a.lq, g));
+                if (sink) { // dry run: an exchange step followed by the gate as a step of its own describes the same thing
+                    sink->exchange(a.gbit, a.lq);
+                    ROp r{};
+                    r.kind = acts[ai + 1].kind; r.target = acts[ai + 1].target; r.g = g; r.src = (int)cur;
+                    sink->take(std::vector<ROp>{r});
+                } else {
+                    SPZ_TRY(dist_exchange_gate(st, a.gbit, a.lq, g));
+                }
                 ++ai;
                 continue;
             }

@@ -170,6 +170,30 @@ def test_eight_ranks_qft_with_chosen_tiles(monkeypatch):
     assert 3 <= stats["exchange"] <= 6, stats
 
 
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("world", [2, 4])
+def test_exchange_fused_with_its_gate_keeps_the_op_accounting(world, fuse, monkeypatch):
+    """SPZ_DIST_FUSE_GATE=1: the gate that triggers an exchange is applied by the exchange kernel and must not be applied
+    again (or dropped) by the scheduler.  The dry run reports it as "exchange, then that gate as a step of its own"."""
+    monkeypatch.setenv("SPZ_DIST_FUSE_GATE", "1")
+    n = 13 + world.bit_length() - 1
+    qc = qft(n, fuse=fuse)
+    workloads.random_layered_circuit(qc, depth=5, seed=2)
+    psi0 = D.random_state(n, 13)
+    got, stats = replay(qc, world, psi0)
+    np.testing.assert_allclose(got, dense(qc, psi0), rtol=0, atol=1e-12)
+    assert stats["exchange"] >= 1
+    # the exchanges asked for by an uncontrolled gate (QFT's H gates) are directly followed by that gate alone, on the bit the
+    # exchange brought in; exchanges asked for by controlled gates (the CX of the layered part) stay plain
+    steps, _ = steps_of_rank(qc, world, 0)
+    fused = 0
+    for i, st in enumerate(steps[:-1]):
+        nxt = steps[i + 1]
+        if st[0] == "exchange" and nxt[0] == "op" and nxt[2] == st[2] and nxt[5] == 0 and nxt[1] not in DIAG:
+            fused += 1
+    assert fused >= world.bit_length() - 1, (fused, [s[0] for s in steps])
+
+
 def test_unfused_sharded_execution(monkeypatch):
     n, world = 10, 4
     qc = random_circuit(n, 120, 23, fuse=False)
