@@ -447,17 +447,38 @@ struct Fuser {
         return rc;
     }
 
-    // an exchange queued in the window (sharded registers): everything scheduled so far must be on the device first
-    int run_exchange(const ROp &x) {
+    // an exchange queued in the window (sharded registers): everything scheduled so far must be on the device first.
+    // `gate`: the uncontrolled non-diagonal op that asked for the exchange, to be applied by the exchange kernel itself
+    // (SPZ_DIST_FUSE_GATE), or null.
+    int run_exchange(const ROp &x, const ROp *gate) {
         SPZ_TRY(emit_group());
-        if (sink) { sink->exchange(x.t2, x.target); return SPZ_OK; }
-        return dist_exchange(st, x.t2, x.target);
+        if (sink) {
+            sink->exchange(x.t2, x.target);
+            if (gate) sink->take(std::vector<ROp>{*gate}); // the dry run describes the pair as two steps
+            return SPZ_OK;
+        }
+        return gate ? dist_exchange_gate(st, x.t2, x.target, gate->g) : dist_exchange(st, x.t2, x.target);
+    }
+    // Is pending[gi] the op that asked for exchange pending[e], and may the exchange kernel apply it?  It is the next op
+    // of the window (same source op), uncontrolled in every sense, and the exchange is all it still waits for: everything
+    // earlier on its qubit consulted the rank bit the qubit sat on, so it already precedes the exchange.
+    bool fusable_trigger(int e, int gi, int undone_preds) const {
+        if (gi >= (int)pending.size()) return false;
+        const ROp &x = pending[e], &g = pending[gi];
+        return g.src == x.src && g.kind != kRopExchange && !g.skip && g.cmask == 0 && g.grefs == 0 && g.const_hi < 0 && undone_preds == 1 &&
+               !is_diagonal_kind(g.kind) && dist_can_fuse_gate(st, g.kind, 0, g.target, x.target);
     }
 
     int schedule_in_order() {
-        for (const ROp &op : pending) {
-            if (op.kind == kRopExchange) SPZ_TRY(run_exchange(op));
-            else SPZ_TRY(add(op));
+        for (size_t i = 0; i < pending.size(); ++i) {
+            const ROp &op = pending[i];
+            if (op.kind == kRopExchange) {
+                const bool fuse_g = fusable_trigger((int)i, (int)i + 1, 1);
+                SPZ_TRY(run_exchange(op, fuse_g ? &pending[i + 1] : nullptr));
+                if (fuse_g) ++i;
+            } else {
+                SPZ_TRY(add(op));
+            }
         }
         return emit_group();
     }
@@ -585,10 +606,17 @@ struct Fuser {
         while (remaining > 0) {
             while (next_exchange < N && (pending[next_exchange].kind != kRopExchange || done[next_exchange])) ++next_exchange;
             if (next_exchange < N && npred[next_exchange] == 0) {
-                SPZ_TRY(run_exchange(pending[next_exchange]));
+                const int gi = next_exchange + 1;
+                const bool fuse_g = gi < N && !done[gi] && fusable_trigger(next_exchange, gi, npred[gi]);
+                SPZ_TRY(run_exchange(pending[next_exchange], fuse_g ? &pending[gi] : nullptr));
                 done[next_exchange] = 1;
                 --remaining;
                 for (int sidx : succ[next_exchange]) --npred[sidx];
+                if (fuse_g) {
+                    done[gi] = 1;
+                    --remaining;
+                    for (int sidx : succ[gi]) --npred[sidx];
+                }
                 continue;
             }
             {

@@ -170,9 +170,11 @@ def test_eight_ranks_qft_with_chosen_tiles(monkeypatch):
     assert 3 <= stats["exchange"] <= 6, stats
 
 
+@pytest.mark.parametrize("window", ["0", "1"])
 @pytest.mark.parametrize("fuse", [True, False])
 @pytest.mark.parametrize("world", [2, 4])
-def test_exchange_fused_with_its_gate_keeps_the_op_accounting(world, fuse, monkeypatch):
+def test_exchange_fused_with_its_gate_keeps_the_op_accounting(world, fuse, window, monkeypatch):
+    monkeypatch.setenv("SPZ_DIST_WINDOW", window)
     """SPZ_DIST_FUSE_GATE=1: the gate that triggers an exchange is applied by the exchange kernel and must not be applied
     again (or dropped) by the scheduler.  The dry run reports it as "exchange, then that gate as a step of its own"."""
     monkeypatch.setenv("SPZ_DIST_FUSE_GATE", "1")

@@ -75,11 +75,12 @@ def main():
         os.environ["SPZ_TILE_SELECT"] = str(int(rng.integers(2)))
         os.environ["SPZ_TILE_LMIN"] = str(int(rng.integers(4, 7)))
         os.environ["SPZ_DIST_WINDOW"] = str(int(rng.integers(2)))  # sharded engine only: windows that span exchanges
+        os.environ["SPZ_DIST_FUSE_GATE"] = str(int(rng.integers(2)))  # sharded engine only: op accounting of fused exchanges
         gen = swap_heavy if rng.random() < 0.3 else random_circuit
         x = rng.random()
         engine = "emu" if x < 0.35 and n <= 14 else "sharded" if x > 0.75 else "numpy"
         desc = dict(it=it, n=n, count=count, seed=seed, exact=exact, gen=gen.__name__, engine=engine,
-                    select=os.environ["SPZ_TILE_SELECT"], lmin=os.environ["SPZ_TILE_LMIN"], window=os.environ["SPZ_DIST_WINDOW"])
+                    select=os.environ["SPZ_TILE_SELECT"], lmin=os.environ["SPZ_TILE_LMIN"], window=os.environ["SPZ_DIST_WINDOW"], fuse_gate=os.environ["SPZ_DIST_FUSE_GATE"])
         try:
             qc = gen(n, count, seed, exact=exact)
             trs = list(qc.transformations)
