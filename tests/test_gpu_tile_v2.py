@@ -213,11 +213,13 @@ def test_fused_exchange_gate_is_bit_identical_gate_by_gate(n, world, monkeypatch
     assert np.array_equal(re, cpu.reals) and np.array_equal(im, cpu.imags)
 
 
+@pytest.mark.parametrize("window", ["0", "1"])
 @pytest.mark.parametrize("n,world", [(15, 2), (16, 4)])
-def test_fused_exchange_gate_inside_execute(n, world, monkeypatch):
+def test_fused_exchange_gate_inside_execute(n, world, window, monkeypatch):
     from spinoza_b200.distributed import DistState
     from tests.test_gpu_dist import gather, run_group, upload_shards
     monkeypatch.setenv("SPZ_DIST_FUSE_GATE", "1")
+    monkeypatch.setenv("SPZ_DIST_WINDOW", window)
     monkeypatch.setenv("SPZ_XG_CTAS", "8")
     init = orc.gen_random_state(n, 48)
     states = DistState.create_local_group(n, world)

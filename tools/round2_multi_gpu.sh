@@ -24,6 +24,8 @@ done
 # exchange fused with the gate that asked for it (kernels_xgate.cuh): QFT and the bench's 1-qubit sweep
 export SPZ_DIST_FUSE_GATE=1
 run qft_dist_fusegate 0 tools/qft_dist.py --local-qubits "$LQ"
+run qft_dist_fusegate 1 tools/qft_dist.py --local-qubits "$LQ"          # both: windows spanning exchanges + fused gates
+run config3_dist_fusegate 1 tools/config3_dist.py --local-qubits "$LQ"
 SPZ_DIST_FUSE_GATE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) \
     bench.py --gpus "$N" --steps 2 --warmup 3 --no-cpu > "gpurun_out/bench_N${N}_fusegate.json" 2> "gpurun_out/bench_N${N}_fusegate.err"
 echo "bench with fused exchange+gate rc=$?"; tail -c 400 "gpurun_out/bench_N${N}_fusegate.json"; echo
