@@ -190,6 +190,9 @@ SPZ_API int spz_dist_connect(spz_state *st, const void *blobs); /* world blobs, 
 SPZ_API int spz_dist_connect_local(spz_state **states, int world);
 SPZ_API int spz_dist_perm(const spz_state *st, int32_t *perm_out); /* logical qubit -> physical bit, n_qubits entries */
 SPZ_API int spz_dist_local_qubits(const spz_state *st);
+/* Clone of a sharded register (core.rs:18), a collective: every rank creates + connects a second register, then copies its
+   shard, the qubit permutation and the measurement RNG state into it with this call. */
+SPZ_API int spz_dist_copy_from(spz_state *dst, const spz_state *src);
 SPZ_API int spz_dist_stats(const spz_state *st, double *out4);  /* exchanges, bytes sent, exchange ms, overlapped exchanges */
 /* planning only (pure host code, no CUDA): what the CPU tests of the sharding logic drive */
 typedef struct spz_dist_plan spz_dist_plan;

@@ -124,6 +124,7 @@ _SIGNATURES = {
     "spz_dist_connect_local": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "spz_dist_perm": (C.c_int, [_vp, _i32p]),
     "spz_dist_local_qubits": (C.c_int, [_vp]),
+    "spz_dist_copy_from": (C.c_int, [_vp, _vp]),
     "spz_dist_stats": (C.c_int, [_vp, _dp]),
     "spz_dist_plan_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_vp)]),
     "spz_dist_plan_destroy": (C.c_int, [_vp]),

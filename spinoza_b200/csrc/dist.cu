@@ -729,6 +729,31 @@ int spz_dist_perm(const spz_state *st, int32_t *perm_out) {
 
 int spz_dist_local_qubits(const spz_state *st) { return st ? st->n : -1; }
 
+// The Clone of a sharded register (core.rs:18 #[derive(Clone)]) is a collective: every rank creates and connects a second
+// register (spz_dist_create / export / connect), then copies its own shard and the shared plan state into it.
+int spz_dist_copy_from(spz_state *dst, const spz_state *csrc) {
+    spz_state *src = const_cast<spz_state *>(csrc);
+    if (!dst || !src || !dst->dist || !src->dist) { set_error("both handles must be shards"); return SPZ_ERR_INVALID_ARG; }
+    DistCtx *d = ctx_of(dst), *s = ctx_of(src);
+    if (dst->len != src->len || d->plan.n != s->plan.n || d->world != s->world || d->rank != s->rank) {
+        set_error("shards of different registers or ranks"); return SPZ_ERR_INVALID_ARG;
+    }
+    SPZ_CUDA(cudaSetDevice(dst->device));
+    SPZ_TRY(dist_join(src));
+    SPZ_TRY(dist_join(dst));
+    SPZ_CUDA(cudaStreamSynchronize(src->stream));
+    const size_t bytes = sizeof(double) * (size_t)src->len;
+    SPZ_CUDA(cudaMemcpyAsync(dst->re, src->re, bytes, cudaMemcpyDeviceToDevice, dst->stream));
+    SPZ_CUDA(cudaMemcpyAsync(dst->im, src->im, bytes, cudaMemcpyDeviceToDevice, dst->stream));
+    SPZ_CUDA(cudaStreamSynchronize(dst->stream));
+    const DistPlan &sp = s->plan;
+    DistPlan &dp = d->plan;
+    for (int q = 0; q < 64; ++q) { dp.perm[q] = sp.perm[q]; dp.inv[q] = sp.inv[q]; dp.last_use[q] = sp.last_use[q]; }
+    dp.clock = sp.clock;
+    dst->rng = src->rng;
+    return SPZ_OK;
+}
+
 int spz_dist_stats(const spz_state *cst, double *out4) {
     if (!cst || !cst->dist || !out4) return SPZ_ERR_INVALID_ARG;
     spz_state *st = const_cast<spz_state *>(cst);

@@ -87,6 +87,7 @@ class DistState(State):
         _check(_lib.spz_dist_create(int(n), env.rank, env.world, dev, C.byref(h)))
         super().__init__(n, dev, _handle=h)
         self.n_local = _lib.spz_dist_local_qubits(self._h)
+        self._local_group = not _connect
         if _connect:
             blob = C.create_string_buffer(IPC_BLOB_BYTES)
             _check(_lib.spz_dist_export(self._h, blob))
@@ -118,8 +119,22 @@ class DistState(State):
         return {"exchanges": int(ex), "overlapped": int(out[3]), "bytes_sent": sent, "exchange_ms": ms,
                 "nvlink_GBps_per_direction": (sent / (ms * 1e-3) / 1e9) if ms > 0 else None}
 
-    def clone(self):
-        raise NotImplementedError("clone of a sharded register")
+    def clone(self) -> "DistState":
+        """#[derive(Clone)] (core.rs:18) for a sharded register.  COLLECTIVE: every rank calls it at the same point (the new
+        register exchanges IPC handles like the first one did).  Shards created with create_local_group are cloned as a
+        group with clone_local_group."""
+        if self._local_group:
+            raise RuntimeError("shards of a local group are cloned together: DistState.clone_local_group(states)")
+        new = DistState(self.n, self.env, device=self.device)
+        _check(_lib.spz_dist_copy_from(new._h, self._h))
+        return new
+
+    @staticmethod
+    def clone_local_group(states: List["DistState"]) -> List["DistState"]:
+        new = DistState.create_local_group(states[0].n, len(states), [s.device for s in states])
+        for d, s in zip(new, states):
+            _check(_lib.spz_dist_copy_from(d._h, s._h))
+        return new
 
     def sample(self, shots: int, seed: int = 0, u01: Optional[np.ndarray] = None) -> np.ndarray:
         """Exact sampling of the whole sharded register: every rank passes the same uniforms, the owning rank answers
