@@ -63,7 +63,7 @@ struct DistCtx {
     int xchg_ctas = 40; // CTAs of the persistent exchange kernel in overlapped mode (SPZ_XCHG_CTAS)
     // fused exchange + gate (opt-in, SPZ_DIST_FUSE_GATE=1): flag values already used, and the size of its persistent grid
     unsigned long long xg_base = 0;
-    int xg_ctas = 96;   // SPZ_XG_CTAS; every CTA must be resident at once, so <= the number of SMs
+    int xg_ctas = 128;  // SPZ_XG_CTAS; every CTA must be resident at once, so <= the number of SMs
     // stats
     double n_exchanges = 0, bytes_sent = 0, ms_accum = 0, n_overlapped = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, free_events;
@@ -353,7 +353,10 @@ bool dist_fuse_gate_enabled() {
 int dist_exchange_gate(spz_state *st, int gbit, int lq, const GateK &g) {
     DistCtx *c = ctx_of(st);
     if (!c->connected) { set_error("dist state used before spz_dist_connect"); return SPZ_ERR_COMM; }
-    constexpr int W = 4, U = 2, THREADS = 256;
+    // Bytes in flight decide the NVLink rate: a step of one CTA reads THREADS * U * W * 16 B = 64 KB from the partner, and a
+    // step lasts a remote-load latency plus a flag round trip (several microseconds), so ~128 CTAs x 64 KB per step are
+    // needed to cover ~700 GB/s.  Tuning on hardware: SPZ_XG_CTAS.
+    constexpr int W = 4, U = 4, THREADS = 256;
     const int n_local = st->n;
     if (lq < LogW<W>::v || n_local - 1 - LogW<W>::v < 0) { set_error("internal: fused exchange needs a vector path"); return SPZ_ERR_INVALID_ARG; }
     const int partner = c->rank ^ (1 << gbit);

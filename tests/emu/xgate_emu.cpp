@@ -37,7 +37,7 @@ void set_error(const char *, ...) {}
 
 namespace {
 
-constexpr int W = 4, U = 2;
+constexpr int W = 4, U = 4; // as dist_exchange_gate launches it
 
 template <int KIND, int THREADS>
 void run_pair(double *re0, double *im0, double *re1, double *im1, int n_local, int lq, const double *s7, int grid, unsigned long long flag_base,

@@ -73,12 +73,12 @@ def run(emu, n_local, lq, kind, params, grid, seed):
 
 @pytest.mark.parametrize("kind,params", KINDS)
 def test_every_gate_every_local_bit(emu, kind, params):
-    n_local = 9                      # 2^8 pairs = 64 vectors; a block of 32 threads x U = 2 takes 64 vectors per step
+    n_local = 10                     # 2^9 pairs = 128 vectors; a block of 32 threads x U = 4 takes 128 vectors per step
     for lq in range(2, n_local):
         run(emu, n_local, lq, kind, params, grid=2, seed=10 * lq + kind)
 
 
-@pytest.mark.parametrize("n_local,grid", [(4, 1), (5, 3), (8, 1), (9, 4), (10, 3), (11, 2), (11, 5)])
+@pytest.mark.parametrize("n_local,grid", [(4, 1), (5, 3), (8, 1), (9, 4), (10, 3), (11, 2), (12, 3), (12, 5)])
 def test_grid_shapes(emu, n_local, grid):
     """more blocks than work, work that does not divide by the grid, several steps per block"""
     run(emu, n_local, n_local - 1, Gate.KIND_H, (), grid, seed=n_local * 7 + grid)
@@ -115,7 +115,7 @@ def tsan(exe, tmp_path, n_local, lq, kind, grid, brk):
 
 
 @pytest.mark.parametrize("kind", [Gate.KIND_H, Gate.KIND_U])
-@pytest.mark.parametrize("n_local,lq,grid", [(10, 9, 2), (10, 3, 3), (11, 5, 2)])
+@pytest.mark.parametrize("n_local,lq,grid", [(11, 10, 2), (11, 3, 3), (12, 5, 2)])
 def test_no_race_between_the_two_ranks(emu_tsan, tmp_path, n_local, lq, kind, grid):
     r, init, out = tsan(emu_tsan, tmp_path, n_local, lq, kind, grid, 0)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -130,5 +130,5 @@ def test_no_race_between_the_two_ranks(emu_tsan, tmp_path, n_local, lq, kind, gr
 
 def test_the_race_check_has_teeth(emu_tsan, tmp_path):
     """rank 1 is given a flag base that makes every acknowledgement look as if it had arrived already"""
-    r, _, _ = tsan(emu_tsan, tmp_path, 11, 5, Gate.KIND_H, 2, 1)
+    r, _, _ = tsan(emu_tsan, tmp_path, 12, 5, Gate.KIND_H, 2, 1)
     assert "data race" in r.stderr
