@@ -335,8 +335,8 @@ def main():
                           "effective_GBps_per_gpu": n_gates * bytes_per_gate_gpu / (t_ms * 1e-3) / 1e9}
         qft["gates"] = n_gates
         qft["qubits"] = n
-        # which fused tile kernel ran: k_tile (default) or the opt-in k_tile2 (csrc/kernels_tile2.cu, SPZ_TILE_V2=1)
-        qft["tile_kernel"] = "k_tile2" if os.environ.get("SPZ_TILE_V2", "0")[:1] == "1" else "k_tile"
+        # which fused tile kernel ran: k_tile3 (csrc/kernels_tile3.cu, TMA; default) or k_tile (SPZ_TILE_V3=0)
+        qft["tile_kernel"] = "k_tile" if os.environ.get("SPZ_TILE_V3", "1")[:1] == "0" else "k_tile3"
         # closed form check on a sample of amplitudes: QFT|x>[k] = 2^(-n/2) exp(2 pi i x rev(k) / 2^n)
         if dist is None:
             x = 0x9E3779B97F4A7C15 % (1 << n)

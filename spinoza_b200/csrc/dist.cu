@@ -523,6 +523,7 @@ int dist_collapse(spz_state *st, int target, int outcome, double scale) {
     if (pt < c->plan.n_local) return launch_collapse(st, pt, outcome, 0, scale);
     const int bit = (c->rank >> (pt - c->plan.n_local)) & 1;
     if (bit == outcome) return launch_scale(st, scale);
+    SPZ_TRY(dist_join(st)); // the memsets below bypass the launch_* helpers: an overlapped exchange may still be writing
     SPZ_CUDA(cudaMemsetAsync(st->re, 0, sizeof(double) * (size_t)st->len, st->stream));
     SPZ_CUDA(cudaMemsetAsync(st->im, 0, sizeof(double) * (size_t)st->len, st->stream));
     return SPZ_OK;
@@ -534,6 +535,9 @@ int dist_fill_basis(spz_state *st, uint64_t logical_index) {
     uint64_t phys = 0;
     for (int q = 0; q < c->plan.n; ++q) if ((logical_index >> q) & 1ull) phys |= 1ull << c->plan.perm[q];
     const int owner = (int)(phys >> c->plan.n_local);
+    // Every rank joins first: an overlapped exchange (second stream) may still be moving amplitudes of this shard, and the
+    // memsets of the non-owner ranks do not go through a launch_* helper that would wait for it.
+    SPZ_TRY(dist_join(st));
     if (owner == c->rank) return launch_fill_basis(st, phys & ((1ull << c->plan.n_local) - 1ull));
     SPZ_CUDA(cudaMemsetAsync(st->re, 0, sizeof(double) * (size_t)st->len, st->stream));
     SPZ_CUDA(cudaMemsetAsync(st->im, 0, sizeof(double) * (size_t)st->len, st->stream));

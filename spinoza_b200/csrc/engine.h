@@ -149,12 +149,17 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
 int max_tile_bits();
 int min_tile_bits();
 int tile_prepare(spz_state *st); // allocate the program ring buffer, set the kernel's shared-memory limit
-// kernels_tile2.cu: opt-in (SPZ_TILE_V2=1) second-generation tile kernel behind the same program format
-bool tile2_enabled();
-bool tile2_eligible(const spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, int n_groups);
-int launch_tile2(spz_state *st, const TilePlan &plan, const TileInstr *h_prog, int n_instr, const TileInstr *d_prog,
-                 const TileGroup *d_groups, int n_groups, const TileTerm *d_terms, int n_terms, bool exact, unsigned first,
-                 unsigned count);
+// The program ring buffer of a state (device memory; a pass's program must stay intact until its kernel has run)
+int tile_ring_alloc(spz_state *st, size_t bytes, char **slot);
+// kernels_tile3.cu: the TMA tile kernel of merged mode (default; SPZ_TILE_V3=0 keeps every pass on k_tile)
+struct Tile3Launch {
+    alignas(64) unsigned char args[512]; // Tile3Args (holds two CUtensorMap)
+    size_t smem;
+};
+bool tile3_enabled();
+int prepare_tile3(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, const TileGroup *groups, int n_groups,
+                  const TileTerm *terms, int n_terms, Tile3Launch *out, bool *handled);
+void run_tile3(spz_state *st, const Tile3Launch &l, unsigned first, unsigned count);
 
 // ---- multi-GPU (dist.cu) ----------------------------------------------------------------------------
 int dist_total_qubits(const spz_state *st);

@@ -400,22 +400,13 @@ int tile_prepare(spz_state *st) {
     return SPZ_OK;
 }
 
-int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, const TileGroup *groups,
-                        int n_groups, const TileTerm *terms, int n_terms, bool exact) {
-    if (n_instr <= 0) return SPZ_OK;
-    if (plan.tile_bits > kMaxTileBits || plan.tile_bits < kRegBits || plan.n_high > kMaxHigh || plan.low_bits < 1 ||
-        plan.tile_bits != plan.low_bits + plan.n_high || plan.tile_bits > st->n) {
-        set_error("bad tile plan T=%d L=%d H=%d n=%d", plan.tile_bits, plan.low_bits, plan.n_high, st->n);
-        return SPZ_ERR_INVALID_ARG;
-    }
-    // Programs are staged in a device ring buffer: a group's program must stay intact until its kernel has run,
-    // so the cursor only wraps after a stream synchronise.
-    const size_t prog_bytes = (sizeof(TileInstr) * (size_t)n_instr + 255) & ~(size_t)255;
-    const size_t group_bytes = (sizeof(TileGroup) * (size_t)n_groups + 255) & ~(size_t)255;
-    const size_t term_bytes = (sizeof(TileTerm) * (size_t)n_terms + 255) & ~(size_t)255;
-    const size_t bytes = prog_bytes + group_bytes + term_bytes;
-    if (n_groups > kMaxTileGroups) { set_error("internal: %d diagonal groups exceed the shared-memory table", n_groups); return SPZ_ERR_INVALID_ARG; }
+// Programs are staged in a device ring buffer: a pass's program must stay intact until its kernel has run, so the cursor
+// only wraps after a stream synchronise.
+int tile_ring_alloc(spz_state *st, size_t bytes, char **slot) {
+    bytes = (bytes + 255) & ~(size_t)255;
     if (st->d_ops_bytes < bytes || !st->d_ops) {
+        // (never taken for programs within the scheduler's per-pass op limit: the buffer is sized in tile_prepare because a
+        // device-wide synchronisation must not happen while another shard's handshake kernel spins on the same GPU)
         if (st->d_ops) { SPZ_CUDA(cudaStreamSynchronize(st->stream)); SPZ_CUDA(cudaFree(st->d_ops)); st->d_ops = nullptr; }
         const size_t cap = std::max<size_t>(bytes * 2, (size_t)4 << 20);
         SPZ_CUDA(cudaMalloc(&st->d_ops, cap));
@@ -426,15 +417,38 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
         SPZ_CUDA(cudaStreamSynchronize(st->stream));
         st->d_ops_cursor = 0;
     }
-    char *slot = static_cast<char *>(st->d_ops) + st->d_ops_cursor;
+    *slot = static_cast<char *>(st->d_ops) + st->d_ops_cursor;
     st->d_ops_cursor += bytes;
+    return SPZ_OK;
+}
+
+int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *prog, int n_instr, const TileGroup *groups,
+                        int n_groups, const TileTerm *terms, int n_terms, bool exact) {
+    if (n_instr <= 0) return SPZ_OK;
+    if (plan.tile_bits > kMaxTileBits || plan.tile_bits < kRegBits || plan.n_high > kMaxHigh || plan.low_bits < 1 ||
+        plan.tile_bits != plan.low_bits + plan.n_high || plan.tile_bits > st->n) {
+        set_error("bad tile plan T=%d L=%d H=%d n=%d", plan.tile_bits, plan.low_bits, plan.n_high, st->n);
+        return SPZ_ERR_INVALID_ARG;
+    }
+    if (n_groups > kMaxTileGroups) { set_error("internal: %d diagonal groups exceed the shared-memory table", n_groups); return SPZ_ERR_INVALID_ARG; }
+    // the TMA kernel takes every merged-mode pass it can (full 12-bit tiles, program within its shared-memory budget)
+    Tile3Launch t3{};
+    bool v3 = false;
+    if (!exact && tile3_enabled()) SPZ_TRY(prepare_tile3(st, plan, prog, n_instr, groups, n_groups, terms, n_terms, &t3, &v3));
+    const size_t prog_bytes = (sizeof(TileInstr) * (size_t)n_instr + 255) & ~(size_t)255;
+    const size_t group_bytes = (sizeof(TileGroup) * (size_t)n_groups + 255) & ~(size_t)255;
+    const size_t term_bytes = (sizeof(TileTerm) * (size_t)n_terms + 255) & ~(size_t)255;
+    TileArgs a{};
+    size_t smem = 0;
+    if (!v3) {
+    char *slot = nullptr;
+    SPZ_TRY(tile_ring_alloc(st, prog_bytes + group_bytes + term_bytes, &slot));
     SPZ_CUDA(cudaMemcpyAsync(slot, prog, sizeof(TileInstr) * (size_t)n_instr, cudaMemcpyHostToDevice, st->stream));
     if (n_groups > 0)
         SPZ_CUDA(cudaMemcpyAsync(slot + prog_bytes, groups, sizeof(TileGroup) * (size_t)n_groups, cudaMemcpyHostToDevice, st->stream));
     if (n_terms > 0)
         SPZ_CUDA(cudaMemcpyAsync(slot + prog_bytes + group_bytes, terms, sizeof(TileTerm) * (size_t)n_terms, cudaMemcpyHostToDevice, st->stream));
 
-    TileArgs a{};
     a.re = st->re; a.im = st->im;
     a.prog = reinterpret_cast<const TileInstr *>(slot);
     a.groups = reinterpret_cast<const TileGroup *>(slot + prog_bytes);
@@ -443,20 +457,16 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
     a.n_instr = n_instr;
     a.T = plan.tile_bits; a.L = plan.low_bits; a.n_high = plan.n_high;
     for (int k = 0; k < plan.n_high; ++k) a.high[k] = plan.high[k];
-    size_t smem = sizeof(double) * 2u * ((size_t)1 << plan.tile_bits) + (size_t)n_groups * (sizeof(double2) + sizeof(unsigned));
+    smem = sizeof(double) * 2u * ((size_t)1 << plan.tile_bits) + (size_t)n_groups * (sizeof(double2) + sizeof(unsigned));
     smem = (smem + 15) & ~(size_t)15;
     a.prog_off = (unsigned)smem;
     a.prog_in_smem = n_instr <= kMaxSmemInstr ? 1 : 0;
     if (a.prog_in_smem) smem += sizeof(TileInstr) * (size_t)n_instr;
+    } // !v3
     const unsigned grid = (unsigned)((uint64_t)st->len >> plan.tile_bits);
     const unsigned threads = 1u << (plan.tile_bits - kRegBits);
-    // opt-in second-generation kernel (kernels_tile2.cu): same program, same staging, fewer instructions per tile
-    const bool v2 = tile2_enabled() && tile2_eligible(st, plan, prog, n_instr, n_groups);
     auto launch = [&](unsigned first, unsigned count) {
-        if (v2) {
-            launch_tile2(st, plan, prog, n_instr, a.prog, a.groups, n_groups, a.terms, n_terms, exact, first, count);
-            return;
-        }
+        if (v3) { run_tile3(st, t3, first, count); return; }
         a.tile_offset = first;
         if (exact) k_tile<true><<<count, threads, smem, st->stream>>>(a);
         else k_tile<false><<<count, threads, smem, st->stream>>>(a);

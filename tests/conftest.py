@@ -33,12 +33,12 @@ def pytest_collection_modifyitems(config, items):
 
 # Tuning switches of the engine change how a circuit is scheduled or which kernel variant runs, never
 # what it computes; the suite pins them to their defaults so that shape-specific assertions do not depend on the caller's shell.
-TUNING_ENV = ("SPZ_TILE_V2", "SPZ_TILE_V2_DIRECT", "SPZ_TILE_LMIN", "SPZ_TILE_SELECT", "SPZ_DIST_WINDOW", "SPZ_TILE_MIN_OPS", "SPZ_DIST_FUSE_GATE", "SPZ_XG_CTAS")
+TUNING_ENV = ("SPZ_TILE_V3", "SPZ_TILE_LMIN", "SPZ_TILE_SELECT", "SPZ_DIST_WINDOW", "SPZ_TILE_MIN_OPS", "SPZ_DIST_FUSE_GATE", "SPZ_XG_CTAS")
 
 
 @pytest.fixture(autouse=True)
 def _default_tuning_env(monkeypatch):
-    if os.environ.get("SPZ_TEST_KEEP_ENV") == "1":  # e.g. the whole GPU suite under SPZ_TILE_V2=1
+    if os.environ.get("SPZ_TEST_KEEP_ENV") == "1":  # e.g. the whole GPU suite under SPZ_TILE_V3=0
         return
     for k in TUNING_ENV:
         monkeypatch.delenv(k, raising=False)

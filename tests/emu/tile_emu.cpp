@@ -1,5 +1,5 @@
-// tile_emu.cpp -- runs the bodies of the fused tile kernels k_tile (spinoza_b200/csrc/kernels_tile.cu) and k_tile2
-// (kernels_tile2.cu) on the CPU, block by block.
+// tile_emu.cpp -- runs the bodies of the fused tile kernels k_tile (spinoza_b200/csrc/kernels_tile.cu) and k_tile3
+// (kernels_tile3.cu: the TMA kernel; its box copies become synchronous swizzled copies here) on the CPU, block by block.
 //
 // Test infrastructure only: built by tests/test_tile_cpu_emulation.py with
 //   g++ -O1 -std=c++17 -ffp-contract=off -shared -fPIC -pthread -I/usr/local/cuda/include -include tests/emu/cuda_cpu_shim.h
@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "../../spinoza_b200/csrc/kernels_tile.cu"
-#include "../../spinoza_b200/csrc/kernels_tile2.cu"
+#include "../../spinoza_b200/csrc/kernels_tile3.cu"
 
 namespace spz_emu {
 unsigned char *dyn_smem = nullptr;
@@ -76,23 +76,27 @@ int parse(const void *blob, long long blob_bytes, Program &P) {
 
 } // namespace
 
-// k_tile2.  info[0..3] <- {ctrl instantiation, first_direct, last_direct, eligible}; returns 1 when the launcher would fall
-// back to k_tile.
-extern "C" int emu_tile2_run(int n_qubits, double *re, double *im, const void *blob, long long blob_bytes, int exact, int direct_level,
-                             int *info) {
+// k_tile3, through the host lowering the launcher uses (tile3_lower / tile3_pack).  info[0..3] <- {some butterfly has an
+// in-tile control, instructions, per-tile groups, shared-memory bytes}; returns 1 when the launcher would fall back to k_tile.
+extern "C" int emu_tile3_run(int n_qubits, double *re, double *im, const void *blob, long long blob_bytes, int *info) {
     Program P;
     if (int rc = parse(blob, blob_bytes, P)) return rc;
-    info[3] = spz::tile2_shape_ok(n_qubits, P.plan, P.prog.data(), P.ni, P.ng) ? 1 : 0;
-    if (!info[3]) return 1;
-    size_t smem = 0;
-    bool ctrl = false;
-    const spz::Tile2Args a = spz::tile2_make_args(re, im, P.plan, P.prog.data(), P.ni, P.prog.data(), P.groups.data(), P.ng, P.terms.data(), P.nt, 0u,
-                                                  direct_level, &smem, &ctrl);
-    info[0] = ctrl ? 1 : 0; info[1] = a.first_direct; info[2] = a.last_direct;
+    if (!spz::tile3_shape_ok(n_qubits, P.plan)) return 1;
+    spz::Lowered3 lw;
+    if (!spz::tile3_lower(P.plan, P.prog.data(), P.ni, P.groups.data(), P.ng, P.terms.data(), P.nt, lw)) return 1;
+    spz::Tile3Args a{};
+    std::vector<unsigned char> packed;
+    spz::tile3_pack(lw, packed, a);
+    const size_t smem = spz::tile3_smem_bytes(a);
+    if (smem > spz::kSmemBudget3) return 1;
+    a.re = re; a.im = im;
+    a.blob = packed.data();
+    a.L = P.plan.low_bits; a.n_high = P.plan.n_high;
+    for (int k = 0; k < P.plan.n_high; ++k) a.high[k] = P.plan.high[k];
+    a.tile_offset = 0;
+    info[0] = lw.ctrl ? 1 : 0; info[1] = a.n_ins; info[2] = a.n_groups; info[3] = (int)smem;
     const unsigned n_blocks = (unsigned)(((uint64_t)1 << n_qubits) >> P.plan.tile_bits);
-    if (exact) run_grid(n_blocks, spz::kThreads2, smem, [&]() { spz::k_tile2<true, true>(a); });
-    else if (ctrl) run_grid(n_blocks, spz::kThreads2, smem, [&]() { spz::k_tile2<false, true>(a); });
-    else run_grid(n_blocks, spz::kThreads2, smem, [&]() { spz::k_tile2<false, false>(a); });
+    run_grid(n_blocks, spz::kThreads3, smem, [&]() { spz::k_tile3(a); });
     return 0;
 }
 
@@ -125,8 +129,8 @@ extern "C" int emu_tile1_run(int n_qubits, double *re, double *im, const void *b
 
 #ifdef SPZ_EMU_MAIN
 // Stand-alone driver (used for the ThreadSanitizer run: a sanitised shared object cannot be loaded into CPython):
-//   tile_emu <kernel 1|2> <n_qubits> <exact 0|1> <state.bin: re[2^n] then im[2^n], f64> <blob.bin> <option>
-// option: k_tile2 = direct level 0..3, k_tile = prog_in_smem 0|1.  The state file is rewritten.
+//   tile_emu <kernel 1|3> <n_qubits> <exact 0|1> <state.bin: re[2^n] then im[2^n], f64> <blob.bin> <option>
+// option: k_tile = prog_in_smem 0|1 (ignored by k_tile3).  The state file is rewritten.
 #include <cstdio>
 #include <cstdlib>
 int main(int argc, char **argv) {
@@ -145,13 +149,13 @@ int main(int argc, char **argv) {
     while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) blob.insert(blob.end(), buf, buf + got);
     std::fclose(f);
     int info[4] = {0, 0, 0, 0};
-    const int rc = kernel == 2 ? emu_tile2_run(n, st.data(), st.data() + len, blob.data(), (long long)blob.size(), exact, option, info)
+    const int rc = kernel == 3 ? emu_tile3_run(n, st.data(), st.data() + len, blob.data(), (long long)blob.size(), info)
                                : emu_tile1_run(n, st.data(), st.data() + len, blob.data(), (long long)blob.size(), exact, option);
     if (rc != 0) return 70 + rc;
     f = std::fopen(argv[4], "wb");
     if (!f || std::fwrite(st.data(), sizeof(double), 2 * len, f) != 2 * len) return 65;
     std::fclose(f);
-    std::printf("kernel=%d ctrl=%d first_direct=%d last_direct=%d\n", kernel, info[0], info[1], info[2]);
+    std::printf("kernel=%d ctrl=%d instructions=%d groups=%d\n", kernel, info[0], info[1], info[2]);
     return 0;
 }
 #endif

@@ -1,0 +1,134 @@
+"""Sharded-register features that are still opt-in (SPZ_TEST_DIST_OPTIN=1): windows that span exchanges (SPZ_DIST_WINDOW=1) and
+the exchange fused with the gate that asked for it (SPZ_DIST_FUSE_GATE=1, kernels_xgate.cuh).  Local groups: every shard on
+the one visible GPU, plain device pointers instead of IPC mappings."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+import spinoza_b200 as sb
+from spinoza_b200 import QuantumCircuit, workloads
+from tests.test_gpu_parity import oracle_ops_from
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("SPZ_TEST_DIST_OPTIN") != "1", reason="opt-in: SPZ_TEST_DIST_OPTIN=1")]
+
+
+# ---- exchange-spanning windows on sharded registers (SPZ_DIST_WINDOW=1, also opt-in until run on hardware) ----------------
+
+@pytest.mark.parametrize("select", ["0", "1"])
+@pytest.mark.parametrize("n,world", [(15, 2), (16, 4), (17, 8)])
+def test_windows_spanning_exchanges_match_the_oracle(n, world, select, monkeypatch):
+    from spinoza_b200.distributed import DistState
+    from tests.test_gpu_dist import gather, run_group, upload_shards
+    monkeypatch.setenv("SPZ_DIST_WINDOW", "1")
+    monkeypatch.setenv("SPZ_TILE_SELECT", select)
+    init = orc.gen_random_state(n, 46)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, init)
+    box = {}
+
+    def body(rank, s):
+        q = QuantumCircuit.from_state(s, fuse=True)
+        workloads.random_layered_circuit(q, depth=12, seed=42)
+        q.qft()
+        if rank == 0:
+            box["ops"] = oracle_ops_from(q)
+        q.execute()
+        s.sync()
+        box[rank] = s.stats()["exchanges"]
+    run_group(states, body)
+    re, im = gather(states)
+    cpu = init.clone()
+    orc.execute(cpu, box["ops"])
+    assert np.max(np.abs(re - cpu.reals)) <= 1e-12 and np.max(np.abs(im - cpu.imags)) <= 1e-12
+    assert len({box[r] for r in range(world)}) == 1   # every rank ran the same exchanges
+
+
+# ---- exchange fused with the gate that asked for it (SPZ_DIST_FUSE_GATE=1, kernels_xgate.cuh; opt-in) --------------------
+
+@pytest.mark.parametrize("n,world", [(12, 2), (14, 4)])
+def test_fused_exchange_gate_is_bit_identical_gate_by_gate(n, world, monkeypatch):
+    """The 1-qubit sweep of the bench on shards: every non-diagonal gate on a global qubit takes the fused kernel."""
+    from spinoza_b200.distributed import DistState
+    from tests.test_gpu_dist import gather, run_group, upload_shards
+    monkeypatch.setenv("SPZ_DIST_FUSE_GATE", "1")
+    monkeypatch.setenv("SPZ_XG_CTAS", "8")   # several shards share one GPU here: every CTA of every shard must be resident
+    init = orc.gen_random_state(n, 47)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, init)
+    seq = [(orc.H, ()), (orc.RX, (1.0,)), (orc.RY, (0.4,)), (orc.X, ()), (orc.Y, ()), (orc.U, (0.1, 0.2, 0.3)), (orc.RZ, (1.0,))]
+    cpu = init.clone()
+    for kind, p in seq:
+        for t in range(n):
+            orc.apply(kind, cpu, t, p)
+
+    def body(rank, s):
+        for kind, p in seq:
+            for t in range(n):
+                sb.apply(sb.Gate(kind, p), s, t)
+        s.sync()
+    run_group(states, body)
+    re, im = gather(states)
+    assert np.array_equal(re, cpu.reals) and np.array_equal(im, cpu.imags)
+
+
+@pytest.mark.parametrize("window", ["0", "1"])
+@pytest.mark.parametrize("n,world", [(15, 2), (16, 4)])
+def test_fused_exchange_gate_inside_execute(n, world, window, monkeypatch):
+    from spinoza_b200.distributed import DistState
+    from tests.test_gpu_dist import gather, run_group, upload_shards
+    monkeypatch.setenv("SPZ_DIST_FUSE_GATE", "1")
+    monkeypatch.setenv("SPZ_DIST_WINDOW", window)
+    monkeypatch.setenv("SPZ_XG_CTAS", "8")
+    init = orc.gen_random_state(n, 48)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, init)
+    box = {}
+
+    def body(rank, s):
+        q = QuantumCircuit.from_state(s, fuse=True)
+        q.qft()
+        workloads.random_layered_circuit(q, depth=6, seed=42)
+        if rank == 0:
+            box["ops"] = oracle_ops_from(q)
+        q.execute()
+        s.sync()
+    run_group(states, body)
+    re, im = gather(states)
+    cpu = init.clone()
+    orc.execute(cpu, box["ops"])
+    assert np.max(np.abs(re - cpu.reals)) <= 1e-12 and np.max(np.abs(im - cpu.imags)) <= 1e-12
+
+
+# ---- clone of a sharded register (spz_dist_copy_from; new in the last hours of round 1, so opt-in like the rest) ---------
+
+def test_clone_of_a_sharded_register_is_independent_and_keeps_the_permutation():
+    from spinoza_b200.distributed import DistState
+    from tests.test_gpu_dist import gather, run_group, upload_shards
+    n, world = 14, 4
+    init = orc.gen_random_state(n, 49)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, init)
+
+    def first(rank, s):
+        for t in (n - 1, n - 2, 3):          # two global targets: the permutation is no longer the identity
+            sb.apply(sb.Gate.H, s, t)
+        s.sync()
+    run_group(states, first)
+    clones = DistState.clone_local_group(states)
+    assert clones[0].perm() == states[0].perm() != list(range(n))
+
+    def second(rank, s):
+        sb.apply(sb.Gate.X, s, 0)            # only the originals move on
+        s.sync()
+    run_group(states, second)
+    cpu = init.clone()
+    for t in (n - 1, n - 2, 3):
+        orc.apply(orc.H, cpu, t)
+    re, im = gather(clones)
+    assert np.array_equal(re, cpu.reals) and np.array_equal(im, cpu.imags)
+    orc.apply(orc.X, cpu, 0)
+    re, im = gather(states)
+    assert np.array_equal(re, cpu.reals) and np.array_equal(im, cpu.imags)

@@ -1,12 +1,14 @@
-"""The bodies of the fused tile kernels -- k_tile (csrc/kernels_tile.cu, the default) and k_tile2 (csrc/kernels_tile2.cu,
-opt-in) -- executed on the CPU: tests/emu/ compiles the kernel sources themselves with g++ (one OS thread per CUDA thread, a
-barrier for __syncthreads) and runs them block by block on the micro-programs that spz_execute would upload
-(spz_debug_compile_pass).  Unlike tests/test_tile_program.py -- an independent NumPy statement of the execution model -- this
-exercises the real indexing code: swizzled staging, register layouts, merged phase runs, exact-mode diagonal arithmetic, and
-for k_tile2 the direct global<->register transfers, the lazy phase flush and the CTRL=false instantiation.
+"""The bodies of the fused tile kernels -- k_tile3 (csrc/kernels_tile3.cu: the TMA kernel that runs every merged-mode pass on
+full 12-bit tiles) and k_tile (csrc/kernels_tile.cu: exact mode, registers below 12 qubits, oversized programs) -- executed on
+the CPU: tests/emu/ compiles the kernel sources themselves with g++ (one OS thread per CUDA thread, a barrier for
+__syncthreads, the TMA box copies as synchronous copies under the same 128-byte swizzle) and runs them block by block on the
+micro-programs that spz_execute would upload (spz_debug_compile_pass), for k_tile3 through the host lowering the launcher uses
+(tile3_lower).  Unlike tests/test_tile_program.py -- an independent NumPy statement of the execution model -- this exercises
+the real code: swizzled register layouts, the lowered instruction format, table-driven phase accumulators, rescaled
+butterflies, exact-mode diagonal arithmetic.
 
-It does not replace the GPU parity tests (no warps, no memory model, no timing).  It exists because k_tile2 was written when
-no GPU time was left, and it lets the CPU suite (-m "not gpu") guard the logic of both kernels.
+It does not replace the GPU parity tests (no warps, no TMA engine, no memory model, no timing); it lets the CPU suite
+(-m "not gpu") guard the logic of both kernels.
 """
 import ctypes as C
 import shutil
@@ -41,8 +43,8 @@ def emu():
            "-include", str(EMU_DIR / "cuda_cpu_shim.h"), "-x", "c++", str(EMU_DIR / "tile_emu.cpp"), "-o", str(lib)]
     subprocess.run(cmd, check=True, cwd=ROOT)
     h = C.CDLL(str(lib))
-    h.emu_tile2_run.restype = C.c_int
-    h.emu_tile2_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    h.emu_tile3_run.restype = C.c_int
+    h.emu_tile3_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_longlong, C.POINTER(C.c_int)]
     h.emu_tile1_run.restype = C.c_int
     h.emu_tile1_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_longlong, C.c_int, C.c_int]
     return h
@@ -56,16 +58,17 @@ def raw_pass(qc, pass_index):
     return bytes(buf[: used.value])
 
 
-def emu_pass(emu, kernel, n, re, im, blob, exact, option, info=None):
+def emu_pass(emu, kernel, n, re, im, blob, exact, option=1, info=None):
     """One fused pass through the emulated kernel.  kernel 1 = k_tile (option: program decoded from shared memory 1 / global
-    memory 0), kernel 2 = k_tile2 (option: direct-transfer level 0..3).  Returns 1 when k_tile2 is not eligible."""
+    memory 0), kernel 3 = k_tile3 (merged mode only).  Returns 1 when k_tile3 is not eligible (the launcher uses k_tile)."""
     if kernel == 1:
         return emu.emu_tile1_run(n, re.ctypes.data, im.ctypes.data, blob, len(blob), 1 if exact else 0, option)
+    assert not exact, "k_tile3 runs merged mode only"
     info = info if info is not None else (C.c_int * 4)()
-    return emu.emu_tile2_run(n, re.ctypes.data, im.ctypes.data, blob, len(blob), 1 if exact else 0, option, info)
+    return emu.emu_tile3_run(n, re.ctypes.data, im.ctypes.data, blob, len(blob), info)
 
 
-def run_emulated(emu, qc, re, im, stats, direct_level=1, kernel=2):
+def run_emulated(emu, qc, re, im, stats, kernel=3):
     """Every fused pass through the emulated kernel; single-op passes through the dense statement."""
     n = qc.n_qubits
     trs = list(qc.transformations)
@@ -82,19 +85,19 @@ def run_emulated(emu, qc, re, im, stats, direct_level=1, kernel=2):
             stats["direct"] = stats.get("direct", 0) + 1
             continue
         info = (C.c_int * 4)()
-        rc = emu_pass(emu, kernel, n, re, im, blob, qc.exact, direct_level if kernel == 2 else (p & 1), info)
+        rc = emu_pass(emu, kernel, n, re, im, blob, qc.exact, (p & 1), info)
         if kernel == 1:
             assert rc == 0, f"pass {p}: emulation failed (rc={rc})"
             stats["k_tile"] = stats.get("k_tile", 0) + 1
             continue
-        if rc == 1:  # too long for k_tile2's shared-memory budget: the launcher falls back to k_tile
-            psi = run_dense_order(n, re + 1j * im, trs, by_pass[p])
-            re[:], im[:] = psi.real, psi.imag
+        if rc == 1:  # too long for k_tile3's shared-memory budget: the launcher falls back to k_tile
+            assert emu_pass(emu, 1, n, re, im, blob, qc.exact, 1) == 0
             stats["fallback"] = stats.get("fallback", 0) + 1
             continue
         assert rc == 0, f"pass {p}: emulation failed (rc={rc})"
-        key = ("ctrl" if info[0] else "noctrl", "ld-direct" if info[1] else "ld-staged", "st-direct" if info[2] else "st-staged")
+        key = "ctrl" if info[0] else "noctrl"
         stats[key] = stats.get(key, 0) + 1
+        stats["groups"] = stats.get("groups", 0) + info[2]
     return re, im
 
 
@@ -134,7 +137,7 @@ def start(n, seed):
     return psi0, np.ascontiguousarray(psi0.real), np.ascontiguousarray(psi0.imag)
 
 
-def test_qft_merged_mode_uses_every_transfer_path(emu):
+def test_qft_merged_mode(emu):
     n = 14
     qc = QuantumCircuit(QuantumRegister(n))
     qc.qft()
@@ -143,12 +146,24 @@ def test_qft_merged_mode_uses_every_transfer_path(emu):
     run_emulated(emu, qc, re, im, stats)
     want = dense_reference(qc, psi0)
     np.testing.assert_allclose(re + 1j * im, want, rtol=0, atol=1e-12)
-    # QFT has no in-tile controls on its butterflies; its first layout is {8..11} (direct load), its last {0..3} (staged store)
-    assert stats.get(("noctrl", "ld-direct", "st-staged"), 0) >= 1, stats
+    # QFT has no in-tile controls on its butterflies, and its controlled phases reach outside the first pass's tile
+    assert stats.get("noctrl", 0) >= 1 and stats.get("groups", 0) >= 1, stats
+
+
+@pytest.mark.parametrize("n", [16, 18])
+def test_qft_several_passes(emu, n):
+    """QFT-16 / QFT-18: two passes, the first with high tile qubits and per-tile constants from the qubits below them."""
+    qc = QuantumCircuit(QuantumRegister(n))
+    qc.qft()
+    psi0, re, im = start(n, n)
+    stats = {}
+    run_emulated(emu, qc, re, im, stats)
+    np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
+    assert stats.get("noctrl", 0) >= 2, stats
 
 
 @pytest.mark.parametrize("select", ["0", "1"], ids=["first-come-tile", "chosen-tile"])
-@pytest.mark.parametrize("kernel", [1, 2], ids=["k_tile", "k_tile2"])
+@pytest.mark.parametrize("kernel", [1, 3], ids=["k_tile", "k_tile3"])
 @pytest.mark.parametrize("n,count,seed", [(13, 160, 31), (14, 220, 32), (15, 120, 33)])
 def test_random_circuits_merged_mode(emu, n, count, seed, kernel, select, monkeypatch):
     monkeypatch.setenv("SPZ_TILE_SELECT", select)  # both ways of choosing a pass's tile qubits (default: chosen from 24 qubits up)
@@ -157,15 +172,45 @@ def test_random_circuits_merged_mode(emu, n, count, seed, kernel, select, monkey
     stats = {}
     run_emulated(emu, qc, re, im, stats, kernel=kernel)
     np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
-    if kernel == 2:
-        assert any(k[0] == "ctrl" for k in stats if isinstance(k, tuple)), stats
+    if kernel == 3:
+        assert stats.get("ctrl", 0) >= 1, stats
     else:
         assert stats.get("k_tile", 0) >= 1
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_reference_cells_merged_mode(emu, seed):
+    """Every gate x control cell the reference supports (incl. U, Y, multi-controlled RX / RY / P, SWAP) through k_tile3."""
+    n = 13
+    qc = reference_cells_circuit(n, 200, 70 + seed)
+    psi0, re, im = start(n, seed)
+    stats = {}
+    run_emulated(emu, qc, re, im, stats)
+    np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
+    assert stats.get("ctrl", 0) >= 1, stats
+
+
+def test_rotations_near_pi_keep_their_matrix(emu):
+    """RX / RY with |cos(theta/2)| tiny are not rescaled (the factored form divides by the cosine), and a long run of strongly
+    rescaled rotations must not drive the pass scale out of range."""
+    n = 12
+    qc = QuantumCircuit(QuantumRegister(n))
+    for t in range(n):
+        qc.rx(np.pi - 1e-9 * (t + 1), t)
+        qc.ry(np.pi + 1e-7 * (t + 1), t)
+        qc.rx(np.pi, t)
+    for rep in range(40):
+        for t in range(n):
+            qc.rx(np.pi - 0.02, t)   # cos(theta/2) ~ 0.01 each: 480 of them would scale by 1e-960
+    psi0, re, im = start(n, 5)
+    run_emulated(emu, qc, re, im, {})
+    assert np.all(np.isfinite(re)) and np.all(np.isfinite(im))
+    np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
+
+
 @pytest.mark.parametrize("n", [5, 8, 11])
 def test_k_tile_small_registers_use_partial_tiles(emu, n):
-    """n < 12: the tile is the whole register and the block has 2^(n-4) threads (k_tile only; k_tile2 needs full tiles)."""
+    """n < 12: the tile is the whole register and the block has 2^(n-4) threads (k_tile only; k_tile3 needs full tiles)."""
     qc = random_circuit(n, 80, 60 + n)
     psi0, re, im = start(n, n)
     stats = {}
@@ -183,23 +228,7 @@ def test_qft_k_tile(emu):
     np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
 
 
-@pytest.mark.parametrize("level", [0, 2, 3])
-def test_every_direct_transfer_level_is_correct(emu, level):
-    """SPZ_TILE_V2_DIRECT only moves the coalescing trade-off; results must not depend on it."""
-    n = 13
-    qc = random_circuit(n, 160, 35)
-    psi0, re, im = start(n, 35)
-    stats = {}
-    run_emulated(emu, qc, re, im, stats, direct_level=level)
-    np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
-    tiles = [k for k in stats if isinstance(k, tuple)]
-    if level == 0:
-        assert all(k[1:] == ("ld-staged", "st-staged") for k in tiles), stats
-    if level == 3:
-        assert all(k[1:] == ("ld-direct", "st-direct") for k in tiles), stats
-
-
-@pytest.mark.parametrize("kernel", [1, 2], ids=["k_tile", "k_tile2"])
+@pytest.mark.parametrize("kernel", [1, 3], ids=["k_tile", "k_tile3"])
 @pytest.mark.parametrize("lmin", ["4", "5"])
 def test_shorter_tile_segments(emu, monkeypatch, lmin, kernel):
     """SPZ_TILE_LMIN = 4 / 5: up to 8 / 7 arbitrary high qubits per pass, segments of 16 / 32 amplitudes."""
@@ -222,11 +251,10 @@ def test_shorter_tile_segments(emu, monkeypatch, lmin, kernel):
     np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
 
 
-def test_vector_direct_transfers(emu):
-    """Level 3 picks 256-bit accesses when register bits 0,1 are tile bits 0,1, 128-bit when only bit 0 is, one amplitude
-    otherwise; build one pass of each shape at both ends and check the modes were really taken."""
+def test_every_register_layout_shape(emu):
+    """Layouts with register bit 0 = tile bit 0 move amplitude pairs with 128-bit shared-memory accesses, the others one
+    amplitude at a time; both at the first and at the last layout of a pass."""
     n = 13
-    modes = set()
     for first, last in (((0, 1, 2, 3), (0, 1, 6, 7)), ((0, 2, 4, 6), (0, 3, 5, 9)), ((2, 3, 4, 5), (1, 2, 10, 11)), ((0, 1, 10, 11), (5, 6, 7, 8))):
         qc = QuantumCircuit(QuantumRegister(n))
         for t in first:
@@ -237,24 +265,12 @@ def test_vector_direct_transfers(emu):
                 qc.h(8)       # force a layout change: 8 is in neither cluster's first half
             qc.ry(0.2 + 0.1 * t, t)
         psi0, re, im = start(n, sum(first) + 7 * sum(last))
-        plan, n_pass = qc.plan()
-        for p in range(n_pass):
-            blob = raw_pass(qc, p)
-            if int(np.frombuffer(blob, dtype="<i4", count=1)[0]) != 0:
-                trs = list(qc.transformations)
-                psi = run_dense_order(n, re + 1j * im, trs, [i for i, pp in plan if pp == p])
-                re[:], im[:] = psi.real, psi.imag
-                continue
-            info = (C.c_int * 4)()
-            assert emu_pass(emu, 2, n, re, im, blob, False, 3, info) == 0
-            modes.add(info[1]); modes.add(info[2])
+        run_emulated(emu, qc, re, im, {})
         np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
-    assert {1, 2, 4} <= modes, modes
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["k_tile", "k_tile2"])
 @pytest.mark.parametrize("n,count,seed", [(13, 60, 41), (14, 80, 42)])
-def test_exact_mode_is_bit_identical_to_the_oracle(emu, n, count, seed, kernel):
+def test_exact_mode_is_bit_identical_to_the_oracle(emu, n, count, seed, kernel=1):
     """EXACT programs replay the reference arithmetic operation by operation; the emulation is built with
     -ffp-contract=off like the oracle, so even on the CPU the two must agree in every bit."""
     qc = reference_cells_circuit(n, count, seed, exact=True)
@@ -278,49 +294,12 @@ def test_exact_mode_is_bit_identical_to_the_oracle(emu, n, count, seed, kernel):
             continue
         info = (C.c_int * 4)()
         rc = emu_pass(emu, kernel, n, re, im, blob, True, 1, info)
-        if rc == 1:   # program too long for k_tile2's shared-memory budget: the launcher falls back to k_tile
-            s = orc.State(n)
-            s.reals[:], s.imags[:] = re, im
-            orc.execute(s, [ops[i] for i in by_pass[p]])
-            re, im = s.reals.copy(), s.imags.copy()
-            continue
         assert rc == 0
         n_tile += 1
     assert n_tile >= 1
     cpu = init.clone()
     orc.execute(cpu, ops)
     assert np.array_equal(re, cpu.reals) and np.array_equal(im, cpu.imags)
-
-
-def test_layouts_that_mix_direct_and_staged_transfers(emu):
-    n = 14
-    cases = []
-    qc = QuantumCircuit(QuantumRegister(n))       # high layout first, low layout last
-    for t in (11, 10, 9, 8):
-        qc.h(t)
-    qc.cp(0.3, 11, 2)
-    for t in (0, 1, 2, 3):
-        qc.ry(0.1 * (t + 1), t)
-    cases.append((qc, ("ld-direct", "st-staged")))
-    qc = QuantumCircuit(QuantumRegister(n))       # low layout first, high layout last (targets outside the low 12 bits)
-    for t in (0, 1, 2, 3):
-        qc.rx(0.2 * (t + 1), t)
-    qc.cp(0.7, 1, 9)
-    for t in (13, 12, 11, 10):
-        qc.h(t)
-    qc.cx(13, 12)
-    cases.append((qc, ("ld-staged", "st-direct")))
-    qc = QuantumCircuit(QuantumRegister(n))       # one high layout only: no shared-memory staging at all
-    for t in (13, 12, 9, 8):
-        qc.u(0.3, 0.2, 0.1 * t, t)
-    qc.crz(0.4, 0, 13) if hasattr(qc, "crz") else qc.cp(0.4, 0, 13)
-    cases.append((qc, ("ld-direct", "st-direct")))
-    for i, (qc, want_paths) in enumerate(cases):
-        psi0, re, im = start(n, 50 + i)
-        stats = {}
-        run_emulated(emu, qc, re, im, stats)
-        np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
-        assert any(isinstance(k, tuple) and k[1:] == want_paths for k in stats), (i, stats)
 
 
 def test_layered_circuit(emu):
@@ -334,13 +313,10 @@ def test_layered_circuit(emu):
 
 # ---- shared-memory protocol under ThreadSanitizer ------------------------------------------------------------------
 # The emulation's barrier is annotated per generation (tests/emu/cuda_cpu_shim.h), so a missing __syncthreads() between a
-# shared-memory store and a load by another thread is a happens-before race that TSan reports deterministically.
-# Mutation check (QFT-15, replace one __syncthreads() at a time by a no-op, both transfer modes): each of the six barriers
-# k_tile2 has -- after seg_off; after the per-term scratch is written; before the staged tile overwrites that scratch; after
-# the tables (and the staged tile) are in place; between store_regs and load_regs of a LAYOUT; before the final copy-out -- is
-# reported when deleted.  The two further barriers k_tile carries per layout change ("everyone has read before anyone's next
-# store_regs") were reported as unnecessary -- a thread's next store goes to the cells it has just read -- and are not in
-# k_tile2.
+# shared-memory store and a load by another thread is a happens-before race that TSan reports deterministically.  k_tile3 has
+# one barrier after its tables are staged (which, in the emulation, also publishes the tile thread 0 copied in; on the GPU
+# that is the mbarrier the TMA boxes complete on), one per layout change between store_regs and load_regs, and one before
+# the tile goes out.  The per-thread accumulator slots F[c][tid] need none.
 
 @pytest.fixture(scope="module")
 def emu_tsan():
@@ -374,10 +350,12 @@ def tsan_run(exe, tmp_path, kernel, n, exact, re, im, blob, option=1):
     return out[: 1 << n].copy(), out[1 << n:].copy(), r.stdout
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["k_tile", "k_tile2"])
+@pytest.mark.parametrize("kernel", [1, 3], ids=["k_tile", "k_tile3"])
 @pytest.mark.parametrize("case", ["qft", "random", "random-exact"])
 def test_no_shared_memory_race_in_any_pass(emu, emu_tsan, tmp_path, case, kernel):
-    n = 15 if case == "qft" else 13   # QFT-15: groups of several outer terms, so the term-parallel reduction of k_tile2 shares scratch
+    if kernel == 3 and case == "random-exact":
+        pytest.skip("k_tile3 runs merged mode only")
+    n = 15 if case == "qft" else 13
     if case == "qft":
         qc = QuantumCircuit(QuantumRegister(n)); qc.qft()
     elif case == "random":
@@ -393,10 +371,10 @@ def test_no_shared_memory_race_in_any_pass(emu, emu_tsan, tmp_path, case, kernel
             continue
         info = (C.c_int * 4)()
         r2, i2 = re.copy(), im.copy()
-        option = p % 4 if kernel == 2 else p % 2  # cycle through the transfer / decode variants as well
+        option = p % 2  # k_tile: both decode variants
         rc = emu_pass(emu, kernel, n, r2, i2, blob, qc.exact, option, info)
         if rc == 1:
-            continue  # not eligible for k_tile2
+            continue  # not eligible for k_tile3
         rt, it, out = tsan_run(emu_tsan, tmp_path, kernel, n, qc.exact, re, im, blob, option)
         assert np.array_equal(rt, r2) and np.array_equal(it, i2)  # same code, same arithmetic, with and without the sanitizer
         seen.add(out.strip())

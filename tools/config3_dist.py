@@ -63,7 +63,7 @@ def main():
             "seconds": ms * 1e-3, "sec_per_gate": ms * 1e-3 / n_gates, "launches": int(launches),
             "exchanges": st1["exchanges"] - st0["exchanges"], "exchange_ms": st1["exchange_ms"] - st0["exchange_ms"],
             "norm2": nrm, "norm2_after_inverse": sb.norm2(s), "roundtrip_max_abs_err_first_sample": back,
-            "switches": {k: os.environ.get(k) for k in ("SPZ_DIST_WINDOW", "SPZ_TILE_SELECT", "SPZ_TILE_V2", "SPZ_TILE_LMIN", "SPZ_NO_OVERLAP")},
+            "switches": {k: os.environ.get(k) for k in ("SPZ_DIST_WINDOW", "SPZ_TILE_SELECT", "SPZ_TILE_V3", "SPZ_TILE_LMIN", "SPZ_NO_OVERLAP")},
         }))
 
 

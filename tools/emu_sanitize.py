@@ -3,7 +3,7 @@ state accesses and undefined behaviour in the index arithmetic, which neither th
 
     python tools/emu_sanitize.py            # ~1 minute, no GPU; exits non-zero on any report
 
-Tile kernels (k_tile, k_tile2 at every transfer level, exact and merged programs, short tile segments) run through the
+Tile kernels (k_tile with both decode variants, k_tile3 through its host lowering; exact and merged programs, short tile segments) run through the
 stand-alone driver of tests/emu/tile_emu.cpp; the one-gate-per-pass kernels through a sanitised shared object loaded into a
 Python started with libasan preloaded.
 """
@@ -44,13 +44,15 @@ def tile(tmp):
             if int(np.frombuffer(blob, dtype="<i4", count=1)[0]) != 0:
                 continue
             (tmp / "blob.bin").write_bytes(blob)
-            for kernel, opts in ((1, (0, 1)), (2, (0, 1, 2, 3))):
+            for kernel, opts in ((1, (0, 1)), (3, (0,))):
+                if kernel == 3 and exact:
+                    continue  # k_tile3 runs merged mode only
                 for opt in opts:
                     np.concatenate([psi.real, psi.imag]).tofile(tmp / "state.bin")
                     r = subprocess.run([str(exe), str(kernel), str(n), str(exact), str(tmp / "state.bin"), str(tmp / "blob.bin"), str(opt)],
                                        capture_output=True, text=True, timeout=300)
                     runs += 1
-                    if r.returncode not in (0, 71) or "ERROR" in r.stderr or "runtime error" in r.stderr:  # 71: not eligible for k_tile2
+                    if r.returncode not in (0, 71) or "ERROR" in r.stderr or "runtime error" in r.stderr:  # 71: not eligible for k_tile3
                         bad += 1
                         print(name, "pass", p, "kernel", kernel, "option", opt, "rc", r.returncode, r.stderr[:1500])
     os.environ.pop("SPZ_TILE_LMIN", None)

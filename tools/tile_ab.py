@@ -1,5 +1,5 @@
-"""A/B timing of the fused tile kernels on one GPU: k_tile (default) against k_tile2 (SPZ_TILE_V2=1) at every direct-transfer
-level (SPZ_TILE_V2_DIRECT=0..3), on QFT-n and on the random layered circuit of BASELINE config 3.
+"""A/B timing of the fused tile kernels on one GPU: k_tile3 (default: TMA, lowered program, rescaled butterflies) against k_tile
+(SPZ_TILE_V3=0), with the scheduler knobs, on QFT-n and on the random layered circuit of BASELINE config 3.
 
     python tools/tile_ab.py [n=30] [reps=5] > gpurun_out/tile_ab.json
 
@@ -21,19 +21,20 @@ from spinoza_b200 import QuantumCircuit, workloads
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-VARIANTS = [("k_tile", {"SPZ_TILE_V2": "0"}),
-            # the round-1 scheduler (first ready ops claim the tile): the 0.82-0.92 s / 30 passes of profiles section 6
-            ("k_tile/first-come-tile", {"SPZ_TILE_V2": "0", "SPZ_TILE_SELECT": "0"})] + [
-    (f"k_tile2/direct{lv}", {"SPZ_TILE_V2": "1", "SPZ_TILE_V2_DIRECT": str(lv)}) for lv in (1, 0, 2, 3)] + [  # 1 = default policy
-    # shorter tile segments: more arbitrary high qubits per pass (config 3: 30 passes -> 21 at L >= 4), worse coalescing
-    ("k_tile/lmin4", {"SPZ_TILE_V2": "0", "SPZ_TILE_LMIN": "4"}), ("k_tile/lmin5", {"SPZ_TILE_V2": "0", "SPZ_TILE_LMIN": "5"}),
-    ("k_tile2/lmin4", {"SPZ_TILE_V2": "1", "SPZ_TILE_LMIN": "4"}), ("k_tile2/lmin5", {"SPZ_TILE_V2": "1", "SPZ_TILE_LMIN": "5"}),
-    # groups of fewer than k ops as k-1 roofline passes instead of one tile pass
-    ("k_tile/minops3", {"SPZ_TILE_V2": "0", "SPZ_TILE_MIN_OPS": "3"}), ("k_tile/minops4", {"SPZ_TILE_V2": "0", "SPZ_TILE_MIN_OPS": "4"})]
+VARIANTS = [("k_tile", {"SPZ_TILE_V3": "0"}),
+            ("k_tile3", {}),
+            # the round-1 scheduler (first ready ops claim the tile)
+            ("k_tile3/first-come-tile", {"SPZ_TILE_SELECT": "0"}),
+            # shorter tile segments: more arbitrary high qubits per pass, smaller TMA boxes
+            ("k_tile3/lmin5", {"SPZ_TILE_LMIN": "5"}), ("k_tile3/lmin4", {"SPZ_TILE_LMIN": "4"}),
+            # groups of fewer than k ops as k-1 roofline passes instead of one tile pass
+            ("k_tile3/minops3", {"SPZ_TILE_MIN_OPS": "3"})]
+if len(sys.argv) > 3:
+    VARIANTS = [v for v in VARIANTS if v[0] in sys.argv[3].split(",")]
 
 
 def set_env(env):
-    for k in ("SPZ_TILE_V2", "SPZ_TILE_V2_DIRECT", "SPZ_TILE_LMIN", "SPZ_TILE_SELECT", "SPZ_TILE_MIN_OPS"):
+    for k in ("SPZ_TILE_V3", "SPZ_TILE_LMIN", "SPZ_TILE_SELECT", "SPZ_TILE_MIN_OPS"):
         os.environ.pop(k, None)
     os.environ.update(env)
 
