@@ -104,29 +104,6 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port of the reference's rayon path on the host cores
 # ------------------------------------------------------------------------------------------------------------
-def cpu_sweep_sample(n: int, threads: int, targets, reps: int = 1):
-    """Times H/RX/RZ on `targets` of an n-qubit state with the oracle (OpenMP mirrors rayon's chunking).
-    Returns (GB/s, seconds, gates)."""
-    import numpy as np
-    import oracle as orc
-    orc.set_threads(threads)
-    s = orc.State(n)
-    amp = 1.0 / math.sqrt(1 << n)
-    s.reals.fill(amp * math.cos(0.3))
-    s.imags.fill(amp * math.sin(0.3))
-    kinds = {"H": orc.H, "RX": orc.RX, "RZ": orc.RZ}
-    orc.apply(orc.H, s, 0)  # touch pages / warm the thread pool
-    t0 = time.perf_counter()
-    gates = 0
-    for _ in range(reps):
-        for name, p in SWEEP_GATES:
-            for t in targets:
-                orc.apply(kinds[name], s, t, p)
-                gates += 1
-    dt = time.perf_counter() - t0
-    return gates * 32.0 * (1 << n) / dt / 1e9, dt, gates
-
-
 def pick_cpu_n(want: int) -> int:
     try:
         avail = 0
@@ -141,8 +118,70 @@ def pick_cpu_n(want: int) -> int:
         return min(want, 28)
 
 
-def cpu_targets(n: int):
-    return sorted({0, n // 2, n - 1})
+def cpu_targets(n: int, threads: int):
+    """Weighted target sample for the CPU sweep.  The reference parallelises a pass over its 2^(n-1-t) chunks
+    (gates.rs:351-372, 601-615), so target n-1 runs on ONE thread, n-2 on two, ...: the top log2(threads) targets are each
+    timed themselves (weight 1); every lower target has at least `threads` chunks and is represented by four of them
+    (0, n/3, 2n/3 and the highest fully parallel one), which share the remaining weight.  Returns [(target, weight)] with
+    weights summing to n, so that sum(weight * seconds) estimates one full sweep over all n targets."""
+    top = max(1, min(n - 1, int(math.ceil(math.log2(max(threads, 1))))))
+    slow = list(range(n - top, n))
+    n_fast = n - top
+    reps = sorted({0, n_fast // 3, (2 * n_fast) // 3, n_fast - 1})
+    return [(t, n_fast / len(reps)) for t in reps] + [(t, 1.0) for t in slow]
+
+
+def cpu_sweep_weighted(n: int, threads: int, full: bool = False):
+    """The 1-qubit sweep on the host cores with the oracle port.  Returns (GB/s over the whole sweep, measured seconds, passes
+    timed, estimated seconds of the full sweep).  full=True times every target instead of the weighted sample."""
+    import oracle as orc
+    orc.set_threads(threads)
+    s = orc.State(n)
+    amp = 1.0 / math.sqrt(1 << n)
+    s.reals.fill(amp * math.cos(0.3))
+    s.imags.fill(amp * math.sin(0.3))
+    kinds = {"H": orc.H, "RX": orc.RX, "RZ": orc.RZ}
+    orc.apply(orc.H, s, 0)  # touch pages / warm the thread pool
+    tw = [(t, 1.0) for t in range(n)] if full else cpu_targets(n, threads)
+    measured = est = 0.0
+    passes = 0
+    for name, p in SWEEP_GATES:
+        for t, w in tw:
+            t0 = time.perf_counter()
+            orc.apply(kinds[name], s, t, p)
+            dt = time.perf_counter() - t0
+            measured += dt
+            est += w * dt
+            passes += 1
+    gates_full = len(SWEEP_GATES) * n
+    return gates_full * 32.0 * (1 << n) / est / 1e9, measured, passes, est
+
+
+def cpu_qft(n: int, threads: int):
+    """BASELINE config 1: QFT-n through the oracle's execute (the reference's one-pass-per-gate loop, circuit.rs:553-599),
+    seconds per gate."""
+    import oracle as orc
+    from spinoza_b200 import QuantumCircuit, QuantumRegister
+    from spinoza_b200.circuit import Controls  # noqa: F401  (kept for symmetry with the parity tests)
+    orc.set_threads(threads)
+    qc = QuantumCircuit(QuantumRegister(n))
+    qc.qft()
+    ops = [orc.make_op(t.gate.kind, t.target, t.gate.params, ctrl_kind=t.controls.kind, ctrl_mask=t.controls.mask())
+           for t in qc.transformations]
+    s = orc.State(n)
+    orc.execute(s, ops[:n])  # warm the thread pool and the pages
+    s = orc.State(n)
+    t0 = time.perf_counter()
+    orc.execute(s, ops)
+    dt = time.perf_counter() - t0
+    return {"seconds": dt, "gates": len(ops), "sec_per_gate": dt / len(ops), "threads": threads}
+
+
+def sweep_config(n: int, n_local: int):
+    """The `config` object of the headline workload: identical in both arms."""
+    return {"workload": f"sweep_1q_H_RX_RZ_all_targets_n{n}", "qubits": n, "local_qubits": n_local,
+            "gates_per_step": len(SWEEP_GATES) * n, "state": "seeded random normalised (utils.rs:168-201 recipe, seed 42)",
+            "l2": "inputs (34 GB per GPU) are larger than L2; no flush needed", "fusion": "off (one HBM pass per gate)"}
 
 
 def run_reference(args, rank: int, world: int):
@@ -150,32 +189,93 @@ def run_reference(args, rank: int, world: int):
         return
     import oracle as orc
     threads = orc.max_threads()
-    n_total = 30 + int(math.log2(max(args.gpus, 1)))
+    n_local = args.qubits or 30
+    n_total = n_local + int(math.log2(max(args.gpus, 1)))
     n = pick_cpu_n(min(n_total, args.cpu_qubits or 30))
-    targets = cpu_targets(n)
-    sample = (f"oracle port (C + OpenMP mirroring rayon chunking, gates.rs:361-372) of H/RX(1.0)/RZ(1.0) on targets "
-              f"{targets} of a {n}-qubit state = {3 * len(targets)} unfused passes per step; full workload is all "
-              f"{n_total} targets at {n_total} qubits")
-    for _ in range(args.warmup):
-        cpu_sweep_sample(n, threads, targets[:1])
+    tw = cpu_targets(n, threads)
+    sample = (f"oracle port (C + OpenMP mirroring rayon's chunking, gates.rs:351-372) of H/RX(1.0)/RZ(1.0) on a {n}-qubit state, "
+              f"{3 * len(tw)} timed passes per step on the weighted target sample {[(t, round(w, 2)) for t, w in tw]} "
+              f"(weights sum to {n}: the top targets, which the reference runs on 1, 2, 4, ... threads, are each timed themselves); "
+              f"value = bytes of the full {n}-target sweep / weighted seconds.  GB/s does not depend on the register size, so the "
+              f"{n}-qubit sample stands for the {n_total}-qubit workload")
+    for _ in range(min(args.warmup, 1)):
+        cpu_sweep_weighted(min(n, 26), threads)
     vals, secs = [], []
     for _ in range(args.steps):
-        v, dt, _g = cpu_sweep_sample(n, threads, targets)
-        vals.append(v); secs.append(dt)
+        v, measured, _passes, est = cpu_sweep_weighted(n, threads)
+        vals.append(v); secs.append(est)
     value = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": "1q_gate_effective_hbm_GBps", "value": value, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"sweep_1q_H_RX_RZ_all_targets_n{n_total}", "qubits": n_total, "sample_qubits": n},
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": sweep_config(n_total, n_local),
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample, "sample_qubits": n},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "the reference is Rust (nightly) and cannot be compiled in this image; this is the oracle's C/OpenMP "
-                "restatement of its rayon path (parallel over 2^(n-1-t) chunks, so target n-1 runs on one thread)",
+                "restatement of its rayon path (parallel over 2^(n-1-t) chunks, so target n-1 runs on one thread); ms_per_step is "
+                "the weighted estimate of one full sweep",
     }
+    if not args.no_extras:
+        try:  # BASELINE config 1: QFT-20 on the CPU at 1 thread and at all host threads
+            line["qft20"] = {"one_thread": cpu_qft(20, 1), "all_threads": cpu_qft(20, threads)}
+        except Exception as e:
+            line["qft20"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
+
+
+
+def qft_closed_form_err(np, state, n, x, env=None, sample=1 << 16):
+    """max |amp - 2^(-n/2) exp(2 pi i x rev(k) / 2^n)| over the first `sample` amplitudes of this GPU's shard (physical
+    index mapped back to the logical k through the qubit permutation); max over ranks when sharded."""
+    cnt = min(sample, len(state))
+    re, im = state.download(0, cnt)
+    if env is not None:
+        perm, n_local, rank = state.perm(), state.n_local, env.rank
+    else:
+        perm, n_local, rank = list(range(n)), n, 0
+    phys = (np.uint64(rank) << np.uint64(n_local)) + np.arange(cnt, dtype=np.uint64)
+    rev = np.zeros(cnt, dtype=np.uint64)
+    for q in range(n):
+        rev |= ((phys >> np.uint64(perm[q])) & np.uint64(1)) << np.uint64(n - 1 - q)
+    ph = ((np.uint64(x) * rev) & np.uint64((1 << n) - 1)).astype(np.float64) / float(1 << n)  # wrap-around is exact mod 2^n
+    want = 2.0 ** (-n / 2) * np.exp(2j * np.pi * ph)
+    err = float(np.max(np.abs((re + 1j * im) - want)))
+    return env.max_float(err) if env is not None else err
+
+
+def sharded_vs_oracle(np, sb, sbd, env, n=20):
+    """Parity of the sharded engine on real NVLink: a 20-qubit register over all ranks runs the layered circuit followed by
+    a QFT through the fused execute; every rank replays the same gate list with the CPU oracle and compares ITS shard
+    (physical order mapped through the permutation).  Returns max |difference| over all ranks."""
+    import oracle as orc
+    from spinoza_b200 import QuantumCircuit, workloads
+    init = orc.gen_random_state(n, 4242)
+    s = sbd.DistState(n, env)
+    nl = s.n_local
+    lo, hi = env.rank << nl, (env.rank + 1) << nl
+    s.upload(np.ascontiguousarray(init.reals[lo:hi]), np.ascontiguousarray(init.imags[lo:hi]))
+    qc = QuantumCircuit.from_state(s, fuse=True)
+    workloads.random_layered_circuit(qc, depth=10, seed=7)
+    qc.qft()
+    ops = [orc.make_op(t.gate.kind, t.target, t.gate.params, ctrl_kind=t.controls.kind, ctrl_mask=t.controls.mask())
+           for t in qc.transformations]
+    x0 = s.stats()["exchanges"]
+    qc.execute()
+    s.sync()
+    orc.execute(init, ops)
+    perm = s.perm()
+    re, im = s.download()
+    phys = (np.int64(env.rank) << np.int64(nl)) + np.arange(1 << nl, dtype=np.int64)
+    logical = np.zeros_like(phys)
+    for q in range(n):
+        logical |= ((phys >> perm[q]) & 1) << q
+    err = float(max(np.max(np.abs(re - init.reals[logical])), np.max(np.abs(im - init.imags[logical]))))
+    out = {"qubits": n, "gates": len(ops), "exchanges": s.stats()["exchanges"] - x0, "max_abs_err": env.max_float(err)}
+    del s
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -191,6 +291,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip per-target table and QFT")
+    ap.add_argument("--no-northstar", action="store_true", help="sharded runs: skip QFT at 2^33 amplitudes per GPU (BASELINE config 4)")
     ap.add_argument("--cpu-qubits", type=int, default=0, help="cap the qubit count of the CPU (reference / cpu_baseline) sample")
     args = ap.parse_args()
 
@@ -281,9 +382,7 @@ def main():
         "metric": "1q_gate_effective_hbm_GBps", "value": value, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"sweep_1q_H_RX_RZ_all_targets_n{n}", "qubits": n, "local_qubits": n_local,
-                   "gates_per_step": gates_per_step, "state": "seeded random normalised (utils.rs:168-201 recipe, seed 42)",
-                   "l2": "inputs (34 GB per GPU) are larger than L2; no flush needed", "fusion": "off (one HBM pass per gate)"},
+        "config": sweep_config(n, n_local),
         "roofline": {"bound": "hbm", "achieved": achieved_gpu, "peak": peak, "unit": "GB/s", "frac": achieved_gpu / peak,
                      "frac_of_nominal_8000": achieved_gpu / 8000.0, "peak_source": peak_src,
                      "kernel": "k_pair_vec / k_pair_low (kernels_direct.cuh)",
@@ -337,19 +436,11 @@ def main():
         qft["qubits"] = n
         # which fused tile kernel ran: k_tile3 (csrc/kernels_tile3.cu, TMA; default) or k_tile (SPZ_TILE_V3=0)
         qft["tile_kernel"] = "k_tile" if os.environ.get("SPZ_TILE_V3", "1")[:1] == "0" else "k_tile3"
-        # closed form check on a sample of amplitudes: QFT|x>[k] = 2^(-n/2) exp(2 pi i x rev(k) / 2^n)
-        if dist is None:
-            x = 0x9E3779B97F4A7C15 % (1 << n)
-            re, im = state.download(0, 4096)
-            k = np.arange(4096, dtype=np.uint64)
-            rev = np.zeros_like(k)
-            for b in range(n):
-                rev |= ((k >> np.uint64(b)) & np.uint64(1)) << np.uint64(n - 1 - b)
-            ph = ((np.uint64(x) * rev) % np.uint64(1 << n)).astype(np.float64) / float(1 << n)
-            want = 2.0 ** (-n / 2) * np.exp(2j * np.pi * ph)
-            qft["max_abs_err_vs_closed_form_first_4096"] = float(np.max(np.abs((re + 1j * im) - want)))
-        else:
-            qft["norm2_after"] = sb.norm2(state)
+        # closed form check, QFT|x>[k] = 2^(-n/2) exp(2 pi i x rev(k) / 2^n), on the first 65 536 amplitudes of every shard
+        x = 0x9E3779B97F4A7C15 % (1 << n)
+        qft["max_abs_err_vs_closed_form"] = qft_closed_form_err(np, state, n, x, dist)
+        qft["norm2_after"] = sb.norm2(state)
+        if dist is not None:
             qft["exchanges_total_incl_sweep"] = state.stats()["exchanges"]
         return qft
 
@@ -396,6 +487,16 @@ def main():
         except Exception as e:
             line["config3"] = {"error": repr(e)}
 
+    # ---- sharded runs: parity against the CPU oracle on real NVLink (20 qubits over all ranks) ----
+    if dist is not None and not args.no_extras:
+        try:
+            line["parity"] = {"qft_closed_form_max_abs_err": line.get("qft", {}).get("max_abs_err_vs_closed_form"),
+                              "sharded_vs_oracle": sharded_vs_oracle(np, sb, sbd, dist, 20),
+                              "what": "QFT of a basis state against the closed form on 65 536 amplitudes of every shard; layered circuit + "
+                                      "QFT at 20 qubits over all ranks against the CPU oracle, every amplitude; max over ranks"}
+        except Exception as e:
+            line["parity"] = {"error": repr(e)}
+
     # ---- end to end through the C ABI with HOST buffers: upload -> sweep -> download, every step ----
     # (sharded: every rank moves its own shard between its pinned host buffers and its GPU; max over ranks)
     def mem_available():
@@ -436,18 +537,66 @@ def main():
         except Exception as e:  # host cannot pin the buffers
             line["e2e"] = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(e)}
 
+    # ---- BASELINE config 4 at its stated size: QFT-(33 + log2 N) with 2^33 amplitudes (137 GB) per GPU ----
+    if dist is not None and not args.no_extras and not args.no_northstar:
+        try:
+            del state
+            state = None
+            nl = 33
+            free_b, _tot = sb.mem_info(local_rank)
+            fits = dist.max_float(0.0 if 16 * (1 << nl) * 1.01 < free_b else 1.0) == 0.0
+            if not fits:
+                line["qft_northstar"] = {"skipped": f"2^33 amplitudes need 137.4 GB per GPU; {free_b / 1e9:.1f} GB free"}
+            else:
+                nn = nl + g
+                t0 = time.perf_counter()
+                big = sbd.DistState(nn, dist)
+                x = 0x9E3779B97F4A7C15 % (1 << nn)
+                big.set_basis(x)
+                big.sync(); barrier()
+                alloc_s = time.perf_counter() - t0
+                qc = QuantumCircuit.from_state(big, fuse=True)
+                qc.qft()
+                n_gates = len(qc.transformations)
+                s0 = big.stats()
+                l1 = sb.launch_count()
+                big.sync(); barrier()
+                big.timer_start()
+                qc.execute()
+                t_ms = dist.max_float(big.timer_stop())
+                barrier()
+                s1 = big.stats()
+                xms = s1["exchange_ms"] - s0["exchange_ms"]
+                sent = s1["bytes_sent"] - s0["bytes_sent"]
+                line["qft_northstar"] = {
+                    "workload": f"QFT-{nn} on {world} GPUs, 2^{nl} amplitudes (137.4 GB) per GPU, fused", "qubits": nn, "gates": n_gates,
+                    "seconds": t_ms * 1e-3, "sec_per_gate": t_ms * 1e-3 / n_gates, "launches": int(sb.launch_count() - l1),
+                    "exchanges": s1["exchanges"] - s0["exchanges"], "overlapped_exchanges": s1["overlapped"] - s0["overlapped"],
+                    "exchange_kernel_ms": xms, "nvlink_GBps_per_direction_per_gpu": (sent / (xms * 1e-3) / 1e9) if xms > 0 else None,
+                    "max_abs_err_vs_closed_form": qft_closed_form_err(np, big, nn, x, dist), "norm2_after": sb.norm2(big),
+                    "alloc_seconds": alloc_s}
+                del big
+        except Exception as e:
+            line["qft_northstar"] = {"error": repr(e)}
+
     # ---- CPU baseline: oracle port on this box's host cores, bounded sample ----
     if rank == 0 and not args.no_cpu and world == 1:
-        del state
+        state = None
         import oracle as orc
         threads = orc.max_threads()
         cn = pick_cpu_n(min(n, args.cpu_qubits or 30))
-        tg = cpu_targets(cn)
-        v, dt, gcount = cpu_sweep_sample(cn, threads, tg)
-        v1, dt1, _ = cpu_sweep_sample(min(cn, 26), 1, cpu_targets(min(cn, 26)))
+        v, measured, passes, est = cpu_sweep_weighted(cn, threads)
+        v1, _m1, _p1, _e1 = cpu_sweep_weighted(min(cn, 26), 1)
         line["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": threads, "kind": "port",
-                                "sample": f"{gcount} unfused passes (H/RX/RZ on targets {tg}) of a {cn}-qubit state, {dt:.1f} s",
+                                "sample": f"{passes} timed unfused passes (H/RX/RZ on the weighted target sample "
+                                          f"{[(t, round(w, 2)) for t, w in cpu_targets(cn, threads)]}) of a {cn}-qubit state, {measured:.1f} s; "
+                                          f"value = bytes of the full sweep / weighted seconds ({est:.1f} s)",
                                 "single_thread_GBps": v1}
+        if not args.no_extras:
+            try:  # BASELINE config 1 (QFT-20 on the CPU, 1 thread and all host threads) next to the GPU's fused QFT-20
+                line["cpu_baseline"]["qft20"] = {"one_thread": cpu_qft(20, 1), "all_threads": cpu_qft(20, threads)}
+            except Exception as e:
+                line["cpu_baseline"]["qft20"] = {"error": repr(e)}
 
     if rank == 0:
         print(json.dumps(line), flush=True)

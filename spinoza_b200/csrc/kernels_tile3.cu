@@ -60,13 +60,13 @@ constexpr int kMaxIns3 = 1024;                      // one skip flag per instruc
 constexpr int kMaxGroups3 = 1024;
 
 // ---- device program ---------------------------------------------------------------------------------------------------
-enum { T3_END = 0, T3_LAYOUT = 1, T3_GATE = 2, T3_ACC = 3, T3_ACCG = 4, T3_OTHER = 5 };
-// gate variants of merged mode (see the header): *T = common scalar factored out (uncontrolled only)
-enum { MK_H = 0, MK_RXT = 1, MK_RYT = 2, MK_X = 3, MK_Y = 4, MK_REAL = 5, MK_RXU = 6, MK_U = 7 };
+enum { T3_END = 0, T3_LAYOUT = 1, T3_GATE = 2, T3_ACC = 3, T3_ACCG = 4, T3_OTHER = 5, T3_PRE = 6 };
+// gate variants of merged mode (see the header and pair3): H = [[1,1],[1,-1]] with 2^-1/2 left to the pass scale, HS the same
+// with the scale applied (controlled H), RX / RY = rotation by three shears, X / Y = exchanges
+enum { MK_H = 0, MK_HS = 1, MK_RX = 2, MK_RY = 3, MK_X = 4, MK_Y = 5 };
 // flag bits
 enum {
     GF_ALL = 1,      // GATE: every pair of every thread (no in-tile control)
-    GF_PRE = 2,      // GATE: accumulator F_{rpos+1} is pending: apply it to the amplitudes with the target bit set first
     GF_OUTER = 4,    // GATE: has controls outside the tile: consult the per-tile skip flag
     AF_LO = 1,       // ACC: table over the low nibble of the thread id at pool2[a .. a+16)
     AF_HI = 2,       // ACC: table over the high nibble at pool2[a+16 .. a+32)
@@ -75,7 +75,7 @@ enum {
     AF_CONST = 16,   // ACCG / OTHER: constant factor at pool2[a]
 };
 struct Ins3 {
-    uint8_t op, kind, rpos, flags; // rpos: GATE register bit; ACC / ACCG accumulator 0..4.  LAYOUT / END flags: pending accumulators
+    uint8_t op, kind, rpos, flags; // rpos: GATE / PRE register bit; ACC / ACCG accumulator 0..4.  LAYOUT / END flags: pending accumulators
     uint16_t km;                   // GATE: pair mask over k0.  OTHER: register mask m
     uint16_t thr;                  // GATE / ACCG / OTHER: control bits in THREAD-ID space (8 bits)
     uint32_t a;                    // LAYOUT: the 4 register-resident tile bits, one byte each.  else: pool offset (see flags)
@@ -99,13 +99,20 @@ struct Lowered3 {
 
 struct Tile3Args {
 #ifndef SPZ_CPU_EMULATION
-    CUtensorMap tm_re, tm_im;      // [len / 16 rows x 16 doubles], box 16 x 2^(L-4), 128-byte swizzle
+    CUtensorMap tm_re, tm_im;      // see make_tensor_maps: 128-byte rows x rows of a segment x up to three runs of high tile qubits
 #endif
+    // How the tile maps to TMA boxes: a box covers the low L bits and the first `rank - 2` runs of contiguous high tile qubits
+    // (2^box_shift amplitudes, contiguous in tile-index order); the n_rest high tile qubits above them are enumerated, one box
+    // per combination.  dim_lo[i] / dim_len[i]: the index bits tensor dimension i spans (its coordinate is that bit field of
+    // the box's first amplitude).
+    int rank, n_rest, box_shift;
+    int rest_bit[kMaxHigh3];
+    int dim_lo[5], dim_len[5];
     double *re, *im;               // (the CPU emulation moves the tile through these)
     const unsigned char *blob;     // device copy of the lowered program
     unsigned ins_bytes, pool_bytes;  // sizes of the two staged sections (multiples of 16)
     unsigned outer_off, groups_off, terms_off; // byte offsets of the other sections inside the blob
-    int n_ins, n_groups;
+    int n_ins, n_groups, n_terms;
     unsigned tile_offset;
     int L, n_high;
     double scale;
@@ -117,9 +124,9 @@ struct Tile3Args {
 __host__ __device__ __forceinline__ unsigned swz3(unsigned j) { return j ^ (((j >> 4) & 7u) << 1); }
 
 __device__ __forceinline__ void cmul3(double &xr, double &xi, double fr, double fi) {
-    const double nr = xr * fr - xi * fi; // contracted by nvcc: 2 FMA-class instructions per component
-    const double ni = xr * fi + xi * fr;
-    xr = nr; xi = ni;
+    const double t = xr; // one live temporary; both results land in their own operand's register (see pair3)
+    xr = xr * fr - xi * fi;
+    xi = t * fi + xi * fr;
 }
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX); the CPU emulation replaces them by synchronous copies ----------------------
@@ -143,13 +150,50 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *tm, int row, void *bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row), "r"(smem_u32(bar)) : "memory");
+// One box of a rank-2..5 tensor map (coordinate 0 is always 0: the 16 doubles of a 128-byte row).
+__device__ __forceinline__ void tma_load_box(int rank, void *dst, const CUtensorMap *tm, const int (&c)[5], void *bar) {
+    const unsigned d = smem_u32(dst), b = smem_u32(bar);
+    const uint64_t m = reinterpret_cast<uint64_t>(tm);
+    switch (rank) {
+    case 2:
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(d), "l"(m), "r"(0), "r"(c[1]), "r"(b) : "memory");
+        break;
+    case 3:
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(d), "l"(m), "r"(0), "r"(c[1]), "r"(c[2]), "r"(b) : "memory");
+        break;
+    case 4:
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                     ::"r"(d), "l"(m), "r"(0), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(b) : "memory");
+        break;
+    default:
+        asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                     ::"r"(d), "l"(m), "r"(0), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(b) : "memory");
+        break;
+    }
 }
-__device__ __forceinline__ void tma_store_box(const CUtensorMap *tm, int row, const void *src) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row), "r"(smem_u32(src)) : "memory");
+__device__ __forceinline__ void tma_store_box(int rank, const CUtensorMap *tm, const int (&c)[5], const void *src) {
+    const unsigned sa = smem_u32(src);
+    const uint64_t m = reinterpret_cast<uint64_t>(tm);
+    switch (rank) {
+    case 2:
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                     ::"l"(m), "r"(0), "r"(c[1]), "r"(sa) : "memory");
+        break;
+    case 3:
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                     ::"l"(m), "r"(0), "r"(c[1]), "r"(c[2]), "r"(sa) : "memory");
+        break;
+    case 4:
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                     ::"l"(m), "r"(0), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(sa) : "memory");
+        break;
+    default:
+        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                     ::"l"(m), "r"(0), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(sa) : "memory");
+        break;
+    }
 }
 __device__ __forceinline__ void tma_store_commit_and_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -159,48 +203,59 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 #endif
 
 // ---- gate variants ------------------------------------------------------------------------------------------------------
-// (a, b) = (re, im) of the amplitude with target bit 0, (c, d) with target bit 1.  Plain operators: nvcc contracts them.
+// (a, b) = (re, im) of the amplitude with target bit 0, (c, d) with target bit 1.
+//
+// EVERY update below is strictly in place: each new value overwrites one of its own operands at that operand's last use.
+// This is not style.  The 32 amplitude values live in registers across the interpreter loop; when an arm computes a new value
+// while the old one is still needed (na = a + c; nc = a - c), ptxas gives the new values a second bank of 64 registers and
+// copies bank to bank around EVERY interpreted instruction (~130 MOVs each, measured: 12 G warp instructions for a 27-gate
+// pass, of which 1.2 G were FP64), and spills what no longer fits.  Written in place, the same loop compiles to no copies.
+//   H        c <- a - c; a <- 2a - c                 (2 ops per component, like the textbook form)
+//   RX / RY  a rotation of two real couples by three shears: x <- x - t y; y <- y + s x; x <- x - t y, t = tan(phi/2),
+//            s = sin(phi), |phi| <= pi/2 (the host reduces the angle; the sign of cos goes to the pass scale or to a phase term)
+//   X / Y    exchanges by three XORs inside an asm block: written as a swap, the compiler sees a renaming and we are back to
+//            bank copies
+__device__ __forceinline__ void xor_swap(double &x, double &y) {
+#ifdef SPZ_CPU_EMULATION
+    const double t = x; x = y; y = t;
+#else
+    asm volatile("xor.b64 %0, %0, %1;\n\txor.b64 %1, %1, %0;\n\txor.b64 %0, %0, %1;" : "+d"(x), "+d"(y));
+#endif
+}
+__device__ __forceinline__ void shear3(double &x, double &y, double t, double sn) {
+    x = x - t * y;
+    y = y + sn * x;
+    x = x - t * y;
+}
 template <int MK>
-__device__ __forceinline__ void pair3(const double (&s)[8], double &a, double &b, double &c, double &d) {
+__device__ __forceinline__ void pair3(const double (&s)[2], double &a, double &b, double &c, double &d) {
     if constexpr (MK == MK_H) {            // [[1, 1], [1, -1]]
-        const double na = a + c, nb = b + d, nc = a - c, nd = b - d;
-        a = na; b = nb; c = nc; d = nd;
-    } else if constexpr (MK == MK_RXT) {   // [[1, i t], [i t, 1]]
-        const double t = s[0];
-        const double na = a - t * d, nb = b + t * c, nc = c - t * b, nd = d + t * a;
-        a = na; b = nb; c = nc; d = nd;
-    } else if constexpr (MK == MK_RYT) {   // [[1, -t], [t, 1]]
-        const double t = s[0];
-        const double na = a - t * c, nb = b - t * d, nc = c + t * a, nd = d + t * b;
-        a = na; b = nb; c = nc; d = nd;
+        c = a - c; a = 2.0 * a - c;
+        d = b - d; b = 2.0 * b - d;
+    } else if constexpr (MK == MK_HS) {    // 2^-1/2 [[1, 1], [1, -1]]
+        c = a - c; a = 2.0 * a - c; c = c * SPZ_SQRT_ONE_HALF; a = a * SPZ_SQRT_ONE_HALF;
+        d = b - d; b = 2.0 * b - d; d = d * SPZ_SQRT_ONE_HALF; b = b * SPZ_SQRT_ONE_HALF;
+    } else if constexpr (MK == MK_RX) {    // [[cos, i sin], [i sin, cos]]: rotates the couples (a, d) and (c, b)
+        shear3(a, d, s[0], s[1]);
+        shear3(c, b, s[0], s[1]);
+    } else if constexpr (MK == MK_RY) {    // [[cos, -sin], [sin, cos]]: rotates the couples (a, c) and (b, d)
+        shear3(a, c, s[0], s[1]);
+        shear3(b, d, s[0], s[1]);
     } else if constexpr (MK == MK_X) {
-        double t = a; a = c; c = t;
-        t = b; b = d; d = t;
-    } else if constexpr (MK == MK_Y) {     // [[0, -i], [i, 0]]
-        const double na = d, nb = -c, nc = -b, nd = a;
-        a = na; b = nb; c = nc; d = nd;
-    } else if constexpr (MK == MK_REAL) {  // real [[s0, s1], [s2, s3]]
-        const double na = s[0] * a + s[1] * c, nb = s[0] * b + s[1] * d;
-        const double nc = s[2] * a + s[3] * c, nd = s[2] * b + s[3] * d;
-        a = na; b = nb; c = nc; d = nd;
-    } else if constexpr (MK == MK_RXU) {   // [[s0, i s1], [i s1, s0]]
-        const double na = s[0] * a - s[1] * d, nb = s[0] * b + s[1] * c;
-        const double nc = s[0] * c - s[1] * b, nd = s[0] * d + s[1] * a;
-        a = na; b = nb; c = nc; d = nd;
-    } else {                               // complex [[s0 + i s1, s2 + i s3], [s4 + i s5, s6 + i s7]]
-        const double na = s[0] * a - s[1] * b + s[2] * c - s[3] * d;
-        const double nb = s[0] * b + s[1] * a + s[2] * d + s[3] * c;
-        const double nc = s[4] * a - s[5] * b + s[6] * c - s[7] * d;
-        const double nd = s[4] * b + s[5] * a + s[6] * d + s[7] * c;
-        a = na; b = nb; c = nc; d = nd;
+        xor_swap(a, c);
+        xor_swap(b, d);
+    } else {                               // Y = [[0, -i], [i, 0]]: s0 <- (d, -c), s1 <- (-b, a)
+        xor_swap(a, d);
+        xor_swap(b, c);
+        b = -b; c = -c;
     }
 }
 template <int MK>
-constexpr int n_scalars3() { return MK == MK_RXT || MK == MK_RYT ? 1 : MK == MK_REAL ? 4 : MK == MK_RXU ? 2 : MK == MK_U ? 8 : 0; }
+constexpr int n_scalars3() { return MK == MK_RX || MK == MK_RY ? 2 : 0; }
 
 template <int MK, int R, bool ALL>
 __device__ __forceinline__ void bfly3(double (&ar)[16], double (&ai)[16], const double *__restrict__ sp, unsigned km) {
-    double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double s[2] = {0.0, 0.0};
 #pragma unroll
     for (int i = 0; i < n_scalars3<MK>(); ++i) s[i] = sp[i];
 #pragma unroll
@@ -216,21 +271,20 @@ __device__ __forceinline__ void bfly3_kind(int kind, bool all, double (&ar)[16],
     if (all) {
         switch (kind) {
         case MK_H: bfly3<MK_H, R, true>(ar, ai, sp, km); break;
-        case MK_RXT: bfly3<MK_RXT, R, true>(ar, ai, sp, km); break;
-        case MK_RYT: bfly3<MK_RYT, R, true>(ar, ai, sp, km); break;
+        case MK_HS: bfly3<MK_HS, R, true>(ar, ai, sp, km); break;
+        case MK_RX: bfly3<MK_RX, R, true>(ar, ai, sp, km); break;
+        case MK_RY: bfly3<MK_RY, R, true>(ar, ai, sp, km); break;
         case MK_X: bfly3<MK_X, R, true>(ar, ai, sp, km); break;
-        case MK_Y: bfly3<MK_Y, R, true>(ar, ai, sp, km); break;
-        case MK_REAL: bfly3<MK_REAL, R, true>(ar, ai, sp, km); break;
-        case MK_RXU: bfly3<MK_RXU, R, true>(ar, ai, sp, km); break;
-        default: bfly3<MK_U, R, true>(ar, ai, sp, km); break;
+        default: bfly3<MK_Y, R, true>(ar, ai, sp, km); break;
         }
     } else {
-        switch (kind) { // the factored variants are uncontrolled by construction
+        switch (kind) {
+        case MK_H: bfly3<MK_H, R, false>(ar, ai, sp, km); break; // (never emitted: a controlled H carries its scale)
+        case MK_HS: bfly3<MK_HS, R, false>(ar, ai, sp, km); break;
+        case MK_RX: bfly3<MK_RX, R, false>(ar, ai, sp, km); break;
+        case MK_RY: bfly3<MK_RY, R, false>(ar, ai, sp, km); break;
         case MK_X: bfly3<MK_X, R, false>(ar, ai, sp, km); break;
-        case MK_Y: bfly3<MK_Y, R, false>(ar, ai, sp, km); break;
-        case MK_REAL: bfly3<MK_REAL, R, false>(ar, ai, sp, km); break;
-        case MK_RXU: bfly3<MK_RXU, R, false>(ar, ai, sp, km); break;
-        default: bfly3<MK_U, R, false>(ar, ai, sp, km); break;
+        default: bfly3<MK_Y, R, false>(ar, ai, sp, km); break;
         }
     }
 }
@@ -270,9 +324,9 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
         return b;
     };
 
-    // ---- tile in: one TMA box per segment and array, all on one mbarrier ----
+    // ---- tile in: TMA boxes (one per array for tiles with up to three runs of high qubits), all on one mbarrier ----
+#ifdef SPZ_CPU_EMULATION
     const unsigned n_seg = 1u << a.n_high;
-    const unsigned seg_bytes = 8u << L;
     auto seg_row = [&](unsigned long long base, unsigned s) -> int { // row (16 doubles) of segment s's first amplitude
         unsigned long long off = 0;
 #pragma unroll
@@ -280,6 +334,19 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
             if (k < a.n_high && ((s >> k) & 1u)) off |= 1ull << a.high[k];
         return (int)((base + off) >> 4);
     };
+#else
+    const unsigned n_box = 1u << a.n_rest;
+    const unsigned box_bytes = 8u << a.box_shift;
+    auto box_coords = [&](unsigned long long base, unsigned e, int (&c)[5]) {
+        unsigned long long addr = base;
+#pragma unroll
+        for (int k = 0; k < kMaxHigh3; ++k)
+            if (k < a.n_rest && ((e >> k) & 1u)) addr |= 1ull << a.rest_bit[k];
+        c[0] = 0;
+#pragma unroll
+        for (int i = 1; i < 5; ++i) c[i] = i < a.rank ? (int)((addr >> a.dim_lo[i]) & ((1ull << a.dim_len[i]) - 1ull)) : 0;
+    };
+#endif
     {
     const unsigned long long base = tile_base();
 #ifndef SPZ_CPU_EMULATION
@@ -290,10 +357,11 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
     }
     __syncthreads();
     if (tid < 32) {
-        for (unsigned s = tid; s < n_seg; s += 32) {
-            const int row = seg_row(base, s);
-            tma_load_box(smem + s * seg_bytes, &a.tm_re, row, bar);
-            tma_load_box(smem + kArrayBytes3 + s * seg_bytes, &a.tm_im, row, bar);
+        for (unsigned e = tid; e < n_box; e += 32) {
+            int c[5];
+            box_coords(base, e, c);
+            tma_load_box(a.rank, smem + e * box_bytes, &a.tm_re, c, bar);
+            tma_load_box(a.rank, smem + kArrayBytes3 + e * box_bytes, &a.tm_im, c, bar);
         }
     }
 #else
@@ -322,21 +390,41 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
             const unsigned long long ocm = outer[i];
             skip[i] = (base & ocm) != ocm ? 1 : 0;
         }
+    }
+    // Per-tile constants: every group's product over those of its terms whose outer bits are set in this tile.  Term-parallel
+    // (one L2 round trip for all terms; factors parked in the still unused accumulator region), then one thread per group
+    // multiplies from shared memory.  A serial walk over a group's terms in global memory costs two dependent L2 round trips
+    // per term: ~8 us at the head of every tile of a QFT pass (18 terms per group), four times the tile's HBM time.
+    {
         const TileGroup *groups = reinterpret_cast<const TileGroup *>(a.blob + a.groups_off);
         const TileTerm *terms = reinterpret_cast<const TileTerm *>(a.blob + a.terms_off);
+        double2 *scr = reinterpret_cast<double2 *>(smem + 2u * kArrayBytes3);
+        for (int t = tid; t < a.n_terms; t += kThreads3) {
+            const TileTerm tm = terms[t];
+            scr[t] = (base & tm.outer) == tm.outer ? make_double2(tm.fr, tm.fi) : make_double2(1.0, 0.0);
+        }
+        __syncthreads();
         for (int g = tid; g < a.n_groups; g += kThreads3) {
             const TileGroup gd = groups[g];
-            double fr = 1.0, fi = 0.0;
-            for (int i = 0; i < gd.count; ++i) {
-                const TileTerm t = terms[gd.first + i];
-                if ((base & t.outer) == t.outer) cmul3(fr, fi, t.fr, t.fi);
+            double fr = 1.0, fi = 0.0, hr = 1.0, hi = 0.0; // two partial products: half the dependent chain
+            int i = 0;
+            for (; i + 2 <= gd.count; i += 2) {
+                const double2 x = scr[gd.first + i], y = scr[gd.first + i + 1];
+                cmul3(fr, fi, x.x, x.y);
+                cmul3(hr, hi, y.x, y.y);
             }
+            if (i < gd.count) { const double2 x = scr[gd.first + i]; cmul3(fr, fi, x.x, x.y); }
+            cmul3(fr, fi, hr, hi);
             gfac[g] = make_double2(fr, fi);
         }
     }
     } // base
-    __syncthreads();
+    __syncthreads(); // program, skip flags and constants staged; the term scratch is free again
 #ifndef SPZ_CPU_EMULATION
+    // One warp waits for the boxes (a failed try_wait costs issue slots the other CTA of this SM could use); after the barrier
+    // the phase is complete and every thread's own try_wait -- its acquire of the TMA writes -- succeeds at once.
+    if (tid < 32) mbar_wait(bar, 0);
+    __syncthreads();
     mbar_wait(bar, 0);
 #endif
 
@@ -434,14 +522,23 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
             const bool thr_ok = (tid & ins.thr) == ins.thr && !((ins.flags & GF_OUTER) && skip[pc]);
             const double *sp = pool + ins.a;
             const bool all = ins.flags & GF_ALL;
-            const bool pre = ins.flags & GF_PRE;
-            // Only the accumulator of the target's own register bit separates the two members of a pair; the others
-            // scale both by the same factor and stay pending.
             switch (ins.rpos) {
-            case 0: if (pre) apply_bit3<0>(ar, ai, facc[1 * kThreads3]); if (thr_ok) bfly3_kind<0>(ins.kind, all, ar, ai, sp, ins.km); break;
-            case 1: if (pre) apply_bit3<1>(ar, ai, facc[2 * kThreads3]); if (thr_ok) bfly3_kind<1>(ins.kind, all, ar, ai, sp, ins.km); break;
-            case 2: if (pre) apply_bit3<2>(ar, ai, facc[3 * kThreads3]); if (thr_ok) bfly3_kind<2>(ins.kind, all, ar, ai, sp, ins.km); break;
-            default: if (pre) apply_bit3<3>(ar, ai, facc[4 * kThreads3]); if (thr_ok) bfly3_kind<3>(ins.kind, all, ar, ai, sp, ins.km); break;
+            case 0: if (thr_ok) bfly3_kind<0>(ins.kind, all, ar, ai, sp, ins.km); break;
+            case 1: if (thr_ok) bfly3_kind<1>(ins.kind, all, ar, ai, sp, ins.km); break;
+            case 2: if (thr_ok) bfly3_kind<2>(ins.kind, all, ar, ai, sp, ins.km); break;
+            default: if (thr_ok) bfly3_kind<3>(ins.kind, all, ar, ai, sp, ins.km); break;
+            }
+            continue;
+        }
+        if (op == T3_PRE) {
+            // Accumulator F_{rpos+1} is pending and a butterfly on register bit rpos follows: apply it to the amplitudes with
+            // that bit set.  Only the accumulator of the target's own bit separates the two members of a pair; the others scale
+            // both by the same factor and stay pending.
+            switch (ins.rpos) {
+            case 0: apply_bit3<0>(ar, ai, facc[1 * kThreads3]); break;
+            case 1: apply_bit3<1>(ar, ai, facc[2 * kThreads3]); break;
+            case 2: apply_bit3<2>(ar, ai, facc[3 * kThreads3]); break;
+            default: apply_bit3<3>(ar, ai, facc[4 * kThreads3]); break;
             }
             continue;
         }
@@ -502,10 +599,11 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
     fence_proxy_async_smem(); // this thread's shared-memory writes become visible to the TMA engine
     __syncthreads();
     if (tid < 32) {
-        for (unsigned s = tid; s < n_seg; s += 32) {
-            const int row = seg_row(base, s);
-            tma_store_box(&a.tm_re, row, smem + s * seg_bytes);
-            tma_store_box(&a.tm_im, row, smem + kArrayBytes3 + s * seg_bytes);
+        for (unsigned e = tid; e < n_box; e += 32) {
+            int c[5];
+            box_coords(base, e, c);
+            tma_store_box(a.rank, &a.tm_re, c, smem + e * box_bytes);
+            tma_store_box(a.rank, &a.tm_im, c, smem + kArrayBytes3 + e * box_bytes);
         }
         tma_store_commit_and_wait_read(); // shared memory must stay alive until the engine has read it
     }
@@ -538,7 +636,7 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
     if (n_instr < 1 || prog[0].op != TI_LAYOUT) return false;
     out = Lowered3();
     int R[4] = {0, 1, 2, 3};
-    unsigned dirty = 0;       // accumulators that are not the identity
+    unsigned dirty = 0;       // accumulators that hold a pending factor
     auto push = [&](const Ins3 &i, uint64_t outer) { out.ins.push_back(i); out.outer.push_back(outer); };
     auto pool2 = [&](double x, double y) -> uint32_t { // a double2 entry: even offset
         if (out.pool.size() & 1) out.pool.push_back(0.0);
@@ -563,99 +661,15 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
         out.groups.push_back(g);
         return (uint32_t)out.groups.size() - 1;
     };
-    // which variant runs a non-diagonal gate, its scalars, and the real factor it leaves to the pass scale
-    struct Variant { int kind = -1; double s[8]; int ns = 0; double factor = 1.0; };
-    // `budget`: how much smaller the pass scale may still get (the amplitudes grow by the inverse until the scale is applied)
-    auto variant_of = [](const TileInstr &t, double budget) -> Variant {
-        Variant v;
-        const bool controlled = t.reg_cmask || t.thr_cmask || t.outer_cmask;
-        const double *s = t.s;
-        auto set = [&](int kind, std::initializer_list<double> sc, double factor) {
-            v.kind = kind; v.ns = 0; v.factor = factor;
-            for (double x : sc) v.s[v.ns++] = x;
-        };
-        // The factored form is as accurate as the matrix for any cosine (same absolute rounding error once the scale is
-        // applied); what bounds it is range: |cos| >= 2^-10 per gate, and the running product stays above 1e-100.
-        constexpr double kMinScale = 1.0 / 1024.0;
-        switch (t.kind) {
-        case SPZ_GATE_H:
-            if (!controlled && SPZ_SQRT_ONE_HALF >= budget) set(MK_H, {}, SPZ_SQRT_ONE_HALF);
-            else set(MK_REAL, {SPZ_SQRT_ONE_HALF, SPZ_SQRT_ONE_HALF, SPZ_SQRT_ONE_HALF, -SPZ_SQRT_ONE_HALF}, 1.0);
-            break;
-        case SPZ_GATE_X: set(MK_X, {}, 1.0); break;
-        case SPZ_GATE_Y: set(MK_Y, {}, 1.0); break;
-        case SPZ_GATE_RX: // [[cs, i ns], [i ns, cs]], s = (cs, ns)   (gate_math.cuh)
-            if (!controlled && std::fabs(s[0]) >= kMinScale && std::fabs(s[0]) >= budget) set(MK_RXT, {s[1] / s[0]}, s[0]);
-            else set(MK_RXU, {s[0], s[1]}, 1.0);
-            break;
-        case SPZ_GATE_RY: // [[cs, -sn], [sn, cs]], s = (sn, cs)
-            if (!controlled && std::fabs(s[1]) >= kMinScale && std::fabs(s[1]) >= budget) set(MK_RYT, {s[0] / s[1]}, s[1]);
-            else set(MK_REAL, {s[1], -s[0], s[0], s[1]}, 1.0);
-            break;
-        case SPZ_GATE_U: // [[a, k + i l], [q + i r, ss + i t]], s = (a, k, l, q, r, ss, t)
-            set(MK_U, {s[0], 0.0, s[1], s[2], s[3], s[4], s[5], s[6]}, 1.0);
-            break;
-        default: break;
-        }
-        return v;
-    };
-    std::vector<Variant> variants((size_t)n_instr);
-    for (int pc = 0; pc < n_instr; ++pc) {
-        if (prog[pc].op != TI_GATE) continue;
-        variants[pc] = variant_of(prog[pc], 1e-100 / std::fabs(out.scale));
-        out.scale *= variants[pc].factor;
-    }
-    // F0 starts as the pass scale in the kernel: when something was factored out it is pending from the first instruction on
-    dirty = out.scale != 1.0 ? 1u : 0u;
-    for (int pc = 0; pc < n_instr; ++pc) {
-        const TileInstr &t = prog[pc];
-        if (t.op == TI_LAYOUT) {
-            Ins3 i{};
-            i.op = T3_LAYOUT;
-            i.flags = (uint8_t)dirty;
-            for (int k = 0; k < 4; ++k) { R[k] = t.rbit[k]; if (R[k] < 0 || R[k] >= kT3 || (k && R[k] <= R[k - 1])) return false; }
-            i.a = (uint32_t)R[0] | ((uint32_t)R[1] << 8) | ((uint32_t)R[2] << 16) | ((uint32_t)R[3] << 24);
-            if (pc > 0) dirty = 0;
-            push(i, 0);
-            continue;
-        }
-        if (t.op == TI_GATE) {
-            Ins3 i{};
-            i.op = T3_GATE;
-            i.rpos = (uint8_t)t.rpos;
-            bool ok = true;
-            i.thr = (uint16_t)to_tid(t.thr_cmask, ok);
-            if (!ok || t.rpos < 0 || t.rpos > 3) return false;
-            i.km = (uint16_t)t.t_mask;
-            const bool in_tile_ctrl = t.reg_cmask || t.thr_cmask;
-            if (in_tile_ctrl) out.ctrl = true; else i.flags |= GF_ALL;
-            if (t.outer_cmask) i.flags |= GF_OUTER;
-            if (dirty & (2u << t.rpos)) { i.flags |= GF_PRE; dirty &= ~(2u << t.rpos); }
-            const Variant &v = variants[pc];
-            if (v.kind < 0) return false;
-            i.kind = (uint8_t)v.kind;
-            if (v.ns) { i.a = (uint32_t)out.pool.size(); out.pool.insert(out.pool.end(), v.s, v.s + v.ns); }
-            push(i, t.outer_cmask);
-            continue;
-        }
-        if (t.op != TI_RUN) return false; // TI_DIAG: exact mode
-        // ---- a merged run of diagonal gates: groups [rpos, rpos + sum of counts), classes m = 0, 1, 2, 4, 8, other ----
-        const int counts[6] = {t.rbit[0], t.rbit[1], t.rbit[2], t.rbit[3], (int)t.reg_cmask, (int)t.thr_cmask};
-        int g = t.rpos;
+
+    // ---- diagonal terms: amplitudes whose tile base contains `outer`, whose THREAD ID contains `thr` and whose register index
+    // contains `m` are multiplied by (fr, fi) ----
+    struct Term { uint64_t outer; uint32_t thr, m; double fr, fi; };
+    auto class_of = [](uint32_t m) { return m == 0 ? 0 : m == 1 ? 1 : m == 2 ? 2 : m == 4 ? 3 : m == 8 ? 4 : 5; };
+    auto emit_terms = [&](const std::vector<Term> &all) {
         for (int cls = 0; cls < 6; ++cls) {
-            // gather this class's terms, masks converted to thread-id space
-            struct Term { uint64_t outer; uint32_t thr, m; double fr, fi; };
             std::vector<Term> ts;
-            for (int k = 0; k < counts[cls]; ++k, ++g) {
-                const TileGroup &gd = groups[g];
-                for (int j = 0; j < gd.count; ++j) {
-                    const TileTerm &tm = terms[gd.first + j];
-                    bool ok = true;
-                    const uint32_t thr = to_tid(tm.thr, ok);
-                    if (!ok) return false;
-                    ts.push_back(Term{tm.outer, thr, tm.m, tm.fr, tm.fi});
-                }
-            }
+            for (const Term &x : all) if (class_of(x.m) == cls) ts.push_back(x);
             if (ts.empty()) continue;
             if (cls < 5) {
                 double lo[16][2], hi[16][2];
@@ -714,7 +728,7 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
                     push(i, 0);
                 }
             } else {
-                // two or more register bits: by (thread mask, register mask)
+                // two or more register bits: by (thread mask, register mask), applied to the amplitudes at once
                 std::vector<std::pair<std::pair<uint32_t, uint32_t>, std::vector<TileTerm>>> byk;
                 for (const Term &x : ts) {
                     size_t k = 0;
@@ -739,13 +753,134 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
                 }
             }
         }
+    };
+
+    // ---- non-diagonal gates: the butterfly variant, its two scalars, what it leaves to the pass scale, and the phase terms
+    // around it ----
+    struct Variant {
+        int kind = -1;
+        double s[2] = {0.0, 0.0};
+        int ns = 0;
+        double factor = 1.0;      // multiplies the pass scale (uncontrolled gates only)
+        bool ctrl_sign = false;   // controlled rotation by more than a quarter turn: -1 on the control subspace
+        bool pre = false, post = false;  // U = diag(1, post) . rotation . diag(1, pre)
+        double pre_f[2] = {1.0, 0.0}, post_f[2] = {1.0, 0.0};
+    };
+    // `budget`: how much smaller the pass scale may still get (the amplitudes grow by the inverse until the scale is applied)
+    auto variant_of = [](const TileInstr &t, double budget) -> Variant {
+        Variant v;
+        const bool controlled = t.reg_cmask || t.thr_cmask || t.outer_cmask;
+        const double *s = t.s;
+        // rotation [[cs, -sn], [sn, cs]] as three shears with |angle| <= pi/2: -R(angle -+ pi) when cs < 0
+        auto rotation = [&](int kind, double cs, double sn) {
+            v.kind = kind;
+            if (cs < 0.0) {
+                cs = -cs; sn = -sn;
+                if (controlled) v.ctrl_sign = true; else v.factor = -1.0;
+            }
+            v.s[0] = sn / (1.0 + cs); v.s[1] = sn; v.ns = 2;
+        };
+        switch (t.kind) {
+        case SPZ_GATE_H:
+            if (!controlled && SPZ_SQRT_ONE_HALF >= budget) { v.kind = MK_H; v.factor = SPZ_SQRT_ONE_HALF; }
+            else v.kind = MK_HS;
+            break;
+        case SPZ_GATE_X: v.kind = MK_X; break;
+        case SPZ_GATE_Y: v.kind = MK_Y; break;
+        case SPZ_GATE_RX: rotation(MK_RX, s[0], s[1]); break; // [[cs, i ns], [i ns, cs]], s = (cs, ns)   (gate_math.cuh)
+        case SPZ_GATE_RY: rotation(MK_RY, s[1], s[0]); break; // [[cs, -sn], [sn, cs]], s = (sn, cs)
+        case SPZ_GATE_U: { // [[ct, k + i l], [q + i r, ss + i tt]] = diag(1, e^{i phi}) [[ct, -st], [st, ct]] diag(1, e^{i lambda})
+            const double ct = s[0], k = s[1], l = s[2], q = s[3], r = s[4], ss = s[5], tt = s[6];
+            const double st = std::hypot(q, r); // |sin|: its sign is absorbed by the two phases
+            if (st > 1e-150) {
+                v.post_f[0] = q / st; v.post_f[1] = r / st;
+                v.pre_f[0] = -k / st; v.pre_f[1] = -l / st;
+            } else { // diagonal: diag(ct, ss + i tt), |ct| = 1
+                v.post_f[0] = ss / ct; v.post_f[1] = tt / ct;
+            }
+            v.pre = !(v.pre_f[0] == 1.0 && v.pre_f[1] == 0.0);
+            v.post = !(v.post_f[0] == 1.0 && v.post_f[1] == 0.0);
+            rotation(MK_RY, ct, st);
+            break; }
+        default: break;
+        }
+        return v;
+    };
+    std::vector<Variant> variants((size_t)n_instr);
+    for (int pc = 0; pc < n_instr; ++pc) {
+        if (prog[pc].op != TI_GATE) continue;
+        variants[pc] = variant_of(prog[pc], 1e-100 / std::fabs(out.scale));
+        out.scale *= variants[pc].factor;
+    }
+    // F0 starts as the pass scale in the kernel: when something was factored out it is pending from the first instruction on
+    dirty = out.scale != 1.0 ? 1u : 0u;
+    for (int pc = 0; pc < n_instr; ++pc) {
+        const TileInstr &t = prog[pc];
+        if (t.op == TI_LAYOUT) {
+            Ins3 i{};
+            i.op = T3_LAYOUT;
+            i.flags = (uint8_t)dirty;
+            for (int k = 0; k < 4; ++k) { R[k] = t.rbit[k]; if (R[k] < 0 || R[k] >= kT3 || (k && R[k] <= R[k - 1])) return false; }
+            i.a = (uint32_t)R[0] | ((uint32_t)R[1] << 8) | ((uint32_t)R[2] << 16) | ((uint32_t)R[3] << 24);
+            if (pc > 0) dirty = 0;
+            push(i, 0);
+            continue;
+        }
+        if (t.op == TI_GATE) {
+            const Variant &v = variants[pc];
+            if (v.kind < 0 || t.rpos < 0 || t.rpos > 3) return false;
+            bool ok = true;
+            const uint32_t thr = to_tid(t.thr_cmask, ok);
+            if (!ok) return false;
+            const uint32_t tbit = 1u << t.rpos;
+            std::vector<Term> before, after;
+            if (v.pre) before.push_back(Term{t.outer_cmask, thr, t.reg_cmask | tbit, v.pre_f[0], v.pre_f[1]});
+            if (v.ctrl_sign) before.push_back(Term{t.outer_cmask, thr, t.reg_cmask, -1.0, 0.0});
+            if (v.post) after.push_back(Term{t.outer_cmask, thr, t.reg_cmask | tbit, v.post_f[0], v.post_f[1]});
+            if (!before.empty()) emit_terms(before);
+            if (dirty & (2u << t.rpos)) { // the accumulator of the target's own register bit is pending: apply it first
+                Ins3 p{};
+                p.op = T3_PRE;
+                p.rpos = (uint8_t)t.rpos;
+                push(p, 0);
+                dirty &= ~(2u << t.rpos);
+            }
+            Ins3 i{};
+            i.op = T3_GATE;
+            i.rpos = (uint8_t)t.rpos;
+            i.thr = (uint16_t)thr;
+            i.km = (uint16_t)t.t_mask;
+            const bool in_tile_ctrl = t.reg_cmask || t.thr_cmask;
+            if (in_tile_ctrl) out.ctrl = true; else i.flags |= GF_ALL;
+            if (t.outer_cmask) i.flags |= GF_OUTER;
+            i.kind = (uint8_t)v.kind;
+            if (v.ns) { i.a = (uint32_t)out.pool.size(); out.pool.insert(out.pool.end(), v.s, v.s + v.ns); }
+            push(i, t.outer_cmask);
+            if (!after.empty()) emit_terms(after);
+            continue;
+        }
+        if (t.op != TI_RUN) return false; // TI_DIAG: exact mode
+        // ---- a merged run of diagonal gates: groups [rpos, rpos + sum of counts), classes m = 0, 1, 2, 4, 8, other ----
+        const int n_run_groups = t.rbit[0] + t.rbit[1] + t.rbit[2] + t.rbit[3] + (int)t.reg_cmask + (int)t.thr_cmask;
+        std::vector<Term> run;
+        for (int g = t.rpos; g < t.rpos + n_run_groups; ++g) {
+            const TileGroup &gd = groups[g];
+            for (int j = 0; j < gd.count; ++j) {
+                const TileTerm &tm = terms[gd.first + j];
+                bool ok = true;
+                const uint32_t thr = to_tid(tm.thr, ok);
+                if (!ok) return false;
+                run.push_back(Term{tm.outer, thr, tm.m, tm.fr, tm.fi});
+            }
+        }
+        emit_terms(run);
     }
     Ins3 e{};
     e.op = T3_END;
     e.flags = (uint8_t)dirty;
     push(e, 0);
     if (out.pool.size() & 1) out.pool.push_back(0.0);
-    return out.ins.size() <= (size_t)kMaxIns3 && out.groups.size() <= (size_t)kMaxGroups3;
+    return out.ins.size() <= (size_t)kMaxIns3 && out.groups.size() <= (size_t)kMaxGroups3 && out.terms.size() <= (size_t)(kAccBytes3 / 16u);
 }
 
 // Serialise for upload (layout: see Lowered3) and fill the size fields of the kernel arguments.
@@ -765,7 +900,7 @@ size_t tile3_pack(const Lowered3 &lw, std::vector<unsigned char> &blob, Tile3Arg
     if (!lw.terms.empty()) std::memcpy(blob.data() + terms_off, lw.terms.data(), lw.terms.size() * sizeof(TileTerm));
     a.ins_bytes = (unsigned)ins_bytes; a.pool_bytes = (unsigned)pool_bytes;
     a.outer_off = (unsigned)outer_off; a.groups_off = (unsigned)groups_off; a.terms_off = (unsigned)terms_off;
-    a.n_ins = (int)lw.ins.size(); a.n_groups = (int)lw.groups.size();
+    a.n_ins = (int)lw.ins.size(); a.n_groups = (int)lw.groups.size(); a.n_terms = (int)lw.terms.size();
     a.scale = lw.scale;
     return total;
 }
@@ -807,18 +942,59 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// 2-D view of one state array: rows of 16 doubles (128 bytes, the widest inner box the 128-byte swizzle allows); a tile
-// segment of 2^L amplitudes is a box of 2^(L-4) rows.
-static int make_tensor_map(CUtensorMap *tm, double *base, int64_t len, int L) {
+// How a tile becomes TMA boxes.  The state array is viewed as a tensor whose dimensions are bit fields of the amplitude index:
+// dim 0 = bits [0, 4) (16 doubles = 128 bytes, the widest inner box the 128-byte swizzle allows), dim 1 = bits [4, p1) up to the
+// first high tile qubit (the box takes the 2^(L-4) rows of a segment), then one dimension per run of contiguous high tile
+// qubits, spanning from the run's first bit to the next run (the box takes the run; the bits above it, which are not tile
+// qubits, are the coordinate).  A tensor map has at most five dimensions, so a box holds the low bits and the three lowest
+// runs; higher tile qubits are enumerated by the kernel, one box per combination.  Tiles whose high qubits form up to three
+// runs -- {24..29}, {12, 13, 20..23}, ... -- move with ONE instruction per array and direction.
+static void plan_boxes(int n_qubits, const TilePlan &plan, Tile3Args &a) {
+    const int L = plan.low_bits;
+    struct Run { int lo, w; };
+    Run runs[kMaxHigh3];
+    int n_runs = 0;
+    for (int k = 0; k < plan.n_high; ++k) {
+        if (n_runs && runs[n_runs - 1].lo + runs[n_runs - 1].w == plan.high[k]) ++runs[n_runs - 1].w;
+        else runs[n_runs++] = Run{plan.high[k], 1};
+    }
+    const int in_box = std::min(n_runs, 3);
+    a.rank = 2 + in_box;
+    a.box_shift = L;
+    a.dim_lo[0] = 0; a.dim_len[0] = 4;
+    a.dim_lo[1] = 4; a.dim_len[1] = (in_box ? runs[0].lo : n_qubits) - 4;
+    for (int r = 0; r < in_box; ++r) {
+        a.dim_lo[2 + r] = runs[r].lo;
+        a.dim_len[2 + r] = (r + 1 < in_box ? runs[r + 1].lo : n_qubits) - runs[r].lo;
+        a.box_shift += runs[r].w;
+    }
+    for (int i = a.rank; i < 5; ++i) { a.dim_lo[i] = 0; a.dim_len[i] = 0; }
+    a.n_rest = 0;
+    for (int r = in_box; r < n_runs; ++r)
+        for (int b = 0; b < runs[r].w; ++b) a.rest_bit[a.n_rest++] = runs[r].lo + b;
+}
+
+static int make_tensor_map(CUtensorMap *tm, double *base, const TilePlan &plan, const Tile3Args &a) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SPZ_ERR_CUDA; }
-    const cuuint64_t gdim[2] = {16, (cuuint64_t)(len >> 4)};
-    const cuuint64_t gstride[1] = {128};
-    const cuuint32_t box[2] = {16, 1u << (L - 4)};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t box[5], estr[5];
+    for (int i = 0; i < a.rank; ++i) {
+        gdim[i] = (cuuint64_t)1 << a.dim_len[i];
+        estr[i] = 1;
+        if (i > 0) gstride[i - 1] = (cuuint64_t)8 << a.dim_lo[i];
+    }
+    box[0] = 16;
+    box[1] = 1u << (plan.low_bits - 4);
+    int k = 0;
+    for (int i = 2; i < a.rank; ++i) { // the run that starts at dim_lo[i]
+        int w = 0;
+        while (k < plan.n_high && plan.high[k] == a.dim_lo[i] + w) { ++w; ++k; }
+        box[i] = 1u << w;
+    }
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)a.rank, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for len=%lld L=%d", (int)r, (long long)len, L); return SPZ_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for rank %d, L=%d", (int)r, a.rank, plan.low_bits); return SPZ_ERR_CUDA; }
     return SPZ_OK;
 }
 
@@ -845,8 +1021,9 @@ int prepare_tile3(spz_state *st, const TilePlan &plan, const TileInstr *prog, in
         SPZ_TRY(tile3_prepare());
         prepared[st->device] = true;
     }
-    SPZ_TRY(make_tensor_map(&a.tm_re, st->re, st->len, plan.low_bits));
-    SPZ_TRY(make_tensor_map(&a.tm_im, st->im, st->len, plan.low_bits));
+    plan_boxes(st->n, plan, a);
+    SPZ_TRY(make_tensor_map(&a.tm_re, st->re, plan, a));
+    SPZ_TRY(make_tensor_map(&a.tm_im, st->im, plan, a));
     char *slot = nullptr;
     SPZ_TRY(tile_ring_alloc(st, bytes, &slot));
     SPZ_CUDA(cudaMemcpyAsync(slot, blob.data(), bytes, cudaMemcpyHostToDevice, st->stream));
