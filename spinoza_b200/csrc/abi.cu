@@ -761,6 +761,7 @@ int spz_destroy(spz_state *st) {
     cudaFree(st->re);
     cudaFree(st->im);
     cudaFree(st->scratch.partials);
+    if (st->scratch.samp) cudaFree(st->scratch.samp); // (allocated stream-ordered; the stream has been synchronised above)
     if (st->scratch.h_result) cudaFreeHost(st->scratch.h_result);
     cudaFree(st->d_ops);
     if (st->ev0) cudaEventDestroy(st->ev0);

@@ -48,6 +48,8 @@ struct Scratch {
     double *partials = nullptr; // device, reduction partials
     size_t n_partials = 0;
     double *h_result = nullptr; // pinned host, small
+    void *samp = nullptr;       // sampler arena (stream-ordered allocation, grown on demand)
+    size_t samp_bytes = 0;
 };
 
 } // namespace spz

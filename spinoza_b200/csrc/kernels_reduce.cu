@@ -251,10 +251,16 @@ int launch_scale(spz_state *st, double scale) {
 }
 
 // ---- sampling ---------------------------------------------------------------------------------------------
-// Exact inverse-CDF sampling with a three-level CDF (replaces the O(num_tests * k) reservoir loop of
-// core.rs:81-112).  Level 0: |amp|^2.  Level 1: sums of blocks of B amplitudes.  Level 2: sums of groups of
-// B level-1 entries.  A shot x = u * total is located by a host search over level 2 (<= 2^(n-2*LOGB)
-// entries), then one warp per shot scans its level-1 group and its amplitude block.
+// Exact inverse-CDF sampling (replaces the O(num_tests * k) reservoir loop of core.rs:81-112), two streaming read passes
+// over the state however many shots are asked for:
+//   pass 1   level 1: |amp|^2 summed per block of B = 4096 amplitudes (k_block_prob); its inclusive prefix per group of
+//            4096 blocks (k_scan_groups) and the prefix over the <= 512 group totals (k_scan_single): a two-level CDF, on
+//            the device;
+//   locate   one thread per shot: x = u * total, two binary searches -> the block that holds the shot and the residual
+//            inside it; a counting sort groups the shots by block (histogram, exclusive scan, scatter);
+//   pass 2   one CTA per block that holds shots: the block's 4096 probabilities are scanned once in shared memory and every
+//            shot of the bucket is a 12-step binary search there (k_sample_blocks).  Blocks without shots are not read.
+// Every sum has a fixed order, so the outcome for a given u is reproducible; atomics only order shots inside a bucket.
 constexpr int kLogB = 12;
 constexpr long long kB = 1ll << kLogB;
 
@@ -268,139 +274,196 @@ __global__ void __launch_bounds__(256) k_block_prob(const double *__restrict__ r
     acc = block_sum(acc);
     if (threadIdx.x == 0) out[b] = acc;
 }
-__global__ void __launch_bounds__(256) k_group_sum(const double *__restrict__ in, long long n_in, double *__restrict__ out) {
-    const long long g = blockIdx.x;
-    const long long lo = g * kB, hi = min(lo + kB, n_in);
-    double acc = 0.0;
-    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += in[i];
-    acc = block_sum(acc);
-    if (threadIdx.x == 0) out[g] = acc;
-}
 
-// Warp-cooperative search: smallest j in [0, cnt) with prefix(j) > x, where prefix accumulates w(lo + j) in a
-// fixed order (lane-contiguous chunks, then lanes in order).  Returns j (clamped to cnt-1) and leaves the
-// residual x - prefix(j-1) in *resid.
-template <typename F>
-__device__ __forceinline__ long long warp_search(F w, long long cnt, double x, double *resid) {
-    const int lane = threadIdx.x & 31;
-    const long long per = (cnt + 31) / 32;
-    const long long b = min((long long)lane * per, cnt), e = min(b + per, cnt);
-    double mine = 0.0;
-    for (long long j = b; j < e; ++j) mine += w(j);
-    // exclusive prefix over lanes
-    double incl = mine;
+// Inclusive scan of 4096 values held 16 per thread (thread t owns v[16t .. 16t+16)) by a 256-thread CTA, in place.
+// Returns the total in every thread.
+template <typename T>
+__device__ __forceinline__ T cta_scan16(T (&v)[16]) {
+    __shared__ T warp_tot[8];
+    __shared__ T cta_tot;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 1; i < 16; ++i) v[i] += v[i - 1];
+    T incl = v[15];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, incl, o);
+        const T t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    const double excl = incl - mine;
-    // owning lane: first lane with incl > x (last non-empty lane if rounding leaves none)
-    const unsigned ballot = __ballot_sync(0xffffffffu, incl > x && e > b);
-    int owner;
-    if (ballot) owner = __ffs(ballot) - 1;
-    else {
-        const unsigned nonempty = __ballot_sync(0xffffffffu, e > b);
-        owner = 31 - __clz(nonempty);
-    }
-    long long found = 0;
-    double r = 0.0;
-    if (lane == owner) {
-        double acc = excl;
-        long long j = b;
-        for (; j < e; ++j) {
-            const double wj = w(j);
-            if (acc + wj > x) break;
-            acc += wj;
-        }
-        if (j >= e) j = e - 1; // rounding guard
-        found = j;
-        // residual relative to the start of element j
-        double acc2 = excl;
-        for (long long q = b; q < j; ++q) acc2 += w(q);
-        r = x - acc2;
-    }
-    found = __shfl_sync(0xffffffffu, found, owner);
-    r = __shfl_sync(0xffffffffu, r, owner);
-    *resid = r;
-    return found;
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    T base = incl - v[15];
+    for (int k = 0; k < w; ++k) base += warp_tot[k];
+    if (threadIdx.x == 255) cta_tot = base + v[15];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += base;
+    __syncthreads();
+    const T total = cta_tot;
+    __syncthreads(); // the statics are reused by the caller's next scan
+    return total;
 }
 
-__global__ void __launch_bounds__(256) k_sample(const double *__restrict__ re, const double *__restrict__ im, long long len,
-                                                const double *__restrict__ l1, long long n_l1,
-                                                const long long *__restrict__ shot_group, const double *__restrict__ shot_resid,
-                                                long long shots, long long *__restrict__ out) {
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long s = warp; s < shots; s += nwarps) {
-        const long long g = shot_group[s];
-        double x = shot_resid[s];
-        const long long l1_lo = g * kB, l1_cnt = min(kB, n_l1 - l1_lo);
-        double r1;
-        const long long jb = warp_search([&](long long j) { return l1[l1_lo + j]; }, l1_cnt, x, &r1);
-        const long long blk = l1_lo + jb;
-        const long long a_lo = blk * kB, a_cnt = min(kB, len - a_lo);
-        double r2;
-        const long long ja = warp_search(
-            [&](long long j) { const double a = re[a_lo + j], b = im[a_lo + j]; return a * a + b * b; }, a_cnt, r1, &r2);
-        if ((threadIdx.x & 31) == 0) out[s] = a_lo + ja;
+// One CTA per group of 4096 entries: local inclusive prefix (in place allowed) and the group's total.
+template <typename T>
+__global__ void __launch_bounds__(256) k_scan_groups(const T *__restrict__ in, long long n_in, T *__restrict__ local_incl, T *__restrict__ totals) {
+    const long long lo = (long long)blockIdx.x * kB;
+    T v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const long long j = lo + threadIdx.x * 16 + i;
+        v[i] = j < n_in ? in[j] : (T)0;
     }
+    const T total = cta_scan16(v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const long long j = lo + threadIdx.x * 16 + i;
+        if (j < n_in) local_incl[j] = v[i];
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = total;
+}
+// Inclusive scan of up to 4096 group totals, in place, one CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) k_scan_single(T *__restrict__ x, int n) {
+    T v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int j = threadIdx.x * 16 + i;
+        v[i] = j < n ? x[j] : (T)0;
+    }
+    cta_scan16(v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int j = threadIdx.x * 16 + i;
+        if (j < n) x[j] = v[i];
+    }
+}
+
+// first j in [0, cnt) with a[j] > x (cnt - 1 if rounding leaves none)
+__device__ __forceinline__ long long upper_index(const double *__restrict__ a, long long cnt, double x) {
+    long long lo = 0, hi = cnt;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (a[mid] > x) hi = mid; else lo = mid + 1;
+    }
+    return lo < cnt ? lo : cnt - 1;
+}
+
+// One thread per shot: the block that holds it, the residual inside the block, and the histogram of shots per block.
+__global__ void __launch_bounds__(256) k_locate(const double *__restrict__ u01, long long shots, const double *__restrict__ pre1, long long n_l1,
+                                                const double *__restrict__ pre2, int n_l2, int *__restrict__ shot_blk,
+                                                double *__restrict__ shot_res, int *__restrict__ count) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= shots) return;
+    double u = u01[s];
+    if (!(u >= 0.0)) u = 0.0;
+    if (u >= 1.0) u = 0x1.fffffffffffffp-1;
+    const double x = u * pre2[n_l2 - 1];
+    const long long g = upper_index(pre2, n_l2, x);
+    const double r1 = x - (g ? pre2[g - 1] : 0.0);
+    const long long lo = g * kB, cnt = min(kB, n_l1 - lo);
+    const long long j = upper_index(pre1 + lo, cnt, r1);
+    const double r2 = r1 - (j ? pre1[lo + j - 1] : 0.0);
+    shot_blk[s] = (int)(lo + j);
+    shot_res[s] = r2;
+    atomicAdd(&count[lo + j], 1);
+}
+// bucket start of block b from the two-level inclusive scan of the histogram
+__device__ __forceinline__ int bucket_start(const int *__restrict__ count, const int *__restrict__ cnt_incl, const int *__restrict__ cnt_tot, long long b) {
+    const long long g = b >> kLogB;
+    return cnt_incl[b] - count[b] + (g ? cnt_tot[g - 1] : 0);
+}
+__global__ void __launch_bounds__(256) k_scatter(long long shots, const int *__restrict__ shot_blk, const int *__restrict__ count,
+                                                 const int *__restrict__ cnt_incl, const int *__restrict__ cnt_tot, int *__restrict__ cursor,
+                                                 int *__restrict__ order) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= shots) return;
+    const int b = shot_blk[s];
+    order[bucket_start(count, cnt_incl, cnt_tot, b) + atomicAdd(&cursor[b], 1)] = (int)s;
+}
+// One CTA per block with shots: scan the block's probabilities once, answer every shot of its bucket.
+__global__ void __launch_bounds__(256) k_sample_blocks(const double *__restrict__ re, const double *__restrict__ im, long long len,
+                                                       const int *__restrict__ count, const int *__restrict__ cnt_incl,
+                                                       const int *__restrict__ cnt_tot, const int *__restrict__ order,
+                                                       const double *__restrict__ shot_res, long long *__restrict__ out) {
+    const long long b = blockIdx.x;
+    const int n_here = count[b];
+    if (n_here == 0) return;
+    __shared__ double incl[kB];
+    const long long lo = b * kB, cnt = min(kB, len - lo);
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { // coalesced read (stride 256), parked transposed in shared memory
+        const long long j = (long long)i * 256 + threadIdx.x;
+        double p = 0.0;
+        if (j < cnt) { const double x = re[lo + j], y = im[lo + j]; p = x * x + y * y; }
+        incl[j] = p;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = incl[threadIdx.x * 16 + i];
+    __syncthreads();
+    cta_scan16(v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) incl[threadIdx.x * 16 + i] = v[i];
+    __syncthreads();
+    const int start = bucket_start(count, cnt_incl, cnt_tot, b);
+    for (int k = threadIdx.x; k < n_here; k += blockDim.x) {
+        const int s = order[start + k];
+        out[s] = lo + upper_index(incl, cnt, shot_res[s]);
+    }
+}
+
+// The sampler's device scratch: one stream-ordered arena kept with the state and grown on demand (cudaMalloc / cudaFree would
+// synchronise the whole device, see spz_create).
+static int sample_arena(spz_state *st, size_t bytes, char **out) {
+    if (st->scratch.samp_bytes < bytes) {
+        if (st->scratch.samp) SPZ_CUDA(cudaFreeAsync(st->scratch.samp, st->stream));
+        st->scratch.samp = nullptr; st->scratch.samp_bytes = 0;
+        const size_t cap = bytes + bytes / 4;
+        SPZ_CUDA(cudaMallocAsync(&st->scratch.samp, cap, st->stream));
+        st->scratch.samp_bytes = cap;
+    }
+    *out = static_cast<char *>(st->scratch.samp);
+    return SPZ_OK;
 }
 
 int launch_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_index) {
     if (shots <= 0) return SPZ_OK;
+    if (shots > 0x7fffffffLL) { set_error("at most 2^31 - 1 shots per call"); return SPZ_ERR_INVALID_ARG; }
     SPZ_TRY(join_pending(st));
     const long long len = st->len;
     const long long n_l1 = (len + kB - 1) / kB;
-    const long long n_l2 = (n_l1 + kB - 1) / kB;
-    double *d_l1 = nullptr, *d_l2 = nullptr, *d_resid = nullptr;
-    long long *d_group = nullptr, *d_out = nullptr;
-    int rc = SPZ_OK;
-    std::vector<double> l2((size_t)n_l2), resid((size_t)shots);
-    std::vector<long long> group((size_t)shots);
-    // stream-ordered allocations: cudaMalloc/cudaFree would synchronise the whole device (see spz_create)
-    auto cleanup = [&]() {
-        cudaFreeAsync(d_l1, st->stream); cudaFreeAsync(d_l2, st->stream); cudaFreeAsync(d_resid, st->stream);
-        cudaFreeAsync(d_group, st->stream); cudaFreeAsync(d_out, st->stream);
-        cudaStreamSynchronize(st->stream);
-    };
-#define SPZ_S(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = cuda_fail(e__, #call, __FILE__, __LINE__); cleanup(); return rc; } } while (0)
-    SPZ_S(cudaMallocAsync(&d_l1, sizeof(double) * (size_t)n_l1, st->stream));
-    SPZ_S(cudaMallocAsync(&d_l2, sizeof(double) * (size_t)n_l2, st->stream));
-    SPZ_S(cudaMallocAsync(&d_resid, sizeof(double) * (size_t)shots, st->stream));
-    SPZ_S(cudaMallocAsync(&d_group, sizeof(long long) * (size_t)shots, st->stream));
-    SPZ_S(cudaMallocAsync(&d_out, sizeof(long long) * (size_t)shots, st->stream));
-    k_block_prob<<<(unsigned)n_l1, 256, 0, st->stream>>>(st->re, st->im, len, d_l1);
-    k_group_sum<<<(unsigned)n_l2, 256, 0, st->stream>>>(d_l1, n_l1, d_l2);
-    count_launch(2);
-    SPZ_S(cudaGetLastError());
-    SPZ_S(cudaMemcpyAsync(l2.data(), d_l2, sizeof(double) * (size_t)n_l2, cudaMemcpyDeviceToHost, st->stream));
-    SPZ_S(cudaStreamSynchronize(st->stream));
-    // host: level-2 CDF and per-shot group + residual
-    std::vector<double> cdf2((size_t)n_l2);
-    double total = 0.0;
-    for (long long g = 0; g < n_l2; ++g) { total += l2[(size_t)g]; cdf2[(size_t)g] = total; }
-    for (int64_t s = 0; s < shots; ++s) {
-        double u = u01[s];
-        if (!(u >= 0.0)) u = 0.0;
-        if (u >= 1.0) u = 0x1.fffffffffffffp-1;
-        const double x = u * total;
-        long long g = std::upper_bound(cdf2.begin(), cdf2.end(), x) - cdf2.begin();
-        if (g >= n_l2) g = n_l2 - 1;
-        group[(size_t)s] = g;
-        resid[(size_t)s] = x - (g ? cdf2[(size_t)g - 1] : 0.0);
-    }
-    SPZ_S(cudaMemcpyAsync(d_group, group.data(), sizeof(long long) * (size_t)shots, cudaMemcpyHostToDevice, st->stream));
-    SPZ_S(cudaMemcpyAsync(d_resid, resid.data(), sizeof(double) * (size_t)shots, cudaMemcpyHostToDevice, st->stream));
-    const long long warps_needed = shots;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((warps_needed * 32 + 255) / 256, 148 * 16));
-    k_sample<<<grid, 256, 0, st->stream>>>(st->re, st->im, len, d_l1, n_l1, d_group, d_resid, shots, d_out);
-    count_launch();
-    SPZ_S(cudaGetLastError());
-    SPZ_S(cudaMemcpyAsync(out_index, d_out, sizeof(long long) * (size_t)shots, cudaMemcpyDeviceToHost, st->stream));
-    SPZ_S(cudaStreamSynchronize(st->stream));
-#undef SPZ_S
-    cleanup();
+    const int n_l2 = (int)((n_l1 + kB - 1) / kB);
+    if (n_l2 > (int)kB) { set_error("register too large for the two-level sampling CDF"); return SPZ_ERR_UNSUPPORTED; }
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_pre1 = 0, o_pre2 = o_pre1 + up(8 * (size_t)n_l1), o_count = o_pre2 + up(8 * (size_t)n_l2);
+    const size_t o_cursor = o_count + up(4 * (size_t)n_l1), o_cincl = o_cursor + up(4 * (size_t)n_l1), o_ctot = o_cincl + up(4 * (size_t)n_l1);
+    const size_t o_u = o_ctot + up(4 * (size_t)n_l2), o_res = o_u + up(8 * (size_t)shots), o_blk = o_res + up(8 * (size_t)shots);
+    const size_t o_order = o_blk + up(4 * (size_t)shots), o_out = o_order + up(4 * (size_t)shots), total = o_out + up(8 * (size_t)shots);
+    char *base = nullptr;
+    SPZ_TRY(sample_arena(st, total, &base));
+    double *pre1 = reinterpret_cast<double *>(base + o_pre1), *pre2 = reinterpret_cast<double *>(base + o_pre2);
+    int *count = reinterpret_cast<int *>(base + o_count), *cursor = reinterpret_cast<int *>(base + o_cursor);
+    int *cincl = reinterpret_cast<int *>(base + o_cincl), *ctot = reinterpret_cast<int *>(base + o_ctot);
+    double *d_u = reinterpret_cast<double *>(base + o_u), *d_res = reinterpret_cast<double *>(base + o_res);
+    int *d_blk = reinterpret_cast<int *>(base + o_blk), *d_order = reinterpret_cast<int *>(base + o_order);
+    long long *d_out = reinterpret_cast<long long *>(base + o_out);
+    cudaStream_t q = st->stream;
+    SPZ_CUDA(cudaMemcpyAsync(d_u, u01, sizeof(double) * (size_t)shots, cudaMemcpyHostToDevice, q));
+    SPZ_CUDA(cudaMemsetAsync(count, 0, o_cincl - o_count, q)); // histogram and cursors
+    k_block_prob<<<(unsigned)n_l1, 256, 0, q>>>(st->re, st->im, len, pre1);
+    k_scan_groups<double><<<(unsigned)n_l2, 256, 0, q>>>(pre1, n_l1, pre1, pre2);
+    k_scan_single<double><<<1, 256, 0, q>>>(pre2, n_l2);
+    const unsigned shot_grid = (unsigned)((shots + 255) / 256);
+    k_locate<<<shot_grid, 256, 0, q>>>(d_u, shots, pre1, n_l1, pre2, n_l2, d_blk, d_res, count);
+    k_scan_groups<int><<<(unsigned)n_l2, 256, 0, q>>>(count, n_l1, cincl, ctot);
+    k_scan_single<int><<<1, 256, 0, q>>>(ctot, n_l2);
+    k_scatter<<<shot_grid, 256, 0, q>>>(shots, d_blk, count, cincl, ctot, cursor, d_order);
+    k_sample_blocks<<<(unsigned)n_l1, 256, 0, q>>>(st->re, st->im, len, count, cincl, ctot, d_order, d_res, d_out);
+    count_launch(8);
+    SPZ_CUDA(cudaGetLastError());
+    SPZ_CUDA(cudaMemcpyAsync(out_index, d_out, sizeof(long long) * (size_t)shots, cudaMemcpyDeviceToHost, q));
+    SPZ_CUDA(cudaStreamSynchronize(q));
     return SPZ_OK;
 }
 

@@ -86,7 +86,7 @@ static_assert(sizeof(Ins3) == 16, "Ins3 is decoded with one 128-bit shared-memor
 // What the host uploads for one pass (one contiguous blob, 16-byte aligned sections):
 //   Ins3 ins[n_ins] | double pool[n_pool] (gate scalars, tables, constants; double2 entries at even offsets)
 //   | uint64 outer[n_ins] (controls outside the tile, GATE only) | TileGroup groups[n_groups] | TileTerm terms[n_terms]
-// Shared memory of a CTA: tile re | tile im | accumulators F[5][256] | ins | pool | gfac[n_groups] | skip[n_ins] | mbarrier
+// Shared memory of a CTA: tile re | tile im | accumulators F[5][256] | the blob | gfac[n_groups] | skip[n_ins] | 2 mbarriers
 struct Lowered3 {
     std::vector<Ins3> ins;
     std::vector<double> pool;
@@ -110,8 +110,8 @@ struct Tile3Args {
     int dim_lo[5], dim_len[5];
     double *re, *im;               // (the CPU emulation moves the tile through these)
     const unsigned char *blob;     // device copy of the lowered program
-    unsigned ins_bytes, pool_bytes;  // sizes of the two staged sections (multiples of 16)
-    unsigned outer_off, groups_off, terms_off; // byte offsets of the other sections inside the blob
+    unsigned ins_bytes, blob_bytes;  // instruction section and whole blob (multiples of 16)
+    unsigned outer_off, groups_off, terms_off; // byte offsets of the other sections inside the blob (the pool follows the instructions)
     int n_ins, n_groups, n_terms;
     unsigned tile_offset;
     int L, n_high;
@@ -149,6 +149,11 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared (addresses and size multiples of 16 bytes), completing on an mbarrier
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 // One box of a rank-2..5 tensor map (coordinate 0 is always 0: the 16 doubles of a 128-byte row).
 __device__ __forceinline__ void tma_load_box(int rank, void *dst, const CUtensorMap *tm, const int (&c)[5], void *bar) {
@@ -230,11 +235,11 @@ __device__ __forceinline__ void shear3(double &x, double &y, double t, double sn
 template <int MK>
 __device__ __forceinline__ void pair3(const double (&s)[2], double &a, double &b, double &c, double &d) {
     if constexpr (MK == MK_H) {            // [[1, 1], [1, -1]]
-        c = a - c; a = 2.0 * a - c;
-        d = b - d; b = 2.0 * b - d;
+        c = a - c; a = fma(2.0, a, -c);
+        d = b - d; b = fma(2.0, b, -d);
     } else if constexpr (MK == MK_HS) {    // 2^-1/2 [[1, 1], [1, -1]]
-        c = a - c; a = 2.0 * a - c; c = c * SPZ_SQRT_ONE_HALF; a = a * SPZ_SQRT_ONE_HALF;
-        d = b - d; b = 2.0 * b - d; d = d * SPZ_SQRT_ONE_HALF; b = b * SPZ_SQRT_ONE_HALF;
+        c = a - c; a = fma(2.0, a, -c); c = c * SPZ_SQRT_ONE_HALF; a = a * SPZ_SQRT_ONE_HALF;
+        d = b - d; b = fma(2.0, b, -d); d = d * SPZ_SQRT_ONE_HALF; b = b * SPZ_SQRT_ONE_HALF;
     } else if constexpr (MK == MK_RX) {    // [[cos, i sin], [i sin, cos]]: rotates the couples (a, d) and (c, b)
         shear3(a, d, s[0], s[1]);
         shear3(c, b, s[0], s[1]);
@@ -268,18 +273,16 @@ __device__ __forceinline__ void bfly3(double (&ar)[16], double (&ai)[16], const 
 template <int R>
 __device__ __forceinline__ void bfly3_kind(int kind, bool all, double (&ar)[16], double (&ai)[16], const double *__restrict__ sp,
                                            unsigned km) {
+    // Unguarded arms only for the three gates that fill a circuit (GF_ALL is set for nothing else); every other case tests the
+    // pair mask, which is the same for all threads.  Fewer arms = less code to keep in the instruction cache.
     if (all) {
         switch (kind) {
         case MK_H: bfly3<MK_H, R, true>(ar, ai, sp, km); break;
-        case MK_HS: bfly3<MK_HS, R, true>(ar, ai, sp, km); break;
         case MK_RX: bfly3<MK_RX, R, true>(ar, ai, sp, km); break;
-        case MK_RY: bfly3<MK_RY, R, true>(ar, ai, sp, km); break;
-        case MK_X: bfly3<MK_X, R, true>(ar, ai, sp, km); break;
-        default: bfly3<MK_Y, R, true>(ar, ai, sp, km); break;
+        default: bfly3<MK_RY, R, true>(ar, ai, sp, km); break;
         }
     } else {
         switch (kind) {
-        case MK_H: bfly3<MK_H, R, false>(ar, ai, sp, km); break; // (never emitted: a controlled H carries its scale)
         case MK_HS: bfly3<MK_HS, R, false>(ar, ai, sp, km); break;
         case MK_RX: bfly3<MK_RX, R, false>(ar, ai, sp, km); break;
         case MK_RY: bfly3<MK_RY, R, false>(ar, ai, sp, km); break;
@@ -303,15 +306,16 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
     SPZ_DYN_SMEM3(smem);
     double *sre = reinterpret_cast<double *>(smem);
     double *sim = reinterpret_cast<double *>(smem + kArrayBytes3);
+    // the whole program blob is staged behind the accumulators (one bulk copy): ins | pool | outer | groups | terms
     const Ins3 *sins = reinterpret_cast<const Ins3 *>(smem + kProgOff3);
     const double *pool = reinterpret_cast<const double *>(smem + kProgOff3 + a.ins_bytes);
-    double2 *gfac = reinterpret_cast<double2 *>(smem + kProgOff3 + a.ins_bytes + a.pool_bytes);
+    double2 *gfac = reinterpret_cast<double2 *>(smem + kProgOff3 + a.blob_bytes);
     // F[c][tid]: accumulator c of this thread.  They live in shared memory (one 128-bit access each, conflict-free) rather
-    // than in 20 registers: with 64 registers of amplitudes and up to 16 of gate scalars the budget of 128 is tight.
+    // than in 20 registers: with 64 registers of amplitudes the budget of 128 is tight.
     double2 *facc = reinterpret_cast<double2 *>(smem + 2u * kArrayBytes3) + threadIdx.x;
     unsigned char *skip = reinterpret_cast<unsigned char *>(gfac + a.n_groups);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(
-        smem + ((kProgOff3 + a.ins_bytes + a.pool_bytes + 16u * (unsigned)a.n_groups + (unsigned)a.n_ins + 15u) & ~15u));
+        smem + ((kProgOff3 + a.blob_bytes + 16u * (unsigned)a.n_groups + (unsigned)a.n_ins + 15u) & ~15u)); // [0] tile, [1] program
     const unsigned tid = threadIdx.x;
     const int L = a.L;
 
@@ -353,6 +357,9 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
     if ((smem_u32(smem) & 1023u) != 0u) __trap(); // the swizzle pattern is anchored to 1 KB-aligned shared addresses
     if (tid == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_expect_tx(bar + 1, a.blob_bytes);
+        bulk_load(smem + kProgOff3, a.blob, a.blob_bytes, bar + 1); // the program: small, lands first
         mbar_expect_tx(bar, 2u * kArrayBytes3);
     }
     __syncthreads();
@@ -377,49 +384,46 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
     }
 #endif
 
-    // ---- while the tile is in flight: stage the program, skip flags, per-tile constants ----
+    // ---- while the tile is in flight: skip flags and per-tile constants, from the staged program ----
+#ifdef SPZ_CPU_EMULATION
+    for (unsigned i = tid; i < (a.blob_bytes >> 4); i += kThreads3)
+        reinterpret_cast<uint4 *>(smem + kProgOff3)[i] = reinterpret_cast<const uint4 *>(a.blob)[i];
+    __syncthreads();
+#else
+    mbar_wait(bar + 1, 0);
+#endif
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.blob);
-        uint4 *dst = reinterpret_cast<uint4 *>(smem + kProgOff3);
-        const unsigned n16 = (a.ins_bytes + a.pool_bytes) >> 4;
-        for (unsigned i = tid; i < n16; i += kThreads3) dst[i] = src[i];
-    }
-    {
-        const unsigned long long *outer = reinterpret_cast<const unsigned long long *>(a.blob + a.outer_off);
+        const unsigned long long *outer = reinterpret_cast<const unsigned long long *>(smem + kProgOff3 + a.outer_off);
         for (int i = tid; i < a.n_ins; i += kThreads3) {
             const unsigned long long ocm = outer[i];
             skip[i] = (base & ocm) != ocm ? 1 : 0;
         }
-    }
-    // Per-tile constants: every group's product over those of its terms whose outer bits are set in this tile.  Term-parallel
-    // (one L2 round trip for all terms; factors parked in the still unused accumulator region), then one thread per group
-    // multiplies from shared memory.  A serial walk over a group's terms in global memory costs two dependent L2 round trips
-    // per term: ~8 us at the head of every tile of a QFT pass (18 terms per group), four times the tile's HBM time.
-    {
-        const TileGroup *groups = reinterpret_cast<const TileGroup *>(a.blob + a.groups_off);
-        const TileTerm *terms = reinterpret_cast<const TileTerm *>(a.blob + a.terms_off);
-        double2 *scr = reinterpret_cast<double2 *>(smem + 2u * kArrayBytes3);
-        for (int t = tid; t < a.n_terms; t += kThreads3) {
-            const TileTerm tm = terms[t];
-            scr[t] = (base & tm.outer) == tm.outer ? make_double2(tm.fr, tm.fi) : make_double2(1.0, 0.0);
-        }
-        __syncthreads();
+        // Per-tile constants: every group's product over those of its terms whose outer bits are set in this tile.  Everything is
+        // in shared memory by now (a walk over a group's terms in global memory costs two dependent L2 round trips per term:
+        // ~8 us at the head of every tile of a QFT pass with 18 terms per group, four times the tile's HBM time); four partial
+        // products keep the dependent chain short.
+        const TileGroup *groups = reinterpret_cast<const TileGroup *>(smem + kProgOff3 + a.groups_off);
+        const TileTerm *terms = reinterpret_cast<const TileTerm *>(smem + kProgOff3 + a.terms_off);
         for (int g = tid; g < a.n_groups; g += kThreads3) {
             const TileGroup gd = groups[g];
-            double fr = 1.0, fi = 0.0, hr = 1.0, hi = 0.0; // two partial products: half the dependent chain
-            int i = 0;
-            for (; i + 2 <= gd.count; i += 2) {
-                const double2 x = scr[gd.first + i], y = scr[gd.first + i + 1];
-                cmul3(fr, fi, x.x, x.y);
-                cmul3(hr, hi, y.x, y.y);
+            double pr[4] = {1.0, 1.0, 1.0, 1.0}, pi[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int i = 0; i < gd.count; i += 4) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (i + k < gd.count) {
+                        const TileTerm &t = terms[gd.first + i + k];
+                        if ((base & t.outer) == t.outer) cmul3(pr[k], pi[k], t.fr, t.fi);
+                    }
+                }
             }
-            if (i < gd.count) { const double2 x = scr[gd.first + i]; cmul3(fr, fi, x.x, x.y); }
-            cmul3(fr, fi, hr, hi);
-            gfac[g] = make_double2(fr, fi);
+            cmul3(pr[0], pi[0], pr[1], pi[1]);
+            cmul3(pr[2], pi[2], pr[3], pi[3]);
+            cmul3(pr[0], pi[0], pr[2], pi[2]);
+            gfac[g] = make_double2(pr[0], pi[0]);
         }
     }
     } // base
-    __syncthreads(); // program, skip flags and constants staged; the term scratch is free again
+    __syncthreads(); // skip flags and constants in place
 #ifndef SPZ_CPU_EMULATION
     // One warp waits for the boxes (a failed try_wait costs issue slots the other CTA of this SM could use); after the barrier
     // the phase is complete and every thread's own try_wait -- its acquire of the TMA writes -- succeeds at once.
@@ -514,8 +518,10 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
 
     load_regs();
 
+    Ins3 next = sins[1];
     for (int pc = 1;; ++pc) {
-        const Ins3 ins = sins[pc];
+        const Ins3 ins = next;
+        next = sins[pc + 1]; // fetched one instruction ahead: its latency hides behind this one's arm (one past END is still the blob)
         const int op = ins.op;
         if (op == T3_GATE) {
             // skipped when a control outside the tile is 0 for this whole tile, or a thread-bit control is 0 for this thread
@@ -677,8 +683,13 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
                 bool use_lo = false, use_hi = false;
                 std::vector<TileTerm> tile_terms;                                  // thr == 0, outer != 0: one constant per tile
                 std::vector<std::pair<uint32_t, std::vector<TileTerm>>> general;   // everything else, by thread mask
+                // a lone table-able term is cheaper as a constant (16 bytes) than as a table (256-512 bytes of shared memory)
+                int n_tabled = 0;
+                for (const Term &x : ts) n_tabled += x.outer == 0 && ((x.thr & 0xF0u) == 0 || (x.thr & 0x0Fu) == 0);
                 for (const Term &x : ts) {
-                    if (x.outer == 0 && (x.thr & 0xF0u) == 0) {
+                    if (n_tabled == 1 && x.outer == 0 && ((x.thr & 0xF0u) == 0 || (x.thr & 0x0Fu) == 0)) {
+                        general.emplace_back(x.thr, std::vector<TileTerm>{TileTerm{0, 0, 0, x.fr, x.fi}});
+                    } else if (x.outer == 0 && (x.thr & 0xF0u) == 0) {
                         for (unsigned e = 0; e < 16; ++e) if ((e & x.thr) == x.thr) cmul_h(lo[e][0], lo[e][1], x.fr, x.fi);
                         use_lo = true;
                     } else if (x.outer == 0 && (x.thr & 0x0Fu) == 0) {
@@ -851,7 +862,8 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
             i.thr = (uint16_t)thr;
             i.km = (uint16_t)t.t_mask;
             const bool in_tile_ctrl = t.reg_cmask || t.thr_cmask;
-            if (in_tile_ctrl) out.ctrl = true; else i.flags |= GF_ALL;
+            if (in_tile_ctrl) out.ctrl = true;
+            else if (v.kind == MK_H || v.kind == MK_RX || v.kind == MK_RY) i.flags |= GF_ALL;
             if (t.outer_cmask) i.flags |= GF_OUTER;
             i.kind = (uint8_t)v.kind;
             if (v.ns) { i.a = (uint32_t)out.pool.size(); out.pool.insert(out.pool.end(), v.s, v.s + v.ns); }
@@ -880,7 +892,7 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
     e.flags = (uint8_t)dirty;
     push(e, 0);
     if (out.pool.size() & 1) out.pool.push_back(0.0);
-    return out.ins.size() <= (size_t)kMaxIns3 && out.groups.size() <= (size_t)kMaxGroups3 && out.terms.size() <= (size_t)(kAccBytes3 / 16u);
+    return out.ins.size() <= (size_t)kMaxIns3 && out.groups.size() <= (size_t)kMaxGroups3;
 }
 
 // Serialise for upload (layout: see Lowered3) and fill the size fields of the kernel arguments.
@@ -898,7 +910,7 @@ size_t tile3_pack(const Lowered3 &lw, std::vector<unsigned char> &blob, Tile3Arg
     std::memcpy(blob.data() + outer_off, lw.outer.data(), lw.outer.size() * sizeof(uint64_t));
     if (!lw.groups.empty()) std::memcpy(blob.data() + groups_off, lw.groups.data(), lw.groups.size() * sizeof(TileGroup));
     if (!lw.terms.empty()) std::memcpy(blob.data() + terms_off, lw.terms.data(), lw.terms.size() * sizeof(TileTerm));
-    a.ins_bytes = (unsigned)ins_bytes; a.pool_bytes = (unsigned)pool_bytes;
+    a.ins_bytes = (unsigned)ins_bytes; a.blob_bytes = (unsigned)total;
     a.outer_off = (unsigned)outer_off; a.groups_off = (unsigned)groups_off; a.terms_off = (unsigned)terms_off;
     a.n_ins = (int)lw.ins.size(); a.n_groups = (int)lw.groups.size(); a.n_terms = (int)lw.terms.size();
     a.scale = lw.scale;
@@ -906,7 +918,7 @@ size_t tile3_pack(const Lowered3 &lw, std::vector<unsigned char> &blob, Tile3Arg
 }
 
 size_t tile3_smem_bytes(const Tile3Args &a) {
-    return ((kProgOff3 + a.ins_bytes + a.pool_bytes + 16u * (size_t)a.n_groups + (size_t)a.n_ins + 15u) & ~(size_t)15u) + 16u;
+    return ((kProgOff3 + a.blob_bytes + 16u * (size_t)a.n_groups + (size_t)a.n_ins + 15u) & ~(size_t)15u) + 16u;
 }
 
 bool tile3_shape_ok(int n_qubits, const TilePlan &plan) {
