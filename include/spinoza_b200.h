@@ -194,6 +194,15 @@ SPZ_API int spz_dist_local_qubits(const spz_state *st);
    shard, the qubit permutation and the measurement RNG state into it with this call. */
 SPZ_API int spz_dist_copy_from(spz_state *dst, const spz_state *src);
 SPZ_API int spz_dist_stats(const spz_state *st, double *out4);  /* exchanges, bytes sent, exchange ms, overlapped exchanges */
+/* Host control plane between the processes of one node, without any framework (csrc/rendezvous.cu; no reference counterpart:
+   the reference is single-process): an all-gather of small blobs and a barrier through files in a shared directory.
+   dir = NULL: /dev/shm/spz_rdv_<MASTER_PORT>_<launcher pid>_<uid>, the same for every rank of one torchrun-style launch. */
+typedef struct spz_rdv spz_rdv;
+SPZ_API int spz_rdv_open(const char *dir, int rank, int world, spz_rdv **out);
+SPZ_API int spz_rdv_allgather(spz_rdv *r, const void *mine, int64_t bytes, void *all); /* all: world * bytes, rank order */
+SPZ_API int spz_rdv_barrier(spz_rdv *r);
+SPZ_API int spz_rdv_close(spz_rdv *r);
+SPZ_API int spz_dist_connect_rdv(spz_state *st, spz_rdv *r); /* spz_dist_export + all-gather + spz_dist_connect + barrier */
 /* planning only (pure host code, no CUDA): what the CPU tests of the sharding logic drive */
 typedef struct spz_dist_plan spz_dist_plan;
 SPZ_API int spz_dist_plan_create(int n_qubits, int world, spz_dist_plan **out);

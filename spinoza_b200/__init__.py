@@ -126,6 +126,11 @@ _SIGNATURES = {
     "spz_dist_local_qubits": (C.c_int, [_vp]),
     "spz_dist_copy_from": (C.c_int, [_vp, _vp]),
     "spz_dist_stats": (C.c_int, [_vp, _dp]),
+    "spz_rdv_open": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "spz_rdv_allgather": (C.c_int, [_vp, C.c_void_p, C.c_int64, C.c_void_p]),
+    "spz_rdv_barrier": (C.c_int, [_vp]),
+    "spz_rdv_close": (C.c_int, [_vp]),
+    "spz_dist_connect_rdv": (C.c_int, [_vp, _vp]),
     "spz_dist_plan_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_vp)]),
     "spz_dist_plan_destroy": (C.c_int, [_vp]),
     "spz_dist_plan_lower": (C.c_int, [_vp, C.c_int, C.POINTER(_Op), C.c_void_p, C.c_int, C.POINTER(C.c_int)]),

@@ -15,7 +15,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libspinoza_b200.so"
-SOURCES = ["abi.cu", "kernels_direct.cu", "kernels_reduce.cu", "kernels_tile.cu", "kernels_tile3.cu", "dist.cu"]
+SOURCES = ["abi.cu", "kernels_direct.cu", "kernels_reduce.cu", "kernels_tile.cu", "kernels_tile3.cu", "dist.cu", "rendezvous.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -1,8 +1,10 @@
-"""Multi-GPU host plumbing: one process per GPU (torchrun), amplitudes sharded by the top log2(world) index bits.
+"""Multi-GPU host plumbing: one process per GPU (torchrun or any launcher that sets RANK / WORLD_SIZE / LOCAL_RANK),
+amplitudes sharded by the top log2(world) index bits.
 
-`torch.distributed` (gloo) is used only to all-gather the CUDA IPC handles of each rank's shard, for
-barriers and for max-over-ranks timing.  The data path is NOT a torch / NCCL collective: global-qubit gates
-are pairwise half-shard exchanges done by our own kernels through IPC-mapped peer pointers over NVLink
+Nothing here imports torch.  The host-side control plane -- all-gathering the CUDA IPC handles of each rank's shard, barriers,
+max-over-ranks of a timing -- is the library's own file rendezvous (`spz_rdv_*`, csrc/rendezvous.cu: small files in
+/dev/shm), the same four C functions a C++ or Rust caller would use.  The data path is no collective library either:
+global-qubit gates are pairwise half-shard exchanges done by our own kernels through IPC-mapped peer pointers over NVLink
 (csrc/dist.cu), and scalar reductions go through the same peer-mapped control blocks.
 
 Every rank must issue the same sequence of calls on its `DistState` (SPMD), exactly like the single-GPU API:
@@ -12,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import struct
 from typing import List, Optional
 
 import numpy as np
@@ -22,58 +25,56 @@ IPC_BLOB_BYTES = 256
 
 
 class DistEnv:
-    def __init__(self, rank: int, world: int, local_rank: int, pg=None):
-        self.rank, self.world, self.local_rank, self._pg = rank, world, local_rank, pg
+    """Rank / world of this process and the rendezvous between the processes of the node."""
+
+    def __init__(self, rank: int, world: int, local_rank: int, rdv_dir: Optional[str] = None, _open: bool = True):
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        self._rdv = None
+        if world > 1 and _open:
+            h = _vp()
+            _check(_lib.spz_rdv_open(rdv_dir.encode() if rdv_dir else None, rank, world, C.byref(h)))
+            self._rdv = h
 
     def barrier(self):
-        if self.world > 1:
-            import torch.distributed as td
-            td.barrier()
+        if self._rdv is not None:
+            _check(_lib.spz_rdv_barrier(self._rdv))
 
     def all_gather_bytes(self, b: bytes) -> List[bytes]:
-        if self.world == 1:
+        """Equal-length blobs, one per rank, in rank order."""
+        if self._rdv is None:
             return [b]
-        import torch.distributed as td
-        out = [None] * self.world
-        td.all_gather_object(out, b)
-        return out
+        out = C.create_string_buffer(len(b) * self.world)
+        _check(_lib.spz_rdv_allgather(self._rdv, b, len(b), out))
+        return [out.raw[i * len(b):(i + 1) * len(b)] for i in range(self.world)]
 
     def max_float(self, x: float) -> float:
-        if self.world == 1:
+        if self._rdv is None:
             return x
-        import torch
-        import torch.distributed as td
-        t = torch.tensor([x], dtype=torch.float64)
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-        return float(t[0])
+        return max(struct.unpack("<d", p)[0] for p in self.all_gather_bytes(struct.pack("<d", float(x))))
+
+    def all_gather_array(self, a: np.ndarray) -> List[np.ndarray]:
+        """Same shape and dtype on every rank."""
+        a = np.ascontiguousarray(a)
+        return [np.frombuffer(p, dtype=a.dtype).reshape(a.shape) for p in self.all_gather_bytes(a.tobytes())]
 
     def gather_arrays(self, a: np.ndarray) -> Optional[List[np.ndarray]]:
-        """Gather one array per rank onto rank 0 (tests / small registers only)."""
-        if self.world == 1:
-            return [a]
-        import torch.distributed as td
-        out = [None] * self.world if self.rank == 0 else None
-        td.gather_object(a, out, dst=0)
-        return out
+        """One array per rank onto rank 0 (tests / small registers only; every rank takes part)."""
+        parts = self.all_gather_array(a)
+        return parts if self.rank == 0 else None
 
     def shutdown(self):
-        if self.world > 1:
-            import torch.distributed as td
-            if td.is_initialized():
-                td.barrier()
-                td.destroy_process_group()
+        if self._rdv is not None:
+            _check(_lib.spz_rdv_close(self._rdv))
+            self._rdv = None
 
 
-def init_from_env(backend: str = "gloo") -> DistEnv:
+def init_from_env(backend: str = "files", rdv_dir: Optional[str] = None) -> DistEnv:
+    """RANK / WORLD_SIZE / LOCAL_RANK as torchrun sets them.  `backend` is kept for callers of the first version (which
+    rendezvoused through torch.distributed): there is one backend now, the library's own."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
-    if world > 1:
-        import torch.distributed as td
-        if not td.is_initialized():
-            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            td.init_process_group(backend=backend, rank=rank, world_size=world)
-    return DistEnv(rank, world, local_rank)
+    return DistEnv(rank, world, local_rank, rdv_dir or os.environ.get("SPZ_RDV_DIR"))
 
 
 class DistState(State):
@@ -89,11 +90,12 @@ class DistState(State):
         self.n_local = _lib.spz_dist_local_qubits(self._h)
         self._local_group = not _connect
         if _connect:
-            blob = C.create_string_buffer(IPC_BLOB_BYTES)
-            _check(_lib.spz_dist_export(self._h, blob))
-            blobs = env.all_gather_bytes(blob.raw)
-            _check(_lib.spz_dist_connect(self._h, b"".join(blobs)))
-            env.barrier()
+            if env._rdv is not None:
+                _check(_lib.spz_dist_connect_rdv(self._h, env._rdv))  # export + all-gather + connect + barrier, in C
+            else:
+                blob = C.create_string_buffer(IPC_BLOB_BYTES)
+                _check(_lib.spz_dist_export(self._h, blob))
+                _check(_lib.spz_dist_connect(self._h, blob.raw))
 
     @staticmethod
     def create_local_group(n: int, world: int, devices: Optional[List[int]] = None) -> List["DistState"]:
@@ -101,7 +103,7 @@ class DistState(State):
         devices[r] (default: all on device 0).  Peers are plain device pointers instead of IPC mappings; the
         kernels, flags and exchange protocol are the same as in the one-process-per-GPU deployment."""
         devices = devices or [0] * world
-        states = [DistState(n, DistEnv(r, world, devices[r]), device=devices[r], _connect=False) for r in range(world)]
+        states = [DistState(n, DistEnv(r, world, devices[r], _open=False), device=devices[r], _connect=False) for r in range(world)]
         arr = (_vp * world)(*[s._h for s in states])
         _check(_lib.spz_dist_connect_local(arr, world))
         return states
@@ -138,16 +140,12 @@ class DistState(State):
 
     def sample(self, shots: int, seed: int = 0, u01: Optional[np.ndarray] = None) -> np.ndarray:
         """Exact sampling of the whole sharded register: every rank passes the same uniforms, the owning rank answers
-        each shot, and the answers are combined with a max all-reduce (gloo)."""
+        each shot (the others report -1), and the answers are combined with an element-wise max over ranks."""
         from . import sample as _sample
         local = _sample(self, shots, seed=seed, u01=u01)
-        if self.env.world == 1:
+        if self.env.world == 1 or self.env._rdv is None:
             return local
-        import torch
-        import torch.distributed as td
-        t = torch.from_numpy(local.copy())
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-        return t.numpy()
+        return np.maximum.reduce(self.env.all_gather_array(local))
 
     def gather_logical(self):
         """Rank 0: the full state in LOGICAL index order (re, im); other ranks: None.  Small registers only."""

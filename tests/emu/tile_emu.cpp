@@ -100,6 +100,20 @@ extern "C" int emu_tile3_run(int n_qubits, double *re, double *im, const void *b
     return 0;
 }
 
+// Shared-memory bytes k_tile3 needs for this pass (0: the lowering refuses it), without running anything.  info as above.
+extern "C" long long emu_tile3_smem(int n_qubits, const void *blob, long long blob_bytes, int *info) {
+    Program P;
+    if (parse(blob, blob_bytes, P)) return -1;
+    if (!spz::tile3_shape_ok(n_qubits, P.plan)) return 0;
+    spz::Lowered3 lw;
+    if (!spz::tile3_lower(P.plan, P.prog.data(), P.ni, P.groups.data(), P.ng, P.terms.data(), P.nt, lw)) return 0;
+    spz::Tile3Args a{};
+    std::vector<unsigned char> packed;
+    spz::tile3_pack(lw, packed, a);
+    info[0] = lw.ctrl ? 1 : 0; info[1] = a.n_ins; info[2] = a.n_groups; info[3] = (int)packed.size();
+    return (long long)spz::tile3_smem_bytes(a);
+}
+
 // k_tile, with the arguments launch_tile_program (kernels_tile.cu) builds.  prog_in_smem: 0 decodes from "global" memory.
 extern "C" int emu_tile1_run(int n_qubits, double *re, double *im, const void *blob, long long blob_bytes, int exact, int prog_in_smem) {
     Program P;

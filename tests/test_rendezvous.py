@@ -1,0 +1,69 @@
+"""The torch-free control plane of sharded registers (csrc/rendezvous.cu through spinoza_b200.distributed.DistEnv): real
+processes, no GPU, no torch -- all-gather, barrier, max over ranks, and that the product's multi-GPU module imports no
+framework."""
+import os
+import re
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+WORKER = r'''
+import os, sys, time
+sys.path.insert(0, os.environ["SPZ_ROOT"])
+import numpy as np
+from spinoza_b200.distributed import init_from_env
+assert "torch" not in sys.modules, "the product's multi-GPU module must not import torch"
+env = init_from_env()
+r, w = env.rank, env.world
+if r == 1:
+    time.sleep(0.2)          # a late rank: the others must wait, not read a partial file
+parts = env.all_gather_bytes(bytes([r]) * 300)
+assert [p[0] for p in parts] == list(range(w)) and all(len(p) == 300 for p in parts)
+for i in range(50):          # many operations in a row: file recycling (seq - 2) must never remove a file still needed
+    assert env.max_float(float(r * 10 + i)) == float((w - 1) * 10 + i)
+    env.barrier()
+arr = env.all_gather_array(np.arange(5, dtype=np.int64) + 100 * r)
+assert [int(a[0]) for a in arr] == [100 * k for k in range(w)]
+got = env.gather_arrays(np.full(3, r, dtype=np.float64))
+assert (got is None) == (r != 0)
+env.shutdown()
+print(f"RDV_OK {r}")
+'''
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_file_rendezvous_between_processes(world):
+    with tempfile.TemporaryDirectory() as d:
+        procs = []
+        for r in range(world):
+            env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), SPZ_RDV_DIR=str(Path(d) / "rdv"),
+                       SPZ_ROOT=str(ROOT), SPZ_RDV_TIMEOUT_MS="60000")
+            procs.append(subprocess.Popen([sys.executable, "-c", WORKER], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        for r, p in enumerate(procs):
+            out, err = p.communicate(timeout=180)
+            assert p.returncode == 0, err[-2000:]
+            assert f"RDV_OK {r}" in out
+
+
+def test_a_missing_rank_times_out_with_a_message():
+    with tempfile.TemporaryDirectory() as d:
+        env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", SPZ_RDV_DIR=str(Path(d) / "rdv"), SPZ_ROOT=str(ROOT),
+                   SPZ_RDV_TIMEOUT_MS="300")
+        code = ("import os, sys; sys.path.insert(0, os.environ['SPZ_ROOT']); import spinoza_b200 as sb\n"
+                "from spinoza_b200.distributed import init_from_env\n"
+                "env = init_from_env()\n"
+                "try:\n    env.barrier()\nexcept sb.SpinozaError as e:\n    print('TIMEOUT', e.status, e)\n")
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr[-1500:]
+        assert "TIMEOUT" in r.stdout and "rank 1 did not reach" in r.stdout
+
+
+def test_no_torch_import_in_the_package():
+    pat = re.compile(r"^\s*(import|from)\s+torch\b", re.M)
+    for p in (ROOT / "spinoza_b200").rglob("*.py"):
+        assert not pat.search(p.read_text()), p
