@@ -60,14 +60,16 @@ constexpr int kMaxIns3 = 1024;                      // one skip flag per instruc
 constexpr int kMaxGroups3 = 1024;
 
 // ---- device program ---------------------------------------------------------------------------------------------------
-enum { T3_END = 0, T3_LAYOUT = 1, T3_GATE = 2, T3_ACC = 3, T3_ACCG = 4, T3_OTHER = 5, T3_PRE = 6 };
+// op byte = the interpreter's arm: one flat switch (a jump table) instead of a chain of tests.  T3_PRE + r: register bit r.
+// T3_GATE + 4 * variant + r: variant 0..2 = H, RX, RY on every pair (no in-tile control), 3..7 = HS, RX, RY, X, Y under a pair mask.
+enum { T3_END = 0, T3_LAYOUT = 1, T3_ACC = 3, T3_ACCG = 4, T3_OTHER = 5, T3_PRE = 8, T3_GATE = 16 };
 // gate variants of merged mode (see the header and pair3): H = [[1,1],[1,-1]] with 2^-1/2 left to the pass scale, HS the same
 // with the scale applied (controlled H), RX / RY = rotation by three shears, X / Y = exchanges
 enum { MK_H = 0, MK_HS = 1, MK_RX = 2, MK_RY = 3, MK_X = 4, MK_Y = 5 };
 // flag bits
 enum {
     GF_ALL = 1,      // GATE: every pair of every thread (no in-tile control)
-    GF_OUTER = 4,    // GATE: has controls outside the tile: consult the per-tile skip flag
+    GF_OUTER = 32,   // GATE: has controls outside the tile: consult the per-tile skip flag
     AF_LO = 1,       // ACC: table over the low nibble of the thread id at pool2[a .. a+16)
     AF_HI = 2,       // ACC: table over the high nibble at pool2[a+16 .. a+32)
     AF_TILE = 4,     // ACC / ACCG / OTHER: per-tile constant gfac[b]
@@ -75,7 +77,8 @@ enum {
     AF_CONST = 16,   // ACCG / OTHER: constant factor at pool2[a]
 };
 struct Ins3 {
-    uint8_t op, kind, rpos, flags; // rpos: GATE / PRE register bit; ACC / ACCG accumulator 0..4.  LAYOUT / END flags: pending accumulators
+    uint8_t op, kind, rpos, flags; // op: see T3_*.  rpos: ACC / ACCG accumulator 0..4 (GATE / PRE: register bit, also in op).
+                                   // LAYOUT / END flags: pending accumulators
     uint16_t km;                   // GATE: pair mask over k0.  OTHER: register mask m
     uint16_t thr;                  // GATE / ACCG / OTHER: control bits in THREAD-ID space (8 bits)
     uint32_t a;                    // LAYOUT: the 4 register-resident tile bits, one byte each.  else: pool offset (see flags)
@@ -268,27 +271,6 @@ __device__ __forceinline__ void bfly3(double (&ar)[16], double (&ai)[16], const 
         if (k0 & (1 << R)) continue;
         const int k1 = k0 | (1 << R);
         if (ALL || (km & (1u << k0))) pair3<MK>(s, ar[k0], ai[k0], ar[k1], ai[k1]); // km is the same for every thread
-    }
-}
-template <int R>
-__device__ __forceinline__ void bfly3_kind(int kind, bool all, double (&ar)[16], double (&ai)[16], const double *__restrict__ sp,
-                                           unsigned km) {
-    // Unguarded arms only for the three gates that fill a circuit (GF_ALL is set for nothing else); every other case tests the
-    // pair mask, which is the same for all threads.  Fewer arms = less code to keep in the instruction cache.
-    if (all) {
-        switch (kind) {
-        case MK_H: bfly3<MK_H, R, true>(ar, ai, sp, km); break;
-        case MK_RX: bfly3<MK_RX, R, true>(ar, ai, sp, km); break;
-        default: bfly3<MK_RY, R, true>(ar, ai, sp, km); break;
-        }
-    } else {
-        switch (kind) {
-        case MK_HS: bfly3<MK_HS, R, false>(ar, ai, sp, km); break;
-        case MK_RX: bfly3<MK_RX, R, false>(ar, ai, sp, km); break;
-        case MK_RY: bfly3<MK_RY, R, false>(ar, ai, sp, km); break;
-        case MK_X: bfly3<MK_X, R, false>(ar, ai, sp, km); break;
-        default: bfly3<MK_Y, R, false>(ar, ai, sp, km); break;
-        }
     }
 }
 template <int R>
@@ -518,63 +500,63 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
 
     load_regs();
 
-    Ins3 next = sins[1];
+    // The interpreter.  Instructions are decoded from raw words (byte fields of a struct cost a dozen PRMTs per instruction
+    // to repack) and fetched one ahead, so that the fetch latency hides behind the current arm.
+    const uint4 *raw = reinterpret_cast<const uint4 *>(sins);
+    uint4 next = raw[1];
     for (int pc = 1;; ++pc) {
-        const Ins3 ins = next;
-        next = sins[pc + 1]; // fetched one instruction ahead: its latency hides behind this one's arm (one past END is still the blob)
-        const int op = ins.op;
-        if (op == T3_GATE) {
-            // skipped when a control outside the tile is 0 for this whole tile, or a thread-bit control is 0 for this thread
-            const bool thr_ok = (tid & ins.thr) == ins.thr && !((ins.flags & GF_OUTER) && skip[pc]);
-            const double *sp = pool + ins.a;
-            const bool all = ins.flags & GF_ALL;
-            switch (ins.rpos) {
-            case 0: if (thr_ok) bfly3_kind<0>(ins.kind, all, ar, ai, sp, ins.km); break;
-            case 1: if (thr_ok) bfly3_kind<1>(ins.kind, all, ar, ai, sp, ins.km); break;
-            case 2: if (thr_ok) bfly3_kind<2>(ins.kind, all, ar, ai, sp, ins.km); break;
-            default: if (thr_ok) bfly3_kind<3>(ins.kind, all, ar, ai, sp, ins.km); break;
-            }
-            continue;
-        }
-        if (op == T3_PRE) {
-            // Accumulator F_{rpos+1} is pending and a butterfly on register bit rpos follows: apply it to the amplitudes with
-            // that bit set.  Only the accumulator of the target's own bit separates the two members of a pair; the others scale
-            // both by the same factor and stay pending.
-            switch (ins.rpos) {
-            case 0: apply_bit3<0>(ar, ai, facc[1 * kThreads3]); break;
-            case 1: apply_bit3<1>(ar, ai, facc[2 * kThreads3]); break;
-            case 2: apply_bit3<2>(ar, ai, facc[3 * kThreads3]); break;
-            default: apply_bit3<3>(ar, ai, facc[4 * kThreads3]); break;
-            }
-            continue;
-        }
-        if (op == T3_ACC) {
-            const double2 *tab = reinterpret_cast<const double2 *>(pool + ins.a);
+        const uint4 w = next;
+        next = raw[pc + 1]; // (one past END is still inside the blob)
+        const unsigned arm = w.x & 0xffu, cls = (w.x >> 16) & 0xffu, flags = w.x >> 24;
+        const unsigned km = w.y & 0xffffu, thr = w.y >> 16;
+        // GATE / ACCG / OTHER act on the threads whose control bits are set; a GATE also needs its controls outside the tile
+        bool ok = (tid & thr) == thr;
+        if (flags & GF_OUTER) ok = ok && !skip[pc];
+        const double *sp = pool + w.z;
+#define SPZ_GATE_ARMS(V, MK, ALL)                                                              \
+    case T3_GATE + 4 * V + 0: if (ok) bfly3<MK, 0, ALL>(ar, ai, sp, km); break;               \
+    case T3_GATE + 4 * V + 1: if (ok) bfly3<MK, 1, ALL>(ar, ai, sp, km); break;               \
+    case T3_GATE + 4 * V + 2: if (ok) bfly3<MK, 2, ALL>(ar, ai, sp, km); break;               \
+    case T3_GATE + 4 * V + 3: if (ok) bfly3<MK, 3, ALL>(ar, ai, sp, km); break;
+        switch (arm) {
+        SPZ_GATE_ARMS(0, MK_H, true)
+        SPZ_GATE_ARMS(1, MK_RX, true)
+        SPZ_GATE_ARMS(2, MK_RY, true)
+        SPZ_GATE_ARMS(3, MK_HS, false)
+        SPZ_GATE_ARMS(4, MK_RX, false)
+        SPZ_GATE_ARMS(5, MK_RY, false)
+        SPZ_GATE_ARMS(6, MK_X, false)
+        SPZ_GATE_ARMS(7, MK_Y, false)
+        // Accumulator F_{r+1} is pending and a butterfly on register bit r follows: apply it to the amplitudes with that bit
+        // set.  Only the accumulator of the target's own bit separates the two members of a pair; the others scale both by the
+        // same factor and stay pending.
+        case T3_PRE + 0: apply_bit3<0>(ar, ai, facc[1 * kThreads3]); break;
+        case T3_PRE + 1: apply_bit3<1>(ar, ai, facc[2 * kThreads3]); break;
+        case T3_PRE + 2: apply_bit3<2>(ar, ai, facc[3 * kThreads3]); break;
+        case T3_PRE + 3: apply_bit3<3>(ar, ai, facc[4 * kThreads3]); break;
+        case T3_ACC: {
+            const double2 *tab = reinterpret_cast<const double2 *>(sp);
             double fr = 1.0, fi = 0.0;
-            if (ins.flags & AF_LO) { const double2 t = tab[tid & 15u]; fr = t.x; fi = t.y; }
-            if (ins.flags & AF_HI) { const double2 t = tab[16u + (tid >> 4)]; cmul3(fr, fi, t.x, t.y); }
-            if (ins.flags & AF_TILE) { const double2 t = gfac[ins.b]; cmul3(fr, fi, t.x, t.y); }
-            acc(ins.rpos, ins.flags & AF_SET, fr, fi);
-            continue;
-        }
-        if (op == T3_ACCG) { // a term that needs thread bits from both nibbles, or thread bits and bits outside the tile
-            const bool hit = (tid & ins.thr) == ins.thr;
-            double2 *f = facc + ins.rpos * kThreads3;
-            if (ins.flags & AF_SET) {
+            if (flags & AF_LO) { const double2 t = tab[tid & 15u]; fr = t.x; fi = t.y; }
+            if (flags & AF_HI) { const double2 t = tab[16u + (tid >> 4)]; cmul3(fr, fi, t.x, t.y); }
+            if (flags & AF_TILE) { const double2 t = gfac[w.w]; cmul3(fr, fi, t.x, t.y); }
+            acc(cls, flags & AF_SET, fr, fi);
+            break; }
+        case T3_ACCG: { // a term that needs thread bits from both nibbles, or thread bits and bits outside the tile
+            double2 *f = facc + cls * kThreads3;
+            if (flags & AF_SET) {
                 // the accumulator held no pending factor: every thread assigns (nothing is ever reset, see flush)
-                *f = hit ? ((ins.flags & AF_TILE) ? gfac[ins.b] : *reinterpret_cast<const double2 *>(pool + ins.a)) : make_double2(1.0, 0.0);
-            } else if (hit) {
-                const double2 t = (ins.flags & AF_TILE) ? gfac[ins.b] : *reinterpret_cast<const double2 *>(pool + ins.a);
-                acc(ins.rpos, false, t.x, t.y);
+                *f = ok ? ((flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp)) : make_double2(1.0, 0.0);
+            } else if (ok) {
+                const double2 t = (flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp);
+                acc(cls, false, t.x, t.y);
             }
-            continue;
-        }
-        if (op == T3_OTHER) { // a diagonal term over two or more register bits: applied at once to the amplitudes it selects
-            if ((tid & ins.thr) != ins.thr) continue;
-            const double2 f = (ins.flags & AF_TILE) ? gfac[ins.b] : *reinterpret_cast<const double2 *>(pool + ins.a);
-            const unsigned m = ins.km;
+            break; }
+        case T3_OTHER: { // a diagonal term over two or more register bits: applied at once to the amplitudes it selects
+            if (!ok) break;
+            const double2 f = (flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp);
 #define SPZ_M4(A, B, C, D) cmul3(ar[A], ai[A], f.x, f.y); cmul3(ar[B], ai[B], f.x, f.y); cmul3(ar[C], ai[C], f.x, f.y); cmul3(ar[D], ai[D], f.x, f.y)
-            switch (m) {
+            switch (km) {
             case 3: SPZ_M4(3, 7, 11, 15); break;
             case 5: SPZ_M4(5, 7, 13, 15); break;
             case 6: SPZ_M4(6, 7, 14, 15); break;
@@ -584,19 +566,23 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
             default:
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
-                    if (((unsigned)k & m) == m) cmul3(ar[k], ai[k], f.x, f.y);
+                    if (((unsigned)k & km) == km) cmul3(ar[k], ai[k], f.x, f.y);
                 break;
             }
 #undef SPZ_M4
-            continue;
+            break; }
+        default: // LAYOUT or END: apply what is pending, registers -> shared memory
+            flush(flags);
+            store_regs();
+            if (arm == T3_LAYOUT) {
+                __syncthreads();
+                lay = w.z;
+                load_regs(); // no second barrier: this thread's next shared-memory access is store_regs() to the cells it has just read
+            }
+            break;
         }
-        // LAYOUT or END: apply what is pending, registers -> shared memory
-        flush(ins.flags);
-        store_regs();
-        if (op == T3_END) break;
-        __syncthreads();
-        lay = ins.a;
-        load_regs(); // no second barrier: this thread's next shared-memory access is store_regs() to the cells it has just read
+#undef SPZ_GATE_ARMS
+        if (arm == T3_END) break;
     }
 
     // ---- tile out ----
@@ -851,21 +837,30 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
             if (!before.empty()) emit_terms(before);
             if (dirty & (2u << t.rpos)) { // the accumulator of the target's own register bit is pending: apply it first
                 Ins3 p{};
-                p.op = T3_PRE;
+                p.op = (uint8_t)(T3_PRE + t.rpos);
                 p.rpos = (uint8_t)t.rpos;
                 push(p, 0);
                 dirty &= ~(2u << t.rpos);
             }
             Ins3 i{};
-            i.op = T3_GATE;
             i.rpos = (uint8_t)t.rpos;
             i.thr = (uint16_t)thr;
             i.km = (uint16_t)t.t_mask;
             const bool in_tile_ctrl = t.reg_cmask || t.thr_cmask;
             if (in_tile_ctrl) out.ctrl = true;
-            else if (v.kind == MK_H || v.kind == MK_RX || v.kind == MK_RY) i.flags |= GF_ALL;
             if (t.outer_cmask) i.flags |= GF_OUTER;
             i.kind = (uint8_t)v.kind;
+            // the arm: unguarded for the three gates that fill a circuit when nothing in the tile controls them, else under the
+            // pair mask (which is all ones for an uncontrolled X, Y or scaled H)
+            int variant;
+            if (!in_tile_ctrl && (v.kind == MK_H || v.kind == MK_RX || v.kind == MK_RY)) {
+                variant = v.kind == MK_H ? 0 : v.kind == MK_RX ? 1 : 2;
+                i.flags |= GF_ALL;
+            } else {
+                if (v.kind == MK_H) return false; // (cannot happen: a controlled H is lowered to HS)
+                variant = v.kind == MK_HS ? 3 : v.kind == MK_RX ? 4 : v.kind == MK_RY ? 5 : v.kind == MK_X ? 6 : 7;
+            }
+            i.op = (uint8_t)(T3_GATE + 4 * variant + t.rpos);
             if (v.ns) { i.a = (uint32_t)out.pool.size(); out.pool.insert(out.pool.end(), v.s, v.s + v.ns); }
             push(i, t.outer_cmask);
             if (!after.empty()) emit_terms(after);
