@@ -28,6 +28,7 @@
 // shared-memory budget stay on k_tile.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -62,7 +63,7 @@ constexpr int kMaxGroups3 = 1024;
 // ---- device program ---------------------------------------------------------------------------------------------------
 // op byte = the interpreter's arm: one flat switch (a jump table) instead of a chain of tests.  T3_PRE + r: register bit r.
 // T3_GATE + 4 * variant + r: variant 0..2 = H, RX, RY on every pair (no in-tile control), 3..7 = HS, RX, RY, X, Y under a pair mask.
-enum { T3_END = 0, T3_LAYOUT = 1, T3_ACC = 3, T3_ACCG = 4, T3_OTHER = 5, T3_PRE = 8, T3_GATE = 16 };
+enum { T3_END = 0, T3_LAYOUT = 1, T3_ACC = 2, T3_ACCG = 3, T3_OTHER = 4, T3_PRE = 5, T3_GATE = 9, T3_N_ARMS = 41 };
 // gate variants of merged mode (see the header and pair3): H = [[1,1],[1,-1]] with 2^-1/2 left to the pass scale, HS the same
 // with the scale applied (controlled H), RX / RY = rotation by three shears, X / Y = exchanges
 enum { MK_H = 0, MK_HS = 1, MK_RX = 2, MK_RY = 3, MK_X = 4, MK_Y = 5 };
@@ -70,6 +71,7 @@ enum { MK_H = 0, MK_HS = 1, MK_RX = 2, MK_RY = 3, MK_X = 4, MK_Y = 5 };
 enum {
     GF_ALL = 1,      // GATE: every pair of every thread (no in-tile control)
     GF_OUTER = 32,   // GATE: has controls outside the tile: consult the per-tile skip flag
+    LF_LAST = 128,   // LAYOUT: the last one of the program: shared memory is free once its registers are loaded
     AF_LO = 1,       // ACC: table over the low nibble of the thread id at pool2[a .. a+16)
     AF_HI = 2,       // ACC: table over the high nibble at pool2[a+16 .. a+32)
     AF_TILE = 4,     // ACC / ACCG / OTHER: per-tile constant gfac[b]
@@ -98,6 +100,7 @@ struct Lowered3 {
     std::vector<TileTerm> terms;   // outer, fr, fi used
     double scale = 1.0;            // product of the factored-out gate scalars: initial value of F0
     bool ctrl = false;             // some butterfly has an in-tile control
+    bool single_layout = true;     // no LAYOUT after the first
 };
 
 struct Tile3Args {
@@ -116,10 +119,12 @@ struct Tile3Args {
     unsigned ins_bytes, blob_bytes;  // instruction section and whole blob (multiples of 16)
     unsigned outer_off, groups_off, terms_off; // byte offsets of the other sections inside the blob (the pool follows the instructions)
     int n_ins, n_groups, n_terms;
-    unsigned tile_offset;
+    unsigned tile_first, tile_end; // this launch's tiles (a pass may be launched in two halves, see dist.cu)
+    int single_layout;             // the program never changes the register layout: the next tile can be fetched at once
     int L, n_high;
     double scale;
     int high[kMaxHigh3];
+    unsigned long long *prof; // SPZ_TILE_PROF=1 (diagnostic): per-phase nanoseconds summed over CTAs, see prepare_tile3
 };
 
 // position of tile index j inside a 32 KB array under the TMA 128-byte swizzle (16-byte chunk index ^= 128-byte row
@@ -181,32 +186,6 @@ __device__ __forceinline__ void tma_load_box(int rank, void *dst, const CUtensor
         break;
     }
 }
-__device__ __forceinline__ void tma_store_box(int rank, const CUtensorMap *tm, const int (&c)[5], const void *src) {
-    const unsigned sa = smem_u32(src);
-    const uint64_t m = reinterpret_cast<uint64_t>(tm);
-    switch (rank) {
-    case 2:
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                     ::"l"(m), "r"(0), "r"(c[1]), "r"(sa) : "memory");
-        break;
-    case 3:
-        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
-                     ::"l"(m), "r"(0), "r"(c[1]), "r"(c[2]), "r"(sa) : "memory");
-        break;
-    case 4:
-        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
-                     ::"l"(m), "r"(0), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(sa) : "memory");
-        break;
-    default:
-        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
-                     ::"l"(m), "r"(0), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(sa) : "memory");
-        break;
-    }
-}
-__device__ __forceinline__ void tma_store_commit_and_wait_read() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
@@ -228,6 +207,14 @@ __device__ __forceinline__ void xor_swap(double &x, double &y) {
     const double t = x; x = y; y = t;
 #else
     asm volatile("xor.b64 %0, %0, %1;\n\txor.b64 %1, %1, %0;\n\txor.b64 %0, %0, %1;" : "+d"(x), "+d"(y));
+#endif
+}
+// 256-bit global store (one full 32-byte sector per lane); plain stores in the CPU emulation build
+__device__ __forceinline__ void st_global4(double *p, double x0, double x1, double x2, double x3) {
+#ifdef SPZ_CPU_EMULATION
+    p[0] = x0; p[1] = x1; p[2] = x2; p[3] = x3;
+#else
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x0), "d"(x1), "d"(x2), "d"(x3) : "memory");
 #endif
 }
 __device__ __forceinline__ void shear3(double &x, double &y, double t, double sn) {
@@ -300,129 +287,98 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
         smem + ((kProgOff3 + a.blob_bytes + 16u * (unsigned)a.n_groups + (unsigned)a.n_ins + 15u) & ~15u)); // [0] tile, [1] program
     const unsigned tid = threadIdx.x;
     const int L = a.L;
+#ifndef SPZ_CPU_EMULATION
+    unsigned long long t_prev = 0;
+    auto stamp = [&](int k) { // thread 0: time since the previous stamp into prof[k]
+        if (a.prof && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (k >= 0) atomicAdd(a.prof + k, t - t_prev);
+            t_prev = t;
+        }
+    };
+    stamp(-1);
+#else
+    auto stamp = [](int) {};
+#endif
 
-    // absolute index of the tile's first amplitude: the CTA id fills the non-tile bit positions
-    auto tile_base = [&]() -> unsigned long long {
-        unsigned long long b = (unsigned long long)(blockIdx.x + a.tile_offset) << L;
+    // absolute index of tile t's first amplitude: the tile number fills the non-tile bit positions
+    auto tile_base = [&](unsigned t) -> unsigned long long {
+        unsigned long long b = (unsigned long long)t << L;
 #pragma unroll
         for (int k = 0; k < kMaxHigh3; ++k)
             if (k < a.n_high) b = insert_zero(b, a.high[k]);
         return b;
     };
-
-    // ---- tile in: TMA boxes (one per array for tiles with up to three runs of high qubits), all on one mbarrier ----
-#ifdef SPZ_CPU_EMULATION
-    const unsigned n_seg = 1u << a.n_high;
-    auto seg_row = [&](unsigned long long base, unsigned s) -> int { // row (16 doubles) of segment s's first amplitude
-        unsigned long long off = 0;
+    // global offset (inside the tile's footprint) of tile index x: the low L bits stay, bit L + k goes to qubit high[k]
+    auto tile_to_global = [&](unsigned x) -> unsigned long long {
+        unsigned long long o = x & ((1u << L) - 1u);
 #pragma unroll
         for (int k = 0; k < kMaxHigh3; ++k)
-            if (k < a.n_high && ((s >> k) & 1u)) off |= 1ull << a.high[k];
-        return (int)((base + off) >> 4);
+            if (k < a.n_high && ((x >> (L + k)) & 1u)) o |= 1ull << a.high[k];
+        return o;
     };
-#else
-    const unsigned n_box = 1u << a.n_rest;
-    const unsigned box_bytes = 8u << a.box_shift;
-    auto box_coords = [&](unsigned long long base, unsigned e, int (&c)[5]) {
-        unsigned long long addr = base;
+
+    // ---- tile in: TMA boxes (one per array for tiles with up to three runs of high qubits) on mbarrier 0.  Called by warp 0. ----
+#ifndef SPZ_CPU_EMULATION
+    auto issue_tile_load = [&](unsigned t) {
+        const unsigned long long base = tile_base(t);
+        const unsigned n_box = 1u << a.n_rest;
+        const unsigned box_bytes = 8u << a.box_shift;
+        if (tid == 0) mbar_expect_tx(bar, 2u * kArrayBytes3);
+        __syncwarp();
+        for (unsigned e = tid; e < n_box; e += 32) {
+            unsigned long long addr = base;
 #pragma unroll
-        for (int k = 0; k < kMaxHigh3; ++k)
-            if (k < a.n_rest && ((e >> k) & 1u)) addr |= 1ull << a.rest_bit[k];
-        c[0] = 0;
+            for (int k = 0; k < kMaxHigh3; ++k)
+                if (k < a.n_rest && ((e >> k) & 1u)) addr |= 1ull << a.rest_bit[k];
+            int c[5];
+            c[0] = 0;
 #pragma unroll
-        for (int i = 1; i < 5; ++i) c[i] = i < a.rank ? (int)((addr >> a.dim_lo[i]) & ((1ull << a.dim_len[i]) - 1ull)) : 0;
+            for (int i = 1; i < 5; ++i) c[i] = i < a.rank ? (int)((addr >> a.dim_lo[i]) & ((1ull << a.dim_len[i]) - 1ull)) : 0;
+            tma_load_box(a.rank, smem + e * box_bytes, &a.tm_re, c, bar);
+            tma_load_box(a.rank, smem + kArrayBytes3 + e * box_bytes, &a.tm_im, c, bar);
+        }
     };
 #endif
-    {
-    const unsigned long long base = tile_base();
+    const unsigned first_tile = a.tile_first + blockIdx.x;
+    if (first_tile >= a.tile_end) return;
+
+    // ---- once per CTA: barriers, the program, the first tile ----
 #ifndef SPZ_CPU_EMULATION
     if ((smem_u32(smem) & 1023u) != 0u) __trap(); // the swizzle pattern is anchored to 1 KB-aligned shared addresses
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_init(bar + 1, 1);
         mbar_expect_tx(bar + 1, a.blob_bytes);
-        bulk_load(smem + kProgOff3, a.blob, a.blob_bytes, bar + 1); // the program: small, lands first
-        mbar_expect_tx(bar, 2u * kArrayBytes3);
+        bulk_load(smem + kProgOff3, a.blob, a.blob_bytes, bar + 1);
     }
     __syncthreads();
-    if (tid < 32) {
-        for (unsigned e = tid; e < n_box; e += 32) {
-            int c[5];
-            box_coords(base, e, c);
-            tma_load_box(a.rank, smem + e * box_bytes, &a.tm_re, c, bar);
-            tma_load_box(a.rank, smem + kArrayBytes3 + e * box_bytes, &a.tm_im, c, bar);
-        }
-    }
+    if (tid < 32) issue_tile_load(first_tile);
+    mbar_wait(bar + 1, 0);
 #else
-    if (tid == 0) { // the emulation's "TMA": rows of 16 doubles, 16-byte chunks XORed with the row number mod 8
-        for (unsigned s = 0; s < n_seg; ++s) {
-            const unsigned long long g0 = (unsigned long long)seg_row(base, s) << 4;
-            for (unsigned j = 0; j < (1u << L); ++j) {
-                const unsigned tj = (s << L) + j;
-                sre[swz3(tj)] = a.re[g0 + j];
-                sim[swz3(tj)] = a.im[g0 + j];
-            }
-        }
-    }
-#endif
-
-    // ---- while the tile is in flight: skip flags and per-tile constants, from the staged program ----
-#ifdef SPZ_CPU_EMULATION
     for (unsigned i = tid; i < (a.blob_bytes >> 4); i += kThreads3)
         reinterpret_cast<uint4 *>(smem + kProgOff3)[i] = reinterpret_cast<const uint4 *>(a.blob)[i];
     __syncthreads();
-#else
-    mbar_wait(bar + 1, 0);
 #endif
-    {
-        const unsigned long long *outer = reinterpret_cast<const unsigned long long *>(smem + kProgOff3 + a.outer_off);
-        for (int i = tid; i < a.n_ins; i += kThreads3) {
-            const unsigned long long ocm = outer[i];
-            skip[i] = (base & ocm) != ocm ? 1 : 0;
-        }
-        // Per-tile constants: every group's product over those of its terms whose outer bits are set in this tile.  Everything is
-        // in shared memory by now (a walk over a group's terms in global memory costs two dependent L2 round trips per term:
-        // ~8 us at the head of every tile of a QFT pass with 18 terms per group, four times the tile's HBM time); four partial
-        // products keep the dependent chain short.
-        const TileGroup *groups = reinterpret_cast<const TileGroup *>(smem + kProgOff3 + a.groups_off);
-        const TileTerm *terms = reinterpret_cast<const TileTerm *>(smem + kProgOff3 + a.terms_off);
-        for (int g = tid; g < a.n_groups; g += kThreads3) {
-            const TileGroup gd = groups[g];
-            double pr[4] = {1.0, 1.0, 1.0, 1.0}, pi[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int i = 0; i < gd.count; i += 4) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (i + k < gd.count) {
-                        const TileTerm &t = terms[gd.first + i + k];
-                        if ((base & t.outer) == t.outer) cmul3(pr[k], pi[k], t.fr, t.fi);
-                    }
-                }
-            }
-            cmul3(pr[0], pi[0], pr[1], pi[1]);
-            cmul3(pr[2], pi[2], pr[3], pi[3]);
-            cmul3(pr[0], pi[0], pr[2], pi[2]);
-            gfac[g] = make_double2(pr[0], pi[0]);
-        }
-    }
-    } // base
-    __syncthreads(); // skip flags and constants in place
-#ifndef SPZ_CPU_EMULATION
-    // One warp waits for the boxes (a failed try_wait costs issue slots the other CTA of this SM could use); after the barrier
-    // the phase is complete and every thread's own try_wait -- its acquire of the TMA writes -- succeeds at once.
-    if (tid < 32) mbar_wait(bar, 0);
-    __syncthreads();
-    mbar_wait(bar, 0);
-#endif
+    stamp(0); // launch -> program staged
 
     // ---- registers ----
     double ar[16], ai[16];
-    facc[0] = make_double2(a.scale, 0.0); // F0 starts as the pass scale (pending from the start when it is not 1: the host knows)
     // The register layout is carried as one word (4 tile bits, one byte each) and expanded where it is used: the swizzled
     // position of amplitude k of this thread is stj ^ (sw0 if k & 1) ^ (sw1 if k & 2) ^ ...  (swz3 is linear over GF(2)).
     unsigned lay = sins[0].a;
+    auto thread_index = [&](int r0, int r1, int r2, int r3) -> unsigned { // this thread's tile index with the register bits clear
+        unsigned x = tid;
+        x = ((x >> r0) << (r0 + 1)) | (x & ((1u << r0) - 1u));
+        x = ((x >> r1) << (r1 + 1)) | (x & ((1u << r1) - 1u));
+        x = ((x >> r2) << (r2 + 1)) | (x & ((1u << r2) - 1u));
+        x = ((x >> r3) << (r3 + 1)) | (x & ((1u << r3) - 1u));
+        return x;
+    };
     auto move_regs = [&](auto &&xfer2, auto &&xfer1) {
         const int r0 = lay & 255u, r1 = (lay >> 8) & 255u, r2 = (lay >> 16) & 255u, r3 = lay >> 24;
-        const unsigned stj = swz3((unsigned)insert_zero(insert_zero(insert_zero(insert_zero(tid, r0), r1), r2), r3));
+        const unsigned stj = swz3(thread_index(r0, r1, r2, r3));
         const unsigned sw0 = swz3(1u << r0), sw1 = swz3(1u << r1), sw2 = swz3(1u << r2), sw3 = swz3(1u << r3);
         if (r0 == 0) { // register bit 0 is tile bit 0: amplitudes k, k + 1 are adjacent in shared memory (128-bit accesses)
 #pragma unroll
@@ -448,6 +404,38 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
                 *reinterpret_cast<double2 *>(sim + s) = make_double2(ai[k], ai[k + 1]);
             },
             [&](int k, unsigned s) { sre[s] = ar[k]; sim[s] = ai[k]; });
+    };
+    // Tile out: straight from the registers under the final layout.  The tile's shared-memory buffer is not involved, which is
+    // what lets the NEXT tile's boxes land in it while this tile is still being computed (see prefetch below).  Lanes run over
+    // the lowest non-register tile bits, so a warp writes runs of consecutive amplitudes; when register bits 0 (and 1) are
+    // tile bits 0 (and 1) a thread's own amplitudes are adjacent and go out as 128-bit (256-bit) stores.
+    auto direct_store = [&](unsigned long long base) {
+        const int r0 = lay & 255u, r1 = (lay >> 8) & 255u, r2 = (lay >> 16) & 255u, r3 = lay >> 24;
+        const unsigned long long g0 = base + tile_to_global(thread_index(r0, r1, r2, r3));
+        const unsigned long long o0 = tile_to_global(1u << r0), o1 = tile_to_global(1u << r1);
+        const unsigned long long o2 = tile_to_global(1u << r2), o3 = tile_to_global(1u << r3);
+        if (r0 == 0 && r1 == 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned long long g = g0 + ((q & 1) ? o2 : 0ull) + ((q & 2) ? o3 : 0ull);
+                st_global4(a.re + g, ar[4 * q], ar[4 * q + 1], ar[4 * q + 2], ar[4 * q + 3]);
+                st_global4(a.im + g, ai[4 * q], ai[4 * q + 1], ai[4 * q + 2], ai[4 * q + 3]);
+            }
+        } else if (r0 == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const unsigned long long g = g0 + ((q & 1) ? o1 : 0ull) + ((q & 2) ? o2 : 0ull) + ((q & 4) ? o3 : 0ull);
+                *reinterpret_cast<double2 *>(a.re + g) = make_double2(ar[2 * q], ar[2 * q + 1]);
+                *reinterpret_cast<double2 *>(a.im + g) = make_double2(ai[2 * q], ai[2 * q + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const unsigned long long g = g0 + ((k & 1) ? o0 : 0ull) + ((k & 2) ? o1 : 0ull) + ((k & 4) ? o2 : 0ull) + ((k & 8) ? o3 : 0ull);
+                a.re[g] = ar[k];
+                a.im[g] = ai[k];
+            }
+        }
     };
     // apply the pending accumulators named by `mask` (the host knows which are pending: it is a property of the program,
     // so nothing is ever reset: an accumulator that has been applied is assigned, not multiplied, by its next update)
@@ -498,120 +486,177 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
         *f = make_double2(fr, fi);
     };
 
-    load_regs();
+    // ---- the CTA's tiles (persistent: 2 CTAs per SM walk the pass) ----
+    unsigned parity = 0;
+    for (unsigned t = first_tile; t < a.tile_end; t += gridDim.x) {
+        const unsigned long long base = tile_base(t);
+        // The next tile is fetched as soon as this one has been read out of shared memory for the last time: after the load
+        // under the final register layout.  Its HBM latency then hides behind the rest of this tile's program and its stores.
+        auto prefetch = [&]() {
+            __syncthreads(); // every thread has read its registers: the buffer is free
+#ifndef SPZ_CPU_EMULATION
+            if (tid < 32 && t + gridDim.x < a.tile_end) {
+                fence_proxy_async_smem(); // the generic-proxy reads above are ordered before the engine's writes
+                issue_tile_load(t + gridDim.x);
+            }
+#endif
+        };
+#ifdef SPZ_CPU_EMULATION
+        if (tid == 0) { // the emulation's "TMA": rows of 16 doubles, 16-byte chunks XORed with the row number mod 8
+            for (unsigned j = 0; j < kTileLen3; ++j) {
+                const unsigned long long g = base + tile_to_global(j);
+                sre[swz3(j)] = a.re[g];
+                sim[swz3(j)] = a.im[g];
+            }
+        }
+#endif
+        // ---- while the tile is in flight: skip flags and per-tile constants, from the staged program ----
+        {
+            const unsigned long long *outer = reinterpret_cast<const unsigned long long *>(smem + kProgOff3 + a.outer_off);
+            for (int i = tid; i < a.n_ins; i += kThreads3) {
+                const unsigned long long ocm = outer[i];
+                skip[i] = (base & ocm) != ocm ? 1 : 0;
+            }
+            // Per-tile constants: every group's product over those of its terms whose outer bits are set in this tile.
+            const TileGroup *groups = reinterpret_cast<const TileGroup *>(smem + kProgOff3 + a.groups_off);
+            const TileTerm *terms = reinterpret_cast<const TileTerm *>(smem + kProgOff3 + a.terms_off);
+#ifndef SPZ_CPU_EMULATION
+            // one warp per group: a lane per term, then a butterfly product over the lanes (5 shuffle rounds).  One thread per
+            // group walking its ~18 terms took 2.5 us per tile of a QFT pass, more than the tile takes to arrive.
+            for (int g = tid >> 5; g < a.n_groups; g += kThreads3 / 32) {
+                const TileGroup gd = groups[g];
+                double fr = 1.0, fi = 0.0;
+                for (int i = tid & 31; i < gd.count; i += 32) {
+                    const TileTerm &tm = terms[gd.first + i];
+                    if ((base & tm.outer) == tm.outer) cmul3(fr, fi, tm.fr, tm.fi);
+                }
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    const double qr = __shfl_xor_sync(0xffffffffu, fr, o), qi = __shfl_xor_sync(0xffffffffu, fi, o);
+                    cmul3(fr, fi, qr, qi); // (every lane ends with the same product up to the order of the factors; lane 0 writes)
+                }
+                if ((tid & 31) == 0) gfac[g] = make_double2(fr, fi);
+            }
+#else
+            for (int g = tid; g < a.n_groups; g += kThreads3) {
+                const TileGroup gd = groups[g];
+                double fr = 1.0, fi = 0.0;
+                for (int i = 0; i < gd.count; ++i) {
+                    const TileTerm &tm = terms[gd.first + i];
+                    if ((base & tm.outer) == tm.outer) cmul3(fr, fi, tm.fr, tm.fi);
+                }
+                gfac[g] = make_double2(fr, fi);
+            }
+#endif
+        }
+        facc[0] = make_double2(a.scale, 0.0); // F0 starts as the pass scale (pending from the start when it is not 1: the host knows)
+        __syncthreads(); // skip flags and constants in place (emulation: the tile too)
+        stamp(1); // constants
+#ifndef SPZ_CPU_EMULATION
+        // One warp waits for the boxes (a failed try_wait costs issue slots the other CTA of this SM could use); after the
+        // barrier the phase is complete and every thread's own try_wait -- its acquire of the TMA writes -- succeeds at once.
+        if (tid < 32) mbar_wait(bar, parity);
+        __syncthreads();
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+#endif
+        stamp(2); // tile arrived
 
-    // The interpreter.  Instructions are decoded from raw words (byte fields of a struct cost a dozen PRMTs per instruction
-    // to repack) and fetched one ahead, so that the fetch latency hides behind the current arm.
-    const uint4 *raw = reinterpret_cast<const uint4 *>(sins);
-    uint4 next = raw[1];
-    for (int pc = 1;; ++pc) {
-        const uint4 w = next;
-        next = raw[pc + 1]; // (one past END is still inside the blob)
-        const unsigned arm = w.x & 0xffu, cls = (w.x >> 16) & 0xffu, flags = w.x >> 24;
-        const unsigned km = w.y & 0xffffu, thr = w.y >> 16;
-        // GATE / ACCG / OTHER act on the threads whose control bits are set; a GATE also needs its controls outside the tile
-        bool ok = (tid & thr) == thr;
-        if (flags & GF_OUTER) ok = ok && !skip[pc];
-        const double *sp = pool + w.z;
+        lay = sins[0].a;
+        load_regs();
+        if (a.single_layout) prefetch();
+
+        // The interpreter.  Instructions are decoded from raw words (byte fields of a struct cost a dozen PRMTs per instruction
+        // to repack) and fetched one ahead, so that the fetch latency hides behind the current arm.
+        const uint4 *raw = reinterpret_cast<const uint4 *>(sins);
+        uint4 next = raw[1];
+        for (int pc = 1;; ++pc) {
+            const uint4 w = next;
+            next = raw[pc + 1]; // (one past END is still inside the blob)
+            const unsigned arm = w.x & 0xffu, cls = (w.x >> 16) & 0xffu, flags = w.x >> 24;
+            const unsigned km = w.y & 0xffffu, thr = w.y >> 16;
+            // GATE / ACCG / OTHER act on the threads whose control bits are set; a GATE also needs its controls outside the tile
+            bool ok = (tid & thr) == thr;
+            if (flags & GF_OUTER) ok = ok && !skip[pc];
+            const double *sp = pool + w.z;
 #define SPZ_GATE_ARMS(V, MK, ALL)                                                              \
     case T3_GATE + 4 * V + 0: if (ok) bfly3<MK, 0, ALL>(ar, ai, sp, km); break;               \
     case T3_GATE + 4 * V + 1: if (ok) bfly3<MK, 1, ALL>(ar, ai, sp, km); break;               \
     case T3_GATE + 4 * V + 2: if (ok) bfly3<MK, 2, ALL>(ar, ai, sp, km); break;               \
     case T3_GATE + 4 * V + 3: if (ok) bfly3<MK, 3, ALL>(ar, ai, sp, km); break;
-        switch (arm) {
-        SPZ_GATE_ARMS(0, MK_H, true)
-        SPZ_GATE_ARMS(1, MK_RX, true)
-        SPZ_GATE_ARMS(2, MK_RY, true)
-        SPZ_GATE_ARMS(3, MK_HS, false)
-        SPZ_GATE_ARMS(4, MK_RX, false)
-        SPZ_GATE_ARMS(5, MK_RY, false)
-        SPZ_GATE_ARMS(6, MK_X, false)
-        SPZ_GATE_ARMS(7, MK_Y, false)
-        // Accumulator F_{r+1} is pending and a butterfly on register bit r follows: apply it to the amplitudes with that bit
-        // set.  Only the accumulator of the target's own bit separates the two members of a pair; the others scale both by the
-        // same factor and stay pending.
-        case T3_PRE + 0: apply_bit3<0>(ar, ai, facc[1 * kThreads3]); break;
-        case T3_PRE + 1: apply_bit3<1>(ar, ai, facc[2 * kThreads3]); break;
-        case T3_PRE + 2: apply_bit3<2>(ar, ai, facc[3 * kThreads3]); break;
-        case T3_PRE + 3: apply_bit3<3>(ar, ai, facc[4 * kThreads3]); break;
-        case T3_ACC: {
-            const double2 *tab = reinterpret_cast<const double2 *>(sp);
-            double fr = 1.0, fi = 0.0;
-            if (flags & AF_LO) { const double2 t = tab[tid & 15u]; fr = t.x; fi = t.y; }
-            if (flags & AF_HI) { const double2 t = tab[16u + (tid >> 4)]; cmul3(fr, fi, t.x, t.y); }
-            if (flags & AF_TILE) { const double2 t = gfac[w.w]; cmul3(fr, fi, t.x, t.y); }
-            acc(cls, flags & AF_SET, fr, fi);
-            break; }
-        case T3_ACCG: { // a term that needs thread bits from both nibbles, or thread bits and bits outside the tile
-            double2 *f = facc + cls * kThreads3;
-            if (flags & AF_SET) {
-                // the accumulator held no pending factor: every thread assigns (nothing is ever reset, see flush)
-                *f = ok ? ((flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp)) : make_double2(1.0, 0.0);
-            } else if (ok) {
-                const double2 t = (flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp);
-                acc(cls, false, t.x, t.y);
-            }
-            break; }
-        case T3_OTHER: { // a diagonal term over two or more register bits: applied at once to the amplitudes it selects
-            if (!ok) break;
-            const double2 f = (flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp);
+            switch (arm) {
+            SPZ_GATE_ARMS(0, MK_H, true)
+            SPZ_GATE_ARMS(1, MK_RX, true)
+            SPZ_GATE_ARMS(2, MK_RY, true)
+            SPZ_GATE_ARMS(3, MK_HS, false)
+            SPZ_GATE_ARMS(4, MK_RX, false)
+            SPZ_GATE_ARMS(5, MK_RY, false)
+            SPZ_GATE_ARMS(6, MK_X, false)
+            SPZ_GATE_ARMS(7, MK_Y, false)
+            // Accumulator F_{r+1} is pending and a butterfly on register bit r follows: apply it to the amplitudes with that
+            // bit set.  Only the accumulator of the target's own bit separates the two members of a pair; the others scale
+            // both by the same factor and stay pending.
+            case T3_PRE + 0: apply_bit3<0>(ar, ai, facc[1 * kThreads3]); break;
+            case T3_PRE + 1: apply_bit3<1>(ar, ai, facc[2 * kThreads3]); break;
+            case T3_PRE + 2: apply_bit3<2>(ar, ai, facc[3 * kThreads3]); break;
+            case T3_PRE + 3: apply_bit3<3>(ar, ai, facc[4 * kThreads3]); break;
+            case T3_ACC: {
+                const double2 *tab = reinterpret_cast<const double2 *>(sp);
+                double fr = 1.0, fi = 0.0;
+                if (flags & AF_LO) { const double2 x = tab[tid & 15u]; fr = x.x; fi = x.y; }
+                if (flags & AF_HI) { const double2 x = tab[16u + (tid >> 4)]; cmul3(fr, fi, x.x, x.y); }
+                if (flags & AF_TILE) { const double2 x = gfac[w.w]; cmul3(fr, fi, x.x, x.y); }
+                acc(cls, flags & AF_SET, fr, fi);
+                break; }
+            case T3_ACCG: { // a term that needs thread bits from both nibbles, or thread bits and bits outside the tile
+                double2 *f = facc + cls * kThreads3;
+                if (flags & AF_SET) {
+                    // the accumulator held no pending factor: every thread assigns (nothing is ever reset, see flush)
+                    *f = ok ? ((flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp)) : make_double2(1.0, 0.0);
+                } else if (ok) {
+                    const double2 x = (flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp);
+                    acc(cls, false, x.x, x.y);
+                }
+                break; }
+            case T3_OTHER: { // a diagonal term over two or more register bits: applied at once to the amplitudes it selects
+                if (!ok) break;
+                const double2 f = (flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp);
 #define SPZ_M4(A, B, C, D) cmul3(ar[A], ai[A], f.x, f.y); cmul3(ar[B], ai[B], f.x, f.y); cmul3(ar[C], ai[C], f.x, f.y); cmul3(ar[D], ai[D], f.x, f.y)
-            switch (km) {
-            case 3: SPZ_M4(3, 7, 11, 15); break;
-            case 5: SPZ_M4(5, 7, 13, 15); break;
-            case 6: SPZ_M4(6, 7, 14, 15); break;
-            case 9: SPZ_M4(9, 11, 13, 15); break;
-            case 10: SPZ_M4(10, 11, 14, 15); break;
-            case 12: SPZ_M4(12, 13, 14, 15); break;
-            default:
+                switch (km) {
+                case 3: SPZ_M4(3, 7, 11, 15); break;
+                case 5: SPZ_M4(5, 7, 13, 15); break;
+                case 6: SPZ_M4(6, 7, 14, 15); break;
+                case 9: SPZ_M4(9, 11, 13, 15); break;
+                case 10: SPZ_M4(10, 11, 14, 15); break;
+                case 12: SPZ_M4(12, 13, 14, 15); break;
+                default:
 #pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    if (((unsigned)k & km) == km) cmul3(ar[k], ai[k], f.x, f.y);
-                break;
-            }
+                    for (int k = 0; k < 16; ++k)
+                        if (((unsigned)k & km) == km) cmul3(ar[k], ai[k], f.x, f.y);
+                    break;
+                }
 #undef SPZ_M4
-            break; }
-        default: // LAYOUT or END: apply what is pending, registers -> shared memory
-            flush(flags);
-            store_regs();
-            if (arm == T3_LAYOUT) {
+                break; }
+            case T3_LAYOUT: // apply what is pending, then change the register-resident bits through shared memory
+                flush(flags & 31u);
+                store_regs();
                 __syncthreads();
                 lay = w.z;
                 load_regs(); // no second barrier: this thread's next shared-memory access is store_regs() to the cells it has just read
+                if (flags & LF_LAST) prefetch();
+                break;
+            default: // END
+                flush(flags & 31u);
+                break;
             }
-            break;
-        }
 #undef SPZ_GATE_ARMS
-        if (arm == T3_END) break;
-    }
-
-    // ---- tile out ----
-    const unsigned long long base = tile_base();
-#ifndef SPZ_CPU_EMULATION
-    fence_proxy_async_smem(); // this thread's shared-memory writes become visible to the TMA engine
-    __syncthreads();
-    if (tid < 32) {
-        for (unsigned e = tid; e < n_box; e += 32) {
-            int c[5];
-            box_coords(base, e, c);
-            tma_store_box(a.rank, &a.tm_re, c, smem + e * box_bytes);
-            tma_store_box(a.rank, &a.tm_im, c, smem + kArrayBytes3 + e * box_bytes);
+            if (arm == T3_END) break;
         }
-        tma_store_commit_and_wait_read(); // shared memory must stay alive until the engine has read it
+        stamp(3); // program interpreted
+        direct_store(base);
+        stamp(4); // stores issued
+        __syncthreads(); // the next tile's flags and constants overwrite what slower warps may still be reading
     }
-#else
-    __syncthreads();
-    if (tid == 0) {
-        for (unsigned s = 0; s < n_seg; ++s) {
-            const unsigned long long g0 = (unsigned long long)seg_row(base, s) << 4;
-            for (unsigned j = 0; j < (1u << L); ++j) {
-                const unsigned tj = (s << L) + j;
-                a.re[g0 + j] = sre[swz3(tj)];
-                a.im[g0 + j] = sim[swz3(tj)];
-            }
-        }
-    }
-#endif
 }
 
 // ---- host: lowering -----------------------------------------------------------------------------------------------------
@@ -886,6 +931,8 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
     e.op = T3_END;
     e.flags = (uint8_t)dirty;
     push(e, 0);
+    for (size_t k = out.ins.size(); k-- > 1;)
+        if (out.ins[k].op == T3_LAYOUT) { out.ins[k].flags |= LF_LAST; out.single_layout = false; break; }
     if (out.pool.size() & 1) out.pool.push_back(0.0);
     return out.ins.size() <= (size_t)kMaxIns3 && out.groups.size() <= (size_t)kMaxGroups3;
 }
@@ -909,6 +956,7 @@ size_t tile3_pack(const Lowered3 &lw, std::vector<unsigned char> &blob, Tile3Arg
     a.outer_off = (unsigned)outer_off; a.groups_off = (unsigned)groups_off; a.terms_off = (unsigned)terms_off;
     a.n_ins = (int)lw.ins.size(); a.n_groups = (int)lw.groups.size(); a.n_terms = (int)lw.terms.size();
     a.scale = lw.scale;
+    a.single_layout = lw.single_layout ? 1 : 0;
     return total;
 }
 
@@ -1035,6 +1083,24 @@ int prepare_tile3(spz_state *st, const TilePlan &plan, const TileInstr *prog, in
     SPZ_TRY(tile_ring_alloc(st, bytes, &slot));
     SPZ_CUDA(cudaMemcpyAsync(slot, blob.data(), bytes, cudaMemcpyHostToDevice, st->stream));
     a.re = st->re; a.im = st->im;
+    a.prof = nullptr;
+    if (const char *e = std::getenv("SPZ_TILE_PROF")) {
+        if (e[0] == '1') { // diagnostic: the previous pass's phase times are printed when the next one is prepared
+            static unsigned long long *d_prof = nullptr;
+            static long long n_cta = 0;
+            if (!d_prof) SPZ_CUDA(cudaMalloc(&d_prof, 8 * sizeof(unsigned long long)));
+            else {
+                unsigned long long h[8];
+                SPZ_CUDA(cudaStreamSynchronize(st->stream));
+                SPZ_CUDA(cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost));
+                if (n_cta) std::fprintf(stderr, "k_tile3 phases, ns per tile: program (once per CTA) %.0f, constants %.0f, tile wait %.0f, interpret %.0f, stores %.0f\n",
+                                        (double)h[0] / n_cta, (double)h[1] / n_cta, (double)h[2] / n_cta, (double)h[3] / n_cta, (double)h[4] / n_cta);
+            }
+            SPZ_CUDA(cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), st->stream));
+            n_cta = st->len >> kT3;
+            a.prof = d_prof;
+        }
+    }
     a.blob = reinterpret_cast<const unsigned char *>(slot);
     a.L = plan.low_bits; a.n_high = plan.n_high;
     for (int k = 0; k < plan.n_high; ++k) a.high[k] = plan.high[k];
@@ -1048,8 +1114,17 @@ int prepare_tile3(spz_state *st, const TilePlan &plan, const TileInstr *prog, in
 void run_tile3(spz_state *st, const Tile3Launch &l, unsigned first, unsigned count) {
     Tile3Args a;
     std::memcpy(&a, l.args, sizeof a);
-    a.tile_offset = first;
-    k_tile3<<<count, kThreads3, l.smem, st->stream>>>(a);
+    a.tile_first = first;
+    a.tile_end = first + count;
+    // persistent: two CTAs per SM walk the tiles of the launch
+    static int sms[64] = {0};
+    int n_sm = 148;
+    if (st->device >= 0 && st->device < 64) {
+        if (!sms[st->device]) cudaDeviceGetAttribute(&sms[st->device], cudaDevAttrMultiProcessorCount, st->device);
+        if (sms[st->device] > 0) n_sm = sms[st->device];
+    }
+    const unsigned grid = std::min<unsigned>(count, 2u * (unsigned)n_sm);
+    k_tile3<<<grid, kThreads3, l.smem, st->stream>>>(a);
 }
 #endif // !SPZ_CPU_EMULATION
 

@@ -33,6 +33,7 @@ void run_grid(unsigned n_blocks, unsigned n_threads, size_t smem_bytes, Kernel k
         pool.emplace_back([&, t]() {
             threadIdx.x = t; threadIdx.y = 0; threadIdx.z = 0;
             blockDim.x = n_threads; blockDim.y = 1; blockDim.z = 1;
+            gridDim.x = n_blocks; gridDim.y = 1; gridDim.z = 1;
             for (unsigned b = 0; b < n_blocks; ++b) {
                 blockIdx.x = b; blockIdx.y = 0; blockIdx.z = 0;
                 kernel();
@@ -93,10 +94,11 @@ extern "C" int emu_tile3_run(int n_qubits, double *re, double *im, const void *b
     a.blob = packed.data();
     a.L = P.plan.low_bits; a.n_high = P.plan.n_high;
     for (int k = 0; k < P.plan.n_high; ++k) a.high[k] = P.plan.high[k];
-    a.tile_offset = 0;
     info[0] = lw.ctrl ? 1 : 0; info[1] = a.n_ins; info[2] = a.n_groups; info[3] = (int)smem;
-    const unsigned n_blocks = (unsigned)(((uint64_t)1 << n_qubits) >> P.plan.tile_bits);
-    run_grid(n_blocks, spz::kThreads3, smem, [&]() { spz::k_tile3(a); });
+    const unsigned n_tiles = (unsigned)(((uint64_t)1 << n_qubits) >> P.plan.tile_bits);
+    a.tile_first = 0; a.tile_end = n_tiles;
+    // the kernel is persistent: fewer CTAs than tiles, so that every CTA walks several (the launcher uses two per SM)
+    run_grid(n_tiles > 3 ? 3 : n_tiles, spz::kThreads3, smem, [&]() { spz::k_tile3(a); });
     return 0;
 }
 
