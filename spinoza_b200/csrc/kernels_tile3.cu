@@ -285,6 +285,8 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
     unsigned char *skip = reinterpret_cast<unsigned char *>(gfac + a.n_groups);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(
         smem + ((kProgOff3 + a.blob_bytes + 16u * (unsigned)a.n_groups + (unsigned)a.n_ins + 15u) & ~15u)); // [0] tile, [1] program
+    // hi_off[s]: offset of tile segment s (the high tile bits of a tile index, deposited at their qubits); built once per CTA
+    unsigned long long *hi_off = bar + 2;
     const unsigned tid = threadIdx.x;
     const int L = a.L;
 #ifndef SPZ_CPU_EMULATION
@@ -311,13 +313,7 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
         return b;
     };
     // global offset (inside the tile's footprint) of tile index x: the low L bits stay, bit L + k goes to qubit high[k]
-    auto tile_to_global = [&](unsigned x) -> unsigned long long {
-        unsigned long long o = x & ((1u << L) - 1u);
-#pragma unroll
-        for (int k = 0; k < kMaxHigh3; ++k)
-            if (k < a.n_high && ((x >> (L + k)) & 1u)) o |= 1ull << a.high[k];
-        return o;
-    };
+    auto tile_to_global = [&](unsigned x) -> unsigned long long { return hi_off[x >> L] + (x & ((1u << L) - 1u)); };
 
     // ---- tile in: TMA boxes (one per array for tiles with up to three runs of high qubits) on mbarrier 0.  Called by warp 0. ----
 #ifndef SPZ_CPU_EMULATION
@@ -343,6 +339,13 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
 #endif
     const unsigned first_tile = a.tile_first + blockIdx.x;
     if (first_tile >= a.tile_end) return;
+    for (unsigned sg = tid; sg < (1u << a.n_high); sg += kThreads3) {
+        unsigned long long o = 0;
+#pragma unroll
+        for (int k = 0; k < kMaxHigh3; ++k)
+            if (k < a.n_high && ((sg >> k) & 1u)) o |= 1ull << a.high[k];
+        hi_off[sg] = o;
+    }
 
     // ---- once per CTA: barriers, the program, the first tile ----
 #ifndef SPZ_CPU_EMULATION
@@ -575,15 +578,15 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
             next = raw[pc + 1]; // (one past END is still inside the blob)
             const unsigned arm = w.x & 0xffu, cls = (w.x >> 16) & 0xffu, flags = w.x >> 24;
             const unsigned km = w.y & 0xffffu, thr = w.y >> 16;
-            // GATE / ACCG / OTHER act on the threads whose control bits are set; a GATE also needs its controls outside the tile
-            bool ok = (tid & thr) == thr;
-            if (flags & GF_OUTER) ok = ok && !skip[pc];
+            // guarded GATE / ACCG / OTHER act on the threads whose control bits are set; a GATE also needs its controls outside the
+            // tile.  The unguarded arms (no control of any kind: the host routes everything else to the guarded ones) test nothing.
+            auto ok = [&]() -> bool { return (tid & thr) == thr && !((flags & GF_OUTER) && skip[pc]); };
             const double *sp = pool + w.z;
-#define SPZ_GATE_ARMS(V, MK, ALL)                                                              \
-    case T3_GATE + 4 * V + 0: if (ok) bfly3<MK, 0, ALL>(ar, ai, sp, km); break;               \
-    case T3_GATE + 4 * V + 1: if (ok) bfly3<MK, 1, ALL>(ar, ai, sp, km); break;               \
-    case T3_GATE + 4 * V + 2: if (ok) bfly3<MK, 2, ALL>(ar, ai, sp, km); break;               \
-    case T3_GATE + 4 * V + 3: if (ok) bfly3<MK, 3, ALL>(ar, ai, sp, km); break;
+#define SPZ_GATE_ARMS(V, MK, ALL)                                                                          \
+    case T3_GATE + 4 * V + 0: if (ALL || ok()) bfly3<MK, 0, ALL>(ar, ai, sp, km); break;                  \
+    case T3_GATE + 4 * V + 1: if (ALL || ok()) bfly3<MK, 1, ALL>(ar, ai, sp, km); break;                  \
+    case T3_GATE + 4 * V + 2: if (ALL || ok()) bfly3<MK, 2, ALL>(ar, ai, sp, km); break;                  \
+    case T3_GATE + 4 * V + 3: if (ALL || ok()) bfly3<MK, 3, ALL>(ar, ai, sp, km); break;
             switch (arm) {
             SPZ_GATE_ARMS(0, MK_H, true)
             SPZ_GATE_ARMS(1, MK_RX, true)
@@ -612,14 +615,14 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
                 double2 *f = facc + cls * kThreads3;
                 if (flags & AF_SET) {
                     // the accumulator held no pending factor: every thread assigns (nothing is ever reset, see flush)
-                    *f = ok ? ((flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp)) : make_double2(1.0, 0.0);
-                } else if (ok) {
+                    *f = ok() ? ((flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp)) : make_double2(1.0, 0.0);
+                } else if (ok()) {
                     const double2 x = (flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp);
                     acc(cls, false, x.x, x.y);
                 }
                 break; }
             case T3_OTHER: { // a diagonal term over two or more register bits: applied at once to the amplitudes it selects
-                if (!ok) break;
+                if (!ok()) break;
                 const double2 f = (flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp);
 #define SPZ_M4(A, B, C, D) cmul3(ar[A], ai[A], f.x, f.y); cmul3(ar[B], ai[B], f.x, f.y); cmul3(ar[C], ai[C], f.x, f.y); cmul3(ar[D], ai[D], f.x, f.y)
                 switch (km) {
@@ -898,11 +901,11 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
             // the arm: unguarded for the three gates that fill a circuit when nothing in the tile controls them, else under the
             // pair mask (which is all ones for an uncontrolled X, Y or scaled H)
             int variant;
-            if (!in_tile_ctrl && (v.kind == MK_H || v.kind == MK_RX || v.kind == MK_RY)) {
+            if (!in_tile_ctrl && !t.outer_cmask && (v.kind == MK_H || v.kind == MK_RX || v.kind == MK_RY)) {
                 variant = v.kind == MK_H ? 0 : v.kind == MK_RX ? 1 : 2;
                 i.flags |= GF_ALL;
             } else {
-                if (v.kind == MK_H) return false; // (cannot happen: a controlled H is lowered to HS)
+                if (v.kind == MK_H) return false; // (cannot happen: an H under any control is lowered to HS)
                 variant = v.kind == MK_HS ? 3 : v.kind == MK_RX ? 4 : v.kind == MK_RY ? 5 : v.kind == MK_X ? 6 : 7;
             }
             i.op = (uint8_t)(T3_GATE + 4 * variant + t.rpos);
@@ -938,7 +941,9 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
 }
 
 // Serialise for upload (layout: see Lowered3) and fill the size fields of the kernel arguments.
-size_t tile3_pack(const Lowered3 &lw, std::vector<unsigned char> &blob, Tile3Args &a) {
+size_t tile3_pack(const Lowered3 &lw, const TilePlan &plan, std::vector<unsigned char> &blob, Tile3Args &a) {
+    a.L = plan.low_bits; a.n_high = plan.n_high;
+    for (int k = 0; k < plan.n_high; ++k) a.high[k] = plan.high[k];
     auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t ins_bytes = up16(lw.ins.size() * sizeof(Ins3));
     const size_t pool_bytes = up16(lw.pool.size() * sizeof(double));
@@ -961,7 +966,7 @@ size_t tile3_pack(const Lowered3 &lw, std::vector<unsigned char> &blob, Tile3Arg
 }
 
 size_t tile3_smem_bytes(const Tile3Args &a) {
-    return ((kProgOff3 + a.blob_bytes + 16u * (size_t)a.n_groups + (size_t)a.n_ins + 15u) & ~(size_t)15u) + 16u;
+    return ((kProgOff3 + a.blob_bytes + 16u * (size_t)a.n_groups + (size_t)a.n_ins + 15u) & ~(size_t)15u) + 16u + 8u * ((size_t)1 << a.n_high);
 }
 
 bool tile3_shape_ok(int n_qubits, const TilePlan &plan) {
@@ -1068,7 +1073,7 @@ int prepare_tile3(spz_state *st, const TilePlan &plan, const TileInstr *prog, in
     if (!tile3_lower(plan, prog, n_instr, groups, n_groups, terms, n_terms, lw)) return SPZ_OK;
     Tile3Args a{};
     std::vector<unsigned char> blob;
-    const size_t bytes = tile3_pack(lw, blob, a);
+    const size_t bytes = tile3_pack(lw, plan, blob, a);
     const size_t smem = tile3_smem_bytes(a);
     if (smem > kSmemBudget3) return SPZ_OK;
     static bool prepared[64] = {false};
@@ -1102,8 +1107,6 @@ int prepare_tile3(spz_state *st, const TilePlan &plan, const TileInstr *prog, in
         }
     }
     a.blob = reinterpret_cast<const unsigned char *>(slot);
-    a.L = plan.low_bits; a.n_high = plan.n_high;
-    for (int k = 0; k < plan.n_high; ++k) a.high[k] = plan.high[k];
     static_assert(sizeof(Tile3Args) <= sizeof(out->args), "Tile3Launch::args too small");
     std::memcpy(out->args, &a, sizeof a);
     out->smem = smem;

@@ -87,13 +87,11 @@ extern "C" int emu_tile3_run(int n_qubits, double *re, double *im, const void *b
     if (!spz::tile3_lower(P.plan, P.prog.data(), P.ni, P.groups.data(), P.ng, P.terms.data(), P.nt, lw)) return 1;
     spz::Tile3Args a{};
     std::vector<unsigned char> packed;
-    spz::tile3_pack(lw, packed, a);
+    spz::tile3_pack(lw, P.plan, packed, a);
     const size_t smem = spz::tile3_smem_bytes(a);
     if (smem > spz::kSmemBudget3) return 1;
     a.re = re; a.im = im;
     a.blob = packed.data();
-    a.L = P.plan.low_bits; a.n_high = P.plan.n_high;
-    for (int k = 0; k < P.plan.n_high; ++k) a.high[k] = P.plan.high[k];
     info[0] = lw.ctrl ? 1 : 0; info[1] = a.n_ins; info[2] = a.n_groups; info[3] = (int)smem;
     const unsigned n_tiles = (unsigned)(((uint64_t)1 << n_qubits) >> P.plan.tile_bits);
     a.tile_first = 0; a.tile_end = n_tiles;
@@ -111,7 +109,7 @@ extern "C" long long emu_tile3_smem(int n_qubits, const void *blob, long long bl
     if (!spz::tile3_lower(P.plan, P.prog.data(), P.ni, P.groups.data(), P.ng, P.terms.data(), P.nt, lw)) return 0;
     spz::Tile3Args a{};
     std::vector<unsigned char> packed;
-    spz::tile3_pack(lw, packed, a);
+    spz::tile3_pack(lw, P.plan, packed, a);
     info[0] = lw.ctrl ? 1 : 0; info[1] = a.n_ins; info[2] = a.n_groups; info[3] = (int)packed.size();
     return (long long)spz::tile3_smem_bytes(a);
 }
