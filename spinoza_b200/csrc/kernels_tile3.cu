@@ -91,6 +91,7 @@ static_assert(sizeof(Ins3) == 16, "Ins3 is decoded with one 128-bit shared-memor
 // What the host uploads for one pass (one contiguous blob, 16-byte aligned sections):
 //   Ins3 ins[n_ins] | double pool[n_pool] (gate scalars, tables, constants; double2 entries at even offsets)
 //   | uint64 outer[n_ins] (controls outside the tile, GATE only) | TileGroup groups[n_groups] | TileTerm terms[n_terms]
+//   | uint8 arms[n_ins - 1] (the op bytes of instructions 1.., what the interpreter dispatches on)
 // Shared memory of a CTA: tile re | tile im | accumulators F[5][256] | the blob | gfac[n_groups] | skip[n_ins] | 2 mbarriers
 struct Lowered3 {
     std::vector<Ins3> ins;
@@ -117,7 +118,7 @@ struct Tile3Args {
     double *re, *im;               // (the CPU emulation moves the tile through these)
     const unsigned char *blob;     // device copy of the lowered program
     unsigned ins_bytes, blob_bytes;  // instruction section and whole blob (multiples of 16)
-    unsigned outer_off, groups_off, terms_off; // byte offsets of the other sections inside the blob (the pool follows the instructions)
+    unsigned outer_off, groups_off, terms_off, arms_off; // byte offsets of the other sections inside the blob (the pool follows the instructions)
     int n_ins, n_groups, n_terms;
     unsigned tile_first, tile_end; // this launch's tiles (a pass may be launched in two halves, see dist.cu)
     int single_layout;             // the program never changes the register layout: the next tile can be fetched at once
@@ -209,6 +210,49 @@ __device__ __forceinline__ void xor_swap(double &x, double &y) {
     asm volatile("xor.b64 %0, %0, %1;\n\txor.b64 %1, %1, %0;\n\txor.b64 %0, %0, %1;" : "+d"(x), "+d"(y));
 #endif
 }
+// Shared-memory loads by 32-bit shared-window address.  Through generic pointers the compiler re-derives the window base
+// (S2R SR_CgaCtaId, LEA) at every use inside the interpreter loop; the emulation's "address" is an offset into its window.
+#ifdef SPZ_CPU_EMULATION
+__device__ __forceinline__ unsigned sm_addr(const void *p) { return (unsigned)(static_cast<const unsigned char *>(p) - spz_emu::dyn_smem); }
+__device__ __forceinline__ uint4 lds128(unsigned a) { return *reinterpret_cast<const uint4 *>(spz_emu::dyn_smem + a); }
+__device__ __forceinline__ double2 lds_d2(unsigned a) { return *reinterpret_cast<const double2 *>(spz_emu::dyn_smem + a); }
+__device__ __forceinline__ double lds_d(unsigned a) { return *reinterpret_cast<const double *>(spz_emu::dyn_smem + a); }
+__device__ __forceinline__ unsigned lds32(unsigned a) { return *reinterpret_cast<const unsigned *>(spz_emu::dyn_smem + a); }
+__device__ __forceinline__ unsigned lds8(unsigned a) { return spz_emu::dyn_smem[a]; }
+#else
+// (volatile: the conversion reads SR_CgaCtaId, a slow special register; left to itself the compiler re-derives the address
+// inside the interpreter loop instead of keeping it)
+__device__ __forceinline__ unsigned sm_addr(const void *p) {
+    unsigned r;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 lds128(unsigned a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds_d2(unsigned a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_d(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds32(unsigned a) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds8(unsigned a) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+#endif
 // 256-bit global store (one full 32-byte sector per lane); plain stores in the CPU emulation build
 __device__ __forceinline__ void st_global4(double *p, double x0, double x1, double x2, double x3) {
 #ifdef SPZ_CPU_EMULATION
@@ -249,10 +293,9 @@ template <int MK>
 constexpr int n_scalars3() { return MK == MK_RX || MK == MK_RY ? 2 : 0; }
 
 template <int MK, int R, bool ALL>
-__device__ __forceinline__ void bfly3(double (&ar)[16], double (&ai)[16], const double *__restrict__ sp, unsigned km) {
+__device__ __forceinline__ void bfly3(double (&ar)[16], double (&ai)[16], unsigned sp, unsigned km) {
     double s[2] = {0.0, 0.0};
-#pragma unroll
-    for (int i = 0; i < n_scalars3<MK>(); ++i) s[i] = sp[i];
+    if (n_scalars3<MK>() == 2) { const double2 v = lds_d2(sp); s[0] = v.x; s[1] = v.y; } // (rotation scalars sit at even pool offsets)
 #pragma unroll
     for (int k0 = 0; k0 < 16; ++k0) {
         if (k0 & (1 << R)) continue;
@@ -339,6 +382,10 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
 #endif
     const unsigned first_tile = a.tile_first + blockIdx.x;
     if (first_tile >= a.tile_end) return;
+    const unsigned sbase = sm_addr(smem);
+    const unsigned ins_addr = sbase + kProgOff3, pool_addr = ins_addr + a.ins_bytes, gfac_addr = ins_addr + a.blob_bytes;
+    const unsigned skip_addr = gfac_addr + 16u * (unsigned)a.n_groups;
+    const unsigned arms_addr = ins_addr + a.arms_off; // the arm bytes of instructions 1, 2, ... (see tile3_pack)
     for (unsigned sg = tid; sg < (1u << a.n_high); sg += kThreads3) {
         unsigned long long o = 0;
 #pragma unroll
@@ -569,33 +616,44 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
         load_regs();
         if (a.single_layout) prefetch();
 
-        // The interpreter.  Instructions are decoded from raw words (byte fields of a struct cost a dozen PRMTs per instruction
-        // to repack) and fetched one ahead, so that the fetch latency hides behind the current arm.
-        const uint4 *raw = reinterpret_cast<const uint4 *>(sins);
-        uint4 next = raw[1];
-        for (int pc = 1;; ++pc) {
-            const uint4 w = next;
-            next = raw[pc + 1]; // (one past END is still inside the blob)
-            const unsigned arm = w.x & 0xffu, cls = (w.x >> 16) & 0xffu, flags = w.x >> 24;
-            const unsigned km = w.y & 0xffffu, thr = w.y >> 16;
-            // guarded GATE / ACCG / OTHER act on the threads whose control bits are set; a GATE also needs its controls outside the
-            // tile.  The unguarded arms (no control of any kind: the host routes everything else to the guarded ones) test nothing.
-            auto ok = [&]() -> bool { return (tid & thr) == thr && !((flags & GF_OUTER) && skip[pc]); };
-            const double *sp = pool + w.z;
-#define SPZ_GATE_ARMS(V, MK, ALL)                                                                          \
-    case T3_GATE + 4 * V + 0: if (ALL || ok()) bfly3<MK, 0, ALL>(ar, ai, sp, km); break;                  \
-    case T3_GATE + 4 * V + 1: if (ALL || ok()) bfly3<MK, 1, ALL>(ar, ai, sp, km); break;                  \
-    case T3_GATE + 4 * V + 2: if (ALL || ok()) bfly3<MK, 2, ALL>(ar, ai, sp, km); break;                  \
-    case T3_GATE + 4 * V + 3: if (ALL || ok()) bfly3<MK, 3, ALL>(ar, ai, sp, km); break;
+        // The interpreter.  Dispatch needs one byte per instruction -- the arm -- and takes it from a register: the arm bytes are
+        // a stream of their own, fetched four at a time one word ahead.  An arm that has operands loads its own 16-byte
+        // instruction word; the hot ones (H on every pair, applying a pending accumulator) have none.  Everything is addressed
+        // by 32-bit shared addresses computed once.
+        unsigned armw = lds32(arms_addr), armn = lds32(arms_addr + 4u);
+        for (unsigned pc = 1;; ++pc) {
+            const unsigned arm = armw & 0xffu;
+            armw >>= 8;
+            if ((pc & 3u) == 0u) { armw = armn; armn = lds32(arms_addr + pc + 4u); } // arms[pc + 1 ..] now; arms[pc + 5 ..] in flight
+            // operand word of this instruction: x = arm | kind << 8 | class << 16 | flags << 24, y = pair mask | thread mask << 16,
+            // z = pool offset (doubles) / layout, w = per-tile constant index
+#define SPZ_W const uint4 w = lds128(ins_addr + 16u * pc)
+            // guarded GATE / ACCG / OTHER act on the threads whose control bits are set; a GATE also needs its controls outside
+            // the tile.  The unguarded arms (no control of any kind: the host routes everything else to the guarded ones) test nothing.
+#define SPZ_OK(w) (((tid & ((w).y >> 16)) == ((w).y >> 16)) && !((((w).x >> 24) & GF_OUTER) && lds8(skip_addr + pc)))
+#define SPZ_GATE_ALL(V, MK)                                                                                  \
+    case T3_GATE + 4 * V + 0: { SPZ_W; bfly3<MK, 0, true>(ar, ai, pool_addr + 8u * w.z, 0xffffu); break; }   \
+    case T3_GATE + 4 * V + 1: { SPZ_W; bfly3<MK, 1, true>(ar, ai, pool_addr + 8u * w.z, 0xffffu); break; }   \
+    case T3_GATE + 4 * V + 2: { SPZ_W; bfly3<MK, 2, true>(ar, ai, pool_addr + 8u * w.z, 0xffffu); break; }   \
+    case T3_GATE + 4 * V + 3: { SPZ_W; bfly3<MK, 3, true>(ar, ai, pool_addr + 8u * w.z, 0xffffu); break; }
+#define SPZ_GATE_GUARDED(V, MK)                                                                                                       \
+    case T3_GATE + 4 * V + 0: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 0, false>(ar, ai, pool_addr + 8u * w.z, w.y & 0xffffu); break; }      \
+    case T3_GATE + 4 * V + 1: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 1, false>(ar, ai, pool_addr + 8u * w.z, w.y & 0xffffu); break; }      \
+    case T3_GATE + 4 * V + 2: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 2, false>(ar, ai, pool_addr + 8u * w.z, w.y & 0xffffu); break; }      \
+    case T3_GATE + 4 * V + 3: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 3, false>(ar, ai, pool_addr + 8u * w.z, w.y & 0xffffu); break; }
             switch (arm) {
-            SPZ_GATE_ARMS(0, MK_H, true)
-            SPZ_GATE_ARMS(1, MK_RX, true)
-            SPZ_GATE_ARMS(2, MK_RY, true)
-            SPZ_GATE_ARMS(3, MK_HS, false)
-            SPZ_GATE_ARMS(4, MK_RX, false)
-            SPZ_GATE_ARMS(5, MK_RY, false)
-            SPZ_GATE_ARMS(6, MK_X, false)
-            SPZ_GATE_ARMS(7, MK_Y, false)
+            // H on every pair has no operand at all
+            case T3_GATE + 0: bfly3<MK_H, 0, true>(ar, ai, 0u, 0xffffu); break;
+            case T3_GATE + 1: bfly3<MK_H, 1, true>(ar, ai, 0u, 0xffffu); break;
+            case T3_GATE + 2: bfly3<MK_H, 2, true>(ar, ai, 0u, 0xffffu); break;
+            case T3_GATE + 3: bfly3<MK_H, 3, true>(ar, ai, 0u, 0xffffu); break;
+            SPZ_GATE_ALL(1, MK_RX)
+            SPZ_GATE_ALL(2, MK_RY)
+            SPZ_GATE_GUARDED(3, MK_HS)
+            SPZ_GATE_GUARDED(4, MK_RX)
+            SPZ_GATE_GUARDED(5, MK_RY)
+            SPZ_GATE_GUARDED(6, MK_X)
+            SPZ_GATE_GUARDED(7, MK_Y)
             // Accumulator F_{r+1} is pending and a butterfly on register bit r follows: apply it to the amplitudes with that
             // bit set.  Only the accumulator of the target's own bit separates the two members of a pair; the others scale
             // both by the same factor and stay pending.
@@ -604,26 +662,32 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
             case T3_PRE + 2: apply_bit3<2>(ar, ai, facc[3 * kThreads3]); break;
             case T3_PRE + 3: apply_bit3<3>(ar, ai, facc[4 * kThreads3]); break;
             case T3_ACC: {
-                const double2 *tab = reinterpret_cast<const double2 *>(sp);
+                SPZ_W;
+                const unsigned flags = w.x >> 24, tab = pool_addr + 8u * w.z;
                 double fr = 1.0, fi = 0.0;
-                if (flags & AF_LO) { const double2 x = tab[tid & 15u]; fr = x.x; fi = x.y; }
-                if (flags & AF_HI) { const double2 x = tab[16u + (tid >> 4)]; cmul3(fr, fi, x.x, x.y); }
-                if (flags & AF_TILE) { const double2 x = gfac[w.w]; cmul3(fr, fi, x.x, x.y); }
-                acc(cls, flags & AF_SET, fr, fi);
+                if (flags & AF_LO) { const double2 x = lds_d2(tab + 16u * (tid & 15u)); fr = x.x; fi = x.y; }
+                if (flags & AF_HI) { const double2 x = lds_d2(tab + 256u + 16u * (tid >> 4)); cmul3(fr, fi, x.x, x.y); }
+                if (flags & AF_TILE) { const double2 x = lds_d2(gfac_addr + 16u * w.w); cmul3(fr, fi, x.x, x.y); }
+                acc((w.x >> 16) & 0xffu, flags & AF_SET, fr, fi);
                 break; }
             case T3_ACCG: { // a term that needs thread bits from both nibbles, or thread bits and bits outside the tile
-                double2 *f = facc + cls * kThreads3;
+                SPZ_W;
+                const unsigned flags = w.x >> 24, cls = (w.x >> 16) & 0xffu;
+                const bool hit = SPZ_OK(w);
+                const unsigned src = (flags & AF_TILE) ? gfac_addr + 16u * w.w : pool_addr + 8u * w.z;
                 if (flags & AF_SET) {
                     // the accumulator held no pending factor: every thread assigns (nothing is ever reset, see flush)
-                    *f = ok() ? ((flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp)) : make_double2(1.0, 0.0);
-                } else if (ok()) {
-                    const double2 x = (flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp);
+                    facc[cls * kThreads3] = hit ? lds_d2(src) : make_double2(1.0, 0.0);
+                } else if (hit) {
+                    const double2 x = lds_d2(src);
                     acc(cls, false, x.x, x.y);
                 }
                 break; }
             case T3_OTHER: { // a diagonal term over two or more register bits: applied at once to the amplitudes it selects
-                if (!ok()) break;
-                const double2 f = (flags & AF_TILE) ? gfac[w.w] : *reinterpret_cast<const double2 *>(sp);
+                SPZ_W;
+                if (!SPZ_OK(w)) break;
+                const double2 f = lds_d2(((w.x >> 24) & AF_TILE) ? gfac_addr + 16u * w.w : pool_addr + 8u * w.z);
+                const unsigned km = w.y & 0xffffu;
 #define SPZ_M4(A, B, C, D) cmul3(ar[A], ai[A], f.x, f.y); cmul3(ar[B], ai[B], f.x, f.y); cmul3(ar[C], ai[C], f.x, f.y); cmul3(ar[D], ai[D], f.x, f.y)
                 switch (km) {
                 case 3: SPZ_M4(3, 7, 11, 15); break;
@@ -640,19 +704,24 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
                 }
 #undef SPZ_M4
                 break; }
-            case T3_LAYOUT: // apply what is pending, then change the register-resident bits through shared memory
-                flush(flags & 31u);
+            case T3_LAYOUT: { // apply what is pending, then change the register-resident bits through shared memory
+                SPZ_W;
+                flush((w.x >> 24) & 31u);
                 store_regs();
                 __syncthreads();
                 lay = w.z;
                 load_regs(); // no second barrier: this thread's next shared-memory access is store_regs() to the cells it has just read
-                if (flags & LF_LAST) prefetch();
-                break;
-            default: // END
-                flush(flags & 31u);
-                break;
+                if ((w.x >> 24) & LF_LAST) prefetch();
+                break; }
+            default: { // END
+                SPZ_W;
+                flush((w.x >> 24) & 31u);
+                break; }
             }
-#undef SPZ_GATE_ARMS
+#undef SPZ_GATE_ALL
+#undef SPZ_GATE_GUARDED
+#undef SPZ_OK
+#undef SPZ_W
             if (arm == T3_END) break;
         }
         stamp(3); // program interpreted
@@ -909,7 +978,7 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
                 variant = v.kind == MK_HS ? 3 : v.kind == MK_RX ? 4 : v.kind == MK_RY ? 5 : v.kind == MK_X ? 6 : 7;
             }
             i.op = (uint8_t)(T3_GATE + 4 * variant + t.rpos);
-            if (v.ns) { i.a = (uint32_t)out.pool.size(); out.pool.insert(out.pool.end(), v.s, v.s + v.ns); }
+            if (v.ns) { i.a = pool2(v.s[0], v.s[1]); }
             push(i, t.outer_cmask);
             if (!after.empty()) emit_terms(after);
             continue;
@@ -950,7 +1019,8 @@ size_t tile3_pack(const Lowered3 &lw, const TilePlan &plan, std::vector<unsigned
     const size_t outer_off = ins_bytes + pool_bytes;
     const size_t groups_off = up16(outer_off + lw.outer.size() * sizeof(uint64_t));
     const size_t terms_off = up16(groups_off + lw.groups.size() * sizeof(TileGroup));
-    const size_t total = up16(terms_off + lw.terms.size() * sizeof(TileTerm));
+    const size_t arms_off = up16(terms_off + lw.terms.size() * sizeof(TileTerm));
+    const size_t total = up16(arms_off + lw.ins.size() + 8); // arm stream: byte j = arm of instruction j + 1; zero (END) padded, read two words ahead
     blob.assign(total, 0);
     std::memcpy(blob.data(), lw.ins.data(), lw.ins.size() * sizeof(Ins3));
     if (!lw.pool.empty()) std::memcpy(blob.data() + ins_bytes, lw.pool.data(), lw.pool.size() * sizeof(double));
@@ -958,7 +1028,8 @@ size_t tile3_pack(const Lowered3 &lw, const TilePlan &plan, std::vector<unsigned
     if (!lw.groups.empty()) std::memcpy(blob.data() + groups_off, lw.groups.data(), lw.groups.size() * sizeof(TileGroup));
     if (!lw.terms.empty()) std::memcpy(blob.data() + terms_off, lw.terms.data(), lw.terms.size() * sizeof(TileTerm));
     a.ins_bytes = (unsigned)ins_bytes; a.blob_bytes = (unsigned)total;
-    a.outer_off = (unsigned)outer_off; a.groups_off = (unsigned)groups_off; a.terms_off = (unsigned)terms_off;
+    for (size_t j = 1; j < lw.ins.size(); ++j) blob[arms_off + j - 1] = lw.ins[j].op;
+    a.outer_off = (unsigned)outer_off; a.groups_off = (unsigned)groups_off; a.terms_off = (unsigned)terms_off; a.arms_off = (unsigned)arms_off;
     a.n_ins = (int)lw.ins.size(); a.n_groups = (int)lw.groups.size(); a.n_terms = (int)lw.terms.size();
     a.scale = lw.scale;
     a.single_layout = lw.single_layout ? 1 : 0;
