@@ -931,22 +931,34 @@ static int execute_impl(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_
 
     const int nq = total_qubits(st);
     int64_t cur = 0; // index of the op being emitted (for the exchange look-ahead)
-    // distance from op `cur` to the next non-diagonal use of every logical qubit (sharded registers only)
-    auto next_uses = [&](uint64_t *nu) {
-        for (int q = 0; q < 64; ++q) nu[q] = UINT64_MAX;
-        for (int64_t j = cur + 1; j < n_ops; ++j) {
+    // distance from op `cur` to the next non-diagonal use of every logical qubit (sharded registers only): the positions of
+    // every qubit's non-diagonal uses are collected once, and a cursor per qubit moves forward with `cur` -- O(n_ops) for the
+    // whole list instead of a rescan of the remaining ops for every emitted op
+    std::vector<int64_t> uses[64];
+    size_t use_cursor[64] = {0};
+    if (st->dist)
+        for (int64_t j = 0; j < n_ops; ++j) {
             const spz_op &o = ops[j];
             if (o.kind == SPZ_GATE_SWAP || is_diagonal_kind(o.kind) || o.kind == SPZ_GATE_UNITARY) continue;
-            if (o.target >= 0 && o.target < 64 && nu[o.target] == UINT64_MAX) nu[o.target] = (uint64_t)(j - cur);
+            if (o.target >= 0 && o.target < 64) uses[o.target].push_back(j);
+        }
+    auto next_uses = [&](uint64_t *nu) {
+        for (int q = 0; q < 64; ++q) {
+            size_t &c = use_cursor[q];
+            while (c < uses[q].size() && uses[q][c] <= cur) ++c;
+            nu[q] = c < uses[q].size() ? (uint64_t)(uses[q][c] - cur) : UINT64_MAX;
         }
     };
 
     // Sharded registers: keep exchanges (and the ops this rank skips, as placeholders) inside the scheduling window instead
-    // of closing the window at every exchange.  Opt-in (SPZ_DIST_WINDOW=1) until it has run on hardware; checked on the
-    // CPU by tests/test_dist_fused_cpu.py.
+    // of closing the window at every exchange.  On by default (SPZ_DIST_WINDOW=0 restores the old windows): checked on the CPU by
+    // tests/test_dist_fused_cpu.py, on one GPU by the local-group tests and on two GPUs over NVLink against the oracle
+    // (bench.py's `parity` extra; QFT-31 on 2 GPUs 65.5 -> 61.5 ms, profiles/round2_summary.md).
     bool window_exchanges = false;
-    if (fuse && st->dist && fuser.reorder && !fuser.exact)
-        if (const char *e = std::getenv("SPZ_DIST_WINDOW")) window_exchanges = e[0] == '1';
+    if (fuse && st->dist && fuser.reorder && !fuser.exact) {
+        window_exchanges = true;
+        if (const char *e = std::getenv("SPZ_DIST_WINDOW")) window_exchanges = e[0] != '0';
+    }
 
     auto emit_local = [&](int kind, const double *p, uint64_t cmask, int target, int t2, int const_hi, bool skip = false,
                           uint32_t grefs = 0) -> int {

@@ -18,9 +18,9 @@ import pytest
 
 import oracle as orc
 import spinoza_b200 as sb
-from spinoza_b200 import Gate, QuantumCircuit
+from spinoza_b200 import Gate, QuantumCircuit, workloads
 from spinoza_b200.distributed import DistState, unpermute
-from tests.test_gpu_parity import GATES, G, build_circuit, random_ops, run_dense
+from tests.test_gpu_parity import GATES, G, build_circuit, oracle_ops_from, random_ops, run_dense
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
@@ -215,3 +215,33 @@ def test_sample_sharded(n, world):
     run_group(states, lambda r, s: (s.set_basis(5), s.sync()))
     outs = run_group(states, lambda r, s: sb.sample(s, 64, seed=1))
     assert np.all(np.max(np.stack(outs), axis=0) == 5)
+
+
+# ---- windows that span exchanges (the default; SPZ_DIST_WINDOW=0 closes the window at every exchange) ----------------------
+
+@pytest.mark.parametrize("window", ["0", "1"])
+@pytest.mark.parametrize("select", ["0", "1"])
+@pytest.mark.parametrize("n,world", [(15, 2), (16, 4), (17, 8)])
+def test_windows_spanning_exchanges_match_the_oracle(n, world, select, window, monkeypatch):
+    monkeypatch.setenv("SPZ_DIST_WINDOW", window)
+    monkeypatch.setenv("SPZ_TILE_SELECT", select)
+    init = orc.gen_random_state(n, 46)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, init)
+    box = {}
+
+    def body(rank, s):
+        q = QuantumCircuit.from_state(s, fuse=True)
+        workloads.random_layered_circuit(q, depth=12, seed=42)
+        q.qft()
+        if rank == 0:
+            box["ops"] = oracle_ops_from(q)
+        q.execute()
+        s.sync()
+        box[rank] = s.stats()["exchanges"]
+    run_group(states, body)
+    re, im = gather(states)
+    cpu = init.clone()
+    orc.execute(cpu, box["ops"])
+    assert np.max(np.abs(re - cpu.reals)) <= 1e-12 and np.max(np.abs(im - cpu.imags)) <= 1e-12
+    assert len({box[r] for r in range(world)}) == 1   # every rank ran the same exchanges

@@ -56,15 +56,17 @@ def main():
     if perm == list(range(n)):
         re1, im1 = s.download(0, cnt)
         back = env.max_float(float(np.max(np.abs((re1 - re0) + 1j * (im1 - im0)))))
+    nrm_inv = sb.norm2(s)  # a collective: every rank
     if env.rank == 0:
         print(json.dumps({
             "workload": f"random layered circuit, {n} qubits, depth {args.depth}, {n_gates} gates, {env.world} GPU(s), "
                         f"2^{s.n_local} amplitudes per GPU",
             "seconds": ms * 1e-3, "sec_per_gate": ms * 1e-3 / n_gates, "launches": int(launches),
             "exchanges": st1["exchanges"] - st0["exchanges"], "exchange_ms": st1["exchange_ms"] - st0["exchange_ms"],
-            "norm2": nrm, "norm2_after_inverse": sb.norm2(s), "roundtrip_max_abs_err_first_sample": back,
+            "norm2": nrm, "norm2_after_inverse": nrm_inv, "roundtrip_max_abs_err_first_sample": back,
             "switches": {k: os.environ.get(k) for k in ("SPZ_DIST_WINDOW", "SPZ_TILE_SELECT", "SPZ_TILE_V3", "SPZ_TILE_LMIN", "SPZ_NO_OVERLAP")},
         }))
+    env.shutdown()
 
 
 if __name__ == "__main__":
