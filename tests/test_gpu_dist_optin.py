@@ -74,32 +74,3 @@ def test_fused_exchange_gate_inside_execute(n, world, window, monkeypatch):
 
 
 # ---- clone of a sharded register (spz_dist_copy_from; new in the last hours of round 1, so opt-in like the rest) ---------
-
-def test_clone_of_a_sharded_register_is_independent_and_keeps_the_permutation():
-    from spinoza_b200.distributed import DistState
-    from tests.test_gpu_dist import gather, run_group, upload_shards
-    n, world = 14, 4
-    init = orc.gen_random_state(n, 49)
-    states = DistState.create_local_group(n, world)
-    upload_shards(states, init)
-
-    def first(rank, s):
-        for t in (n - 1, n - 2, 3):          # two global targets: the permutation is no longer the identity
-            sb.apply(sb.Gate.H, s, t)
-        s.sync()
-    run_group(states, first)
-    clones = DistState.clone_local_group(states)
-    assert clones[0].perm() == states[0].perm() != list(range(n))
-
-    def second(rank, s):
-        sb.apply(sb.Gate.X, s, 0)            # only the originals move on
-        s.sync()
-    run_group(states, second)
-    cpu = init.clone()
-    for t in (n - 1, n - 2, 3):
-        orc.apply(orc.H, cpu, t)
-    re, im = gather(clones)
-    assert np.array_equal(re, cpu.reals) and np.array_equal(im, cpu.imags)
-    orc.apply(orc.X, cpu, 0)
-    re, im = gather(states)
-    assert np.array_equal(re, cpu.reals) and np.array_equal(im, cpu.imags)
