@@ -419,6 +419,11 @@ def main():
         qft = {}
         n_gates = n + n * (n - 1) // 2
         for label, fuse in (("fused", True), ("unfused", False)):
+            if fuse:  # one untimed run: the first fused execute pays one-time costs (kernel attributes, the TMA descriptor encoder)
+                state.set_basis(1)
+                warm = QuantumCircuit.from_state(state, fuse=True)
+                warm.qft()
+                warm.execute()
             state.set_basis(0x9E3779B97F4A7C15 % (1 << n))
             qc = QuantumCircuit.from_state(state, fuse=fuse)
             qc.qft()

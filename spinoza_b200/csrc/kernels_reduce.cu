@@ -385,9 +385,11 @@ __global__ void __launch_bounds__(256) k_sample_blocks(const double *__restrict_
                                                        const int *__restrict__ count, const int *__restrict__ cnt_incl,
                                                        const int *__restrict__ cnt_tot, const int *__restrict__ order,
                                                        const double *__restrict__ shot_res, long long *__restrict__ out) {
+    // blockIdx.y splits the bucket of a block that holds many shots (a peaked distribution puts most of 2^20 shots into a few
+    // blocks): slice y serves shots y * 256 + tid, stepping by 256 * gridDim.y, after scanning the block itself
     const long long b = blockIdx.x;
     const int n_here = count[b];
-    if (n_here == 0) return;
+    if (n_here <= (int)(blockIdx.y * blockDim.x)) return;
     __shared__ double incl[kB];
     const long long lo = b * kB, cnt = min(kB, len - lo);
     double v[16];
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(256) k_sample_blocks(const double *__restrict_
     for (int i = 0; i < 16; ++i) incl[threadIdx.x * 16 + i] = v[i];
     __syncthreads();
     const int start = bucket_start(count, cnt_incl, cnt_tot, b);
-    for (int k = threadIdx.x; k < n_here; k += blockDim.x) {
+    for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < n_here; k += blockDim.x * gridDim.y) {
         const int s = order[start + k];
         out[s] = lo + upper_index(incl, cnt, shot_res[s]);
     }
@@ -459,7 +461,8 @@ int launch_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_
     k_scan_groups<int><<<(unsigned)n_l2, 256, 0, q>>>(count, n_l1, cincl, ctot);
     k_scan_single<int><<<1, 256, 0, q>>>(ctot, n_l2);
     k_scatter<<<shot_grid, 256, 0, q>>>(shots, d_blk, count, cincl, ctot, cursor, d_order);
-    k_sample_blocks<<<(unsigned)n_l1, 256, 0, q>>>(st->re, st->im, len, count, cincl, ctot, d_order, d_res, d_out);
+    const unsigned slices = (unsigned)std::min<int64_t>(16, std::max<int64_t>(1, shots / 4096)); // (a slice without shots exits at once)
+    k_sample_blocks<<<dim3((unsigned)n_l1, slices), 256, 0, q>>>(st->re, st->im, len, count, cincl, ctot, d_order, d_res, d_out);
     count_launch(8);
     SPZ_CUDA(cudaGetLastError());
     SPZ_CUDA(cudaMemcpyAsync(out_index, d_out, sizeof(long long) * (size_t)shots, cudaMemcpyDeviceToHost, q));
