@@ -91,7 +91,6 @@ static_assert(sizeof(Ins3) == 16, "Ins3 is decoded with one 128-bit shared-memor
 // What the host uploads for one pass (one contiguous blob, 16-byte aligned sections):
 //   Ins3 ins[n_ins] | double pool[n_pool] (gate scalars, tables, constants; double2 entries at even offsets)
 //   | uint64 outer[n_ins] (controls outside the tile, GATE only) | TileGroup groups[n_groups] | TileTerm terms[n_terms]
-//   | uint8 arms[n_ins - 1] (the op bytes of instructions 1.., what the interpreter dispatches on)
 // Shared memory of a CTA: tile re | tile im | accumulators F[5][256] | the blob | gfac[n_groups] | skip[n_ins] | 2 mbarriers
 struct Lowered3 {
     std::vector<Ins3> ins;
@@ -118,7 +117,7 @@ struct Tile3Args {
     double *re, *im;               // (the CPU emulation moves the tile through these)
     const unsigned char *blob;     // device copy of the lowered program
     unsigned ins_bytes, blob_bytes;  // instruction section and whole blob (multiples of 16)
-    unsigned outer_off, groups_off, terms_off, arms_off; // byte offsets of the other sections inside the blob (the pool follows the instructions)
+    unsigned outer_off, groups_off, terms_off; // byte offsets of the other sections inside the blob (the pool follows the instructions)
     int n_ins, n_groups, n_terms;
     unsigned tile_first, tile_end; // this launch's tiles (a pass may be launched in two halves, see dist.cu)
     int single_layout;             // the program never changes the register layout: the next tile can be fetched at once
@@ -133,9 +132,11 @@ struct Tile3Args {
 __host__ __device__ __forceinline__ unsigned swz3(unsigned j) { return j ^ (((j >> 4) & 7u) << 1); }
 
 __device__ __forceinline__ void cmul3(double &xr, double &xi, double fr, double fi) {
-    const double t = xr; // one live temporary; both results land in their own operand's register (see pair3)
-    xr = xr * fr - xi * fi;
-    xi = t * fi + xi * fr;
+    // two products into temporaries, then each result lands in its own operand's register by one FMA (see pair3): no copy of
+    // the old real part is needed (t = xr; ... cost two MOVs per multiply, a sixth of the kernel's integer instructions)
+    const double p = xi * fi, q = xr * fi;
+    xr = fma(xr, fr, -p);
+    xi = fma(xi, fr, q);
 }
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX); the CPU emulation replaces them by synchronous copies ----------------------
@@ -218,6 +219,8 @@ __device__ __forceinline__ uint4 lds128(unsigned a) { return *reinterpret_cast<c
 __device__ __forceinline__ double2 lds_d2(unsigned a) { return *reinterpret_cast<const double2 *>(spz_emu::dyn_smem + a); }
 __device__ __forceinline__ double lds_d(unsigned a) { return *reinterpret_cast<const double *>(spz_emu::dyn_smem + a); }
 __device__ __forceinline__ unsigned lds32(unsigned a) { return *reinterpret_cast<const unsigned *>(spz_emu::dyn_smem + a); }
+__device__ __forceinline__ void sts_d2(unsigned a, double x, double y) { *reinterpret_cast<double2 *>(spz_emu::dyn_smem + a) = make_double2(x, y); }
+__device__ __forceinline__ void sts_d(unsigned a, double x) { *reinterpret_cast<double *>(spz_emu::dyn_smem + a) = x; }
 __device__ __forceinline__ unsigned lds8(unsigned a) { return spz_emu::dyn_smem[a]; }
 #else
 // (volatile: the conversion reads SR_CgaCtaId, a slow special register; left to itself the compiler re-derives the address
@@ -247,6 +250,10 @@ __device__ __forceinline__ unsigned lds32(unsigned a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void sts_d2(unsigned a, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void sts_d(unsigned a, double x) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(x) : "memory"); }
 __device__ __forceinline__ unsigned lds8(unsigned a) {
     unsigned v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
@@ -260,6 +267,15 @@ __device__ __forceinline__ void st_global4(double *p, double x0, double x1, doub
 #else
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x0), "d"(x1), "d"(x2), "d"(x3) : "memory");
 #endif
+}
+// The value, but opaque to the optimiser: expressions derived from it are computed where they are used.  Without it the
+// compiler hoists every arm's address arithmetic (accumulator c of this thread, ...) to the head of the interpreter loop and
+// recomputes all of it for every interpreted instruction.
+__device__ __forceinline__ unsigned opaque(unsigned v) {
+#ifndef SPZ_CPU_EMULATION
+    asm volatile("" : "+r"(v));
+#endif
+    return v;
 }
 __device__ __forceinline__ void shear3(double &x, double &y, double t, double sn) {
     x = x - t * y;
@@ -324,7 +340,6 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
     double2 *gfac = reinterpret_cast<double2 *>(smem + kProgOff3 + a.blob_bytes);
     // F[c][tid]: accumulator c of this thread.  They live in shared memory (one 128-bit access each, conflict-free) rather
     // than in 20 registers: with 64 registers of amplitudes the budget of 128 is tight.
-    double2 *facc = reinterpret_cast<double2 *>(smem + 2u * kArrayBytes3) + threadIdx.x;
     unsigned char *skip = reinterpret_cast<unsigned char *>(gfac + a.n_groups);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(
         smem + ((kProgOff3 + a.blob_bytes + 16u * (unsigned)a.n_groups + (unsigned)a.n_ins + 15u) & ~15u)); // [0] tile, [1] program
@@ -385,7 +400,7 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
     const unsigned sbase = sm_addr(smem);
     const unsigned ins_addr = sbase + kProgOff3, pool_addr = ins_addr + a.ins_bytes, gfac_addr = ins_addr + a.blob_bytes;
     const unsigned skip_addr = gfac_addr + 16u * (unsigned)a.n_groups;
-    const unsigned arms_addr = ins_addr + a.arms_off; // the arm bytes of instructions 1, 2, ... (see tile3_pack)
+    const unsigned facc_addr = sbase + 2u * kArrayBytes3 + 16u * tid; // this thread's accumulator 0; accumulator c is 16 * kThreads3 * c further
     for (unsigned sg = tid; sg < (1u << a.n_high); sg += kThreads3) {
         unsigned long long o = 0;
 #pragma unroll
@@ -426,34 +441,34 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
         x = ((x >> r3) << (r3 + 1)) | (x & ((1u << r3) - 1u));
         return x;
     };
+    // (byte offsets inside the re array; the im array is kArrayBytes3 further; shared addresses, not generic pointers)
     auto move_regs = [&](auto &&xfer2, auto &&xfer1) {
         const int r0 = lay & 255u, r1 = (lay >> 8) & 255u, r2 = (lay >> 16) & 255u, r3 = lay >> 24;
-        const unsigned stj = swz3(thread_index(r0, r1, r2, r3));
-        const unsigned sw0 = swz3(1u << r0), sw1 = swz3(1u << r1), sw2 = swz3(1u << r2), sw3 = swz3(1u << r3);
+        const unsigned stj = 8u * swz3(thread_index(r0, r1, r2, r3));
+        const unsigned sw0 = 8u * swz3(1u << r0), sw1 = 8u * swz3(1u << r1), sw2 = 8u * swz3(1u << r2), sw3 = 8u * swz3(1u << r3);
         if (r0 == 0) { // register bit 0 is tile bit 0: amplitudes k, k + 1 are adjacent in shared memory (128-bit accesses)
 #pragma unroll
-            for (int k = 0; k < 16; k += 2) xfer2(k, stj ^ ((k & 2) ? sw1 : 0u) ^ ((k & 4) ? sw2 : 0u) ^ ((k & 8) ? sw3 : 0u));
+            for (int k = 0; k < 16; k += 2) xfer2(k, sbase + (stj ^ ((k & 2) ? sw1 : 0u) ^ ((k & 4) ? sw2 : 0u) ^ ((k & 8) ? sw3 : 0u)));
         } else {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) xfer1(k, stj ^ ((k & 1) ? sw0 : 0u) ^ ((k & 2) ? sw1 : 0u) ^ ((k & 4) ? sw2 : 0u) ^ ((k & 8) ? sw3 : 0u));
+            for (int k = 0; k < 16; ++k) xfer1(k, sbase + (stj ^ ((k & 1) ? sw0 : 0u) ^ ((k & 2) ? sw1 : 0u) ^ ((k & 4) ? sw2 : 0u) ^ ((k & 8) ? sw3 : 0u)));
         }
     };
     auto load_regs = [&]() {
         move_regs(
             [&](int k, unsigned s) {
-                const double2 r = *reinterpret_cast<const double2 *>(sre + s);
-                const double2 m = *reinterpret_cast<const double2 *>(sim + s);
+                const double2 r = lds_d2(s), m = lds_d2(s + kArrayBytes3);
                 ar[k] = r.x; ar[k + 1] = r.y; ai[k] = m.x; ai[k + 1] = m.y;
             },
-            [&](int k, unsigned s) { ar[k] = sre[s]; ai[k] = sim[s]; });
+            [&](int k, unsigned s) { ar[k] = lds_d(s); ai[k] = lds_d(s + kArrayBytes3); });
     };
     auto store_regs = [&]() {
         move_regs(
             [&](int k, unsigned s) {
-                *reinterpret_cast<double2 *>(sre + s) = make_double2(ar[k], ar[k + 1]);
-                *reinterpret_cast<double2 *>(sim + s) = make_double2(ai[k], ai[k + 1]);
+                sts_d2(s, ar[k], ar[k + 1]);
+                sts_d2(s + kArrayBytes3, ai[k], ai[k + 1]);
             },
-            [&](int k, unsigned s) { sre[s] = ar[k]; sim[s] = ai[k]; });
+            [&](int k, unsigned s) { sts_d(s, ar[k]); sts_d(s + kArrayBytes3, ai[k]); });
     };
     // Tile out: straight from the registers under the final layout.  The tile's shared-memory buffer is not involved, which is
     // what lets the NEXT tile's boxes land in it while this tile is still being computed (see prefetch below).  Lanes run over
@@ -489,25 +504,29 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
     };
     // apply the pending accumulators named by `mask` (the host knows which are pending: it is a property of the program,
     // so nothing is ever reset: an accumulator that has been applied is assigned, not multiplied, by its next update)
-    auto flush = [&](unsigned mask) {
+    // `cmask`: the classes whose pending factor is a constant the host folded (entry c of the five-entry table at shared address
+    // `tab`) instead of the thread's accumulator
+    auto flush = [&](unsigned mask, unsigned cmask, unsigned tab) {
         if (!mask) return;
+        const unsigned fa = opaque(facc_addr);
+        auto pending = [&](unsigned c) -> double2 { return lds_d2((cmask >> c) & 1u ? tab + 16u * c : fa + c * 16u * kThreads3); };
         if (__popc(mask) <= 2) {
             if (mask & 1u) {
-                const double2 f = facc[0];
+                const double2 f = pending(0);
 #pragma unroll
                 for (int k = 0; k < 16; ++k) cmul3(ar[k], ai[k], f.x, f.y);
             }
-            if (mask & 2u) apply_bit3<0>(ar, ai, facc[1 * kThreads3]);
-            if (mask & 4u) apply_bit3<1>(ar, ai, facc[2 * kThreads3]);
-            if (mask & 8u) apply_bit3<2>(ar, ai, facc[3 * kThreads3]);
-            if (mask & 16u) apply_bit3<3>(ar, ai, facc[4 * kThreads3]);
+            if (mask & 2u) apply_bit3<0>(ar, ai, pending(1));
+            if (mask & 4u) apply_bit3<1>(ar, ai, pending(2));
+            if (mask & 8u) apply_bit3<2>(ar, ai, pending(3));
+            if (mask & 16u) apply_bit3<3>(ar, ai, pending(4));
             return;
         }
         // three or more: expand the 16 per-amplitude factors (15 complex multiplies) and apply them once
         const double2 one = make_double2(1.0, 0.0);
-        const double2 f0 = (mask & 1u) ? facc[0] : one, f1 = (mask & 2u) ? facc[1 * kThreads3] : one;
-        const double2 f2 = (mask & 4u) ? facc[2 * kThreads3] : one, f3 = (mask & 8u) ? facc[3 * kThreads3] : one;
-        const double2 f4 = (mask & 16u) ? facc[4 * kThreads3] : one;
+        const double2 f0 = (mask & 1u) ? pending(0) : one, f1 = (mask & 2u) ? pending(1) : one;
+        const double2 f2 = (mask & 4u) ? pending(2) : one, f3 = (mask & 8u) ? pending(3) : one;
+        const double2 f4 = (mask & 16u) ? pending(4) : one;
 #pragma unroll
         for (int b3 = 0; b3 < 2; ++b3) {
             double g3r = f0.x, g3i = f0.y;
@@ -531,9 +550,9 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
         }
     };
     auto acc = [&](unsigned cls, bool set, double fr, double fi) {
-        double2 *f = facc + cls * kThreads3;
-        if (!set) { const double2 old = *f; cmul3(fr, fi, old.x, old.y); }
-        *f = make_double2(fr, fi);
+        const unsigned f = opaque(facc_addr) + cls * 16u * kThreads3;
+        if (!set) { const double2 old = lds_d2(f); cmul3(fr, fi, old.x, old.y); }
+        sts_d2(f, fr, fi);
     };
 
     // ---- the CTA's tiles (persistent: 2 CTAs per SM walk the pass) ----
@@ -599,7 +618,7 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
             }
 #endif
         }
-        facc[0] = make_double2(a.scale, 0.0); // F0 starts as the pass scale (pending from the start when it is not 1: the host knows)
+        sts_d2(facc_addr, a.scale, 0.0); // F0 starts as the pass scale (pending from the start when it is not 1: the host knows)
         __syncthreads(); // skip flags and constants in place (emulation: the tile too)
         stamp(1); // constants
 #ifndef SPZ_CPU_EMULATION
@@ -616,21 +635,21 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
         load_regs();
         if (a.single_layout) prefetch();
 
-        // The interpreter.  Dispatch needs one byte per instruction -- the arm -- and takes it from a register: the arm bytes are
-        // a stream of their own, fetched four at a time one word ahead.  An arm that has operands loads its own 16-byte
-        // instruction word; the hot ones (H on every pair, applying a pending accumulator) have none.  Everything is addressed
-        // by 32-bit shared addresses computed once.
-        unsigned armw = lds32(arms_addr), armn = lds32(arms_addr + 4u);
-        for (unsigned pc = 1;; ++pc) {
-            const unsigned arm = armw & 0xffu;
-            armw >>= 8;
-            if ((pc & 3u) == 0u) { armw = armn; armn = lds32(arms_addr + pc + 4u); } // arms[pc + 1 ..] now; arms[pc + 5 ..] in flight
-            // operand word of this instruction: x = arm | kind << 8 | class << 16 | flags << 24, y = pair mask | thread mask << 16,
-            // z = pool offset (doubles) / layout, w = per-tile constant index
-#define SPZ_W const uint4 w = lds128(ins_addr + 16u * pc)
+        // The interpreter.  Dispatch needs one byte per instruction -- the arm -- and takes it from a register: the first word of
+        // the NEXT instruction is fetched before the current one runs (the blob is padded, so the fetch past END reads zeros).
+        // An arm that has operands loads its own 16-byte instruction: x = arm | kind << 8 | class << 16 | flags << 24, y = pair
+        // mask | thread mask << 16, z = pool offset (doubles) / layout, w = per-tile constant index; the hot H on every pair has
+        // none.  Everything is addressed by 32-bit shared addresses computed once.  (The arms take nothing from the prefetched
+        // word but the arm byte: a second use would cost a register copy per interpreted instruction.)
+        unsigned ip = ins_addr + 16u;
+        unsigned xn = lds32(ip);
+        for (;; ip += 16u) {
+            const unsigned arm = xn & 0xffu;
+            xn = lds32(ip + 16u);
+#define SPZ_W const uint4 w = lds128(ip); const unsigned x = w.x
             // guarded GATE / ACCG / OTHER act on the threads whose control bits are set; a GATE also needs its controls outside
             // the tile.  The unguarded arms (no control of any kind: the host routes everything else to the guarded ones) test nothing.
-#define SPZ_OK(w) (((tid & ((w).y >> 16)) == ((w).y >> 16)) && !((((w).x >> 24) & GF_OUTER) && lds8(skip_addr + pc)))
+#define SPZ_OK(w) (((tid & ((w).y >> 16)) == ((w).y >> 16)) && !(((x >> 24) & GF_OUTER) && lds8(skip_addr + ((ip - ins_addr) >> 4))))
 #define SPZ_GATE_ALL(V, MK)                                                                                  \
     case T3_GATE + 4 * V + 0: { SPZ_W; bfly3<MK, 0, true>(ar, ai, pool_addr + 8u * w.z, 0xffffu); break; }   \
     case T3_GATE + 4 * V + 1: { SPZ_W; bfly3<MK, 1, true>(ar, ai, pool_addr + 8u * w.z, 0xffffu); break; }   \
@@ -641,6 +660,15 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
     case T3_GATE + 4 * V + 1: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 1, false>(ar, ai, pool_addr + 8u * w.z, w.y & 0xffffu); break; }      \
     case T3_GATE + 4 * V + 2: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 2, false>(ar, ai, pool_addr + 8u * w.z, w.y & 0xffffu); break; }      \
     case T3_GATE + 4 * V + 3: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 3, false>(ar, ai, pool_addr + 8u * w.z, w.y & 0xffffu); break; }
+            // Accumulator F_{r+1} -- or a constant of the pool, when the host folded the pending factor (AF_CONST) -- is pending
+            // and a butterfly on register bit r follows: apply it to the amplitudes with that bit set.  Only the accumulator of the
+            // target's own bit separates the two members of a pair; the others scale both by the same factor and stay pending.
+#define SPZ_PRE(R)                                                                                                                    \
+    case T3_PRE + R: {                                                                                                                \
+        SPZ_W;                                                                                                                        \
+        const unsigned src = ((x >> 24) & AF_CONST) ? pool_addr + 8u * w.z : opaque(facc_addr) + (R + 1) * 16u * kThreads3;           \
+        apply_bit3<R>(ar, ai, lds_d2(src));                                                                                           \
+        break; }
             switch (arm) {
             // H on every pair has no operand at all
             case T3_GATE + 0: bfly3<MK_H, 0, true>(ar, ai, 0u, 0xffffu); break;
@@ -654,39 +682,37 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
             SPZ_GATE_GUARDED(5, MK_RY)
             SPZ_GATE_GUARDED(6, MK_X)
             SPZ_GATE_GUARDED(7, MK_Y)
-            // Accumulator F_{r+1} is pending and a butterfly on register bit r follows: apply it to the amplitudes with that
-            // bit set.  Only the accumulator of the target's own bit separates the two members of a pair; the others scale
-            // both by the same factor and stay pending.
-            case T3_PRE + 0: apply_bit3<0>(ar, ai, facc[1 * kThreads3]); break;
-            case T3_PRE + 1: apply_bit3<1>(ar, ai, facc[2 * kThreads3]); break;
-            case T3_PRE + 2: apply_bit3<2>(ar, ai, facc[3 * kThreads3]); break;
-            case T3_PRE + 3: apply_bit3<3>(ar, ai, facc[4 * kThreads3]); break;
+            SPZ_PRE(0)
+            SPZ_PRE(1)
+            SPZ_PRE(2)
+            SPZ_PRE(3)
             case T3_ACC: {
                 SPZ_W;
-                const unsigned flags = w.x >> 24, tab = pool_addr + 8u * w.z;
+                const unsigned flags = x >> 24, tab = pool_addr + 8u * w.z;
                 double fr = 1.0, fi = 0.0;
-                if (flags & AF_LO) { const double2 x = lds_d2(tab + 16u * (tid & 15u)); fr = x.x; fi = x.y; }
-                if (flags & AF_HI) { const double2 x = lds_d2(tab + 256u + 16u * (tid >> 4)); cmul3(fr, fi, x.x, x.y); }
-                if (flags & AF_TILE) { const double2 x = lds_d2(gfac_addr + 16u * w.w); cmul3(fr, fi, x.x, x.y); }
-                acc((w.x >> 16) & 0xffu, flags & AF_SET, fr, fi);
+                if (flags & AF_LO) { const double2 v = lds_d2(tab + 16u * (tid & 15u)); fr = v.x; fi = v.y; }
+                if (flags & AF_HI) { const double2 v = lds_d2(tab + 256u + 16u * (tid >> 4)); cmul3(fr, fi, v.x, v.y); }
+                if (flags & AF_TILE) { const double2 v = lds_d2(gfac_addr + 16u * w.w); cmul3(fr, fi, v.x, v.y); }
+                acc((x >> 16) & 0xffu, flags & AF_SET, fr, fi);
                 break; }
             case T3_ACCG: { // a term that needs thread bits from both nibbles, or thread bits and bits outside the tile
                 SPZ_W;
-                const unsigned flags = w.x >> 24, cls = (w.x >> 16) & 0xffu;
+                const unsigned flags = x >> 24, cls = (x >> 16) & 0xffu;
                 const bool hit = SPZ_OK(w);
                 const unsigned src = (flags & AF_TILE) ? gfac_addr + 16u * w.w : pool_addr + 8u * w.z;
                 if (flags & AF_SET) {
                     // the accumulator held no pending factor: every thread assigns (nothing is ever reset, see flush)
-                    facc[cls * kThreads3] = hit ? lds_d2(src) : make_double2(1.0, 0.0);
+                    const double2 v = hit ? lds_d2(src) : make_double2(1.0, 0.0);
+                    sts_d2(opaque(facc_addr) + cls * 16u * kThreads3, v.x, v.y);
                 } else if (hit) {
-                    const double2 x = lds_d2(src);
-                    acc(cls, false, x.x, x.y);
+                    const double2 v = lds_d2(src);
+                    acc(cls, false, v.x, v.y);
                 }
                 break; }
             case T3_OTHER: { // a diagonal term over two or more register bits: applied at once to the amplitudes it selects
                 SPZ_W;
                 if (!SPZ_OK(w)) break;
-                const double2 f = lds_d2(((w.x >> 24) & AF_TILE) ? gfac_addr + 16u * w.w : pool_addr + 8u * w.z);
+                const double2 f = lds_d2(((x >> 24) & AF_TILE) ? gfac_addr + 16u * w.w : pool_addr + 8u * w.z);
                 const unsigned km = w.y & 0xffffu;
 #define SPZ_M4(A, B, C, D) cmul3(ar[A], ai[A], f.x, f.y); cmul3(ar[B], ai[B], f.x, f.y); cmul3(ar[C], ai[C], f.x, f.y); cmul3(ar[D], ai[D], f.x, f.y)
                 switch (km) {
@@ -706,24 +732,25 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
                 break; }
             case T3_LAYOUT: { // apply what is pending, then change the register-resident bits through shared memory
                 SPZ_W;
-                flush((w.x >> 24) & 31u);
+                flush((x >> 24) & 31u, w.y & 31u, pool_addr + 8u * w.w);
                 store_regs();
                 __syncthreads();
                 lay = w.z;
                 load_regs(); // no second barrier: this thread's next shared-memory access is store_regs() to the cells it has just read
-                if ((w.x >> 24) & LF_LAST) prefetch();
+                if ((x >> 24) & LF_LAST) prefetch();
                 break; }
             default: { // END
                 SPZ_W;
-                flush((w.x >> 24) & 31u);
-                break; }
+                flush((x >> 24) & 31u, w.y & 31u, pool_addr + 8u * w.w);
+                goto program_done; }
             }
 #undef SPZ_GATE_ALL
 #undef SPZ_GATE_GUARDED
+#undef SPZ_PRE
 #undef SPZ_OK
 #undef SPZ_W
-            if (arm == T3_END) break;
         }
+    program_done:
         stamp(3); // program interpreted
         direct_store(base);
         stamp(4); // stores issued
@@ -775,10 +802,48 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
     // contains `m` are multiplied by (fr, fi) ----
     struct Term { uint64_t outer; uint32_t thr, m; double fr, fi; };
     auto class_of = [](uint32_t m) { return m == 0 ? 0 : m == 1 ? 1 : m == 2 ? 2 : m == 4 ? 3 : m == 8 ? 4 : 5; };
+    // Factors that depend on nothing but a register bit (no thread bit, no bit outside the tile: an RZ or P on a register-resident
+    // qubit, the global phase of any RZ) are the same number for every thread of every tile, so the HOST accumulates them, one
+    // pending constant per class, and the device sees them once, where the class is consumed: as the operand of the PRE in front of
+    // a butterfly on that bit, or as one ACCG in front of a flush.  In a layered circuit that is a quarter of all instructions.
+    double hostK[5][2] = {{1.0, 0.0}, {1.0, 0.0}, {1.0, 0.0}, {1.0, 0.0}, {1.0, 0.0}};
+    bool kpend[5] = {false, false, false, false, false};
+    auto fold_const = [&](int cls) { // the pending constant of a class joins its accumulator
+        if (!kpend[cls]) return;
+        Ins3 i{};
+        i.op = T3_ACCG;
+        i.rpos = (uint8_t)cls;
+        i.flags = AF_CONST;
+        i.a = pool2(hostK[cls][0], hostK[cls][1]);
+        if (!(dirty & (1u << cls))) i.flags |= AF_SET;
+        dirty |= 1u << cls;
+        push(i, 0);
+        hostK[cls][0] = 1.0; hostK[cls][1] = 0.0; kpend[cls] = false;
+    };
+    // LAYOUT / END apply everything that is pending: flags = the classes, km = those of them whose factor is a host constant
+    // (a class with both: the constant joins the accumulator first), b = the five-entry constant table in the pool
+    auto flush_operands = [&](Ins3 &i) {
+        unsigned cmask = 0;
+        for (int cls = 0; cls < 5; ++cls) {
+            if (kpend[cls] && (dirty & (1u << cls))) fold_const(cls);
+            if (kpend[cls]) cmask |= 1u << cls;
+        }
+        i.flags = (uint8_t)(dirty | cmask);
+        i.km = (uint16_t)cmask;
+        if (cmask) {
+            i.b = pool2(hostK[0][0], hostK[0][1]);
+            for (int cls = 1; cls < 5; ++cls) pool2(hostK[cls][0], hostK[cls][1]);
+            for (int cls = 0; cls < 5; ++cls) { hostK[cls][0] = 1.0; hostK[cls][1] = 0.0; kpend[cls] = false; }
+        }
+    };
     auto emit_terms = [&](const std::vector<Term> &all) {
         for (int cls = 0; cls < 6; ++cls) {
             std::vector<Term> ts;
-            for (const Term &x : all) if (class_of(x.m) == cls) ts.push_back(x);
+            for (const Term &x : all) {
+                if (class_of(x.m) != cls) continue;
+                if (cls < 5 && x.outer == 0 && x.thr == 0) { cmul_h(hostK[cls][0], hostK[cls][1], x.fr, x.fi); kpend[cls] = true; continue; }
+                ts.push_back(x);
+            }
             if (ts.empty()) continue;
             if (cls < 5) {
                 double lo[16][2], hi[16][2];
@@ -933,7 +998,8 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
         if (t.op == TI_LAYOUT) {
             Ins3 i{};
             i.op = T3_LAYOUT;
-            i.flags = (uint8_t)dirty;
+            if (pc > 0) flush_operands(i);
+            else i.flags = (uint8_t)dirty;
             for (int k = 0; k < 4; ++k) { R[k] = t.rbit[k]; if (R[k] < 0 || R[k] >= kT3 || (k && R[k] <= R[k - 1])) return false; }
             i.a = (uint32_t)R[0] | ((uint32_t)R[1] << 8) | ((uint32_t)R[2] << 16) | ((uint32_t)R[3] << 24);
             if (pc > 0) dirty = 0;
@@ -952,10 +1018,19 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
             if (v.ctrl_sign) before.push_back(Term{t.outer_cmask, thr, t.reg_cmask, -1.0, 0.0});
             if (v.post) after.push_back(Term{t.outer_cmask, thr, t.reg_cmask | tbit, v.post_f[0], v.post_f[1]});
             if (!before.empty()) emit_terms(before);
-            if (dirty & (2u << t.rpos)) { // the accumulator of the target's own register bit is pending: apply it first
+            // the factor pending on the target's own register bit is applied first: the class's accumulator, or the host's constant
+            // (both: the constant joins the accumulator)
+            if (kpend[t.rpos + 1] && (dirty & (2u << t.rpos))) fold_const(t.rpos + 1);
+            if (kpend[t.rpos + 1] || (dirty & (2u << t.rpos))) {
                 Ins3 p{};
                 p.op = (uint8_t)(T3_PRE + t.rpos);
                 p.rpos = (uint8_t)t.rpos;
+                if (kpend[t.rpos + 1]) {
+                    double (&K)[2] = hostK[t.rpos + 1];
+                    p.flags = AF_CONST;
+                    p.a = pool2(K[0], K[1]);
+                    K[0] = 1.0; K[1] = 0.0; kpend[t.rpos + 1] = false;
+                }
                 push(p, 0);
                 dirty &= ~(2u << t.rpos);
             }
@@ -1001,7 +1076,7 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
     }
     Ins3 e{};
     e.op = T3_END;
-    e.flags = (uint8_t)dirty;
+    flush_operands(e);
     push(e, 0);
     for (size_t k = out.ins.size(); k-- > 1;)
         if (out.ins[k].op == T3_LAYOUT) { out.ins[k].flags |= LF_LAST; out.single_layout = false; break; }
@@ -1019,8 +1094,7 @@ size_t tile3_pack(const Lowered3 &lw, const TilePlan &plan, std::vector<unsigned
     const size_t outer_off = ins_bytes + pool_bytes;
     const size_t groups_off = up16(outer_off + lw.outer.size() * sizeof(uint64_t));
     const size_t terms_off = up16(groups_off + lw.groups.size() * sizeof(TileGroup));
-    const size_t arms_off = up16(terms_off + lw.terms.size() * sizeof(TileTerm));
-    const size_t total = up16(arms_off + lw.ins.size() + 8); // arm stream: byte j = arm of instruction j + 1; zero (END) padded, read two words ahead
+    const size_t total = up16(terms_off + lw.terms.size() * sizeof(TileTerm)) + 16; // (the interpreter prefetches one word past END)
     blob.assign(total, 0);
     std::memcpy(blob.data(), lw.ins.data(), lw.ins.size() * sizeof(Ins3));
     if (!lw.pool.empty()) std::memcpy(blob.data() + ins_bytes, lw.pool.data(), lw.pool.size() * sizeof(double));
@@ -1028,8 +1102,7 @@ size_t tile3_pack(const Lowered3 &lw, const TilePlan &plan, std::vector<unsigned
     if (!lw.groups.empty()) std::memcpy(blob.data() + groups_off, lw.groups.data(), lw.groups.size() * sizeof(TileGroup));
     if (!lw.terms.empty()) std::memcpy(blob.data() + terms_off, lw.terms.data(), lw.terms.size() * sizeof(TileTerm));
     a.ins_bytes = (unsigned)ins_bytes; a.blob_bytes = (unsigned)total;
-    for (size_t j = 1; j < lw.ins.size(); ++j) blob[arms_off + j - 1] = lw.ins[j].op;
-    a.outer_off = (unsigned)outer_off; a.groups_off = (unsigned)groups_off; a.terms_off = (unsigned)terms_off; a.arms_off = (unsigned)arms_off;
+    a.outer_off = (unsigned)outer_off; a.groups_off = (unsigned)groups_off; a.terms_off = (unsigned)terms_off;
     a.n_ins = (int)lw.ins.size(); a.n_groups = (int)lw.groups.size(); a.n_terms = (int)lw.terms.size();
     a.scale = lw.scale;
     a.single_layout = lw.single_layout ? 1 : 0;

@@ -114,6 +114,20 @@ extern "C" long long emu_tile3_smem(int n_qubits, const void *blob, long long bl
     return (long long)spz::tile3_smem_bytes(a);
 }
 
+// The lowered k_tile3 program of one pass, for tools/dump_tile3.py: copies up to max_ins 16-byte instructions, returns their
+// number (-1: parse error, 0: the lowering refuses the pass).  info <- {in-tile control, instructions, groups, terms}.
+extern "C" int emu_tile3_dump(int n_qubits, const void *blob, long long blob_bytes, void *out_ins, int max_ins, int *info) {
+    Program P;
+    if (parse(blob, blob_bytes, P)) return -1;
+    if (!spz::tile3_shape_ok(n_qubits, P.plan)) return 0;
+    spz::Lowered3 lw;
+    if (!spz::tile3_lower(P.plan, P.prog.data(), P.ni, P.groups.data(), P.ng, P.terms.data(), P.nt, lw)) return 0;
+    const int n = (int)lw.ins.size() < max_ins ? (int)lw.ins.size() : max_ins;
+    std::memcpy(out_ins, lw.ins.data(), (size_t)n * sizeof(spz::Ins3));
+    info[0] = lw.ctrl ? 1 : 0; info[1] = (int)lw.ins.size(); info[2] = (int)lw.groups.size(); info[3] = (int)lw.terms.size();
+    return n;
+}
+
 // k_tile, with the arguments launch_tile_program (kernels_tile.cu) builds.  prog_in_smem: 0 decodes from "global" memory.
 extern "C" int emu_tile1_run(int n_qubits, double *re, double *im, const void *blob, long long blob_bytes, int exact, int prog_in_smem) {
     Program P;
