@@ -83,10 +83,14 @@ struct Ins3 {
                                    // LAYOUT / END flags: pending accumulators
     uint16_t km;                   // GATE: pair mask over k0.  OTHER: register mask m
     uint16_t thr;                  // GATE / ACCG / OTHER: control bits in THREAD-ID space (8 bits)
-    uint32_t a;                    // LAYOUT: the 4 register-resident tile bits, one byte each.  else: pool offset (see flags)
-    uint32_t b;                    // per-tile constant index
+    uint32_t a;                    // LAYOUT: the 4 register-resident tile bits, one byte each.  ACC: pool offset of its tables
+    uint32_t b;                    // per-tile constant index (LAYOUT / END: pool offset of the pending-constant table)
+    double s[2];                   // the instruction's own scalars: a rotation's (tan, sin), the constant of a PRE / ACCG / OTHER
+                                   // with AF_CONST -- in the instruction, so that an arm's operand is ONE load at a known address
+                                   // (through the pool it was instruction word -> address -> scalars: two dependent loads)
 };
-static_assert(sizeof(Ins3) == 16, "Ins3 is decoded with one 128-bit shared-memory load");
+static_assert(sizeof(Ins3) == 32, "Ins3 is decoded with 128-bit shared-memory loads: operand words at +0, scalars at +16");
+constexpr unsigned kIns3 = 32;
 
 // What the host uploads for one pass (one contiguous blob, 16-byte aligned sections):
 //   Ins3 ins[n_ins] | double pool[n_pool] (gate scalars, tables, constants; double2 entries at even offsets)
@@ -400,7 +404,9 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
     const unsigned sbase = sm_addr(smem);
     const unsigned ins_addr = sbase + kProgOff3, pool_addr = ins_addr + a.ins_bytes, gfac_addr = ins_addr + a.blob_bytes;
     const unsigned skip_addr = gfac_addr + 16u * (unsigned)a.n_groups;
-    const unsigned facc_addr = sbase + 2u * kArrayBytes3 + 16u * tid; // this thread's accumulator 0; accumulator c is 16 * kThreads3 * c further
+    // this thread's accumulator 0; accumulator c is 16 * kThreads3 * c further.  (facc_base + 16 * opaque(tid) inside the interpreter:
+    // two instructions in the arm that needs them instead of three at the head of the loop for every instruction.)
+    const unsigned facc_base = sbase + 2u * kArrayBytes3, facc_addr = facc_base + 16u * tid;
     for (unsigned sg = tid; sg < (1u << a.n_high); sg += kThreads3) {
         unsigned long long o = 0;
 #pragma unroll
@@ -508,7 +514,7 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
     // `tab`) instead of the thread's accumulator
     auto flush = [&](unsigned mask, unsigned cmask, unsigned tab) {
         if (!mask) return;
-        const unsigned fa = opaque(facc_addr);
+        const unsigned fa = (facc_base + 16u * opaque(tid));
         auto pending = [&](unsigned c) -> double2 { return lds_d2((cmask >> c) & 1u ? tab + 16u * c : fa + c * 16u * kThreads3); };
         if (__popc(mask) <= 2) {
             if (mask & 1u) {
@@ -550,7 +556,7 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
         }
     };
     auto acc = [&](unsigned cls, bool set, double fr, double fi) {
-        const unsigned f = opaque(facc_addr) + cls * 16u * kThreads3;
+        const unsigned f = (facc_base + 16u * opaque(tid)) + cls * 16u * kThreads3;
         if (!set) { const double2 old = lds_d2(f); cmul3(fr, fi, old.x, old.y); }
         sts_d2(f, fr, fi);
     };
@@ -641,34 +647,40 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
         // mask | thread mask << 16, z = pool offset (doubles) / layout, w = per-tile constant index; the hot H on every pair has
         // none.  Everything is addressed by 32-bit shared addresses computed once.  (The arms take nothing from the prefetched
         // word but the arm byte: a second use would cost a register copy per interpreted instruction.)
-        unsigned ip = ins_addr + 16u;
+        unsigned ip = ins_addr + kIns3;
         unsigned xn = lds32(ip);
-        for (;; ip += 16u) {
+        for (;; ip += kIns3) {
             const unsigned arm = xn & 0xffu;
-            xn = lds32(ip + 16u);
+            xn = lds32(ip + kIns3);
 #define SPZ_W const uint4 w = lds128(ip); const unsigned x = w.x
             // guarded GATE / ACCG / OTHER act on the threads whose control bits are set; a GATE also needs its controls outside
             // the tile.  The unguarded arms (no control of any kind: the host routes everything else to the guarded ones) test nothing.
-#define SPZ_OK(w) (((tid & ((w).y >> 16)) == ((w).y >> 16)) && !(((x >> 24) & GF_OUTER) && lds8(skip_addr + ((ip - ins_addr) >> 4))))
+#define SPZ_OK(w) (((tid & ((w).y >> 16)) == ((w).y >> 16)) && !(((x >> 24) & GF_OUTER) && lds8(skip_addr + ((ip - ins_addr) >> 5))))
 #define SPZ_GATE_ALL(V, MK)                                                                                  \
-    case T3_GATE + 4 * V + 0: { SPZ_W; bfly3<MK, 0, true>(ar, ai, pool_addr + 8u * w.z, 0xffffu); break; }   \
-    case T3_GATE + 4 * V + 1: { SPZ_W; bfly3<MK, 1, true>(ar, ai, pool_addr + 8u * w.z, 0xffffu); break; }   \
-    case T3_GATE + 4 * V + 2: { SPZ_W; bfly3<MK, 2, true>(ar, ai, pool_addr + 8u * w.z, 0xffffu); break; }   \
-    case T3_GATE + 4 * V + 3: { SPZ_W; bfly3<MK, 3, true>(ar, ai, pool_addr + 8u * w.z, 0xffffu); break; }
+    case T3_GATE + 4 * V + 0: { bfly3<MK, 0, true>(ar, ai, ip + 16u, 0xffffu); break; }             \
+    case T3_GATE + 4 * V + 1: { bfly3<MK, 1, true>(ar, ai, ip + 16u, 0xffffu); break; }             \
+    case T3_GATE + 4 * V + 2: { bfly3<MK, 2, true>(ar, ai, ip + 16u, 0xffffu); break; }             \
+    case T3_GATE + 4 * V + 3: { bfly3<MK, 3, true>(ar, ai, ip + 16u, 0xffffu); break; }          
 #define SPZ_GATE_GUARDED(V, MK)                                                                                                       \
-    case T3_GATE + 4 * V + 0: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 0, false>(ar, ai, pool_addr + 8u * w.z, w.y & 0xffffu); break; }      \
-    case T3_GATE + 4 * V + 1: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 1, false>(ar, ai, pool_addr + 8u * w.z, w.y & 0xffffu); break; }      \
-    case T3_GATE + 4 * V + 2: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 2, false>(ar, ai, pool_addr + 8u * w.z, w.y & 0xffffu); break; }      \
-    case T3_GATE + 4 * V + 3: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 3, false>(ar, ai, pool_addr + 8u * w.z, w.y & 0xffffu); break; }
+    case T3_GATE + 4 * V + 0: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 0, false>(ar, ai, ip + 16u, w.y & 0xffffu); break; }      \
+    case T3_GATE + 4 * V + 1: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 1, false>(ar, ai, ip + 16u, w.y & 0xffffu); break; }      \
+    case T3_GATE + 4 * V + 2: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 2, false>(ar, ai, ip + 16u, w.y & 0xffffu); break; }      \
+    case T3_GATE + 4 * V + 3: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 3, false>(ar, ai, ip + 16u, w.y & 0xffffu); break; }
             // Accumulator F_{r+1} -- or a constant of the pool, when the host folded the pending factor (AF_CONST) -- is pending
             // and a butterfly on register bit r follows: apply it to the amplitudes with that bit set.  Only the accumulator of the
             // target's own bit separates the two members of a pair; the others scale both by the same factor and stay pending.
 #define SPZ_PRE(R)                                                                                                                    \
     case T3_PRE + R: {                                                                                                                \
         SPZ_W;                                                                                                                        \
-        const unsigned src = ((x >> 24) & AF_CONST) ? pool_addr + 8u * w.z : opaque(facc_addr) + (R + 1) * 16u * kThreads3;           \
+        const unsigned src = ((x >> 24) & AF_CONST) ? ip + 16u : (facc_base + 16u * opaque(tid)) + (R + 1) * 16u * kThreads3;                      \
         apply_bit3<R>(ar, ai, lds_d2(src));                                                                                           \
         break; }
+            // nvcc lowers a switch to a tree of compares and branches, never to a jump table; the build rewrites the tree that
+            // follows this marker into one indirect branch (brx.idx / BRX) in the PTX: spinoza_b200/ptx_jump_table.py
+#ifndef SPZ_CPU_EMULATION
+            asm volatile("// SPZ_JUMP_TABLE 41");
+#endif
+            static_assert(T3_N_ARMS == 41, "the jump-table marker above carries the number of arms");
             switch (arm) {
             // H on every pair has no operand at all
             case T3_GATE + 0: bfly3<MK_H, 0, true>(ar, ai, 0u, 0xffffu); break;
@@ -699,11 +711,11 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
                 SPZ_W;
                 const unsigned flags = x >> 24, cls = (x >> 16) & 0xffu;
                 const bool hit = SPZ_OK(w);
-                const unsigned src = (flags & AF_TILE) ? gfac_addr + 16u * w.w : pool_addr + 8u * w.z;
+                const unsigned src = (flags & AF_TILE) ? gfac_addr + 16u * w.w : ip + 16u;
                 if (flags & AF_SET) {
                     // the accumulator held no pending factor: every thread assigns (nothing is ever reset, see flush)
                     const double2 v = hit ? lds_d2(src) : make_double2(1.0, 0.0);
-                    sts_d2(opaque(facc_addr) + cls * 16u * kThreads3, v.x, v.y);
+                    sts_d2((facc_base + 16u * opaque(tid)) + cls * 16u * kThreads3, v.x, v.y);
                 } else if (hit) {
                     const double2 v = lds_d2(src);
                     acc(cls, false, v.x, v.y);
@@ -712,7 +724,7 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
             case T3_OTHER: { // a diagonal term over two or more register bits: applied at once to the amplitudes it selects
                 SPZ_W;
                 if (!SPZ_OK(w)) break;
-                const double2 f = lds_d2(((x >> 24) & AF_TILE) ? gfac_addr + 16u * w.w : pool_addr + 8u * w.z);
+                const double2 f = lds_d2(((x >> 24) & AF_TILE) ? gfac_addr + 16u * w.w : ip + 16u);
                 const unsigned km = w.y & 0xffffu;
 #define SPZ_M4(A, B, C, D) cmul3(ar[A], ai[A], f.x, f.y); cmul3(ar[B], ai[B], f.x, f.y); cmul3(ar[C], ai[C], f.x, f.y); cmul3(ar[D], ai[D], f.x, f.y)
                 switch (km) {
@@ -814,7 +826,7 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
         i.op = T3_ACCG;
         i.rpos = (uint8_t)cls;
         i.flags = AF_CONST;
-        i.a = pool2(hostK[cls][0], hostK[cls][1]);
+        i.s[0] = hostK[cls][0]; i.s[1] = hostK[cls][1];
         if (!(dirty & (1u << cls))) i.flags |= AF_SET;
         dirty |= 1u << cls;
         push(i, 0);
@@ -900,7 +912,7 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
                     else {
                         double fr = 1.0, fi = 0.0;
                         for (const TileTerm &x : gp.second) cmul_h(fr, fi, x.fr, x.fi);
-                        i.flags |= AF_CONST; i.a = pool2(fr, fi);
+                        i.flags |= AF_CONST; i.s[0] = fr; i.s[1] = fi;
                     }
                     if (!(dirty & (1u << cls))) i.flags |= AF_SET;
                     dirty |= 1u << cls;
@@ -926,7 +938,7 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
                     else {
                         double fr = 1.0, fi = 0.0;
                         for (const TileTerm &x : gp.second) cmul_h(fr, fi, x.fr, x.fi);
-                        i.flags |= AF_CONST; i.a = pool2(fr, fi);
+                        i.flags |= AF_CONST; i.s[0] = fr; i.s[1] = fi;
                     }
                     push(i, 0);
                 }
@@ -1028,7 +1040,7 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
                 if (kpend[t.rpos + 1]) {
                     double (&K)[2] = hostK[t.rpos + 1];
                     p.flags = AF_CONST;
-                    p.a = pool2(K[0], K[1]);
+                    p.s[0] = K[0]; p.s[1] = K[1];
                     K[0] = 1.0; K[1] = 0.0; kpend[t.rpos + 1] = false;
                 }
                 push(p, 0);
@@ -1053,7 +1065,7 @@ bool tile3_lower(const TilePlan &plan, const TileInstr *prog, int n_instr, const
                 variant = v.kind == MK_HS ? 3 : v.kind == MK_RX ? 4 : v.kind == MK_RY ? 5 : v.kind == MK_X ? 6 : 7;
             }
             i.op = (uint8_t)(T3_GATE + 4 * variant + t.rpos);
-            if (v.ns) { i.a = pool2(v.s[0], v.s[1]); }
+            if (v.ns) { i.s[0] = v.s[0]; i.s[1] = v.s[1]; }
             push(i, t.outer_cmask);
             if (!after.empty()) emit_terms(after);
             continue;
@@ -1094,7 +1106,7 @@ size_t tile3_pack(const Lowered3 &lw, const TilePlan &plan, std::vector<unsigned
     const size_t outer_off = ins_bytes + pool_bytes;
     const size_t groups_off = up16(outer_off + lw.outer.size() * sizeof(uint64_t));
     const size_t terms_off = up16(groups_off + lw.groups.size() * sizeof(TileGroup));
-    const size_t total = up16(terms_off + lw.terms.size() * sizeof(TileTerm)) + 16; // (the interpreter prefetches one word past END)
+    const size_t total = up16(terms_off + lw.terms.size() * sizeof(TileTerm)) + kIns3; // (the interpreter prefetches one word past END)
     blob.assign(total, 0);
     std::memcpy(blob.data(), lw.ins.data(), lw.ins.size() * sizeof(Ins3));
     if (!lw.pool.empty()) std::memcpy(blob.data() + ins_bytes, lw.pool.data(), lw.pool.size() * sizeof(double));
