@@ -23,12 +23,13 @@
 namespace spz {
 
 constexpr int kMaxRanks = 16;
+constexpr int kMaxChunks = 8;
 constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 struct CtrlBlock { // lives in device memory of each rank, mapped by every peer
     unsigned long long ready[kMaxRanks];
     unsigned long long done[kMaxRanks];
-    unsigned long long done1[kMaxRanks]; // second chunk of an overlapped exchange
+    unsigned long long done_k[kMaxChunks][kMaxRanks]; // chunk k of an overlapped exchange has landed
     unsigned long long red_epoch[2][kMaxRanks];
     double red_slot[2][kMaxRanks];
     double red_result;
@@ -53,12 +54,15 @@ struct DistCtx {
     CtrlBlock **d_table = nullptr; // device copy of peer_ctrl[] for k_allreduce
     bool connected = false, ipc = false;
     unsigned long long epoch = 0, red_epoch = 0;
-    // overlapped exchange (second stream): the shard is exchanged in two halves split by local bit `split_bit`; the
-    // fused pass that follows starts on half 0 while half 1 is still on the wire
+    // overlapped exchange (second stream): the shard is exchanged in n_chunks chunks along the top bits of the pair list (the
+    // top local bits that are not the traded one); the consumer that follows -- a fused pass or a one-gate pass -- starts on
+    // chunk 0 while the others are still on the wire
     cudaStream_t xstream = nullptr;
-    cudaEvent_t ev_main = nullptr, ev_half[2] = {nullptr, nullptr};
+    cudaEvent_t ev_main = nullptr, ev_chunk[kMaxChunks] = {};
     bool split_pending = false;
-    int split_bit = -1;
+    int split_chunks = 0;      // chunks of the exchange in flight
+    int split_lq = -1;         // the local bit it trades: the chunks are contiguous ranges of the shard iff it is below the chunk bits
+    int n_chunks = 4;          // SPZ_XCHG_CHUNKS (1, 2, 4 or 8)
     bool overlap = true;
     int xchg_ctas = 40; // CTAs of the persistent exchange kernel in overlapped mode (SPZ_XCHG_CTAS)
     // fused exchange + gate (opt-in, SPZ_DIST_FUSE_GATE=1): flag values already used, and the size of its persistent grid
@@ -303,31 +307,31 @@ int dist_exchange(spz_state *st, int gbit, int lq) {
         if (vec) k_exchange_vec<W, U, THREADS><<<(unsigned)((cnt + per - 1) / per), THREADS, 0, stream>>>(r);
         else k_exchange_scalar<<<(unsigned)std::max<long long>(1, std::min<long long>((cnt + 255) / 256, 148 * 8)), 256, 0, stream>>>(r);
     };
-    // The top bit of the pair-list index is the top local bit that is not lq: halves of the pair list are halves of
-    // the shard along that bit.  Overlapped mode needs a vector path and at least 4 vectors per half.
-    const int top = (lq == n_local - 1) ? n_local - 2 : n_local - 1;
-    if (c->overlap && vec && nvec >= 64 && top >= 0) {
-        // stream X: [ready handshake] [half 0: my quarter] [done0 handshake] ev_half[0] [half 1] [done1] ev_half[1]
+    // The top bits of the pair-list index are the top local bits that are not lq: chunks of the pair list are chunks of the
+    // shard along those bits.  Overlapped mode needs a vector path and enough vectors per chunk.
+    int K = c->n_chunks;
+    while (K > 1 && nvec < 64ll * K) K >>= 1;
+    if (c->overlap && vec && nvec >= 64 && n_local >= 2) {
+        // stream X: [ready handshake] { [chunk k: my half of it] [done_k handshake] ev_chunk[k] } for k = 0 .. K-1
         SPZ_CUDA(cudaEventRecord(c->ev_main, st->stream));
         SPZ_CUDA(cudaStreamWaitEvent(c->xstream, c->ev_main, 0));
         k_handshake<<<1, 1, 0, c->xstream>>>(&c->peer_ctrl[partner]->ready[c->rank], &c->ctrl->ready[partner], e, &c->ctrl->error);
         SPZ_CUDA(cudaEventRecord(ev.first, c->xstream));
-        for (int h = 0; h < 2; ++h) {
-            const long long hb = h * (nvec / 2) + my_bit * (nvec / 4);
+        for (int h = 0; h < K; ++h) {
+            const long long hb = h * (nvec / K) + my_bit * (nvec / (2 * K));
             XArgs r = a;
-            r.nvec_begin = hb; r.nvec_end = hb + nvec / 4;
+            r.nvec_begin = hb; r.nvec_end = hb + nvec / (2 * K);
             k_exchange_vec_persistent<W, U, THREADS><<<(unsigned)c->xchg_ctas, THREADS, 0, c->xstream>>>(r);
-            unsigned long long *peer_done = h ? &c->peer_ctrl[partner]->done1[c->rank] : &c->peer_ctrl[partner]->done[c->rank];
-            const unsigned long long *my_done = h ? &c->ctrl->done1[partner] : &c->ctrl->done[partner];
-            k_handshake<<<1, 1, 0, c->xstream>>>(peer_done, my_done, e, &c->ctrl->error);
-            if (h == 1) SPZ_CUDA(cudaEventRecord(ev.second, c->xstream));
-            SPZ_CUDA(cudaEventRecord(c->ev_half[h], c->xstream));
+            k_handshake<<<1, 1, 0, c->xstream>>>(&c->peer_ctrl[partner]->done_k[h][c->rank], &c->ctrl->done_k[h][partner], e, &c->ctrl->error);
+            if (h == K - 1) SPZ_CUDA(cudaEventRecord(ev.second, c->xstream));
+            SPZ_CUDA(cudaEventRecord(c->ev_chunk[h], c->xstream));
         }
         c->pending.push_back(ev);
         c->split_pending = true;
-        c->split_bit = top;
+        c->split_chunks = K;
+        c->split_lq = lq;
         c->n_overlapped += 1;
-        count_launch(5);
+        count_launch(1 + 2 * K);
     } else {
         k_handshake<<<1, 1, 0, st->stream>>>(&c->peer_ctrl[partner]->ready[c->rank], &c->ctrl->ready[partner], e, &c->ctrl->error);
         SPZ_CUDA(cudaEventRecord(ev.first, st->stream));
@@ -411,17 +415,27 @@ bool dist_can_fuse_gate(const spz_state *st, int kind, uint64_t logical_cmask, i
 int dist_join(spz_state *st) {
     DistCtx *c = ctx_of(st);
     if (!c || !c->split_pending) return SPZ_OK;
-    SPZ_CUDA(cudaStreamWaitEvent(st->stream, c->ev_half[1], 0));
+    SPZ_CUDA(cudaStreamWaitEvent(st->stream, c->ev_chunk[c->split_chunks - 1], 0));
     c->split_pending = false;
     return SPZ_OK;
 }
 
-// For the tile pass that directly follows an overlapped exchange: returns the two events to wait for and the local
-// bit that separates the halves; the caller launches half 0 after ev[0] and half 1 after ev[1].
-bool dist_take_split(spz_state *st, int *split_bit, cudaEvent_t *ev0, cudaEvent_t *ev1) {
+// For the consumer that directly follows an overlapped exchange.  The exchange lands in *n_chunks chunks; when they are
+// contiguous ranges of the shard (the traded bit lies below the chunk bits) chunk k is amplitudes [k, k + 1) * len / n_chunks and
+// ev[k] fires when it is complete on this rank, so the caller may work on it while the later ones are on the wire.  Returns false
+// when nothing is in flight.  When the chunks are not contiguous ranges *n_chunks is 1 and ev[0] is the last event (a plain join).
+bool dist_take_chunks(spz_state *st, int *n_chunks, cudaEvent_t *ev) {
     DistCtx *c = ctx_of(st);
     if (!c || !c->split_pending) return false;
-    *split_bit = c->split_bit; *ev0 = c->ev_half[0]; *ev1 = c->ev_half[1];
+    int K = c->split_chunks, bits = 0;
+    while ((1 << bits) < K) ++bits;
+    if (c->split_lq >= st->n - bits) { // the traded bit is one of the top bits: report the whole exchange as one chunk
+        *n_chunks = 1;
+        ev[0] = c->ev_chunk[K - 1];
+    } else {
+        *n_chunks = K;
+        for (int k = 0; k < K; ++k) ev[k] = c->ev_chunk[k];
+    }
     c->split_pending = false;
     return true;
 }
@@ -609,8 +623,7 @@ void dist_destroy(spz_state *st) {
     for (auto &e : c->free_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (c->xstream) { cudaStreamSynchronize(c->xstream); cudaStreamDestroy(c->xstream); }
     if (c->ev_main) cudaEventDestroy(c->ev_main);
-    if (c->ev_half[0]) cudaEventDestroy(c->ev_half[0]);
-    if (c->ev_half[1]) cudaEventDestroy(c->ev_half[1]);
+    for (int k = 0; k < kMaxChunks; ++k) if (c->ev_chunk[k]) cudaEventDestroy(c->ev_chunk[k]);
     cudaFree(c->d_table);
     cudaFree(c->ctrl);
     delete c;
@@ -650,8 +663,8 @@ int spz_dist_create(int n_qubits, int rank, int world, int device, spz_state **o
         e = cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, hi);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_half[0], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_half[1], cudaEventDisableTiming);
+    for (int k = 0; k < kMaxChunks; ++k) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_chunk[k], cudaEventDisableTiming);
+    if (const char *v = getenv("SPZ_XCHG_CHUNKS")) { const int k = atoi(v); if (k == 1 || k == 2 || k == 4 || k == 8) c->n_chunks = k; }
     if (getenv("SPZ_NO_OVERLAP")) c->overlap = false;
     if (const char *v = getenv("SPZ_XCHG_CTAS")) { const int k = atoi(v); if (k >= 1 && k <= 1024) c->xchg_ctas = k; }
     if (const char *v = getenv("SPZ_XG_CTAS")) { const int k = atoi(v); if (k >= 1 && k <= kMaxXgCtas) c->xg_ctas = k; }

@@ -171,7 +171,7 @@ int dist_exchange(spz_state *st, int gbit, int lq);
 bool dist_can_fuse_gate(const spz_state *st, int kind, uint64_t logical_cmask, int target, int lq);
 int dist_exchange_gate(spz_state *st, int gbit, int lq, const GateK &g);
 int dist_join(spz_state *st); // main stream waits for an overlapped exchange still in flight
-bool dist_take_split(spz_state *st, int *split_bit, cudaEvent_t *ev0, cudaEvent_t *ev1);
+bool dist_take_chunks(spz_state *st, int *n_chunks, cudaEvent_t *ev); // ev: room for 8 (see dist.cu)
 inline int join_pending(spz_state *st) { return st->dist ? dist_join(st) : SPZ_OK; }
 int dist_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int hi);
 int dist_reduce_scalar(spz_state *st, int mode, int target, double *out);

@@ -63,9 +63,40 @@ static void dispatch_kind(bool low, const PairArgs &a, cudaStream_t s) {
     }
 }
 
+static int launch_gate_on(spz_state *st, double *re, double *im, int n, const GateK &g, uint64_t ctrl_mask, int target);
+
 int launch_gate(spz_state *st, const GateK &g, uint64_t ctrl_mask, int target) {
+#ifndef SPZ_CPU_EMULATION
+    // Directly after an overlapped exchange (dist.cu) the shard lands in K contiguous chunks.  A gate whose target and controls
+    // lie below the chunk bits acts on every chunk separately -- a chunk is a register of n - log2(K) qubits at an offset -- so it
+    // runs chunk by chunk behind the wire: the one-gate pass that asked for the exchange costs 1/K of its time on top of it.
+    int K = 0;
+    cudaEvent_t ev[8] = {};
+    if (st->dist && dist_take_chunks(st, &K, ev)) {
+        int parts = 1;
+        for (int bits = 1; (1 << bits) <= K && st->n - bits >= 12; ++bits) {
+            const int q = st->n - bits;
+            if (q == target || ((ctrl_mask >> q) & 1ull)) break;
+            parts = 1 << bits;
+        }
+        int bits = 0;
+        while ((1 << bits) < parts) ++bits;
+        if (target < 0 || target >= st->n - bits) parts = 1, bits = 0; // (out of range: reported below)
+        for (int j = 0; j < parts; ++j) {
+            SPZ_CUDA(cudaStreamWaitEvent(st->stream, ev[(j + 1) * (K / parts) - 1], 0));
+            const size_t off = (size_t)j << (st->n - bits);
+            SPZ_TRY(launch_gate_on(st, st->re + off, st->im + off, st->n - bits, g, ctrl_mask, target));
+        }
+        return SPZ_OK;
+    }
+#else
     SPZ_TRY(join_pending(st));
-    const int n = st->n;
+#endif
+    return launch_gate_on(st, st->re, st->im, st->n, g, ctrl_mask, target);
+}
+
+// the gate on the register of n qubits at (re, im): the state's own arrays, or one contiguous chunk of them
+static int launch_gate_on(spz_state *st, double *re, double *im, int n, const GateK &g, uint64_t ctrl_mask, int target) {
     if (target < 0 || target >= n) { set_error("target %d out of range for %d qubits", target, n); return SPZ_ERR_INVALID_ARG; }
     if ((ctrl_mask >> target) & 1ull) { set_error("target %d is also a control", target); return SPZ_ERR_INVALID_ARG; }
     if (n < 64 && (ctrl_mask >> n)) { set_error("control mask 0x%llx exceeds %d qubits", (unsigned long long)ctrl_mask, n); return SPZ_ERR_INVALID_ARG; }
@@ -78,7 +109,7 @@ int launch_gate(spz_state *st, const GateK &g, uint64_t ctrl_mask, int target) {
 
     if (n - LOGW - nins_vec >= 0 && nins_vec <= kMaxIns) {
         PairArgs a{};
-        a.re = st->re; a.im = st->im;
+        a.re = re; a.im = im;
         a.nvec = 1ll << (n - LOGW - nins_vec);
         a.setmask = ctrl_mask & ~low_bits_mask;
         a.tbit = low ? 0ull : (1ull << target);
@@ -104,7 +135,7 @@ int launch_gate(spz_state *st, const GateK &g, uint64_t ctrl_mask, int target) {
     } else {
         if (n_ctrl + 1 > kMaxIns) { set_error("too many controls"); return SPZ_ERR_INVALID_ARG; }
         ScalarArgs a{};
-        a.re = st->re; a.im = st->im;
+        a.re = re; a.im = im;
         a.npairs = 1ll << (n - 1 - n_ctrl);
         a.setmask = ctrl_mask;
         a.tbit = 1ull << target;

@@ -471,29 +471,26 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
         if (exact) k_tile<true><<<count, threads, smem, st->stream>>>(a);
         else k_tile<false><<<count, threads, smem, st->stream>>>(a);
     };
-    // Directly after an overlapped exchange (dist.cu) the shard arrives in two halves along local bit `sb`.  If sb is
-    // the highest bit outside the tile, the halves are the two halves of the grid: start on the first while the second
-    // is still on the wire.
-    int sb = -1;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (st->dist && dist_take_split(st, &sb, &e0, &e1)) {
-        bool top_outer = grid >= 2 && sb >= plan.low_bits;
-        for (int k = 0; k < plan.n_high; ++k) if (plan.high[k] == sb) top_outer = false;
-        for (int q = sb + 1; q < st->n && top_outer; ++q) { // every higher local bit must be a tile bit
-            bool is_tile = false;
+    // Directly after an overlapped exchange (dist.cu) the shard arrives in K contiguous chunks.  Tile numbers count through the
+    // bits outside the tile, so as long as the top log2(parts) local bits are outside the tile, the chunks are ranges of the
+    // grid: start on the first while the others are still on the wire.
+    int K = 0;
+    cudaEvent_t ev[8] = {};
+    if (st->dist && dist_take_chunks(st, &K, ev)) {
+        int parts = 1;
+        for (int bits = 1; (1 << bits) <= K && (grid >> bits) >= 1; ++bits) {
+            const int q = st->n - bits; // the next lower local bit must not be a tile bit
+            bool is_tile = q < plan.low_bits;
             for (int k = 0; k < plan.n_high; ++k) if (plan.high[k] == q) is_tile = true;
-            if (!is_tile) top_outer = false;
+            if (is_tile) break;
+            parts = 1 << bits;
         }
-        if (top_outer) {
-            SPZ_CUDA(cudaStreamWaitEvent(st->stream, e0, 0));
-            launch(0, grid / 2);
-            SPZ_CUDA(cudaStreamWaitEvent(st->stream, e1, 0));
-            launch(grid / 2, grid - grid / 2);
-            count_launch();
-        } else {
-            SPZ_CUDA(cudaStreamWaitEvent(st->stream, e1, 0));
-            launch(0, grid);
+        for (int j = 0; j < parts; ++j) {
+            SPZ_CUDA(cudaStreamWaitEvent(st->stream, ev[(j + 1) * (K / parts) - 1], 0));
+            const unsigned first = (unsigned)((uint64_t)grid * j / parts), end = (unsigned)((uint64_t)grid * (j + 1) / parts);
+            launch(first, end - first);
         }
+        if (parts > 1) count_launch(parts - 1);
     } else {
         launch(0, grid);
     }

@@ -112,17 +112,34 @@ int spz_rdv_barrier(spz_rdv *r) {
 
 int spz_rdv_close(spz_rdv *r) {
     if (!r) return SPZ_OK;
-    // leave the last two operations' files to the slower ranks; the directory is removed by whoever empties it
-    if (r->seq >= 1) { /* files seq-1 may still be read by others: a final barrier makes them safe to delete */
-        if (spz_rdv_barrier(r) == SPZ_OK) {
-            unlink(rdv_path(r, r->seq - 2, r->rank).c_str());
-            if (r->seq >= 3) unlink(rdv_path(r, r->seq - 3, r->rank).c_str());
+    // A rank may delete a file only when it knows that every rank has read it, and it learns that from the NEXT operation's
+    // files.  (The first version unlinked its own file of the final barrier as soon as the barrier returned: a rank that
+    // published a moment later found the file gone and polled until the time-out -- a 600 s hang at exit, seen on 2 of 7 two-GPU
+    // runs.)  So closing is: a barrier S; then every rank but 0 publishes one more file, S + 1, and leaves without waiting;
+    // rank 0 waits for those files -- whoever published S + 1 has passed S, i.e. has read everything -- and removes all that
+    // is left, the directory included.
+    if (r->world > 1 && spz_rdv_barrier(r) == SPZ_OK) {
+        const long long fin = r->seq; // S + 1
+        if (r->rank != 0) {
+            const std::string name = rdv_path(r, fin, r->rank), tmp = name + ".tmp";
+            if (FILE *f = std::fopen(tmp.c_str(), "wb")) { std::fclose(f); std::rename(tmp.c_str(), name.c_str()); }
+        } else {
+            const auto t0 = std::chrono::steady_clock::now();
+            bool all_left = true;
+            for (int p = 1; p < r->world && all_left; ++p) {
+                const std::string name = rdv_path(r, fin, p);
+                while (access(name.c_str(), F_OK) != 0) {
+                    if (std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count() > 10000) { all_left = false; break; }
+                    std::this_thread::sleep_for(std::chrono::microseconds(200));
+                }
+            }
+            if (all_left) {
+                for (long long q = fin - 3 < 0 ? 0 : fin - 3; q <= fin; ++q)
+                    for (int p = 0; p < r->world; ++p) unlink(rdv_path(r, q, p).c_str());
+                rmdir(r->dir.c_str());
+            }
         }
     }
-    // the final barrier's own files stay until the directory is reused or the machine reboots (a few bytes in /dev/shm); rank 0
-    // removes what it can
-    unlink(rdv_path(r, r->seq - 1, r->rank).c_str());
-    rmdir(r->dir.c_str());
     delete r;
     return SPZ_OK;
 }

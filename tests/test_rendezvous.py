@@ -67,3 +67,38 @@ def test_no_torch_import_in_the_package():
     pat = re.compile(r"^\s*(import|from)\s+torch\b", re.M)
     for p in (ROOT / "spinoza_b200").rglob("*.py"):
         assert not pat.search(p.read_text()), p
+
+
+CLOSE_WORKER = r'''
+import os, sys, time
+sys.path.insert(0, os.environ["SPZ_ROOT"])
+from spinoza_b200.distributed import DistEnv
+r, w = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+t0 = time.time()
+for i in range(int(os.environ["ROUNDS"])):          # one rendezvous per round, each in its own directory: open, one op, close
+    env = DistEnv(r, w, r, os.environ["SPZ_RDV_DIR"] + f"_{i}")
+    if (i + r) % w == 0:
+        time.sleep(0.002)                            # ranks arrive at the closing barrier in every order
+    env.barrier()
+    env.shutdown()
+print(f"CLOSE_OK {r} {time.time() - t0:.2f}")
+'''
+
+
+def test_close_never_removes_a_file_another_rank_still_has_to_read():
+    """spz_rdv_close used to unlink its own file of the final barrier right after the barrier returned; a rank that published a
+    moment later polled for the missing file until the time-out (600 s hangs at exit of two-GPU runs).  300 open/close rounds
+    with the ranks arriving in every order: every round must finish, well inside the per-operation time-out."""
+    world = 3
+    with tempfile.TemporaryDirectory() as d:
+        procs = []
+        for r in range(world):
+            env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), SPZ_RDV_DIR=str(Path(d) / "rdv"),
+                       SPZ_ROOT=str(ROOT), SPZ_RDV_TIMEOUT_MS="4000", ROUNDS="300")
+            procs.append(subprocess.Popen([sys.executable, "-c", CLOSE_WORKER], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        for r, p in enumerate(procs):
+            out, err = p.communicate(timeout=300)
+            assert p.returncode == 0, err[-2000:]
+            assert f"CLOSE_OK {r}" in out
+            assert float(out.split()[-1]) < 60.0, out  # a single lost file costs 4 s; 300 clean rounds take a few seconds
+        assert not [x for x in Path(d).iterdir()], "rank 0 removes every rendezvous directory once all ranks have left"
