@@ -93,6 +93,39 @@ pub mod ffi {
             out: *mut f64,
         ) -> c_int;
         pub fn spz_sample(st: *mut spz_state, u01: *const f64, shots: i64, out_index: *mut i64) -> c_int;
+        pub fn spz_norm2(st: *mut spz_state, out: *mut f64) -> c_int;
+        pub fn spz_sync(st: *mut spz_state) -> c_int;
+        // sharded registers (include/spinoza_b200.h, "multi-GPU"): one process per GPU, or several shards in one process
+        pub fn spz_dist_create(n_qubits: c_int, rank: c_int, world: c_int, device: c_int, out: *mut *mut spz_state) -> c_int;
+        pub fn spz_dist_export(st: *mut spz_state, blob: *mut u8) -> c_int;
+        pub fn spz_dist_connect(st: *mut spz_state, blobs: *const u8) -> c_int;
+        pub fn spz_dist_connect_local(states: *mut *mut spz_state, world: c_int) -> c_int;
+        pub fn spz_dist_connect_rdv(st: *mut spz_state, r: *mut spz_rdv) -> c_int;
+        pub fn spz_dist_perm(st: *const spz_state, perm_out: *mut i32) -> c_int;
+        pub fn spz_dist_local_qubits(st: *const spz_state) -> c_int;
+        pub fn spz_dist_copy_from(dst: *mut spz_state, src: *const spz_state) -> c_int;
+        pub fn spz_dist_stats(st: *const spz_state, out4: *mut f64) -> c_int;
+        pub fn spz_rdv_open(dir: *const c_char, rank: c_int, world: c_int, out: *mut *mut spz_rdv) -> c_int;
+        pub fn spz_rdv_allgather(r: *mut spz_rdv, mine: *const u8, bytes: i64, all: *mut u8) -> c_int;
+        pub fn spz_rdv_barrier(r: *mut spz_rdv) -> c_int;
+        pub fn spz_rdv_close(r: *mut spz_rdv) -> c_int;
+    }
+
+    #[repr(C)]
+    pub struct spz_rdv {
+        _private: [u8; 0],
+    }
+    pub const SPZ_IPC_BLOB_BYTES: usize = 256;
+}
+
+/// `spinoza::math` (math.rs): the amplitude type `Gate::to_matrix` returns.
+pub mod math {
+    use super::Float;
+
+    #[derive(Clone, Copy, Debug, PartialEq)]
+    pub struct Amplitude {
+        pub re: Float,
+        pub im: Float,
     }
 }
 
@@ -187,7 +220,63 @@ pub mod core {
         });
         out
     }
-    /// Exact inverse-CDF sampling (replaces `reservoir_sampling`, core.rs:125): one basis-state index per uniform.
+    /// `spinoza::core::Reservoir` (core.rs:65-121).  Same construction and read-out; the filling is the engine's exact
+    /// inverse-CDF sampler (one read pass over the device state, `spz_sample`) instead of `num_tests` host-side weighted
+    /// replacement rounds, so every entry is an exact draw from |amplitude|^2 whatever `num_tests` is.
+    pub struct Reservoir {
+        entries: Vec<usize>,
+        seed: u64,
+    }
+
+    impl Reservoir {
+        /// core.rs:73-78
+        pub fn new(k: usize) -> Self {
+            let t = std::time::SystemTime::now().duration_since(std::time::UNIX_EPOCH).map(|d| d.as_nanos() as u64).unwrap_or(0);
+            Self { entries: vec![0; k], seed: t ^ 0x9E37_79B9_7F4A_7C15 } // the reference draws from thread_rng: unseeded
+        }
+        /// Deterministic draws (tests).
+        pub fn with_seed(k: usize, seed: u64) -> Self {
+            Self { entries: vec![0; k], seed }
+        }
+        fn uniforms(&mut self) -> Vec<Float> {
+            // splitmix64, 53 mantissa bits per draw: the generator the engine and its oracle use everywhere
+            let mut x = self.seed;
+            let u: Vec<Float> = (0..self.entries.len())
+                .map(|_| {
+                    x = x.wrapping_add(0x9E37_79B9_7F4A_7C15);
+                    let mut z = x;
+                    z = (z ^ (z >> 30)).wrapping_mul(0xBF58_476D_1CE4_E5B9);
+                    z = (z ^ (z >> 27)).wrapping_mul(0x94D0_49BB_1331_11EB);
+                    ((z ^ (z >> 31)) >> 11) as Float * (1.0 / 9007199254740992.0)
+                })
+                .collect();
+            self.seed = x;
+            u
+        }
+        /// core.rs:101-112 takes the host slices of the state; here the state lives on the device, so it takes the `State`.
+        /// `num_tests` is accepted for source compatibility (see the type's comment).
+        pub fn sampling(&mut self, state: &State, _num_tests: usize) {
+            let u = self.uniforms();
+            self.entries = sample(state, &u).into_iter().map(|i| i as usize).collect();
+        }
+        /// core.rs:115-121
+        pub fn get_outcome_count(&self) -> std::collections::HashMap<usize, usize> {
+            let mut samples = std::collections::HashMap::new();
+            for e in &self.entries {
+                *samples.entry(*e).or_insert(0) += 1;
+            }
+            samples
+        }
+    }
+
+    /// core.rs:125-129
+    pub fn reservoir_sampling(state: &State, reservoir_size: usize, num_tests: usize) -> Reservoir {
+        let mut reservoir = Reservoir::new(reservoir_size);
+        reservoir.sampling(state, num_tests);
+        reservoir
+    }
+
+    /// Exact inverse-CDF sampling (what `Reservoir::sampling` runs on, core.rs:125): one basis-state index per uniform.
     pub fn sample(state: &State, u01: &[Float]) -> Vec<i64> {
         let mut out = vec![0i64; u01.len()];
         check(unsafe { ffi::spz_sample(state.h, u01.as_ptr(), u01.len() as i64, out.as_mut_ptr()) });
@@ -227,6 +316,40 @@ pub mod gates {
                 Self::RZ(t) => Self::RZ(-t),
                 Self::U(theta, phi, lambda) => Self::U(-theta, -lambda, -phi),
                 Self::M | Self::BitFlipNoise(_) => unimplemented!(),
+            }
+        }
+        /// gates.rs:95-190: the 2 x 2 matrix, row-major.  (M, SWAP, BitFlipNoise: `unimplemented!()` like the reference.)
+        pub fn to_matrix(&self) -> [math::Amplitude; 4] {
+            let a = |re: Float, im: Float| math::Amplitude { re, im };
+            let r = std::f64::consts::FRAC_1_SQRT_2;
+            match *self {
+                Self::H => [a(r, 0.0), a(r, 0.0), a(r, 0.0), a(-r, 0.0)],
+                Self::X => [a(0.0, 0.0), a(1.0, 0.0), a(1.0, 0.0), a(0.0, 0.0)],
+                Self::Y => [a(0.0, 0.0), a(0.0, -1.0), a(0.0, 1.0), a(0.0, 0.0)],
+                Self::Z => [a(1.0, 0.0), a(0.0, 0.0), a(0.0, 0.0), a(-1.0, 0.0)],
+                Self::P(t) => [a(1.0, 0.0), a(0.0, 0.0), a(0.0, 0.0), a(t.cos(), t.sin())],
+                Self::RX(t) => {
+                    let (s, c) = (t / 2.0).sin_cos();
+                    [a(c, 0.0), a(0.0, -s), a(0.0, -s), a(c, 0.0)]
+                }
+                Self::RY(t) => {
+                    let (s, c) = (t / 2.0).sin_cos();
+                    [a(c, 0.0), a(-s, 0.0), a(s, 0.0), a(c, 0.0)]
+                }
+                Self::RZ(t) => {
+                    let (s, c) = (t / 2.0).sin_cos();
+                    [a(c, -s), a(0.0, 0.0), a(0.0, 0.0), a(c, s)]
+                }
+                Self::U(theta, phi, lambda) => {
+                    let (s, c) = (theta / 2.0).sin_cos();
+                    [
+                        a(c, 0.0),
+                        a(-lambda.cos() * s, -lambda.sin() * s),
+                        a(phi.cos() * s, phi.sin() * s),
+                        a((phi + lambda).cos() * c, (phi + lambda).sin() * c),
+                    ]
+                }
+                _ => unimplemented!(),
             }
         }
         pub(crate) fn to_ffi(&self) -> ffi::spz_gate {
@@ -494,5 +617,104 @@ pub mod circuit {
                 ffi::spz_execute(self.state.h, ops.as_ptr(), ops.len() as i64, self.exec_flags, &mut self.measured_qubits, &mut self.measured_qubits_vals)
             });
         }
+    }
+}
+
+/// Sharded registers: the 2^n amplitudes spread over the GPUs of one node by the top log2(world) index bits
+/// (include/spinoza_b200.h, "multi-GPU"; no counterpart in the reference).  A shard IS a `core::State`: `gates::apply`,
+/// `circuit::QuantumCircuit::execute`, `measurement::measure_qubit` and the reductions are the same calls, made by every rank
+/// in the same order; gates on a global qubit exchange half a shard with the partner GPU over NVLink inside the call.
+pub mod dist {
+    use super::core::State;
+    use super::*;
+
+    /// The host-side control plane between the processes of a node (csrc/rendezvous.cu): files under /dev/shm, no framework.
+    pub struct Rendezvous {
+        h: *mut ffi::spz_rdv,
+        pub rank: usize,
+        pub world: usize,
+    }
+    impl Rendezvous {
+        /// `dir = None`: one directory per launch, derived from MASTER_PORT and the launcher's pid.
+        pub fn open(dir: Option<&str>, rank: usize, world: usize) -> Self {
+            let c = dir.map(|d| std::ffi::CString::new(d).expect("rendezvous directory"));
+            let mut h = std::ptr::null_mut();
+            check(unsafe { ffi::spz_rdv_open(c.as_ref().map_or(std::ptr::null(), |s| s.as_ptr()), rank as c_int, world as c_int, &mut h) });
+            Self { h, rank, world }
+        }
+        /// RANK / WORLD_SIZE as torchrun- or mpirun-style launchers export them.
+        pub fn from_env() -> Self {
+            let get = |k: &str, d: usize| std::env::var(k).ok().and_then(|v| v.parse().ok()).unwrap_or(d);
+            Self::open(std::env::var("SPZ_RDV_DIR").ok().as_deref(), get("RANK", 0), get("WORLD_SIZE", 1))
+        }
+        pub fn barrier(&mut self) {
+            check(unsafe { ffi::spz_rdv_barrier(self.h) });
+        }
+        /// Equal-length blobs, one per rank, in rank order.
+        pub fn all_gather(&mut self, mine: &[u8]) -> Vec<u8> {
+            let mut all = vec![0u8; mine.len() * self.world];
+            check(unsafe { ffi::spz_rdv_allgather(self.h, mine.as_ptr(), mine.len() as i64, all.as_mut_ptr()) });
+            all
+        }
+        pub fn max_float(&mut self, x: Float) -> Float {
+            self.all_gather(&x.to_le_bytes()).chunks(8).map(|c| Float::from_le_bytes(c.try_into().unwrap())).fold(Float::MIN, Float::max)
+        }
+    }
+    impl Drop for Rendezvous {
+        fn drop(&mut self) {
+            unsafe { ffi::spz_rdv_close(self.h) };
+        }
+    }
+
+    /// This rank's shard of an n-qubit register, |0..0>, connected to the other ranks' shards (CUDA IPC over NVLink).
+    pub fn sharded_state(n: usize, rdv: &mut Rendezvous, device: i32) -> State {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { ffi::spz_dist_create(n as c_int, rdv.rank as c_int, rdv.world as c_int, device as c_int, &mut h) });
+        check(unsafe { ffi::spz_dist_connect_rdv(h, rdv.h) });
+        State { h, n: n as u8 }
+    }
+
+    /// All `world` shards in ONE process (tests, or one process driving several GPUs): plain device pointers, same kernels.
+    pub fn local_group(n: usize, world: usize, devices: &[i32]) -> Vec<State> {
+        let mut hs: Vec<*mut ffi::spz_state> = (0..world)
+            .map(|r| {
+                let mut h = std::ptr::null_mut();
+                check(unsafe { ffi::spz_dist_create(n as c_int, r as c_int, world as c_int, devices[r % devices.len()] as c_int, &mut h) });
+                h
+            })
+            .collect();
+        check(unsafe { ffi::spz_dist_connect_local(hs.as_mut_ptr(), world as c_int) });
+        hs.into_iter().map(|h| State { h, n: n as u8 }).collect()
+    }
+
+    /// Where each logical qubit lives now (physical index bit; bits >= `local_qubits` are rank bits).
+    pub fn perm(state: &State) -> Vec<usize> {
+        let mut p = vec![0i32; state.n as usize];
+        check(unsafe { ffi::spz_dist_perm(state.h, p.as_mut_ptr()) });
+        p.into_iter().map(|x| x as usize).collect()
+    }
+    pub fn local_qubits(state: &State) -> usize {
+        unsafe { ffi::spz_dist_local_qubits(state.h) as usize }
+    }
+    /// Collective copy of a sharded register (`Clone` of the reference's `State`, rank by rank).
+    pub fn copy_from(dst: &mut State, src: &State) {
+        check(unsafe { ffi::spz_dist_copy_from(dst.h, src.h) });
+    }
+    pub struct Stats {
+        pub exchanges: f64,
+        pub bytes_sent: f64,
+        pub exchange_ms: f64,
+        pub overlapped: f64,
+    }
+    pub fn stats(state: &State) -> Stats {
+        let mut o = [0.0f64; 4];
+        check(unsafe { ffi::spz_dist_stats(state.h, o.as_mut_ptr()) });
+        Stats { exchanges: o[0], bytes_sent: o[1], exchange_ms: o[2], overlapped: o[3] }
+    }
+    /// sum |amplitude|^2 over all ranks (a collective).
+    pub fn norm2(state: &State) -> Float {
+        let mut out = 0.0;
+        check(unsafe { ffi::spz_norm2(state.h, &mut out) });
+        out
     }
 }

@@ -12,8 +12,10 @@
 //   spinoza::QuantumRegister q(3); spinoza::QuantumCircuit qc({&q}); qc.h(0); qc.cx(0, 1); qc.execute();
 #pragma once
 
+#include <array>
 #include <cmath>
 #include <cstdint>
+#include <map>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -36,6 +38,10 @@ inline void check(int status) {
 }
 
 // ---- Gate, gates.rs:44-92 -----------------------------------------------------------------------------------
+struct Amplitude { // math.rs
+    Float re, im;
+};
+
 struct Gate {
     spz_gate g{};
     static Gate make(int kind, Float a = 0, Float b = 0, Float c = 0, int t0 = 0, int t1 = 0) {
@@ -62,6 +68,29 @@ struct Gate {
         default: throw Error(SPZ_ERR_UNSUPPORTED, "Gate::inverse: unimplemented!() (gates.rs:86)");
         }
     }
+    // Gate::to_matrix, gates.rs:95-190: the 2 x 2 matrix, row-major
+    std::array<Amplitude, 4> to_matrix() const {
+        const Float r = 0.70710678118654752440;
+        auto half = [&](Float &sn, Float &cs) { sn = std::sin(g.p[0] / 2); cs = std::cos(g.p[0] / 2); };
+        Float sn = 0, cs = 0;
+        switch (g.kind) {
+        case SPZ_GATE_H: return {{{r, 0}, {r, 0}, {r, 0}, {-r, 0}}};
+        case SPZ_GATE_X: return {{{0, 0}, {1, 0}, {1, 0}, {0, 0}}};
+        case SPZ_GATE_Y: return {{{0, 0}, {0, -1}, {0, 1}, {0, 0}}};
+        case SPZ_GATE_Z: return {{{1, 0}, {0, 0}, {0, 0}, {-1, 0}}};
+        case SPZ_GATE_P: return {{{1, 0}, {0, 0}, {0, 0}, {std::cos(g.p[0]), std::sin(g.p[0])}}};
+        case SPZ_GATE_RX: half(sn, cs); return {{{cs, 0}, {0, -sn}, {0, -sn}, {cs, 0}}};
+        case SPZ_GATE_RY: half(sn, cs); return {{{cs, 0}, {-sn, 0}, {sn, 0}, {cs, 0}}};
+        case SPZ_GATE_RZ: half(sn, cs); return {{{cs, -sn}, {0, 0}, {0, 0}, {cs, sn}}};
+        case SPZ_GATE_U: {
+            half(sn, cs);
+            const Float phi = g.p[1], lam = g.p[2];
+            return {{{cs, 0}, {-std::cos(lam) * sn, -std::sin(lam) * sn}, {std::cos(phi) * sn, std::sin(phi) * sn},
+                     {std::cos(phi + lam) * cs, std::sin(phi + lam) * cs}}};
+        }
+        default: throw Error(SPZ_ERR_UNSUPPORTED, "Gate::to_matrix: unimplemented!() (gates.rs:188)");
+        }
+    }
 };
 
 // ---- State, core.rs:18-51 -----------------------------------------------------------------------------------
@@ -82,8 +111,10 @@ class State {
     void set(const std::vector<Float> &re, const std::vector<Float> &im) { check(spz_upload(h_, re.data(), im.data(), 0, (int64_t)re.size())); }
     void set_seed(std::uint64_t seed) { check(spz_set_seed(h_, seed)); }
     spz_state *handle() const { return h_; }
+    static State adopt(spz_state *h) { State s; s.h_ = h; return s; } // a handle made elsewhere (spinoza::dist)
 
   private:
+    State() = default;
     spz_state *h_ = nullptr;
 };
 
@@ -125,6 +156,96 @@ inline std::vector<Float> xyz_expectation_value(char observable, const State &st
     check(spz_xyz_expectation_value(state.handle(), observable, t.data(), (int)t.size(), out.data()));
     return out;
 }
+
+// ---- core.rs:65-129: Reservoir / reservoir_sampling ------------------------------------------------------------------
+// Same construction and read-out as the reference; the filling is the engine's exact inverse-CDF sampler (spz_sample, one read
+// pass over the device state) instead of num_tests rounds of weighted replacement, so every entry is an exact draw from
+// |amplitude|^2 whatever num_tests is.
+class Reservoir {
+  public:
+    explicit Reservoir(std::size_t k, std::uint64_t seed = 0x9E3779B97F4A7C15ull) : entries_(k, 0), seed_(seed) {}
+    void sampling(const State &state, std::size_t /*num_tests*/) {
+        std::vector<Float> u(entries_.size());
+        for (auto &x : u) { // splitmix64, 53 bits per draw
+            seed_ += 0x9E3779B97F4A7C15ull;
+            std::uint64_t z = seed_;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            x = (Float)((z ^ (z >> 31)) >> 11) * (1.0 / 9007199254740992.0);
+        }
+        std::vector<int64_t> idx(u.size());
+        check(spz_sample(state.handle(), u.data(), (int64_t)u.size(), idx.data()));
+        for (std::size_t i = 0; i < idx.size(); ++i) entries_[i] = (std::size_t)idx[i];
+    }
+    std::map<std::size_t, std::size_t> get_outcome_count() const { // core.rs:115-121
+        std::map<std::size_t, std::size_t> samples;
+        for (auto e : entries_) ++samples[e];
+        return samples;
+    }
+    const std::vector<std::size_t> &entries() const { return entries_; }
+
+  private:
+    std::vector<std::size_t> entries_;
+    std::uint64_t seed_;
+};
+inline Reservoir reservoir_sampling(const State &state, std::size_t reservoir_size, std::size_t num_tests) { // core.rs:125
+    Reservoir reservoir(reservoir_size);
+    reservoir.sampling(state, num_tests);
+    return reservoir;
+}
+
+// ---- sharded registers (no counterpart in the reference; include/spinoza_b200.h "multi-GPU") ---------------------------------
+// A shard IS a State: apply / QuantumCircuit::execute / measure_qubit / the reductions are the same calls, made by every rank in
+// the same order.
+namespace dist {
+class Rendezvous { // the host-side control plane between the processes of a node (csrc/rendezvous.cu)
+  public:
+    Rendezvous(int rank, int world, const char *dir = nullptr) : rank(rank), world(world) { check(spz_rdv_open(dir, rank, world, &h_)); }
+    Rendezvous(const Rendezvous &) = delete;
+    ~Rendezvous() { if (h_) spz_rdv_close(h_); }
+    void barrier() { check(spz_rdv_barrier(h_)); }
+    Float max_float(Float x) {
+        std::vector<Float> all((std::size_t)world);
+        check(spz_rdv_allgather(h_, &x, sizeof x, all.data()));
+        Float m = all[0];
+        for (Float v : all) m = v > m ? v : m;
+        return m;
+    }
+    spz_rdv *handle() const { return h_; }
+    const int rank, world;
+
+  private:
+    spz_rdv *h_ = nullptr;
+};
+// this rank's shard of an n-qubit register, connected to the other processes' shards over CUDA IPC
+inline State sharded_state(std::size_t n, Rendezvous &rdv, int device) {
+    spz_state *h = nullptr;
+    check(spz_dist_create((int)n, rdv.rank, rdv.world, device, &h));
+    State s = State::adopt(h);
+    check(spz_dist_connect_rdv(h, rdv.handle()));
+    return s;
+}
+// all `world` shards in one process (plain device pointers, same kernels)
+inline std::vector<State> local_group(std::size_t n, int world, const std::vector<int> &devices = {0}) {
+    std::vector<spz_state *> hs((std::size_t)world, nullptr);
+    std::vector<State> out;
+    for (int r = 0; r < world; ++r) {
+        check(spz_dist_create((int)n, r, world, devices[(std::size_t)r % devices.size()], &hs[(std::size_t)r]));
+        out.push_back(State::adopt(hs[(std::size_t)r]));
+    }
+    check(spz_dist_connect_local(hs.data(), world));
+    return out;
+}
+inline std::vector<std::size_t> perm(const State &s, std::size_t n_total) { // logical qubit -> physical index bit
+    std::vector<int32_t> p(n_total);
+    check(spz_dist_perm(s.handle(), p.data()));
+    return std::vector<std::size_t>(p.begin(), p.end());
+}
+inline std::size_t local_qubits(const State &s) { return (std::size_t)spz_dist_local_qubits(s.handle()); }
+inline Float norm2(const State &s) { Float v = 0; check(spz_norm2(s.handle(), &v)); return v; } // a collective
+struct Stats { double exchanges, bytes_sent, exchange_ms, overlapped; };
+inline Stats stats(const State &s) { double o[4]; check(spz_dist_stats(s.handle(), o)); return {o[0], o[1], o[2], o[3]}; }
+} // namespace dist
 
 // ---- circuit.rs ---------------------------------------------------------------------------------------------------
 struct QuantumRegister { // circuit.rs:13-51

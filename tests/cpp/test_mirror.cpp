@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <thread>
 #include "../../spinoza_b200/cpp/spinoza.hpp"
 
 using namespace spinoza;
@@ -91,6 +92,65 @@ int main() {
         bool inv = false;
         try { Gate::M().inverse(); } catch (const Error &) { inv = true; } // gates.rs:2050-2055
         if (!inv) { std::printf("FAIL m_inverse\n"); ++fails; }
+    }
+    { // Gate::to_matrix gates.rs:95-190: unitary rows, and the entries of RX / U
+        auto m = Gate::RX(1.0).to_matrix();
+        close_to(m[0].re, std::cos(0.5), 1e-15, "rx00"); close_to(m[1].im, -std::sin(0.5), 1e-15, "rx01");
+        auto u = Gate::U(1.0, 2.0, 3.0).to_matrix();
+        close_to(u[1].re, -std::cos(3.0) * std::sin(0.5), 1e-15, "u01"); close_to(u[3].im, std::sin(5.0) * std::cos(0.5), 1e-15, "u11");
+        for (const Gate &g : {Gate::H(), Gate::Y(), Gate::P(0.3), Gate::RY(0.7), Gate::RZ(1.1), Gate::U(0.1, 0.2, 0.3)}) {
+            auto a = g.to_matrix();
+            close_to(a[0].re * a[0].re + a[0].im * a[0].im + a[1].re * a[1].re + a[1].im * a[1].im, 1.0, 1e-14, "row0 norm");
+            close_to(a[0].re * a[2].re + a[0].im * a[2].im + a[1].re * a[3].re + a[1].im * a[3].im, 0.0, 1e-14, "rows orthogonal (re)");
+        }
+    }
+    { // Reservoir / reservoir_sampling core.rs:65-129: a basis state has one outcome; a uniform state spreads
+        State s(10);
+        apply(Gate::X(), s, 3); apply(Gate::X(), s, 7);
+        auto r = reservoir_sampling(s, 1000, 10000);
+        auto h = r.get_outcome_count();
+        if (h.size() != 1 || h.begin()->first != ((1u << 3) | (1u << 7)) || h.begin()->second != 1000) { std::printf("FAIL reservoir basis\n"); ++fails; }
+        State t(4);
+        for (std::size_t q = 0; q < 4; ++q) apply(Gate::H(), t, q);
+        auto h2 = reservoir_sampling(t, 16000, 0).get_outcome_count();
+        if (h2.size() != 16) { std::printf("FAIL reservoir uniform: %zu outcomes\n", h2.size()); ++fails; }
+        for (auto &kv : h2) if (kv.second < 800 || kv.second > 1200) { std::printf("FAIL reservoir count %zu\n", kv.second); ++fails; }
+    }
+    { // sharded register through the ABI only: 4 shards in this process against the single-GPU state, QFT + a global-qubit gate
+        const std::size_t n = 14;
+        auto shards = dist::local_group(n, 4);
+        State one(n);
+        auto run = [&](State &s) {
+            apply(Gate::X(), s, 2); apply(Gate::H(), s, n - 1); c_apply(Gate::P(0.7), s, n - 1, 0);
+            apply(Gate::RX(0.3), s, n - 2); apply(Gate::RY(1.1), s, 5); c_apply(Gate::X(), s, n - 2, 1);
+        };
+        run(one);
+        { // one host thread per shard: a call may block on a device-side handshake with the partner shard
+            std::vector<std::thread> drivers;
+            for (auto &sh : shards) drivers.emplace_back([&run, &sh]() { run(sh); });
+            for (auto &t : drivers) t.join();
+        }
+        auto p = dist::perm(shards[0], n);
+        const std::size_t nl = dist::local_qubits(shards[0]);
+        auto re1 = one.reals(), im1 = one.imags();
+        double worst = 0;
+        for (std::size_t r = 0; r < shards.size(); ++r) {
+            auto re = shards[r].reals(), im = shards[r].imags();
+            for (std::size_t i = 0; i < re.size(); ++i) {
+                const std::size_t phys = (r << nl) | i;
+                std::size_t logical = 0;
+                for (std::size_t q = 0; q < n; ++q) if ((phys >> p[q]) & 1u) logical |= (std::size_t)1 << q;
+                worst = std::fmax(worst, std::fmax(std::fabs(re[i] - re1[logical]), std::fabs(im[i] - im1[logical])));
+            }
+        }
+        if (worst != 0.0) { std::printf("FAIL sharded vs single: %g\n", worst); ++fails; }
+        if (dist::stats(shards[0]).exchanges < 1) { std::printf("FAIL no exchange happened\n"); ++fails; }
+        // a collective: every shard takes part, each driven from its own host thread (one process per GPU in deployment)
+        std::vector<double> norms(shards.size(), 0.0);
+        std::vector<std::thread> pool;
+        for (std::size_t r = 0; r < shards.size(); ++r) pool.emplace_back([&, r]() { norms[r] = dist::norm2(shards[r]); });
+        for (auto &t : pool) t.join();
+        for (double v : norms) close_to(v, 1.0, 1e-12, "sharded norm");
     }
     if (fails) { std::printf("%d failures\n", fails); return 1; }
     std::printf("CPP_MIRROR_OK\n");

@@ -15,7 +15,7 @@ EXE = ROOT / "tests" / "cpp" / "_build" / "test_mirror"
 def build():
     EXE.parent.mkdir(exist_ok=True)
     lib = Path(sb.library_path())
-    cmd = ["/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++", "-std=c++17", "-O1", str(SRC), "-o", str(EXE),
+    cmd = ["/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++", "-std=c++17", "-O1", "-pthread", str(SRC), "-o", str(EXE),
            f"-L{lib.parent}", "-lspinoza_b200", f"-Wl,-rpath,{lib.parent}"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
