@@ -281,6 +281,16 @@ def sharded_vs_oracle(np, sb, sbd, env, n=20):
 # ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
+def measured_traffic(n_local):
+    p = ROOT / "profiles" / f"round2_traffic_n{n_local}.json"
+    try:
+        d = json.loads(p.read_text())
+        return {"traffic": d["traffic_full_pass_mean"],
+                "traffic_source": f"profiles/{p.name}: mean DRAM read + write of the H / RX launches, {d['source']}"}
+    except Exception:
+        return {"traffic": None, "traffic_source": f"no profiles/{p.name} (run tools/measure_traffic.py {n_local})"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -387,16 +397,15 @@ def main():
                      "frac_of_nominal_8000": achieved_gpu / 8000.0, "peak_source": peak_src,
                      "kernel": "k_pair_vec / k_pair_low (kernels_direct.cuh)",
                      "algorithmic_bytes_per_launch": bytes_per_gate_gpu, "avg_launch_ms": per_gate_ms,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one k_pair_vec launch at n = 30, from the committed
-                     # ncu --set full capture (profiles/round1_k_pair_vec_ncu_full_raw.csv); only valid for 30 local qubits
-                     "traffic": 34.30e9 if n_local == 30 else None,
-                     "traffic_source": "profiles/round1_k_pair_vec_ncu_full_raw.csv (17.18 GB read + 17.12 GB written)"},
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep's kernels at this size, measured by
+                     # tools/measure_traffic.py (an ncu pass, committed under profiles/); null when no measurement exists for it
+                     **measured_traffic(n_local)},
         "clocks": clocks, "gpu_launches": int(launches),
     }
     if nvlink is not None:
         line["nvlink"] = nvlink
 
-    # ---- per-(gate, target) table, single GPU only: 1 warm-up + 5 timed reps each ----
+    # ---- per-(gate, target) table, single GPU only: 1 warm-up + 20 timed reps each ----
     if rank == 0 and dist is None and not args.no_extras:
         table = {}
         for (name, _p), gate in zip(SWEEP_GATES, gates):
@@ -404,9 +413,9 @@ def main():
             for t in targets:
                 apply(gate, t)
                 state.timer_start()
-                for _ in range(5):
+                for _ in range(20):
                     apply(gate, t)
-                row.append(bytes_per_gate_gpu * 5 / (state.timer_stop() * 1e-3) / 1e9)
+                row.append(bytes_per_gate_gpu * 20 / (state.timer_stop() * 1e-3) / 1e9)
             table[name] = [round(x, 1) for x in row]
         flat = [x for r in table.values() for x in r]
         worst = min(((x, nm, t) for nm, r in table.items() for t, x in enumerate(r)))
@@ -522,7 +531,7 @@ def main():
             him = sb.HostBuffer(1 << n_local)
             state.init_random(42)
             state.download_into(hre, him)
-            e2e_steps = max(1, min(args.steps, 2))
+            e2e_steps = max(1, min(args.steps, 5))
             state.upload_from(hre, him); step(); state.download_into(hre, him)  # warm-up
             barrier()
             t0 = time.perf_counter()

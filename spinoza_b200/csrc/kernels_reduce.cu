@@ -263,14 +263,48 @@ int launch_scale(spz_state *st, double scale) {
 // Every sum has a fixed order, so the outcome for a given u is reproducible; atomics only order shots inside a bucket.
 constexpr int kLogB = 12;
 constexpr long long kB = 1ll << kLogB;
+constexpr int kSliceShots = 1024; // shots one CTA of pass 2 serves; a block with more gets extra CTAs from a device-built list
 
-// out[b] = sum over i in [b*B, (b+1)*B) of |amp_i|^2 ; one CTA per block, fixed summation order
+__device__ __forceinline__ double4 ld_nc_256(const double *p) { // 32-byte aligned, read once
+    double4 v;
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+// One atomic per warp and distinct key instead of one per lane: a peaked distribution sends most of 2^20 shots to a handful of
+// blocks, and a million atomics on one address serialise.  Returns this lane's slot: the old counter value plus its rank among
+// the lanes of the warp that hold the same key.
+__device__ __forceinline__ int warp_slot(int *counter, int key, bool active) {
+    const unsigned live = __ballot_sync(0xffffffffu, active);
+    if (!active) return 0;
+    const unsigned same = __match_any_sync(live, key);
+    const int leader = __ffs(same) - 1, lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter + key, __popc(same));
+    base = __shfl_sync(same, base, leader);
+    return base + __popc(same & ((1u << lane) - 1u));
+}
+
+// out[b] = sum over i in [b*B, (b+1)*B) of |amp_i|^2 ; one CTA per block, fixed summation order.  Full blocks are read as 256-bit
+// vectors, all eight loads of a thread in flight before the first add (the pass is a pure HBM read).
 __global__ void __launch_bounds__(256) k_block_prob(const double *__restrict__ re, const double *__restrict__ im,
                                                     long long len, double *__restrict__ out) {
     const long long b = blockIdx.x;
     const long long lo = b * kB, hi = min(lo + kB, len);
     double acc = 0.0;
-    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += re[i] * re[i] + im[i] * im[i];
+    if (hi - lo == kB) {
+        double4 x[4], y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            x[i] = ld_nc_256(re + lo + 4 * (i * 256 + threadIdx.x));
+            y[i] = ld_nc_256(im + lo + 4 * (i * 256 + threadIdx.x));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            acc += (x[i].x * x[i].x + y[i].x * y[i].x) + (x[i].y * x[i].y + y[i].y * y[i].y) + (x[i].z * x[i].z + y[i].z * y[i].z) +
+                   (x[i].w * x[i].w + y[i].w * y[i].w);
+    } else {
+        for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += re[i] * re[i] + im[i] * im[i];
+    }
     acc = block_sum(acc);
     if (threadIdx.x == 0) out[b] = acc;
 }
@@ -353,19 +387,23 @@ __global__ void __launch_bounds__(256) k_locate(const double *__restrict__ u01, 
                                                 const double *__restrict__ pre2, int n_l2, int *__restrict__ shot_blk,
                                                 double *__restrict__ shot_res, int *__restrict__ count) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= shots) return;
-    double u = u01[s];
-    if (!(u >= 0.0)) u = 0.0;
-    if (u >= 1.0) u = 0x1.fffffffffffffp-1;
-    const double x = u * pre2[n_l2 - 1];
-    const long long g = upper_index(pre2, n_l2, x);
-    const double r1 = x - (g ? pre2[g - 1] : 0.0);
-    const long long lo = g * kB, cnt = min(kB, n_l1 - lo);
-    const long long j = upper_index(pre1 + lo, cnt, r1);
-    const double r2 = r1 - (j ? pre1[lo + j - 1] : 0.0);
-    shot_blk[s] = (int)(lo + j);
-    shot_res[s] = r2;
-    atomicAdd(&count[lo + j], 1);
+    const bool active = s < shots;
+    int blk = 0;
+    if (active) {
+        double u = u01[s];
+        if (!(u >= 0.0)) u = 0.0;
+        if (u >= 1.0) u = 0x1.fffffffffffffp-1;
+        const double x = u * pre2[n_l2 - 1];
+        const long long g = upper_index(pre2, n_l2, x);
+        const double r1 = x - (g ? pre2[g - 1] : 0.0);
+        const long long lo = g * kB, cnt = min(kB, n_l1 - lo);
+        const long long j = upper_index(pre1 + lo, cnt, r1);
+        const double r2 = r1 - (j ? pre1[lo + j - 1] : 0.0);
+        blk = (int)(lo + j);
+        shot_blk[s] = blk;
+        shot_res[s] = r2;
+    }
+    warp_slot(count, blk, active);
 }
 // bucket start of block b from the two-level inclusive scan of the histogram
 __device__ __forceinline__ int bucket_start(const int *__restrict__ count, const int *__restrict__ cnt_incl, const int *__restrict__ cnt_tot, long long b) {
@@ -376,29 +414,58 @@ __global__ void __launch_bounds__(256) k_scatter(long long shots, const int *__r
                                                  const int *__restrict__ cnt_incl, const int *__restrict__ cnt_tot, int *__restrict__ cursor,
                                                  int *__restrict__ order) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= shots) return;
-    const int b = shot_blk[s];
-    order[bucket_start(count, cnt_incl, cnt_tot, b) + atomicAdd(&cursor[b], 1)] = (int)s;
+    const bool active = s < shots;
+    const int b = active ? shot_blk[s] : 0;
+    const int slot = warp_slot(cursor, b, active);
+    if (active) order[bucket_start(count, cnt_incl, cnt_tot, b) + slot] = (int)s;
 }
-// One CTA per block with shots: scan the block's probabilities once, answer every shot of its bucket.
+// The extra work of pass 2: block b holds count[b] shots, its own CTA serves the first kSliceShots of them, and every further
+// slice of kSliceShots becomes an item (b, slice) of a list -- at most shots / kSliceShots items in all.
+__global__ void __launch_bounds__(256) k_hot_list(const int *__restrict__ count, long long n_l1, int *__restrict__ n_items, int2 *__restrict__ items,
+                                                  int max_items) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_l1) return;
+    const int extra = (count[b] - 1) / kSliceShots; // slices 1 .. extra
+    if (extra <= 0) return;
+    const int at = atomicAdd(n_items, extra);
+    for (int k = 0; k < extra && at + k < max_items; ++k) items[at + k] = make_int2((int)b, k + 1);
+}
+// One CTA per block with shots: scan the block's probabilities once, answer the shots [slice * kSliceShots, (slice + 1) *
+// kSliceShots) of its bucket.  Launched twice: over all blocks (slice 0; a block without shots is not read), and over the
+// device-built list of further slices of the blocks that hold more than kSliceShots shots (items != nullptr).
 __global__ void __launch_bounds__(256) k_sample_blocks(const double *__restrict__ re, const double *__restrict__ im, long long len,
                                                        const int *__restrict__ count, const int *__restrict__ cnt_incl,
                                                        const int *__restrict__ cnt_tot, const int *__restrict__ order,
-                                                       const double *__restrict__ shot_res, long long *__restrict__ out) {
-    // blockIdx.y splits the bucket of a block that holds many shots (a peaked distribution puts most of 2^20 shots into a few
-    // blocks): slice y serves shots y * 256 + tid, stepping by 256 * gridDim.y, after scanning the block itself
-    const long long b = blockIdx.x;
+                                                       const double *__restrict__ shot_res, long long *__restrict__ out,
+                                                       const int *__restrict__ n_items, const int2 *__restrict__ items) {
+    long long b = blockIdx.x;
+    int slice = 0;
+    if (items) {
+        if ((int)blockIdx.x >= *n_items) return;
+        const int2 it = items[blockIdx.x];
+        b = it.x; slice = it.y;
+    }
     const int n_here = count[b];
-    if (n_here <= (int)(blockIdx.y * blockDim.x)) return;
+    if (n_here <= slice * kSliceShots) return;
     __shared__ double incl[kB];
     const long long lo = b * kB, cnt = min(kB, len - lo);
     double v[16];
+    if (cnt == kB) { // 256-bit reads, parked in shared memory in index order
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { // coalesced read (stride 256), parked transposed in shared memory
-        const long long j = (long long)i * 256 + threadIdx.x;
-        double p = 0.0;
-        if (j < cnt) { const double x = re[lo + j], y = im[lo + j]; p = x * x + y * y; }
-        incl[j] = p;
+        for (int i = 0; i < 4; ++i) {
+            const int j = 4 * (i * 256 + threadIdx.x);
+            const double4 x = ld_nc_256(re + lo + j), y = ld_nc_256(im + lo + j);
+            incl[j] = x.x * x.x + y.x * y.x; incl[j + 1] = x.y * x.y + y.y * y.y;
+            incl[j + 2] = x.z * x.z + y.z * y.z; incl[j + 3] = x.w * x.w + y.w * y.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const long long j = (long long)i * 256 + threadIdx.x;
+            double p = 0.0;
+            if (j < cnt) { const double x = re[lo + j], y = im[lo + j]; p = x * x + y * y; }
+            incl[j] = p;
+        }
     }
     __syncthreads();
 #pragma unroll
@@ -409,7 +476,8 @@ __global__ void __launch_bounds__(256) k_sample_blocks(const double *__restrict_
     for (int i = 0; i < 16; ++i) incl[threadIdx.x * 16 + i] = v[i];
     __syncthreads();
     const int start = bucket_start(count, cnt_incl, cnt_tot, b);
-    for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < n_here; k += blockDim.x * gridDim.y) {
+    const int k_end = min(n_here, (slice + 1) * kSliceShots);
+    for (int k = slice * kSliceShots + threadIdx.x; k < k_end; k += blockDim.x) {
         const int s = order[start + k];
         out[s] = lo + upper_index(incl, cnt, shot_res[s]);
     }
@@ -441,7 +509,9 @@ int launch_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_
     const size_t o_pre1 = 0, o_pre2 = o_pre1 + up(8 * (size_t)n_l1), o_count = o_pre2 + up(8 * (size_t)n_l2);
     const size_t o_cursor = o_count + up(4 * (size_t)n_l1), o_cincl = o_cursor + up(4 * (size_t)n_l1), o_ctot = o_cincl + up(4 * (size_t)n_l1);
     const size_t o_u = o_ctot + up(4 * (size_t)n_l2), o_res = o_u + up(8 * (size_t)shots), o_blk = o_res + up(8 * (size_t)shots);
-    const size_t o_order = o_blk + up(4 * (size_t)shots), o_out = o_order + up(4 * (size_t)shots), total = o_out + up(8 * (size_t)shots);
+    const int max_items = (int)(shots / kSliceShots) + 1;
+    const size_t o_order = o_blk + up(4 * (size_t)shots), o_out = o_order + up(4 * (size_t)shots), o_items = o_out + up(8 * (size_t)shots);
+    const size_t o_nitems = o_items + up(8 * (size_t)max_items), total = o_nitems + 256;
     char *base = nullptr;
     SPZ_TRY(sample_arena(st, total, &base));
     double *pre1 = reinterpret_cast<double *>(base + o_pre1), *pre2 = reinterpret_cast<double *>(base + o_pre2);
@@ -450,7 +520,10 @@ int launch_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_
     double *d_u = reinterpret_cast<double *>(base + o_u), *d_res = reinterpret_cast<double *>(base + o_res);
     int *d_blk = reinterpret_cast<int *>(base + o_blk), *d_order = reinterpret_cast<int *>(base + o_order);
     long long *d_out = reinterpret_cast<long long *>(base + o_out);
+    int2 *d_items = reinterpret_cast<int2 *>(base + o_items);
+    int *d_nitems = reinterpret_cast<int *>(base + o_nitems);
     cudaStream_t q = st->stream;
+    SPZ_CUDA(cudaMemsetAsync(d_nitems, 0, sizeof(int), q));
     SPZ_CUDA(cudaMemcpyAsync(d_u, u01, sizeof(double) * (size_t)shots, cudaMemcpyHostToDevice, q));
     SPZ_CUDA(cudaMemsetAsync(count, 0, o_cincl - o_count, q)); // histogram and cursors
     k_block_prob<<<(unsigned)n_l1, 256, 0, q>>>(st->re, st->im, len, pre1);
@@ -461,9 +534,10 @@ int launch_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_
     k_scan_groups<int><<<(unsigned)n_l2, 256, 0, q>>>(count, n_l1, cincl, ctot);
     k_scan_single<int><<<1, 256, 0, q>>>(ctot, n_l2);
     k_scatter<<<shot_grid, 256, 0, q>>>(shots, d_blk, count, cincl, ctot, cursor, d_order);
-    const unsigned slices = (unsigned)std::min<int64_t>(16, std::max<int64_t>(1, shots / 4096)); // (a slice without shots exits at once)
-    k_sample_blocks<<<dim3((unsigned)n_l1, slices), 256, 0, q>>>(st->re, st->im, len, count, cincl, ctot, d_order, d_res, d_out);
-    count_launch(8);
+    k_hot_list<<<(unsigned)((n_l1 + 255) / 256), 256, 0, q>>>(count, n_l1, d_nitems, d_items, max_items);
+    k_sample_blocks<<<(unsigned)n_l1, 256, 0, q>>>(st->re, st->im, len, count, cincl, ctot, d_order, d_res, d_out, nullptr, nullptr);
+    k_sample_blocks<<<(unsigned)max_items, 256, 0, q>>>(st->re, st->im, len, count, cincl, ctot, d_order, d_res, d_out, d_nitems, d_items);
+    count_launch(10);
     SPZ_CUDA(cudaGetLastError());
     SPZ_CUDA(cudaMemcpyAsync(out_index, d_out, sizeof(long long) * (size_t)shots, cudaMemcpyDeviceToHost, q));
     SPZ_CUDA(cudaStreamSynchronize(q));

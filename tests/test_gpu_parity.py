@@ -533,6 +533,33 @@ def test_sample_matches_oracle_cdf(n):
     assert len(bad) <= 2
 
 
+def test_sample_peaked_distribution_many_shots_matches_oracle_cdf():
+    """Most of 2^17 shots land in one or two blocks of 4096 amplitudes: the warp-aggregated histogram, and the extra pass-2 CTAs
+    of blocks that hold more than 1024 shots (k_hot_list), against the oracle's CDF walk."""
+    n = 15
+    cpu = orc.gen_random_state(n, 77)
+    w = np.full(1 << n, 0.02 / (1 << n))
+    w[5000] = 0.6
+    w[5001] = 0.1
+    w[20000] = 0.28
+    phase = np.arctan2(cpu.imags, cpu.reals)
+    amp = np.sqrt(w / w.sum())
+    cpu.reals[:] = amp * np.cos(phase)
+    cpu.imags[:] = amp * np.sin(phase)
+    gpu = to_gpu(cpu)
+    u = orc.uniforms(7, 1 << 17)
+    got = sb.sample(gpu, len(u), u01=u)
+    want = orc.sample_cdf(cpu, u)
+    bad = np.nonzero(got != want)[0]
+    cdf = np.cumsum(cpu.reals ** 2 + cpu.imags ** 2)
+    for k in bad:  # only legal when u sits within rounding of a CDF boundary
+        assert abs(int(got[k]) - int(want[k])) == 1
+        assert abs(cdf[min(got[k], want[k])] - u[k] * cdf[-1]) < 1e-12
+    assert len(bad) <= 8
+    counts = np.bincount(got, minlength=1 << n)
+    assert abs(counts[5000] / len(u) - 0.6) < 0.01 and abs(counts[20000] / len(u) - 0.28) < 0.01
+
+
 def test_sample_chi_square():
     n = 6
     cpu = orc.gen_random_state(n, 99)
