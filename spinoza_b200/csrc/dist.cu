@@ -268,14 +268,9 @@ static int check_comm_error(spz_state *st) {
 
 int dist_join(spz_state *st);
 
-int dist_exchange(spz_state *st, int gbit, int lq) {
-    DistCtx *c = ctx_of(st);
-    if (!c->connected) { set_error("dist state used before spz_dist_connect"); return SPZ_ERR_COMM; }
-    const int partner = c->rank ^ (1 << gbit);
-    const int my_bit = (c->rank >> gbit) & 1;
-    SPZ_TRY(dist_join(st)); // a previous overlapped exchange must have landed completely
-    const unsigned long long e = ++c->epoch;
-    // recycle the timing events of exchanges that have already finished (keeps the pool bounded on long runs)
+// A pair of timing events for one exchange; the pairs of exchanges that have finished are recycled (keeps the pool bounded on
+// long runs -- used by both exchange paths).
+static int take_timing_events(DistCtx *c, std::pair<cudaEvent_t, cudaEvent_t> *ev) {
     if (c->pending.size() >= 32) {
         size_t keep = 0;
         for (auto &e : c->pending) {
@@ -290,9 +285,20 @@ int dist_exchange(spz_state *st, int gbit, int lq) {
         c->pending.resize(keep);
         cudaGetLastError(); // cudaErrorNotReady from the query is not an error
     }
+    if (!c->free_events.empty()) { *ev = c->free_events.back(); c->free_events.pop_back(); }
+    else { SPZ_CUDA(cudaEventCreate(&ev->first)); SPZ_CUDA(cudaEventCreate(&ev->second)); }
+    return SPZ_OK;
+}
+
+int dist_exchange(spz_state *st, int gbit, int lq) {
+    DistCtx *c = ctx_of(st);
+    if (!c->connected) { set_error("dist state used before spz_dist_connect"); return SPZ_ERR_COMM; }
+    const int partner = c->rank ^ (1 << gbit);
+    const int my_bit = (c->rank >> gbit) & 1;
+    SPZ_TRY(dist_join(st)); // a previous overlapped exchange must have landed completely
+    const unsigned long long e = ++c->epoch;
     std::pair<cudaEvent_t, cudaEvent_t> ev;
-    if (!c->free_events.empty()) { ev = c->free_events.back(); c->free_events.pop_back(); }
-    else { SPZ_CUDA(cudaEventCreate(&ev.first)); SPZ_CUDA(cudaEventCreate(&ev.second)); }
+    SPZ_TRY(take_timing_events(c, &ev));
     XArgs a{};
     a.mine_re = st->re; a.mine_im = st->im; a.peer_re = c->peer_re[partner]; a.peer_im = c->peer_im[partner];
     a.lq = lq; a.my_bit = my_bit;
@@ -364,11 +370,28 @@ int dist_exchange_gate(spz_state *st, int gbit, int lq, const GateK &g) {
     const int n_local = st->n;
     if (lq < LogW<W>::v || n_local - 1 - LogW<W>::v < 0) { set_error("internal: fused exchange needs a vector path"); return SPZ_ERR_INVALID_ARG; }
     const int partner = c->rank ^ (1 << gbit);
+    // (checked before anything is launched or counted: an error here must leave this rank in step with its partner)
+    const void *kern = nullptr;
+    switch (g.kind) {
+    case SPZ_GATE_H: kern = (const void *)k_exchange_gate<SPZ_GATE_H, W, U, THREADS>; break;
+    case SPZ_GATE_X: kern = (const void *)k_exchange_gate<SPZ_GATE_X, W, U, THREADS>; break;
+    case SPZ_GATE_Y: kern = (const void *)k_exchange_gate<SPZ_GATE_Y, W, U, THREADS>; break;
+    case SPZ_GATE_RX: kern = (const void *)k_exchange_gate<SPZ_GATE_RX, W, U, THREADS>; break;
+    case SPZ_GATE_RY: kern = (const void *)k_exchange_gate<SPZ_GATE_RY, W, U, THREADS>; break;
+    case SPZ_GATE_U: kern = (const void *)k_exchange_gate<SPZ_GATE_U, W, U, THREADS>; break;
+    default: set_error("internal: gate kind %d cannot be fused into an exchange", g.kind); return SPZ_ERR_INVALID_ARG;
+    }
+    // CTA b of one rank talks to CTA b of the other through spin flags, so every CTA of both kernels must be resident at once:
+    // no more CTAs than the device can hold, half of that when the two shards share the device (a local group on one GPU).
+    int per_sm = 0, n_sm = 0;
+    SPZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, 0));
+    SPZ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, st->device));
+    int resident = std::max(1, per_sm * n_sm);
+    if (!c->ipc) resident = std::max(1, resident / 2);
     SPZ_TRY(dist_join(st));
     const unsigned long long e = ++c->epoch;
     std::pair<cudaEvent_t, cudaEvent_t> ev;
-    if (!c->free_events.empty()) { ev = c->free_events.back(); c->free_events.pop_back(); }
-    else { SPZ_CUDA(cudaEventCreate(&ev.first)); SPZ_CUDA(cudaEventCreate(&ev.second)); }
+    SPZ_TRY(take_timing_events(c, &ev));
     XGArgs a{};
     a.mine_re = st->re; a.mine_im = st->im; a.peer_re = c->peer_re[partner]; a.peer_im = c->peer_im[partner];
     a.nvec = 1ll << (n_local - 1 - LogW<W>::v);
@@ -379,18 +402,13 @@ int dist_exchange_gate(spz_state *st, int gbit, int lq, const GateK &g) {
     a.timeout_ns = kSpinTimeoutNs;
     for (int k = 0; k < 7; ++k) a.s[k] = g.s[k];
     const long long per = (long long)THREADS * U;
-    const int ctas = (int)std::max<long long>(1, std::min<long long>(std::min(c->xg_ctas, kMaxXgCtas), (a.nvec + per - 1) / per));
+    const int ctas = (int)std::max<long long>(1, std::min<long long>(std::min(std::min(c->xg_ctas, kMaxXgCtas), resident), (a.nvec + per - 1) / per));
     c->xg_base += (unsigned long long)((a.nvec + per * ctas - 1) / (per * ctas)); // steps of the busiest CTA, the same on both ranks
     k_handshake<<<1, 1, 0, st->stream>>>(&c->peer_ctrl[partner]->ready[c->rank], &c->ctrl->ready[partner], e, &c->ctrl->error);
     SPZ_CUDA(cudaEventRecord(ev.first, st->stream));
-    switch (g.kind) {
-    case SPZ_GATE_H: k_exchange_gate<SPZ_GATE_H, W, U, THREADS><<<ctas, THREADS, 0, st->stream>>>(a); break;
-    case SPZ_GATE_X: k_exchange_gate<SPZ_GATE_X, W, U, THREADS><<<ctas, THREADS, 0, st->stream>>>(a); break;
-    case SPZ_GATE_Y: k_exchange_gate<SPZ_GATE_Y, W, U, THREADS><<<ctas, THREADS, 0, st->stream>>>(a); break;
-    case SPZ_GATE_RX: k_exchange_gate<SPZ_GATE_RX, W, U, THREADS><<<ctas, THREADS, 0, st->stream>>>(a); break;
-    case SPZ_GATE_RY: k_exchange_gate<SPZ_GATE_RY, W, U, THREADS><<<ctas, THREADS, 0, st->stream>>>(a); break;
-    case SPZ_GATE_U: k_exchange_gate<SPZ_GATE_U, W, U, THREADS><<<ctas, THREADS, 0, st->stream>>>(a); break;
-    default: set_error("internal: gate kind %d cannot be fused into an exchange", g.kind); return SPZ_ERR_INVALID_ARG;
+    {
+        void *params[] = {&a};
+        SPZ_CUDA(cudaLaunchKernel(kern, dim3((unsigned)ctas), dim3(THREADS), params, 0, st->stream));
     }
     SPZ_CUDA(cudaEventRecord(ev.second, st->stream));
     c->pending.push_back(ev);

@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256, 2) k_tile(const TileArgs a) {
 int tile_prepare(spz_state *st) {
     if (!st->d_ops) {
         const size_t cap = (size_t)4 << 20;
-        SPZ_CUDA(cudaMalloc(&st->d_ops, cap));
+        SPZ_CUDA(cudaMallocAsync(&st->d_ops, cap, st->stream)); // (stream-ordered, so that tile_ring_alloc may regrow it with cudaFreeAsync)
         st->d_ops_bytes = cap;
         st->d_ops_cursor = 0;
     }
@@ -405,11 +405,12 @@ int tile_prepare(spz_state *st) {
 int tile_ring_alloc(spz_state *st, size_t bytes, char **slot) {
     bytes = (bytes + 255) & ~(size_t)255;
     if (st->d_ops_bytes < bytes || !st->d_ops) {
-        // (never taken for programs within the scheduler's per-pass op limit: the buffer is sized in tile_prepare because a
-        // device-wide synchronisation must not happen while another shard's handshake kernel spins on the same GPU)
-        if (st->d_ops) { SPZ_CUDA(cudaStreamSynchronize(st->stream)); SPZ_CUDA(cudaFree(st->d_ops)); st->d_ops = nullptr; }
+        // (rare: the buffer is sized in tile_prepare for programs within the scheduler's per-pass op limit.)  Stream-ordered
+        // allocation: cudaMalloc / cudaFree synchronise the whole device, which must not happen while another shard's handshake
+        // kernel spins on the same GPU; the old buffer is released behind the passes that still read it.
+        if (st->d_ops) { SPZ_CUDA(cudaFreeAsync(st->d_ops, st->stream)); st->d_ops = nullptr; st->d_ops_bytes = 0; }
         const size_t cap = std::max<size_t>(bytes * 2, (size_t)4 << 20);
-        SPZ_CUDA(cudaMalloc(&st->d_ops, cap));
+        SPZ_CUDA(cudaMallocAsync(&st->d_ops, cap, st->stream));
         st->d_ops_bytes = cap;
         st->d_ops_cursor = 0;
     }
