@@ -65,6 +65,8 @@ struct DistCtx {
     int n_chunks = 4;          // SPZ_XCHG_CHUNKS (1, 2, 4 or 8)
     bool overlap = true;
     int xchg_ctas = 40; // CTAs of the persistent exchange kernel in overlapped mode (SPZ_XCHG_CTAS)
+    bool xchg_tma = false;   // SPZ_XCHG_TMA=1: bulk-copy variant (k_exchange_tma), SPZ_XCHG_TMA_CTAS one-warp CTAs
+    int xchg_tma_ctas = 32;
     // fused exchange + gate (opt-in, SPZ_DIST_FUSE_GATE=1): flag values already used, and the size of its persistent grid
     unsigned long long xg_base = 0;
     int xg_ctas = 128;  // SPZ_XG_CTAS; every CTA must be resident at once, so <= the number of SMs
@@ -230,6 +232,72 @@ __global__ void __launch_bounds__(THREADS) k_exchange_vec_persistent(const XArgs
     }
 }
 
+// TMA variant of the persistent exchange (opt-in, SPZ_XCHG_TMA=1): the same in-place swap, moved by the copy engine of the SM
+// instead of by loads and stores of its threads.  A CTA is one warp; lane 0 issues, per step, four 1-D bulk loads of one
+// contiguous run (mine re / im, partner's re / im over NVLink) into a shared-memory stage on an mbarrier, and when they have
+// landed four bulk stores that write each side's run to the other side.  kXtStages stages are in flight per CTA.  The traded
+// bit lq >= 8, so a run (the 2^lq amplitudes below the traded bit) is >= 2 KB; runs longer than kXtRun doubles are cut.
+constexpr int kXtStages = 3;
+constexpr unsigned kXtRun = 2048;          // doubles per bulk copy: 16 KB
+__global__ void __launch_bounds__(32) k_exchange_tma(const XArgs a) {
+#ifndef SPZ_CPU_EMULATION
+    extern __shared__ __align__(128) unsigned char xsm[];
+    const unsigned run = min((unsigned long long)kXtRun, 1ull << a.lq);      // doubles per piece
+    const unsigned bytes = run * 8u;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(xsm + (size_t)kXtStages * 4u * kXtRun * 8u);
+    const unsigned long long lbit = 1ull << a.lq;
+    // pieces of the pair list: [nvec_begin, nvec_end) vectors of 4 doubles -> pieces of `run` doubles
+    const unsigned long long p_begin = ((unsigned long long)a.nvec_begin * 4ull) / run, p_end = ((unsigned long long)a.nvec_end * 4ull) / run;
+    if (threadIdx.x != 0) return;
+    auto sh = [&](const void *p) { return (unsigned)__cvta_generic_to_shared(p); };
+    for (int s = 0; s < kXtStages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sh(bar + s)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    auto addr_of = [&](unsigned long long piece, unsigned long long *mine, unsigned long long *peer) {
+        const unsigned long long base = insert_zero(piece * run, a.lq);
+        *mine = a.my_bit ? base : (base | lbit);
+        *peer = a.my_bit ? (base | lbit) : base;
+    };
+    auto issue_loads = [&](unsigned long long piece, int s) {
+        unsigned long long im_, ip_;
+        addr_of(piece, &im_, &ip_);
+        unsigned char *st = xsm + (size_t)s * 4u * kXtRun * 8u;
+        const unsigned b = sh(bar + s);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(4u * bytes) : "memory");
+        const double *src[4] = {a.peer_re + ip_, a.peer_im + ip_, a.mine_re + im_, a.mine_im + im_}; // NVLink loads first
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sh(st + (size_t)k * kXtRun * 8u)), "l"(src[k]), "r"(bytes), "r"(b) : "memory");
+    };
+    unsigned phase[kXtStages] = {0, 0, 0};
+    unsigned long long next = p_begin + blockIdx.x;
+    // prologue: fill the stages
+    int filled = 0;
+    for (; filled < kXtStages && next < p_end; ++filled, next += gridDim.x) issue_loads(next, filled);
+    unsigned long long cur = p_begin + blockIdx.x;
+    for (int s = 0; cur < p_end; cur += gridDim.x, s = (s + 1) % kXtStages) {
+        const unsigned b = sh(bar + s);
+        asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(b), "r"(phase[s]) : "memory");
+        phase[s] ^= 1u;
+        unsigned long long im_, ip_;
+        addr_of(cur, &im_, &ip_);
+        unsigned char *st = xsm + (size_t)s * 4u * kXtRun * 8u;
+        double *dst[4] = {a.mine_re + im_, a.mine_im + im_, a.peer_re + ip_, a.peer_im + ip_}; // what came from the partner stays here, mine goes there
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst[k]), "r"(sh(st + (size_t)k * kXtRun * 8u)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (next < p_end) {
+            // the stage is refilled once its stores have read it
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            issue_loads(next, s);
+            next += gridDim.x;
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // every store complete before the done handshake that follows in the stream
+#endif
+}
+
 __global__ void k_exchange_scalar(const XArgs a) {
     const unsigned long long lbit = 1ull << a.lq;
     for (long long v = a.nvec_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; v < a.nvec_end;
@@ -327,7 +395,10 @@ int dist_exchange(spz_state *st, int gbit, int lq) {
             const long long hb = h * (nvec / K) + my_bit * (nvec / (2 * K));
             XArgs r = a;
             r.nvec_begin = hb; r.nvec_end = hb + nvec / (2 * K);
-            k_exchange_vec_persistent<W, U, THREADS><<<(unsigned)c->xchg_ctas, THREADS, 0, c->xstream>>>(r);
+            if (c->xchg_tma && lq >= 8 && ((r.nvec_end - r.nvec_begin) * 4) % (long long)std::min<unsigned long long>(kXtRun, 1ull << lq) == 0)
+                k_exchange_tma<<<(unsigned)c->xchg_tma_ctas, 32, (size_t)kXtStages * 4u * kXtRun * 8u + 64, c->xstream>>>(r);
+            else
+                k_exchange_vec_persistent<W, U, THREADS><<<(unsigned)c->xchg_ctas, THREADS, 0, c->xstream>>>(r);
             k_handshake<<<1, 1, 0, c->xstream>>>(&c->peer_ctrl[partner]->done_k[h][c->rank], &c->ctrl->done_k[h][partner], e, &c->ctrl->error);
             if (h == K - 1) SPZ_CUDA(cudaEventRecord(ev.second, c->xstream));
             SPZ_CUDA(cudaEventRecord(c->ev_chunk[h], c->xstream));
@@ -682,6 +753,9 @@ int spz_dist_create(int n_qubits, int rank, int world, int device, spz_state **o
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming);
     for (int k = 0; k < kMaxChunks; ++k) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_chunk[k], cudaEventDisableTiming);
+    if (const char *v = getenv("SPZ_XCHG_TMA")) c->xchg_tma = v[0] == '1';
+    if (const char *v = getenv("SPZ_XCHG_TMA_CTAS")) { const int k = atoi(v); if (k >= 1 && k <= 148) c->xchg_tma_ctas = k; }
+    if (c->xchg_tma) cudaFuncSetAttribute(k_exchange_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kXtStages * 4u * kXtRun * 8u + 64));
     if (const char *v = getenv("SPZ_XCHG_CHUNKS")) { const int k = atoi(v); if (k == 1 || k == 2 || k == 4 || k == 8) c->n_chunks = k; }
     if (getenv("SPZ_NO_OVERLAP")) c->overlap = false;
     if (const char *v = getenv("SPZ_XCHG_CTAS")) { const int k = atoi(v); if (k >= 1 && k <= 1024) c->xchg_ctas = k; }

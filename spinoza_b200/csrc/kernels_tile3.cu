@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #ifndef SPZ_CPU_EMULATION
@@ -321,6 +322,33 @@ __device__ __forceinline__ void bfly3(double (&ar)[16], double (&ai)[16], unsign
         if (k0 & (1 << R)) continue;
         const int k1 = k0 | (1 << R);
         if (ALL || (km & (1u << k0))) pair3<MK>(s, ar[k0], ai[k0], ar[k1], ai[k1]); // km is the same for every thread
+    }
+}
+// X / Y under a pair mask.  The mask of a guarded exchange is one of a few shapes: every pair (the controls are thread bits or
+// bits outside the tile), or the pairs whose register index has one other register bit set (a CX between two register-resident
+// qubits: four pairs).  Testing the mask once and running a branch-free block costs 48-96 logic instructions; testing it
+// pair by pair cost a compare, a branch and a reconvergence point per pair on top (~90-130 per exchange, and a CX is a fifth
+// of a layered circuit).
+template <int MK, int R>
+__device__ __forceinline__ void perm3(double (&ar)[16], double (&ai)[16], unsigned km) {
+    const double s[2] = {0.0, 0.0};
+    auto with_bit = [&](auto c_tag) {
+        constexpr int C = decltype(c_tag)::value;
+#pragma unroll
+        for (int k0 = 0; k0 < 16; ++k0)
+            if (!(k0 & (1 << R)) && (k0 & (1 << C))) pair3<MK>(s, ar[k0], ai[k0], ar[k0 | (1 << R)], ai[k0 | (1 << R)]);
+    };
+    constexpr unsigned m0 = 0xAAAAu, m1 = 0xCCCCu, m2 = 0xF0F0u, m3 = 0xFF00u; // register indices with bit 0 / 1 / 2 / 3 set
+    if (km == 0xffffu) {
+#pragma unroll
+        for (int k0 = 0; k0 < 16; ++k0)
+            if (!(k0 & (1 << R))) pair3<MK>(s, ar[k0], ai[k0], ar[k0 | (1 << R)], ai[k0 | (1 << R)]);
+    } else if (R != 0 && km == m0) { with_bit(std::integral_constant<int, R != 0 ? 0 : 1>());
+    } else if (R != 1 && km == m1) { with_bit(std::integral_constant<int, R != 1 ? 1 : 0>());
+    } else if (R != 2 && km == m2) { with_bit(std::integral_constant<int, R != 2 ? 2 : 0>());
+    } else if (R != 3 && km == m3) { with_bit(std::integral_constant<int, R != 3 ? 3 : 0>());
+    } else {
+        bfly3<MK, R, false>(ar, ai, 0u, km);
     }
 }
 template <int R>
@@ -666,6 +694,11 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
     case T3_GATE + 4 * V + 1: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 1, false>(ar, ai, ip + 16u, w.y & 0xffffu); break; }      \
     case T3_GATE + 4 * V + 2: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 2, false>(ar, ai, ip + 16u, w.y & 0xffffu); break; }      \
     case T3_GATE + 4 * V + 3: { SPZ_W; if (SPZ_OK(w)) bfly3<MK, 3, false>(ar, ai, ip + 16u, w.y & 0xffffu); break; }
+#define SPZ_PERM_GUARDED(V, MK)                                                                              \
+    case T3_GATE + 4 * V + 0: { SPZ_W; if (SPZ_OK(w)) perm3<MK, 0>(ar, ai, w.y & 0xffffu); break; }          \
+    case T3_GATE + 4 * V + 1: { SPZ_W; if (SPZ_OK(w)) perm3<MK, 1>(ar, ai, w.y & 0xffffu); break; }          \
+    case T3_GATE + 4 * V + 2: { SPZ_W; if (SPZ_OK(w)) perm3<MK, 2>(ar, ai, w.y & 0xffffu); break; }          \
+    case T3_GATE + 4 * V + 3: { SPZ_W; if (SPZ_OK(w)) perm3<MK, 3>(ar, ai, w.y & 0xffffu); break; }
             // Accumulator F_{r+1} -- or a constant of the pool, when the host folded the pending factor (AF_CONST) -- is pending
             // and a butterfly on register bit r follows: apply it to the amplitudes with that bit set.  Only the accumulator of the
             // target's own bit separates the two members of a pair; the others scale both by the same factor and stay pending.
@@ -692,8 +725,8 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
             SPZ_GATE_GUARDED(3, MK_HS)
             SPZ_GATE_GUARDED(4, MK_RX)
             SPZ_GATE_GUARDED(5, MK_RY)
-            SPZ_GATE_GUARDED(6, MK_X)
-            SPZ_GATE_GUARDED(7, MK_Y)
+            SPZ_PERM_GUARDED(6, MK_X)
+            SPZ_PERM_GUARDED(7, MK_Y)
             SPZ_PRE(0)
             SPZ_PRE(1)
             SPZ_PRE(2)
@@ -758,6 +791,7 @@ __global__ void __launch_bounds__(kThreads3, 2) k_tile3(const
             }
 #undef SPZ_GATE_ALL
 #undef SPZ_GATE_GUARDED
+#undef SPZ_PERM_GUARDED
 #undef SPZ_PRE
 #undef SPZ_OK
 #undef SPZ_W
