@@ -1,8 +1,9 @@
-"""The one sharded-register feature that stays opt-in (SPZ_TEST_DIST_OPTIN=1): the exchange fused with the gate that asked for it
+"""The one sharded-register feature that is off by default in the product: the exchange fused with the gate that asked for it
 (SPZ_DIST_FUSE_GATE=1, kernels_xgate.cuh).  It is correct on hardware -- these tests pass on a B200, and bench.py's sharded
 parity extra passes with it on two GPUs over NVLink -- but slower than exchange + gate: its peer traffic is loads only and
-reaches 385 GB/s per direction against 660 GB/s for the load + store exchange (profiles/round2_summary.md), so it is off by
-default.  Local groups: every shard on the one visible GPU, plain device pointers instead of IPC mappings."""
+reaches 385 GB/s per direction against 660 GB/s for the load + store exchange (profiles/round2_summary.md).  The kernel ships
+in the library, so its tests run with the rest of the GPU suite (SPZ_TEST_DIST_OPTIN=0 skips them).  Local groups: every
+shard on the one visible GPU, plain device pointers instead of IPC mappings."""
 import os
 
 import numpy as np
@@ -14,7 +15,7 @@ from spinoza_b200 import QuantumCircuit, workloads
 from tests.test_gpu_parity import oracle_ops_from
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SPZ_TEST_DIST_OPTIN") != "1", reason="opt-in: SPZ_TEST_DIST_OPTIN=1")]
+              pytest.mark.skipif(os.environ.get("SPZ_TEST_DIST_OPTIN") == "0", reason="SPZ_TEST_DIST_OPTIN=0")]
 
 
 # ---- exchange fused with the gate that asked for it (SPZ_DIST_FUSE_GATE=1, kernels_xgate.cuh; opt-in) --------------------
