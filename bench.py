@@ -532,11 +532,15 @@ def main():
             state.init_random(42)
             state.download_into(hre, him)
             e2e_steps = max(1, min(args.steps, 5))
-            state.upload_from(hre, him); step(); state.download_into(hre, him)  # warm-up
+            # spz_upload_async: the state arrives in four pieces on a copy stream and the gates on targets below the piece bits
+            # follow piece by piece behind the bus; spz_download waits for everything (SPZ_BENCH_SYNC_UPLOAD=1: spz_upload)
+            sync_upload = os.environ.get("SPZ_BENCH_SYNC_UPLOAD") == "1"
+            upload = state.upload_from if sync_upload else state.upload_async
+            upload(hre, him); step(); state.download_into(hre, him)  # warm-up
             barrier()
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
-                state.upload_from(hre, him)
+                upload(hre, him)
                 step()
                 state.download_into(hre, him)
             dt = (time.perf_counter() - t0) / e2e_steps
@@ -545,7 +549,7 @@ def main():
             line["e2e"] = {"value": gates_per_step * bytes_per_gate_total / dt / 1e9, "unit": "GB/s",
                            "h2d_bytes_per_step": 2 * nbytes * world, "d2h_bytes_per_step": 2 * nbytes * world,
                            "ms_per_step": dt * 1e3, "steps": e2e_steps,
-                           "what": f"pinned host re/im -> spz_upload -> {gates_per_step} x spz_apply -> spz_download (whole state"
+                           "what": f"pinned host re/im -> {'spz_upload' if sync_upload else 'spz_upload_async'} -> {gates_per_step} x spz_apply -> spz_download (whole state"
                                    + (", every rank its own shard" if dist is not None else "") + "), wall clock, max over ranks"}
             del hre, him
         except Exception as e:  # host cannot pin the buffers

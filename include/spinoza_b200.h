@@ -110,6 +110,12 @@ SPZ_API int spz_init_random(spz_state *st, uint64_t seed);          /* utils.rs:
 /* `state.reals[..] / state.imags[..]` access (tests index the Vecs directly, e.g. gates.rs:1541) */
 SPZ_API int spz_upload(spz_state *st, const double *re, const double *im, int64_t offset, int64_t count);
 SPZ_API int spz_download(const spz_state *st, double *re, double *im, int64_t offset, int64_t count);
+/* Whole-state upload that returns at once (no counterpart in the reference, whose State lives in host memory: this is
+   `State { reals, imags, n }` for a device-resident state, overlapped with what follows).  The state arrives in contiguous
+   pieces on a copy stream and the gates / fused passes issued next run piece by piece behind the bus.  re / im: page-locked
+   (spz_alloc_host), 2^n doubles each (the shard's length for a sharded register), untouched until the next spz_sync,
+   spz_download or spz_upload. */
+SPZ_API int spz_upload_async(spz_state *st, const double *re, const double *im);
 SPZ_API int spz_sync(spz_state *st);
 /* page-locked host buffers for spz_upload / spz_download at full PCIe speed (plain malloc memory also works) */
 SPZ_API int spz_alloc_host(uint64_t bytes, void **out);

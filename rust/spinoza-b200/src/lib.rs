@@ -93,6 +93,9 @@ pub mod ffi {
             out: *mut f64,
         ) -> c_int;
         pub fn spz_sample(st: *mut spz_state, u01: *const f64, shots: i64, out_index: *mut i64) -> c_int;
+        pub fn spz_upload_async(st: *mut spz_state, re: *const f64, im: *const f64) -> c_int;
+        pub fn spz_alloc_host(bytes: u64, out: *mut *mut std::ffi::c_void) -> c_int;
+        pub fn spz_free_host(ptr: *mut std::ffi::c_void) -> c_int;
         pub fn spz_norm2(st: *mut spz_state, out: *mut f64) -> c_int;
         pub fn spz_sync(st: *mut spz_state) -> c_int;
         // sharded registers (include/spinoza_b200.h, "multi-GPU"): one process per GPU, or several shards in one process
@@ -185,6 +188,16 @@ pub mod core {
         }
         pub fn set_seed(&mut self, seed: u64) {
             check(unsafe { ffi::spz_set_seed(self.h, seed) });
+        }
+        /// Whole-state upload that returns at once; the gates issued next follow the state piece by piece as it arrives.
+        /// # Safety
+        /// `reals` / `imags` must be page-locked (`spz_alloc_host`), hold `len()` values each and stay alive and untouched until
+        /// the next `sync` / `reals()` / `imags()`.
+        pub unsafe fn upload_async(&mut self, reals: *const Float, imags: *const Float) {
+            check(ffi::spz_upload_async(self.h, reals, imags));
+        }
+        pub fn sync(&mut self) {
+            check(unsafe { ffi::spz_sync(self.h) });
         }
     }
     impl Clone for State {

@@ -95,6 +95,7 @@ _SIGNATURES = {
     "spz_set_basis": (C.c_int, [_vp, C.c_uint64]),
     "spz_init_random": (C.c_int, [_vp, C.c_uint64]),
     "spz_upload": (C.c_int, [_vp, _dp, _dp, C.c_int64, C.c_int64]),
+    "spz_upload_async": (C.c_int, [_vp, _dp, _dp]),
     "spz_download": (C.c_int, [_vp, _dp, _dp, C.c_int64, C.c_int64]),
     "spz_sync": (C.c_int, [_vp]),
     "spz_alloc_host": (C.c_int, [C.c_uint64, C.POINTER(_vp)]),
@@ -372,6 +373,14 @@ class State:
 
     def upload_from(self, re: "HostBuffer", im: "HostBuffer", offset: int = 0):
         _check(_lib.spz_upload(self._h, re.ptr(), im.ptr(), offset, re.count))
+
+    def upload_async(self, re: "HostBuffer", im: "HostBuffer"):
+        """Whole-state upload from page-locked buffers that returns at once: the gates issued next follow the pieces as they
+        arrive.  The buffers must stay alive and untouched until the next sync() / download."""
+        if re.count != len(self) or im.count != len(self):
+            raise ValueError("upload_async moves the whole state: buffers of len(state) doubles")
+        self._async_src = (re, im)  # keep the buffers alive
+        _check(_lib.spz_upload_async(self._h, re.ptr(), im.ptr()))
 
     def download_into(self, re: "HostBuffer", im: "HostBuffer", offset: int = 0):
         _check(_lib.spz_download(self._h, re.ptr(), im.ptr(), offset, re.count))

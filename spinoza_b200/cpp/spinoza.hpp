@@ -109,6 +109,11 @@ class State {
     std::vector<Float> imags() const { std::vector<Float> v(len()); check(spz_download(h_, nullptr, v.data(), 0, (int64_t)v.size())); return v; }
     std::pair<Float, Float> amp(std::size_t i) const { Float r, m; check(spz_download(h_, &r, &m, (int64_t)i, 1)); return {r, m}; }
     void set(const std::vector<Float> &re, const std::vector<Float> &im) { check(spz_upload(h_, re.data(), im.data(), 0, (int64_t)re.size())); }
+    // whole-state upload that returns at once (page-locked buffers of len() doubles, untouched until the next sync / download):
+    // the gates issued next follow the state piece by piece as it arrives
+    void upload_async(const Float *re_pinned, const Float *im_pinned) { check(spz_upload_async(h_, re_pinned, im_pinned)); }
+    void download_into(Float *re, Float *im) const { check(spz_download(h_, re, im, 0, (int64_t)len())); }
+    void sync() { check(spz_sync(h_)); }
     void set_seed(std::uint64_t seed) { check(spz_set_seed(h_, seed)); }
     spz_state *handle() const { return h_; }
     static State adopt(spz_state *h) { State s; s.h_ = h; return s; } // a handle made elsewhere (spinoza::dist)

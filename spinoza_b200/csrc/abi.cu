@@ -45,6 +45,34 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int arrival_join(spz_state *st) {
+    spz_state::Arrival &a = st->arrival;
+    if (a.lanes_active) { // the per-piece streams hand the state back to the main stream
+        for (int k = 0; k < a.chunks; ++k) {
+            SPZ_CUDA(cudaEventRecord(a.ev[k], a.lane[k]));
+            SPZ_CUDA(cudaStreamWaitEvent(st->stream, a.ev[k], 0));
+        }
+        a.lanes_active = false;
+    }
+    if (a.pending) {
+        SPZ_CUDA(cudaStreamWaitEvent(st->stream, a.ev[a.chunks - 1], 0));
+        a.pending = false;
+    }
+    return SPZ_OK;
+}
+
+bool take_chunks(spz_state *st, int *n_chunks, cudaEvent_t *ev) {
+    spz_state::Arrival &a = st->arrival;
+    if (a.lanes_active) { arrival_join(st); return false; }
+    if (a.pending) { // (an upload waits for everything before it, so no exchange can be in flight at the same time)
+        *n_chunks = a.chunks;
+        for (int k = 0; k < a.chunks; ++k) ev[k] = a.ev[k];
+        a.pending = false;
+        return true;
+    }
+    return st->dist && dist_take_chunks(st, n_chunks, ev);
+}
+
 #include "gate_resolve.inl" // int resolve_gate(kind, params, out): shared with the CPU emulation harness (tests/emu/)
 
 static inline uint64_t splitmix64(uint64_t *x) {
@@ -755,6 +783,11 @@ int spz_create(int n_qubits, int device, spz_state **out) {
 int spz_destroy(spz_state *st) {
     if (!st) return SPZ_OK;
     cudaSetDevice(st->device);
+    if (st->arrival.copy) { cudaStreamSynchronize(st->arrival.copy); cudaStreamDestroy(st->arrival.copy); }
+    for (cudaStream_t l : st->arrival.lane) if (l) { cudaStreamSynchronize(l); cudaStreamDestroy(l); }
+    for (cudaEvent_t e : st->arrival.ev) if (e) cudaEventDestroy(e);
+    if (st->arrival.ready) cudaEventDestroy(st->arrival.ready);
+    st->arrival.pending = false;
     if (st->dist) dist_join(st);
     if (st->stream) cudaStreamSynchronize(st->stream);
     if (st->dist) dist_destroy(st);
@@ -798,6 +831,7 @@ int spz_upload(spz_state *st, const double *re, const double *im, int64_t offset
     SPZ_CHECK_STATE(st);
     if (offset < 0 || count < 0 || offset + count > st->len) { set_error("upload range [%lld, +%lld) outside the state", (long long)offset, (long long)count); return SPZ_ERR_INVALID_ARG; }
     SPZ_TRY(join_pending(st));
+    st->arrival.streaming = false;
     const size_t bytes = sizeof(double) * (size_t)count;
     if (re) SPZ_CUDA(cudaMemcpyAsync(st->re + offset, re, bytes, cudaMemcpyHostToDevice, st->stream));
     if (im) SPZ_CUDA(cudaMemcpyAsync(st->im + offset, im, bytes, cudaMemcpyHostToDevice, st->stream));
@@ -805,9 +839,57 @@ int spz_upload(spz_state *st, const double *re, const double *im, int64_t offset
     return SPZ_OK;
 }
 
+// Whole-state upload that returns at once: K pieces on a copy stream, each with its event, so that the gates issued next run
+// piece by piece behind the bus (launch_gate / launch_tile_program take the chunk events) instead of after the last byte.
+// The host buffers must be page-locked (spz_alloc_host) and stay untouched until the next spz_sync / spz_download.
+int spz_upload_async(spz_state *st, const double *re, const double *im) {
+    if (!st || !re || !im) { set_error("spz_upload_async: null argument"); return SPZ_ERR_INVALID_ARG; }
+    SPZ_CUDA(cudaSetDevice(st->device));
+    SPZ_TRY(join_pending(st));
+    spz_state::Arrival &a = st->arrival;
+    int K = 4;
+    while (K > 1 && (st->len >> 12) < K) K >>= 1;
+    if (!a.copy) {
+        SPZ_CUDA(cudaStreamCreateWithFlags(&a.copy, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : a.ev) SPZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        SPZ_CUDA(cudaEventCreateWithFlags(&a.ready, cudaEventDisableTiming));
+        int least = 0, greatest = 0;
+        SPZ_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest)); // (numerically: greatest <= least)
+        for (int k = 0; k < 8; ++k) SPZ_CUDA(cudaStreamCreateWithPriority(&a.lane[k], cudaStreamNonBlocking, std::min(least, greatest + k)));
+    }
+    SPZ_CUDA(cudaEventRecord(a.ready, st->stream));
+    SPZ_CUDA(cudaStreamWaitEvent(a.copy, a.ready, 0));
+    const size_t piece = (size_t)st->len / (size_t)K;
+    for (int k = 0; k < K; ++k) {
+        SPZ_CUDA(cudaMemcpyAsync(st->re + k * piece, re + k * piece, sizeof(double) * piece, cudaMemcpyHostToDevice, a.copy));
+        SPZ_CUDA(cudaMemcpyAsync(st->im + k * piece, im + k * piece, sizeof(double) * piece, cudaMemcpyHostToDevice, a.copy));
+        SPZ_CUDA(cudaEventRecord(a.ev[k], a.copy));
+    }
+    a.chunks = K;
+    a.pending = true;
+    a.streaming = true;
+    return SPZ_OK;
+}
+
 int spz_download(const spz_state *st, double *re, double *im, int64_t offset, int64_t count) {
     SPZ_CHECK_STATE(st);
     if (offset < 0 || count < 0 || offset + count > st->len) { set_error("download range [%lld, +%lld) outside the state", (long long)offset, (long long)count); return SPZ_ERR_INVALID_ARG; }
+    {
+        // The end of a streamed round trip (spz_upload_async ... gates ... spz_download of the whole state): every piece leaves
+        // from its own lane as soon as that lane has finished its run, while the later pieces are still being computed.
+        spz_state::Arrival &a = const_cast<spz_state *>(st)->arrival;
+        a.streaming = false;
+        if (a.lanes_active && !a.pending && offset == 0 && count == st->len && re && im) {
+            const size_t piece = (size_t)st->len / (size_t)a.chunks;
+            for (int k = 0; k < a.chunks; ++k) {
+                SPZ_CUDA(cudaMemcpyAsync(re + k * piece, st->re + k * piece, sizeof(double) * piece, cudaMemcpyDeviceToHost, a.lane[k]));
+                SPZ_CUDA(cudaMemcpyAsync(im + k * piece, st->im + k * piece, sizeof(double) * piece, cudaMemcpyDeviceToHost, a.lane[k]));
+            }
+            for (int k = 0; k < a.chunks; ++k) SPZ_CUDA(cudaStreamSynchronize(a.lane[k]));
+            a.lanes_active = false;
+            return SPZ_OK;
+        }
+    }
     SPZ_TRY(join_pending(const_cast<spz_state *>(st)));
     const size_t bytes = sizeof(double) * (size_t)count;
     if (re) SPZ_CUDA(cudaMemcpyAsync(re, st->re + offset, bytes, cudaMemcpyDeviceToHost, st->stream));

@@ -363,7 +363,7 @@ int dist_exchange(spz_state *st, int gbit, int lq) {
     if (!c->connected) { set_error("dist state used before spz_dist_connect"); return SPZ_ERR_COMM; }
     const int partner = c->rank ^ (1 << gbit);
     const int my_bit = (c->rank >> gbit) & 1;
-    SPZ_TRY(dist_join(st)); // a previous overlapped exchange must have landed completely
+    SPZ_TRY(join_pending(st)); // a previous overlapped exchange must have landed completely
     const unsigned long long e = ++c->epoch;
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     SPZ_TRY(take_timing_events(c, &ev));
@@ -459,7 +459,7 @@ int dist_exchange_gate(spz_state *st, int gbit, int lq, const GateK &g) {
     SPZ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, st->device));
     int resident = std::max(1, per_sm * n_sm);
     if (!c->ipc) resident = std::max(1, resident / 2);
-    SPZ_TRY(dist_join(st));
+    SPZ_TRY(join_pending(st));
     const unsigned long long e = ++c->epoch;
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     SPZ_TRY(take_timing_events(c, &ev));
@@ -531,7 +531,7 @@ bool dist_take_chunks(spz_state *st, int *n_chunks, cudaEvent_t *ev) {
 
 int dist_allreduce(spz_state *st, const double *dev_value, double host_value, double *host_out, double **dev_out) {
     DistCtx *c = ctx_of(st);
-    SPZ_TRY(dist_join(st));
+    SPZ_TRY(join_pending(st));
     if (!c->connected) { set_error("dist state used before spz_dist_connect"); return SPZ_ERR_COMM; }
     SPZ_TRY(ensure_scratch(st));
     const unsigned long long e = ++c->red_epoch;
@@ -549,14 +549,18 @@ int dist_allreduce(spz_state *st, const double *dev_value, double host_value, do
     return SPZ_OK;
 }
 
-int dist_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int hi) {
-    SPZ_TRY(dist_join(st));
-    const long long count = st->len >> __builtin_popcountll(local_cmask);
+int diag_const_on(spz_state *st, double *re, double *im, long long len, const GateK &g, uint64_t cmask, int hi) {
+    const long long count = len >> __builtin_popcountll(cmask);
     const int grid = (int)std::max<long long>(1, std::min<long long>((count + 255) / 256, 148 * 16));
-    k_diag_const<<<grid, 256, 0, st->stream>>>(st->re, st->im, count, local_cmask, g.kind, hi, g);
+    k_diag_const<<<grid, 256, 0, st->stream>>>(re, im, count, cmask, g.kind, hi, g);
     count_launch();
     SPZ_CUDA(cudaGetLastError());
     return SPZ_OK;
+}
+
+int dist_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int hi) {
+    SPZ_TRY(join_pending(st));
+    return diag_const_on(st, st->re, st->im, st->len, g, local_cmask, hi);
 }
 
 // Lower one logical gate and run the resulting actions immediately (the unfused path).
@@ -626,7 +630,7 @@ int dist_collapse(spz_state *st, int target, int outcome, double scale) {
     if (pt < c->plan.n_local) return launch_collapse(st, pt, outcome, 0, scale);
     const int bit = (c->rank >> (pt - c->plan.n_local)) & 1;
     if (bit == outcome) return launch_scale(st, scale);
-    SPZ_TRY(dist_join(st)); // the memsets below bypass the launch_* helpers: an overlapped exchange may still be writing
+    SPZ_TRY(join_pending(st)); // the memsets below bypass the launch_* helpers: an overlapped exchange may still be writing
     SPZ_CUDA(cudaMemsetAsync(st->re, 0, sizeof(double) * (size_t)st->len, st->stream));
     SPZ_CUDA(cudaMemsetAsync(st->im, 0, sizeof(double) * (size_t)st->len, st->stream));
     return SPZ_OK;
@@ -640,7 +644,7 @@ int dist_fill_basis(spz_state *st, uint64_t logical_index) {
     const int owner = (int)(phys >> c->plan.n_local);
     // Every rank joins first: an overlapped exchange (second stream) may still be moving amplitudes of this shard, and the
     // memsets of the non-owner ranks do not go through a launch_* helper that would wait for it.
-    SPZ_TRY(dist_join(st));
+    SPZ_TRY(join_pending(st));
     if (owner == c->rank) return launch_fill_basis(st, phys & ((1ull << c->plan.n_local) - 1ull));
     SPZ_CUDA(cudaMemsetAsync(st->re, 0, sizeof(double) * (size_t)st->len, st->stream));
     SPZ_CUDA(cudaMemsetAsync(st->im, 0, sizeof(double) * (size_t)st->len, st->stream));
@@ -851,8 +855,8 @@ int spz_dist_copy_from(spz_state *dst, const spz_state *csrc) {
         set_error("shards of different registers or ranks"); return SPZ_ERR_INVALID_ARG;
     }
     SPZ_CUDA(cudaSetDevice(dst->device));
-    SPZ_TRY(dist_join(src));
-    SPZ_TRY(dist_join(dst));
+    SPZ_TRY(join_pending(const_cast<spz_state *>(src)));
+    SPZ_TRY(join_pending(dst));
     SPZ_CUDA(cudaStreamSynchronize(src->stream));
     const size_t bytes = sizeof(double) * (size_t)src->len;
     SPZ_CUDA(cudaMemcpyAsync(dst->re, src->re, bytes, cudaMemcpyDeviceToDevice, dst->stream));
@@ -871,7 +875,7 @@ int spz_dist_stats(const spz_state *cst, double *out4) {
     spz_state *st = const_cast<spz_state *>(cst);
     DistCtx *c = ctx_of(st);
     SPZ_CUDA(cudaSetDevice(st->device));
-    SPZ_TRY(dist_join(st)); // an overlapped exchange may still be running on the second stream
+    SPZ_TRY(join_pending(st)); // an overlapped exchange may still be running on the second stream
     SPZ_CUDA(cudaStreamSynchronize(st->stream));
     for (auto &e : c->pending) {
         float ms = 0.f;

@@ -69,6 +69,23 @@ struct spz_state {
     size_t d_ops_bytes = 0;
     size_t d_ops_cursor = 0;
     void *dist = nullptr; // spz::DistCtx* when this handle is one shard of a multi-GPU register (dist.cu)
+    // A whole-state upload in flight on the copy stream (spz_upload_async): the state arrives in `chunks` contiguous pieces,
+    // ev[k] fires when piece k is complete.  The pass that follows runs piece by piece behind the bus (see take_chunks).
+    struct Arrival {
+        bool pending = false;
+        int chunks = 0;
+        cudaStream_t copy = nullptr;
+        cudaEvent_t ev[8] = {};
+        cudaEvent_t ready = nullptr; // main stream -> copy stream: everything queued before the upload has finished
+        // One stream per piece: a RUN of one-gate passes behind the upload is issued gate by gate, but must execute piece by
+        // piece (all gates on piece 0 while piece 1 is on the bus, ...), which a single stream cannot express.
+        cudaStream_t lane[8] = {};   // lane 0 has the highest priority: it finishes its run first, so its piece can leave first
+        bool lanes_active = false;
+        // "Streaming" between spz_upload_async and the spz_download that ends the round trip: runs of gates that act inside
+        // the pieces keep going to the lanes (also after a join), so that the download of piece 0 can start while the other
+        // pieces are still being computed.
+        bool streaming = false;
+    } arrival;
 };
 
 namespace spz {
@@ -172,8 +189,17 @@ bool dist_can_fuse_gate(const spz_state *st, int kind, uint64_t logical_cmask, i
 int dist_exchange_gate(spz_state *st, int gbit, int lq, const GateK &g);
 int dist_join(spz_state *st); // main stream waits for an overlapped exchange still in flight
 bool dist_take_chunks(spz_state *st, int *n_chunks, cudaEvent_t *ev); // ev: room for 8 (see dist.cu)
-inline int join_pending(spz_state *st) { return st->dist ? dist_join(st) : SPZ_OK; }
+int arrival_join(spz_state *st); // main stream waits for an asynchronous upload still in flight (abi.cu)
+inline int join_pending(spz_state *st) {
+    if (st->arrival.pending || st->arrival.lanes_active) { const int rc = arrival_join(st); if (rc != SPZ_OK) return rc; }
+    return st->dist ? dist_join(st) : SPZ_OK;
+}
+// For the pass that directly follows a chunked arrival -- an asynchronous upload or an overlapped exchange: the state lands in
+// *n_chunks contiguous pieces, ev[k] fires when piece k is complete (ev: room for 8).  False when nothing is in flight.
+bool take_chunks(spz_state *st, int *n_chunks, cudaEvent_t *ev);
 int dist_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int hi);
+// the same constant-factor pass on one contiguous piece of the state (launched on st->stream; no join)
+int diag_const_on(spz_state *st, double *re, double *im, long long len, const GateK &g, uint64_t cmask, int hi);
 int dist_reduce_scalar(spz_state *st, int mode, int target, double *out);
 int dist_collapse(spz_state *st, int target, int outcome, double scale);
 int dist_fill_basis(spz_state *st, uint64_t logical_index);

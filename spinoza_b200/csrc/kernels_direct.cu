@@ -70,9 +70,50 @@ int launch_gate(spz_state *st, const GateK &g, uint64_t ctrl_mask, int target) {
     // Directly after an overlapped exchange (dist.cu) the shard lands in K contiguous chunks.  A gate whose target and controls
     // lie below the chunk bits acts on every chunk separately -- a chunk is a register of n - log2(K) qubits at an offset -- so it
     // runs chunk by chunk behind the wire: the one-gate pass that asked for the exchange costs 1/K of its time on top of it.
+    // Behind an asynchronous upload (spz_upload_async), and until the download that ends the round trip, a RUN of gates that act
+    // inside the pieces goes to one stream per piece: every gate of the run works on piece 0 while piece 1 is still on the bus
+    // (and, at the other end, piece 0 leaves while piece 3 is still being computed).  A gate acts inside the pieces when its
+    // target lies below the piece bits, or when it is diagonal (a piece bit is a constant of the piece: a constant factor, as
+    // for a global qubit of a sharded register); a control on a piece bit selects pieces.  The first op that needs the whole
+    // state joins the lanes.
+    {
+        spz_state::Arrival &a = st->arrival;
+        if ((a.pending || a.lanes_active || (a.streaming && st->n >= 24 && !st->dist)) && a.chunks > 1) {
+            int bits = 0;
+            while ((1 << bits) < a.chunks) ++bits;
+            const int nl = st->n - bits;
+            const bool diag = g.kind == SPZ_GATE_Z || g.kind == SPZ_GATE_P || g.kind == SPZ_GATE_RZ;
+            const bool t_piece = target >= nl;
+            const bool ok = nl >= 12 && target >= 0 && target < st->n && !((ctrl_mask >> target) & 1ull) && (st->n >= 64 || !(ctrl_mask >> st->n)) &&
+                            (!t_piece || diag);
+            if (ok) {
+                if (a.pending) {
+                    for (int k = 0; k < a.chunks; ++k) SPZ_CUDA(cudaStreamWaitEvent(a.lane[k], a.ev[k], 0));
+                    a.pending = false;
+                } else if (!a.lanes_active) { // (re)start the lanes behind what the main stream has been given so far
+                    SPZ_CUDA(cudaEventRecord(a.ready, st->stream));
+                    for (int k = 0; k < a.chunks; ++k) SPZ_CUDA(cudaStreamWaitEvent(a.lane[k], a.ready, 0));
+                }
+                a.lanes_active = true;
+                const unsigned c_piece = (unsigned)(ctrl_mask >> nl);
+                const uint64_t c_local = ctrl_mask & ((1ull << nl) - 1ull);
+                cudaStream_t main_stream = st->stream;
+                int rc = SPZ_OK;
+                for (int k = 0; k < a.chunks && rc == SPZ_OK; ++k) {
+                    if (((unsigned)k & c_piece) != c_piece) continue; // a control that is 0 throughout this piece
+                    const size_t off = (size_t)k << nl;
+                    st->stream = a.lane[k]; // (the launch helpers take the stream from the state)
+                    if (t_piece) rc = diag_const_on(st, st->re + off, st->im + off, 1ll << nl, g, c_local, (k >> (target - nl)) & 1);
+                    else rc = launch_gate_on(st, st->re + off, st->im + off, nl, g, c_local, target);
+                }
+                st->stream = main_stream;
+                return rc;
+            }
+        }
+    }
     int K = 0;
     cudaEvent_t ev[8] = {};
-    if (st->dist && dist_take_chunks(st, &K, ev)) {
+    if (take_chunks(st, &K, ev)) {
         int parts = 1;
         for (int bits = 1; (1 << bits) <= K && st->n - bits >= 12; ++bits) {
             const int q = st->n - bits;

@@ -477,7 +477,7 @@ int launch_tile_program(spz_state *st, const TilePlan &plan, const TileInstr *pr
     // grid: start on the first while the others are still on the wire.
     int K = 0;
     cudaEvent_t ev[8] = {};
-    if (st->dist && dist_take_chunks(st, &K, ev)) {
+    if (take_chunks(st, &K, ev)) {
         int parts = 1;
         for (int bits = 1; (1 << bits) <= K && (grid >> bits) >= 1; ++bits) {
             const int q = st->n - bits; // the next lower local bit must not be a tile bit

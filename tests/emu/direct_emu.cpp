@@ -25,6 +25,7 @@ void set_error(const char *fmt, ...) {
 int cuda_fail(cudaError_t, const char *, const char *, int) { return SPZ_ERR_CUDA; }
 void count_launch(int) {}
 int dist_join(spz_state *) { return SPZ_OK; }
+int arrival_join(spz_state *) { return SPZ_OK; }
 #include "../../spinoza_b200/csrc/gate_resolve.inl"
 } // namespace spz
 

@@ -506,6 +506,84 @@ def test_extension_cells_match_dense():  # controlled Z / mc H etc.: the referen
     assert np.max(np.abs(s.amps() - psi)) < 1e-14
 
 
+def test_async_upload_then_gates_equals_upload_then_gates():
+    """spz_upload_async: gates and fused passes issued right after it follow the pieces of the state as they arrive (low targets
+    chunk by chunk, high targets and controls after the last piece).  Bit-identical to the synchronous upload."""
+    n = 20
+    cpu = orc.gen_random_state(n, 5)
+    hre, him = sb.HostBuffer(1 << n), sb.HostBuffer(1 << n)
+    hre.array[:] = cpu.reals
+    him.array[:] = cpu.imags
+
+    def gates(s):
+        sb.apply(Gate.H, s, 3)
+        sb.apply(Gate.RX(0.7), s, n - 3)       # below the piece bits: follows the pieces
+        sb.apply(Gate.RY(0.2), s, n - 1)       # a piece bit: after the last piece
+        sb.c_apply(Gate.P(0.4), s, n - 2, 5)   # control on a piece bit
+        sb.apply(Gate.RZ(1.3), s, 0)
+
+    a = sb.State(n)
+    a.upload_from(hre, him)
+    gates(a)
+    for rep in range(3):                       # repeated: the copy stream must wait for the gates of the previous round
+        b = sb.State(n) if rep == 0 else b
+        b.upload_async(hre, him)
+        gates(b)
+        assert np.array_equal(a.download()[0], b.download()[0]) and np.array_equal(a.download()[1], b.download()[1])
+    # a fused pass right behind the upload
+    c = sb.State(n)
+    c.upload_from(hre, him)
+    qa = QuantumCircuit.from_state(c, fuse=True); qa.qft(); qa.execute()
+    d = sb.State(n)
+    d.upload_async(hre, him)
+    qb = QuantumCircuit.from_state(d, fuse=True); qb.qft(); qb.execute()
+    assert np.array_equal(c.download()[0], d.download()[0]) and np.array_equal(c.download()[1], d.download()[1])
+    # reductions and a second upload join the copy stream
+    d.upload_async(hre, him)
+    assert abs(sb.norm2(d) - 1.0) < 1e-12
+    d.upload_async(hre, him)
+    d.upload_async(hre, him)
+    assert np.array_equal(d.download()[0], cpu.reals)
+
+
+def test_streamed_round_trip_equals_the_synchronous_one():
+    """upload_async -> a sweep of gates -> download_into: runs of gates that act inside the pieces go to one stream per piece
+    (also after a join, from 24 qubits), diagonal gates on a piece bit become constant factors per piece, controls on piece bits
+    select pieces, and the download leaves piece by piece from the lanes.  Bit-identical to upload -> gates -> download."""
+    n = 24
+    cpu = orc.gen_random_state(n, 11)
+    hre, him = sb.HostBuffer(1 << n), sb.HostBuffer(1 << n)
+    ore, oim = sb.HostBuffer(1 << n), sb.HostBuffer(1 << n)
+
+    def sweep(s):
+        for g in (Gate.H, Gate.RX(1.0), Gate.RZ(1.0)):
+            for t in range(n):
+                sb.apply(g, s, t)
+        sb.apply(Gate.P(0.3), s, n - 1)
+        sb.apply(Gate.Z, s, n - 2)
+        sb.c_apply(Gate.RY(0.4), s, n - 1, 2)          # control on a piece bit, target inside
+        sb.c_apply(Gate.P(0.9), s, n - 2, n - 1)       # diagonal, control and target on piece bits
+        sb.mc_apply(Gate.X, s, [n - 1, 3], None, 7)
+        sb.c_apply(Gate.RZ(0.2), s, 4, n - 1)          # diagonal on a piece bit under a local control
+
+    hre.array[:] = cpu.reals
+    him.array[:] = cpu.imags
+    a = sb.State(n)
+    a.upload_from(hre, him)
+    sweep(a)
+    want_re, want_im = a.download()
+    b = sb.State(n)
+    for rep in range(2):
+        b.upload_async(hre, him)
+        sweep(b)
+        b.download_into(ore, oim)
+        assert np.array_equal(ore.array, want_re) and np.array_equal(oim.array, want_im), rep
+    # after the round trip the state is an ordinary one again
+    sb.apply(Gate.H, b, 0)
+    sb.apply(Gate.H, a, 0)
+    assert np.array_equal(a.download()[0], b.download()[0])
+
+
 # ---- sampling ------------------------------------------------------------------------------------------------
 def test_sample_basis_state_is_exact():  # core.rs:272-291
     n = 3
