@@ -559,6 +559,8 @@ int diag_const_on(spz_state *st, double *re, double *im, long long len, const Ga
 }
 
 int dist_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int hi) {
+    int rc = SPZ_OK;
+    if (lanes_diag_const(st, g, local_cmask, hi, &rc)) return rc; // a streamed round trip: piece by piece
     SPZ_TRY(join_pending(st));
     return diag_const_on(st, st->re, st->im, st->len, g, local_cmask, hi);
 }

@@ -198,6 +198,7 @@ inline int join_pending(spz_state *st) {
 // *n_chunks contiguous pieces, ev[k] fires when piece k is complete (ev: room for 8).  False when nothing is in flight.
 bool take_chunks(spz_state *st, int *n_chunks, cudaEvent_t *ev);
 int dist_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int hi);
+bool lanes_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int hi, int *rc); // kernels_direct.cu (streaming)
 // the same constant-factor pass on one contiguous piece of the state (launched on st->stream; no join)
 int diag_const_on(spz_state *st, double *re, double *im, long long len, const GateK &g, uint64_t cmask, int hi);
 int dist_reduce_scalar(spz_state *st, int mode, int target, double *out);

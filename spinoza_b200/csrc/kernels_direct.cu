@@ -65,6 +65,53 @@ static void dispatch_kind(bool low, const PairArgs &a, cudaStream_t s) {
 
 static int launch_gate_on(spz_state *st, double *re, double *im, int n, const GateK &g, uint64_t ctrl_mask, int target);
 
+#ifndef SPZ_CPU_EMULATION
+// Streaming (see launch_gate): the number of pieces if an op that acts inside the pieces may go to the per-piece lanes now, else 0.
+int lanes_possible(spz_state *st, int *bits_out) {
+    spz_state::Arrival &a = st->arrival;
+    if (!((a.pending || a.lanes_active || (a.streaming && st->n >= 24)) && a.chunks > 1)) return 0;
+    int bits = 0;
+    while ((1 << bits) < a.chunks) ++bits;
+    if (st->n - bits < 12) return 0;
+    *bits_out = bits;
+    return a.chunks;
+}
+// The lanes wait for what they follow: the pieces of an upload in flight, or (restart after a join) what the main stream has been
+// given so far -- for a shard, including an exchange still in flight.
+int lanes_start(spz_state *st) {
+    spz_state::Arrival &a = st->arrival;
+    if (a.pending) {
+        for (int k = 0; k < a.chunks; ++k) SPZ_CUDA(cudaStreamWaitEvent(a.lane[k], a.ev[k], 0));
+        a.pending = false;
+    } else if (!a.lanes_active) {
+        if (st->dist) SPZ_TRY(dist_join(st));
+        SPZ_CUDA(cudaEventRecord(a.ready, st->stream));
+        for (int k = 0; k < a.chunks; ++k) SPZ_CUDA(cudaStreamWaitEvent(a.lane[k], a.ready, 0));
+    }
+    a.lanes_active = true;
+    return SPZ_OK;
+}
+// A constant diagonal factor on every amplitude whose (local) controls are set -- a diagonal gate whose target is a global qubit of
+// a sharded register -- piece by piece on the lanes when the state is being streamed.  False: the caller runs it on the whole shard.
+bool lanes_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int hi, int *rc) {
+    int bits = 0;
+    const int chunks = lanes_possible(st, &bits);
+    if (!chunks) return false;
+    const int nl = st->n - bits;
+    *rc = lanes_start(st);
+    const unsigned c_piece = (unsigned)(local_cmask >> nl);
+    const uint64_t c_local = local_cmask & ((1ull << nl) - 1ull);
+    cudaStream_t main_stream = st->stream;
+    for (int k = 0; k < chunks && *rc == SPZ_OK; ++k) {
+        if (((unsigned)k & c_piece) != c_piece) continue;
+        st->stream = st->arrival.lane[k];
+        *rc = diag_const_on(st, st->re + ((size_t)k << nl), st->im + ((size_t)k << nl), 1ll << nl, g, c_local, hi);
+    }
+    st->stream = main_stream;
+    return true;
+}
+#endif
+
 int launch_gate(spz_state *st, const GateK &g, uint64_t ctrl_mask, int target) {
 #ifndef SPZ_CPU_EMULATION
     // Directly after an overlapped exchange (dist.cu) the shard lands in K contiguous chunks.  A gate whose target and controls
@@ -77,38 +124,27 @@ int launch_gate(spz_state *st, const GateK &g, uint64_t ctrl_mask, int target) {
     // for a global qubit of a sharded register); a control on a piece bit selects pieces.  The first op that needs the whole
     // state joins the lanes.
     {
-        spz_state::Arrival &a = st->arrival;
-        if ((a.pending || a.lanes_active || (a.streaming && st->n >= 24 && !st->dist)) && a.chunks > 1) {
-            int bits = 0;
-            while ((1 << bits) < a.chunks) ++bits;
-            const int nl = st->n - bits;
-            const bool diag = g.kind == SPZ_GATE_Z || g.kind == SPZ_GATE_P || g.kind == SPZ_GATE_RZ;
-            const bool t_piece = target >= nl;
-            const bool ok = nl >= 12 && target >= 0 && target < st->n && !((ctrl_mask >> target) & 1ull) && (st->n >= 64 || !(ctrl_mask >> st->n)) &&
-                            (!t_piece || diag);
-            if (ok) {
-                if (a.pending) {
-                    for (int k = 0; k < a.chunks; ++k) SPZ_CUDA(cudaStreamWaitEvent(a.lane[k], a.ev[k], 0));
-                    a.pending = false;
-                } else if (!a.lanes_active) { // (re)start the lanes behind what the main stream has been given so far
-                    SPZ_CUDA(cudaEventRecord(a.ready, st->stream));
-                    for (int k = 0; k < a.chunks; ++k) SPZ_CUDA(cudaStreamWaitEvent(a.lane[k], a.ready, 0));
-                }
-                a.lanes_active = true;
-                const unsigned c_piece = (unsigned)(ctrl_mask >> nl);
-                const uint64_t c_local = ctrl_mask & ((1ull << nl) - 1ull);
-                cudaStream_t main_stream = st->stream;
-                int rc = SPZ_OK;
-                for (int k = 0; k < a.chunks && rc == SPZ_OK; ++k) {
-                    if (((unsigned)k & c_piece) != c_piece) continue; // a control that is 0 throughout this piece
-                    const size_t off = (size_t)k << nl;
-                    st->stream = a.lane[k]; // (the launch helpers take the stream from the state)
-                    if (t_piece) rc = diag_const_on(st, st->re + off, st->im + off, 1ll << nl, g, c_local, (k >> (target - nl)) & 1);
-                    else rc = launch_gate_on(st, st->re + off, st->im + off, nl, g, c_local, target);
-                }
-                st->stream = main_stream;
-                return rc;
+        int bits = 0;
+        const int chunks = lanes_possible(st, &bits);
+        const int nl = st->n - bits;
+        const bool diag = g.kind == SPZ_GATE_Z || g.kind == SPZ_GATE_P || g.kind == SPZ_GATE_RZ;
+        const bool t_piece = target >= nl;
+        if (chunks && target >= 0 && target < st->n && !((ctrl_mask >> target) & 1ull) && (st->n >= 64 || !(ctrl_mask >> st->n)) &&
+            (!t_piece || diag)) {
+            SPZ_TRY(lanes_start(st));
+            const unsigned c_piece = (unsigned)(ctrl_mask >> nl);
+            const uint64_t c_local = ctrl_mask & ((1ull << nl) - 1ull);
+            cudaStream_t main_stream = st->stream;
+            int rc = SPZ_OK;
+            for (int k = 0; k < chunks && rc == SPZ_OK; ++k) {
+                if (((unsigned)k & c_piece) != c_piece) continue; // a control that is 0 throughout this piece
+                const size_t off = (size_t)k << nl;
+                st->stream = st->arrival.lane[k]; // (the launch helpers take the stream from the state)
+                if (t_piece) rc = diag_const_on(st, st->re + off, st->im + off, 1ll << nl, g, c_local, (k >> (target - nl)) & 1);
+                else rc = launch_gate_on(st, st->re + off, st->im + off, nl, g, c_local, target);
             }
+            st->stream = main_stream;
+            return rc;
         }
     }
     int K = 0;
