@@ -70,7 +70,11 @@ typedef struct {
 } spz_gate;
 
 /* Controls enum, circuit.rs:55-70 */
-typedef enum { SPZ_CTRL_NONE = 0, SPZ_CTRL_SINGLE = 1, SPZ_CTRL_ONES = 2, SPZ_CTRL_MIXED = 3 } spz_ctrl_kind;
+typedef enum {
+    SPZ_CTRL_NONE = 0, SPZ_CTRL_SINGLE = 1, SPZ_CTRL_ONES = 2,
+    SPZ_CTRL_MIXED = 3, /* zeros are DROPPED from the mask, as mc_apply does (gates.rs:298-311) */
+    SPZ_CTRL_SIGNED = 4 /* extension, not in the reference: zeros_mask (a subset of ctrl_mask) are true negative controls */
+} spz_ctrl_kind;
 
 /* QuantumTransformation, circuit.rs:113-120 (flattened; 64 bytes) */
 typedef struct {
@@ -131,6 +135,9 @@ SPZ_API int spz_mc_apply(spz_state *st, const spz_gate *gate, const int32_t *con
                  const int32_t *zeros, int n_zeros, int target);
 /* extension: any 1-qubit gate under any all-ones control mask */
 SPZ_API int spz_mc_apply_mask(spz_state *st, const spz_gate *gate, uint64_t ctrl_mask, int target);
+/* extension: signed controls -- every qubit of ones_mask must be 1 and every qubit of zeros_mask must be 0 (disjoint masks).
+   What Controls::Mixed { zeros } (circuit.rs:61-69) describes and mc_apply does not do (gates.rs:298-311 drops the zeros). */
+SPZ_API int spz_mc_apply_signed(spz_state *st, const spz_gate *gate, uint64_t ones_mask, uint64_t zeros_mask, int target);
 SPZ_API int spz_iqft(spz_state *st, const int32_t *targets, int n_targets);             /* iqft core.rs:184 */
 
 /* ---- QuantumCircuit::execute, circuit.rs:552-600 ---------------------------------------------- */

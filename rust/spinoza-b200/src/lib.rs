@@ -64,6 +64,7 @@ pub mod ffi {
         pub fn spz_apply(st: *mut spz_state, gate: *const spz_gate, target: c_int) -> c_int;
         pub fn spz_c_apply(st: *mut spz_state, gate: *const spz_gate, control: c_int, target: c_int) -> c_int;
         pub fn spz_cc_apply(st: *mut spz_state, gate: *const spz_gate, c0: c_int, c1: c_int, target: c_int) -> c_int;
+        pub fn spz_mc_apply_signed(st: *mut spz_state, gate: *const spz_gate, ones_mask: u64, zeros_mask: u64, target: c_int) -> c_int;
         pub fn spz_mc_apply(
             st: *mut spz_state,
             gate: *const spz_gate,
@@ -396,6 +397,13 @@ pub mod gates {
     /// gates.rs:272
     pub fn cc_apply(gate: Gate, state: &mut State, control0: usize, control1: usize, target: usize) {
         check(unsafe { ffi::spz_cc_apply(state.h, &gate.to_ffi(), control0 as c_int, control1 as c_int, target as c_int) });
+    }
+    /// Extension (not in the reference): every qubit of `ones` must be 1 and every qubit of `zeros` must be 0 -- the negative
+    /// controls `Controls::Mixed { zeros }` describes and `mc_apply` drops (gates.rs:298-311).
+    pub fn mc_apply_signed(gate: Gate, state: &mut State, ones: &[usize], zeros: &[usize], target: usize) {
+        let om = ones.iter().fold(0u64, |m, &q| m | (1u64 << q));
+        let zm = zeros.iter().fold(0u64, |m, &q| m | (1u64 << q));
+        check(unsafe { ffi::spz_mc_apply_signed(state.h, &gate.to_ffi(), om, zm, target as c_int) });
     }
     /// gates.rs:290
     pub fn mc_apply(gate: Gate, state: &mut State, controls: &[usize], zeros: Option<HashSet<usize>>, target: usize) {

@@ -105,6 +105,7 @@ _SIGNATURES = {
     "spz_cc_apply": (C.c_int, [_vp, C.POINTER(_Gate), C.c_int, C.c_int, C.c_int]),
     "spz_mc_apply": (C.c_int, [_vp, C.POINTER(_Gate), _i32p, C.c_int, _i32p, C.c_int, C.c_int]),
     "spz_mc_apply_mask": (C.c_int, [_vp, C.POINTER(_Gate), C.c_uint64, C.c_int]),
+    "spz_mc_apply_signed": (C.c_int, [_vp, C.POINTER(_Gate), C.c_uint64, C.c_uint64, C.c_int]),
     "spz_iqft": (C.c_int, [_vp, _i32p, C.c_int]),
     "spz_execute": (C.c_int, [_vp, C.POINTER(_Op), C.c_int64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "spz_set_seed": (C.c_int, [_vp, C.c_uint64]),
@@ -466,6 +467,15 @@ def mc_apply_mask(gate: Gate, state: State, ctrl_mask: int, target: int):
     _check(_lib.spz_mc_apply_mask(state._h, C.byref(g), ctrl_mask, target))
 
 
+def mc_apply_signed(gate: Gate, state: State, ones: Iterable[int], zeros: Iterable[int], target: int):
+    """Extension (not in the reference): `gate` on `target` where every qubit of `ones` is 1 and every qubit of `zeros` is 0 --
+    the negative controls `Controls::Mixed { zeros }` describes but mc_apply drops (gates.rs:298-311).  One pass."""
+    g = gate._c()
+    om = sum(1 << int(q) for q in set(ones))
+    zm = sum(1 << int(q) for q in set(zeros))
+    _check(_lib.spz_mc_apply_signed(state._h, C.byref(g), om, zm, target))
+
+
 def iqft(state: State, targets: Sequence[int]):
     """`iqft(&mut state, targets)` core.rs:184."""
     ts, n = _i32(targets)
@@ -538,7 +548,7 @@ from . import openqasm  # noqa: E402
 from . import distributed  # noqa: E402
 
 __all__ = [
-    "PI", "SpinozaError", "Gate", "State", "HostBuffer", "apply", "c_apply", "cc_apply", "mc_apply", "mc_apply_mask", "iqft",
+    "PI", "SpinozaError", "Gate", "State", "HostBuffer", "apply", "c_apply", "cc_apply", "mc_apply", "mc_apply_mask", "mc_apply_signed", "iqft",
     "measure_qubit", "prob0", "norm2", "qubit_expectation_value", "xyz_expectation_value", "sample", "uniforms",
     "Controls", "QuantumCircuit", "QuantumRegister", "QuantumTransformation", "EXEC_FUSE", "EXEC_NO_FUSE", "EXEC_EXACT",
     "openqasm", "device_count", "device_name", "mem_info", "launch_count", "library_path",

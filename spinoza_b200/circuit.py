@@ -39,9 +39,10 @@ class QuantumRegister:
 
 
 class Controls:
-    """circuit.rs:55-109.  kind in {NONE, SINGLE, ONES, MIXED}."""
+    """circuit.rs:55-109.  kind in {NONE, SINGLE, ONES, MIXED}; SIGNED is this engine's extension: `zeros` (a subset of
+    `controls`) fire on 0 -- what `Mixed { zeros }` describes and the reference's mc_apply drops (gates.rs:298-311)."""
 
-    NONE, SINGLE, ONES, MIXED = range(4)
+    NONE, SINGLE, ONES, MIXED, SIGNED = range(5)
     __slots__ = ("kind", "controls", "zeros")
 
     def __init__(self, kind: int, controls: Sequence[int] = (), zeros: Iterable[int] = ()):
@@ -62,6 +63,14 @@ class Controls:
     @staticmethod
     def mixed(controls: Sequence[int], zeros: Iterable[int]) -> "Controls":
         return Controls(Controls.MIXED, controls, zeros)
+
+    @staticmethod
+    def signed(controls: Sequence[int], zeros: Iterable[int]) -> "Controls":
+        """Extension: every qubit of `controls` is a control; those listed in `zeros` must be 0, the others 1."""
+        zeros = set(zeros)
+        if not zeros <= set(controls):
+            raise ValueError("Controls.signed: zeros must be a subset of controls")
+        return Controls(Controls.SIGNED, controls, zeros)
 
     @staticmethod
     def _from(controls: Sequence[int], zeros: Optional[set]) -> "Controls":  # circuit.rs:73-86
@@ -289,6 +298,23 @@ class QuantumCircuit:
             for tr in circuit.transformations:
                 self.add(QuantumTransformation(tr.gate, reg.get_shift() + tr.target,
                                                tr.controls.new_with_control(control, reg.get_shift())))
+
+    def expanded(self) -> "QuantumCircuit":
+        """The same circuit with every SIGNED control written as X on its zero-controls around the all-ones gate -- what
+        `execute` schedules for fused passes and sharded registers (csrc/abi.cu: SPZ_CTRL_SIGNED).  `plan()` needs this form."""
+        from . import Gate
+        out = QuantumCircuit.__new__(QuantumCircuit)
+        out.__dict__.update(self.__dict__)
+        out.transformations = []
+        for tr in self.transformations:
+            if tr.controls.kind != Controls.SIGNED or not tr.controls.zeros:
+                out.transformations.append(tr)
+                continue
+            zs = sorted(tr.controls.zeros)
+            out.transformations += [QuantumTransformation(Gate.X, z, Controls.none()) for z in zs]
+            out.transformations.append(QuantumTransformation(tr.gate, tr.target, Controls._from(tr.controls.controls, None)))
+            out.transformations += [QuantumTransformation(Gate.X, z, Controls.none()) for z in zs]
+        return out
 
     def _encode(self):
         from . import _Op

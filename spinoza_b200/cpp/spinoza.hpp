@@ -138,6 +138,14 @@ inline void mc_apply(const Gate &gate, State &state, const std::vector<std::size
     if (zeros) z.assign(zeros->begin(), zeros->end());
     check(spz_mc_apply(state.handle(), &gate.g, c.data(), (int)c.size(), zeros ? z.data() : nullptr, (int)z.size(), (int)target));
 }
+// extension (not in the reference): ones must be 1, zeros must be 0 -- true negative controls, one pass
+inline void mc_apply_signed(const Gate &gate, State &state, const std::vector<std::size_t> &ones,
+                            const std::vector<std::size_t> &zeros, std::size_t target) {
+    uint64_t om = 0, zm = 0;
+    for (std::size_t q : ones) om |= 1ull << q;
+    for (std::size_t q : zeros) zm |= 1ull << q;
+    check(spz_mc_apply_signed(state.handle(), &gate.g, om, zm, (int)target));
+}
 inline void iqft(State &state, const std::vector<std::size_t> &targets) { // core.rs:184
     std::vector<int32_t> t(targets.begin(), targets.end());
     check(spz_iqft(state.handle(), t.data(), (int)t.size()));
@@ -270,6 +278,8 @@ struct Controls { // circuit.rs:55-109
     static Controls Single(std::size_t c) { Controls x; x.kind = SPZ_CTRL_SINGLE; x.controls = {c}; return x; }
     static Controls Ones(std::vector<std::size_t> cs) { Controls x; x.kind = SPZ_CTRL_ONES; x.controls = std::move(cs); return x; }
     static Controls Mixed(std::vector<std::size_t> cs, std::set<std::size_t> zs) { Controls x; x.kind = SPZ_CTRL_MIXED; x.controls = std::move(cs); x.zeros = std::move(zs); return x; }
+    // extension: zs (a subset of cs) are true negative controls
+    static Controls Signed(std::vector<std::size_t> cs, std::set<std::size_t> zs) { Controls x = Mixed(std::move(cs), std::move(zs)); x.kind = SPZ_CTRL_SIGNED; return x; }
     static Controls from(const std::vector<std::size_t> &cs, const std::set<std::size_t> *zs) { // circuit.rs:73-86
         if (zs) return Mixed(cs, *zs);
         if (cs.empty()) return None();

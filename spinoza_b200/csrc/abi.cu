@@ -108,6 +108,28 @@ static int apply_masked(spz_state *st, int kind, const double *p, uint64_t ctrl_
     return launch_gate(st, g, ctrl_mask, target);
 }
 
+// Signed controls (extension; SURVEY 2.3 B4 -- the reference's Controls::Mixed only pretends to have them): ones must be 1,
+// zeros must be 0.  One launch of the ordinary pair kernel on a single-GPU register; a sharded register conjugates with X on
+// the zero-controls (correct wherever those qubits live; an X on a global qubit is an exchange).
+static int apply_signed(spz_state *st, int kind, const double *p, uint64_t ones, uint64_t zeros, int target) {
+    if (ones & zeros) { set_error("a qubit cannot be both a positive and a negative control (0x%llx)", (unsigned long long)(ones & zeros)); return SPZ_ERR_INVALID_ARG; }
+    const int nq = total_qubits(st);
+    if ((nq < 64 && ((ones | zeros) >> nq)) || target < 0 || target >= nq || (((ones | zeros) >> target) & 1ull)) {
+        set_error("bad signed controls (ones 0x%llx, zeros 0x%llx, target %d, %d qubits)", (unsigned long long)ones, (unsigned long long)zeros, target, nq);
+        return SPZ_ERR_INVALID_ARG;
+    }
+    if (!zeros) return apply_masked(st, kind, p, ones, target);
+    if (!st->dist) {
+        GateK g;
+        SPZ_TRY(resolve_gate(kind, p, &g));
+        return launch_gate_signed(st, g, ones | zeros, zeros, target);
+    }
+    for (int q = 0; q < nq; ++q) if ((zeros >> q) & 1ull) SPZ_TRY(apply_masked(st, SPZ_GATE_X, nullptr, 0, q));
+    SPZ_TRY(apply_masked(st, kind, p, ones | zeros, target));
+    for (int q = 0; q < nq; ++q) if ((zeros >> q) & 1ull) SPZ_TRY(apply_masked(st, SPZ_GATE_X, nullptr, 0, q));
+    return SPZ_OK;
+}
+
 static int swap_impl(spz_state *st, int t0, int t1) {
     if (st->dist) return dist_apply_masked(st, SPZ_GATE_SWAP, nullptr, t0, t1, 0, 0); // relabel, no data moves
     return launch_swap(st, t0, t1);
@@ -965,6 +987,12 @@ int spz_mc_apply_mask(spz_state *st, const spz_gate *gate, uint64_t ctrl_mask, i
     return apply_masked(st, gate->kind, gate->p, ctrl_mask, target);
 }
 
+int spz_mc_apply_signed(spz_state *st, const spz_gate *gate, uint64_t ones_mask, uint64_t zeros_mask, int target) {
+    SPZ_CHECK_STATE(st);
+    SPZ_TRY(controlled_ok(gate, "mc_apply_signed"));
+    return apply_signed(st, gate->kind, gate->p, ones_mask, zeros_mask, target);
+}
+
 int spz_mc_apply(spz_state *st, const spz_gate *gate, const int32_t *controls, int n_controls, const int32_t *zeros,
                  int n_zeros, int target) {
     SPZ_CHECK_STATE(st);
@@ -1172,6 +1200,18 @@ static int execute_impl(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_
             SPZ_TRY(emit(kind, op.p, op.ctrl_mask, op.target, 0));
         } else if (op.ctrl_kind == SPZ_CTRL_MIXED) { // circuit.rs:588-596 -> mc_apply drops the zeros (gates.rs:298-311)
             SPZ_TRY(emit(kind, op.p, op.ctrl_mask & ~op.zeros_mask, op.target, 0));
+        } else if (op.ctrl_kind == SPZ_CTRL_SIGNED) { // extension: zeros_mask are true negative controls (a subset of ctrl_mask)
+            const uint64_t zeros = op.zeros_mask;
+            if (zeros & ~op.ctrl_mask) { set_error("Signed controls: zeros_mask must be a subset of ctrl_mask"); return SPZ_ERR_INVALID_ARG; }
+            if (nq < 64 && (op.ctrl_mask >> nq)) { set_error("control outside the register"); return SPZ_ERR_INVALID_ARG; }
+            if (zeros && !fuse && !st->dist) { // one launch of the pair kernel (a dry run records one pass of the same shape)
+                if (sink) SPZ_TRY(emit(kind, op.p, op.ctrl_mask, op.target, 0));
+                else SPZ_TRY(apply_signed(st, kind, op.p, op.ctrl_mask & ~zeros, zeros, op.target));
+            } else { // X on the zero-controls around the all-ones form: the X's ride in the same fused passes
+                for (int q = 0; q < nq; ++q) if ((zeros >> q) & 1ull) SPZ_TRY(emit(SPZ_GATE_X, nullptr, 0, q, 0));
+                SPZ_TRY(emit(kind, op.p, op.ctrl_mask, op.target, 0));
+                for (int q = 0; q < nq; ++q) if ((zeros >> q) & 1ull) SPZ_TRY(emit(SPZ_GATE_X, nullptr, 0, q, 0));
+            }
         } else {
             set_error("bad ctrl_kind %d", op.ctrl_kind);
             return SPZ_ERR_INVALID_ARG;
@@ -1194,6 +1234,10 @@ int spz_plan_fusion(int n_qubits, const spz_op *ops, int64_t n_ops, uint32_t fla
     dummy.len = (int64_t)1 << n_qubits;
     PlanSink sink;
     SPZ_TRY(execute_impl(&dummy, ops, n_ops, flags, nullptr, nullptr, &sink));
+    if (sink.order.size() > (size_t)n_ops) { // the output arrays hold one entry per op of the caller's list
+        set_error("plan: the list expands to %zu scheduled ops (negative controls become X . op . X in fused passes); expand it before planning", sink.order.size());
+        return SPZ_ERR_UNSUPPORTED;
+    }
     for (size_t i = 0; i < sink.order.size(); ++i) { out_order[i] = sink.order[i]; out_pass[i] = sink.group[i]; }
     for (size_t i = sink.order.size(); i < (size_t)n_ops; ++i) { out_order[i] = -1; out_pass[i] = -1; }
     *out_n_passes = sink.n_groups;

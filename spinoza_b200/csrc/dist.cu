@@ -908,6 +908,10 @@ int spz_dist_plan_lower(spz_dist_plan *p, int rank, const spz_op *op, spz_dist_a
     case SPZ_CTRL_NONE: break;
     case SPZ_CTRL_SINGLE: case SPZ_CTRL_ONES: cmask = op->ctrl_mask; break;
     case SPZ_CTRL_MIXED: cmask = op->ctrl_mask & ~op->zeros_mask; break;
+    case SPZ_CTRL_SIGNED: // spz_execute lowers negative controls to X . op . X (three ops): expand before planning op by op
+        if (op->zeros_mask) return SPZ_ERR_UNSUPPORTED;
+        cmask = op->ctrl_mask;
+        break;
     default: return SPZ_ERR_INVALID_ARG;
     }
     if (op->kind == SPZ_GATE_M || op->kind == SPZ_GATE_UNITARY || op->kind == SPZ_GATE_BITFLIP) return SPZ_ERR_UNSUPPORTED;

@@ -93,6 +93,8 @@ namespace spz {
 // ---- kernel launchers (kernels_direct.cu) -------------------------------------------------------
 // Apply resolved gate g to `target` for every amplitude whose index has all bits of ctrl_mask set.
 int launch_gate(spz_state *st, const GateK &g, uint64_t ctrl_mask, int target);
+// The same with signed controls: the qubits of neg_mask (a subset of ctrl_mask) must be 0 instead of 1 (extension).
+int launch_gate_signed(spz_state *st, const GateK &g, uint64_t ctrl_mask, uint64_t neg_mask, int target);
 int launch_swap(spz_state *st, int t0, int t1);
 
 // ---- reductions and state utilities (kernels_reduce.cu) -----------------------------------------

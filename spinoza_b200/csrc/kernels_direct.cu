@@ -63,7 +63,7 @@ static void dispatch_kind(bool low, const PairArgs &a, cudaStream_t s) {
     }
 }
 
-static int launch_gate_on(spz_state *st, double *re, double *im, int n, const GateK &g, uint64_t ctrl_mask, int target);
+static int launch_gate_on(spz_state *st, double *re, double *im, int n, const GateK &g, uint64_t ctrl_mask, int target, uint64_t neg_mask = 0);
 
 #ifndef SPZ_CPU_EMULATION
 // Streaming (see launch_gate): the number of pieces if an op that acts inside the pieces may go to the per-piece lanes now, else 0.
@@ -172,8 +172,19 @@ int launch_gate(spz_state *st, const GateK &g, uint64_t ctrl_mask, int target) {
     return launch_gate_on(st, st->re, st->im, st->n, g, ctrl_mask, target);
 }
 
+// A gate under signed controls (the spz_mc_apply_signed extension): every qubit of ctrl_mask is a control, those also in
+// neg_mask fire on 0 instead of 1.  The pair set is the same shape -- zero bits inserted at every control position -- only the
+// value OR-ed back in differs, so the kernels and their traffic are those of the all-ones form.  Whole-state op: joins anything
+// in flight.
+int launch_gate_signed(spz_state *st, const GateK &g, uint64_t ctrl_mask, uint64_t neg_mask, int target) {
+    if (neg_mask & ~ctrl_mask) { set_error("negative controls 0x%llx are not a subset of the controls 0x%llx", (unsigned long long)neg_mask, (unsigned long long)ctrl_mask); return SPZ_ERR_INVALID_ARG; }
+    if (!neg_mask) return launch_gate(st, g, ctrl_mask, target);
+    SPZ_TRY(join_pending(st));
+    return launch_gate_on(st, st->re, st->im, st->n, g, ctrl_mask, target, neg_mask);
+}
+
 // the gate on the register of n qubits at (re, im): the state's own arrays, or one contiguous chunk of them
-static int launch_gate_on(spz_state *st, double *re, double *im, int n, const GateK &g, uint64_t ctrl_mask, int target) {
+static int launch_gate_on(spz_state *st, double *re, double *im, int n, const GateK &g, uint64_t ctrl_mask, int target, uint64_t neg_mask) {
     if (target < 0 || target >= n) { set_error("target %d out of range for %d qubits", target, n); return SPZ_ERR_INVALID_ARG; }
     if ((ctrl_mask >> target) & 1ull) { set_error("target %d is also a control", target); return SPZ_ERR_INVALID_ARG; }
     if (n < 64 && (ctrl_mask >> n)) { set_error("control mask 0x%llx exceeds %d qubits", (unsigned long long)ctrl_mask, n); return SPZ_ERR_INVALID_ARG; }
@@ -188,9 +199,10 @@ static int launch_gate_on(spz_state *st, double *re, double *im, int n, const Ga
         PairArgs a{};
         a.re = re; a.im = im;
         a.nvec = 1ll << (n - LOGW - nins_vec);
-        a.setmask = ctrl_mask & ~low_bits_mask;
+        a.setmask = ctrl_mask & ~neg_mask & ~low_bits_mask;
         a.tbit = low ? 0ull : (1ull << target);
         a.lane_cmask = (int)(ctrl_mask & low_bits_mask);
+        a.lane_cval = (int)(ctrl_mask & ~neg_mask & low_bits_mask);
         a.tlow = low ? target : 0;
         int k = 0;
         for (int q = LOGW; q < n; ++q)
@@ -214,7 +226,7 @@ static int launch_gate_on(spz_state *st, double *re, double *im, int n, const Ga
         ScalarArgs a{};
         a.re = re; a.im = im;
         a.npairs = 1ll << (n - 1 - n_ctrl);
-        a.setmask = ctrl_mask;
+        a.setmask = ctrl_mask & ~neg_mask;
         a.tbit = 1ull << target;
         a.kind = g.kind;
         int k = 0;

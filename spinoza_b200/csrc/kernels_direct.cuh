@@ -11,10 +11,11 @@
 // re[s0], re[s1], im[s0], im[s1].  All loads of the U vectors are issued before any arithmetic.
 //
 //   k_pair_vec : target bit >= log2(W).  vector index v -> amplitude index by inserting zero bits at the
-//                target and control positions (controls then set to 1); s1 = s0 | 2^t.
+//                target and control positions (controls then set to 1 -- or left 0 for a negative control, the
+//                spz_mc_apply_signed extension); s1 = s0 | 2^t.
 //   k_pair_low : target bit <  log2(W): the pair lives inside one vector, updated in registers.
 //   k_pair_scalar: fully general scalar fallback (tiny states, n < log2(W)+1).
-// Controls below log2(W) become a lane predicate (lane_cmask).
+// Controls below log2(W) become a lane predicate (lane_cmask / lane_cval).
 #pragma once
 
 #include "gate_math.cuh"
@@ -31,6 +32,7 @@ struct PairArgs {
     unsigned long long tbit;     // 1 << target (k_pair_vec), unused in k_pair_low
     int nins;                    // number of zero-bit insertions
     int lane_cmask;              // control bits < log2(W)
+    int lane_cval;               // the value those bits must have (= lane_cmask unless some are negative controls)
     int tlow;                    // k_pair_low: the target bit (0 or 1)
     unsigned char pos[kMaxIns];  // ascending insertion positions (amplitude-index bit numbers)
     double s[7];
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(THREADS) k_pair_vec(const PairArgs a) {
         if (v < a.nvec) {
 #pragma unroll
             for (int l = 0; l < W; ++l) {
-                if ((l & a.lane_cmask) == a.lane_cmask) {
+                if ((l & a.lane_cmask) == a.lane_cval) {
                     double x0 = 0.0, y0 = 0.0;
                     if constexpr (S0) { x0 = r0[u].v[l]; y0 = m0[u].v[l]; }
                     pair_update<KIND>(a.s, x0, y0, r1[u].v[l], m1[u].v[l]);
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(THREADS) k_pair_low(const PairArgs a) {
 #pragma unroll
             for (int l = 0; l < W; ++l) {
                 // lanes with target bit clear drive the pair (l, l | tb)
-                if (!(l & tb) && ((l & a.lane_cmask) == a.lane_cmask)) {
+                if (!(l & tb) && ((l & a.lane_cmask) == a.lane_cval)) {
                     // W is 2 or 4 and tb in {1,2}: resolve l|tb with compile-time-indexable selects
                     if (tb == 1) pair_update<KIND>(a.s, r[u].v[l], m[u].v[l], r[u].v[(l | 1) % W], m[u].v[(l | 1) % W]);
                     else         pair_update<KIND>(a.s, r[u].v[l], m[u].v[l], r[u].v[(l | 2) % W], m[u].v[(l | 2) % W]);

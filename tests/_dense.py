@@ -36,12 +36,13 @@ def matrix(kind, p=()):
     raise ValueError(kind)
 
 
-def apply_matrix(psi, n, m, target, ctrl_mask=0):
-    """psi: complex vector of length 2^n (qubit q <-> bit q of the index). Returns a new vector."""
+def apply_matrix(psi, n, m, target, ctrl_mask=0, neg_mask=0):
+    """psi: complex vector of length 2^n (qubit q <-> bit q of the index). Returns a new vector.
+    Every qubit of ctrl_mask is a control; those also in neg_mask fire on 0 (the signed-controls extension)."""
     idx = np.arange(1 << n, dtype=np.int64)
     sel0 = ((idx >> target) & 1) == 0
     if ctrl_mask:
-        sel0 &= (idx & ctrl_mask) == ctrl_mask
+        sel0 &= (idx & ctrl_mask) == (ctrl_mask & ~neg_mask)
     s0 = idx[sel0]
     s1 = s0 | (1 << target)
     out = psi.copy()

@@ -45,6 +45,14 @@ extern "C" int emu_apply(int n, double *re, double *im, int kind, const double *
     return spz::launch_gate(&st, g, ctrl_mask, target);
 }
 
+extern "C" int emu_apply_signed(int n, double *re, double *im, int kind, const double *params, unsigned long long ctrl_mask,
+                                unsigned long long neg_mask, int target) {
+    spz_state st = make_state(n, re, im);
+    spz::GateK g;
+    if (int rc = spz::resolve_gate(kind, params, &g)) return rc;
+    return spz::launch_gate_signed(&st, g, ctrl_mask, neg_mask, target);
+}
+
 extern "C" int emu_swap(int n, double *re, double *im, int t0, int t1) {
     spz_state st = make_state(n, re, im);
     return spz::launch_swap(&st, t0, t1);

@@ -44,6 +44,8 @@ def emu():
     h = C.CDLL(str(lib))
     h.emu_apply.restype = C.c_int
     h.emu_apply.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_ulonglong, C.c_int]
+    h.emu_apply_signed.restype = C.c_int
+    h.emu_apply_signed.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_ulonglong, C.c_ulonglong, C.c_int]
     h.emu_swap.restype = C.c_int
     h.emu_swap.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     h.emu_last_error.restype = C.c_char_p
@@ -116,6 +118,50 @@ def test_cells_the_reference_panics_on_match_the_dense_statement(emu, n):
             assert emu_apply(emu, n, re, im, kind, params, cm, t) == 0
             want = D.apply_matrix(psi, n, D.matrix(kind, params), t, cm)
             np.testing.assert_allclose(re + 1j * im, want, rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 7, 10])
+def test_signed_controls_equal_x_conjugation_bit_exact(emu, n):
+    """The spz_mc_apply_signed extension (true negative controls; the reference's Mixed { zeros } drops them, gates.rs:298-311):
+    one launch must give exactly what X on the zero-controls, the all-ones gate of the oracle, and X again give -- X is an
+    exchange, so the same pair updates run on the same values.  Controls below and above log2(W), every target."""
+    rng = np.random.default_rng(900 + n)
+    for kind, params in ONE_Q:
+        for t in range(n):
+            others = [q for q in range(n) if q != t]
+            for _ in range(6):
+                k = int(rng.integers(1, min(4, len(others)) + 1))
+                cs = [int(c) for c in rng.choice(others, size=k, replace=False)]
+                zs = [c for c in cs if rng.random() < 0.6] or [cs[0]]
+                cm, zm = sum(1 << c for c in cs), sum(1 << c for c in zs)
+                cpu, re, im = fresh(n, 700 + t)
+                psi = cpu.amps()
+                p = (C.c_double * 3)(*(list(params) + [0.0] * (3 - len(params))))
+                assert emu.emu_apply_signed(n, re.ctypes.data, im.ctypes.data, kind, p, cm, zm, t) == 0, emu.emu_last_error()
+                want = D.apply_matrix(psi, n, D.matrix(kind, params), t, cm, zm)
+                np.testing.assert_allclose(re + 1j * im, want, rtol=0, atol=1e-14)
+                if kind == Gate.KIND_Z or (k > 1 and (kind, params) not in MC_OK):
+                    continue  # cells the oracle (like the reference) has no loop for: the dense statement above stands alone
+                for z in zs:
+                    orc.apply(Gate.KIND_X, cpu, z, ())
+                if k == 1:
+                    orc.c_apply(kind, cpu, cs[0], t, params)
+                else:
+                    orc.mc_apply(kind, cpu, cs, None, t, params)
+                for z in zs:
+                    orc.apply(Gate.KIND_X, cpu, z, ())
+                assert np.array_equal(re, cpu.reals) and np.array_equal(im, cpu.imags), (kind, cs, zs, t)
+
+
+def test_signed_controls_argument_errors(emu):
+    n = 4
+    _, re, im = fresh(n, 2)
+    p = (C.c_double * 3)(0.0, 0.0, 0.0)
+    assert emu.emu_apply_signed(n, re.ctypes.data, im.ctypes.data, Gate.KIND_X, p, 0b0010, 0b0100, 0) != 0  # zeros not in controls
+    assert emu.emu_apply_signed(n, re.ctypes.data, im.ctypes.data, Gate.KIND_X, p, 0b0011, 0b0001, 0) != 0  # target is a control
+    before = re.copy()
+    assert emu.emu_apply_signed(n, re.ctypes.data, im.ctypes.data, Gate.KIND_X, p, 0b0110, 0, 0) == 0       # no zeros: plain mc gate
+    assert not np.array_equal(before, re)
 
 
 @pytest.mark.parametrize("n", [2, 3, 4, 5, 8, 10])

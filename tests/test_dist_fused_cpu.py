@@ -227,3 +227,25 @@ def test_diagonal_gates_on_rank_bits_never_exchange():
     got, stats = replay(qc, world, psi0)
     np.testing.assert_allclose(got, dense(qc, psi0), rtol=0, atol=1e-12)
     assert stats["exchange"] == 0
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("world", [2, 4])
+def test_signed_controls_on_a_sharded_register(world, fuse):
+    """Negative controls (SPZ_CTRL_SIGNED) on local and on global qubits: lowered to X . gate . X, so a zero-control that lives
+    in the rank bits costs exchanges but must give the dense statement with that control at 0."""
+    n = 13 + world.bit_length() - 1
+    rng = np.random.default_rng(5 + world)
+    qc = random_circuit(n, 40, 91, fuse=fuse)
+    kinds = [Gate.KIND_X, Gate.KIND_P, Gate.KIND_RX, Gate.KIND_RY, Gate.KIND_H, Gate.KIND_RZ]
+    for i in range(12):
+        t = int(rng.integers(n))
+        others = [q for q in range(n) if q != t]
+        cs = [int(c) for c in rng.choice(others, size=int(rng.integers(1, 4)), replace=False)]
+        if i % 3 == 0 and t != n - 1:
+            cs = list({*cs, n - 1})           # a global qubit among the controls ...
+        zs = {cs[-1]} | {c for c in cs if rng.random() < 0.4}   # ... and among the zeros
+        qc.add(sb.QuantumTransformation(Gate(kinds[i % len(kinds)], (0.3 + 0.1 * i, 0.0, 0.0)), t, sb.Controls.signed(cs, zs)))
+    psi0 = D.random_state(n, 14)
+    got, stats = replay(qc, world, psi0)
+    np.testing.assert_allclose(got, dense(qc, psi0), rtol=0, atol=1e-12)

@@ -81,6 +81,38 @@ def test_direct_gates_sharded_vs_single_gpu(n, world):
     assert states[0].stats()["exchanges"] > 0
 
 
+@pytest.mark.parametrize("n,world", [(7, 2), (10, 4)])
+def test_signed_controls_sharded_vs_single_gpu(n, world):
+    """spz_mc_apply_signed on a sharded register (X on the zero-controls around the all-ones gate, wherever those qubits live)
+    against the single-GPU one-launch form: bit for bit."""
+    cpu = orc.gen_random_state(n, 5 * n + world)
+    ref = sb.State.from_arrays(cpu.reals, cpu.imags)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, cpu)
+    rng = np.random.default_rng(n * world)
+    seq = []
+    for i in range(30):
+        kind, p = GATES[int(rng.integers(len(GATES)))]
+        t = int(rng.integers(n))
+        others = [q for q in range(n) if q != t]
+        cs = [int(c) for c in rng.choice(others, size=int(rng.integers(1, 4)), replace=False)]
+        if i % 4 == 0 and t != n - 1 and n - 1 not in cs:
+            cs.append(n - 1)                      # a global qubit as a zero-control
+        zs = [cs[-1]] + [c for c in cs[:-1] if rng.random() < 0.4]
+        seq.append((kind, p, [c for c in cs if c not in zs], zs, t))
+
+    def body(rank, s):
+        for kind, p, ones, zs, t in seq:
+            sb.mc_apply_signed(G(kind, p), s, ones, zs, t)
+        s.sync()
+    run_group(states, body)
+    for kind, p, ones, zs, t in seq:
+        sb.mc_apply_signed(G(kind, p), ref, ones, zs, t)
+    re, im = gather(states)
+    rre, rim = ref.download()
+    assert np.array_equal(re, rre) and np.array_equal(im, rim)
+
+
 @pytest.mark.parametrize("n,world,fuse", [(8, 2, True), (10, 4, True), (10, 4, False), (13, 8, True), (16, 4, True)])
 def test_execute_sharded_vs_dense(n, world, fuse):
     ops = random_ops(n, 150, seed=n * 7 + world, with_swap=True)

@@ -506,6 +506,76 @@ def test_extension_cells_match_dense():  # controlled Z / mc H etc.: the referen
     assert np.max(np.abs(s.amps() - psi)) < 1e-14
 
 
+@pytest.mark.parametrize("n", [3, 6, 13])
+def test_signed_controls_one_launch_equals_x_conjugation(n):
+    """spz_mc_apply_signed (extension; the reference's Mixed { zeros } drops the zeros, gates.rs:298-311): true negative controls
+    in ONE launch of the pair kernel.  X is an exchange, so X(zeros) . oracle gate . X(zeros) is bit-identical where the oracle
+    has the cell, and the dense statement covers the rest."""
+    rng = np.random.default_rng(300 + n)
+    for kind, p in GATES:
+        for _ in range(8):
+            t = int(rng.integers(n))
+            others = [q for q in range(n) if q != t]
+            cs = [int(c) for c in rng.choice(others, size=int(rng.integers(1, min(3, len(others)) + 1)), replace=False)]
+            zs = [c for c in cs if rng.random() < 0.6] or [cs[0]]
+            ones = [c for c in cs if c not in zs]
+            init = orc.gen_random_state(n, int(rng.integers(1 << 20)))
+            s = to_gpu(init)
+            before = sb.launch_count()
+            sb.mc_apply_signed(G(kind, p), s, ones, zs, t)
+            assert sb.launch_count() - before == 1
+            cm, zm = sum(1 << c for c in cs), sum(1 << c for c in zs)
+            want = D.apply_matrix(init.amps(), n, D.matrix(kind, p), t, cm, zm)
+            assert np.max(np.abs(s.amps() - want)) < 1e-14, (kind, cs, zs, t)
+            if kind == orc.Z or (len(cs) > 1 and kind not in (orc.X, orc.P, orc.RX, orc.RY)):
+                continue
+            cpu = init.clone()
+            for z in zs:
+                orc.apply(orc.X, cpu, z)
+            if len(cs) == 1:
+                orc.c_apply(kind, cpu, cs[0], t, p)
+            else:
+                orc.mc_apply(kind, cpu, cs, None, t, p)
+            for z in zs:
+                orc.apply(orc.X, cpu, z)
+            assert_same(s, cpu, what=f"signed {kind} controls {cs} zeros {zs} target {t}")
+    s = sb.State(4)
+    with pytest.raises(sb.SpinozaError):
+        sb.mc_apply_signed(Gate.X, s, [1], [1], 0)     # both signs
+    with pytest.raises(sb.SpinozaError):
+        sb.mc_apply_signed(Gate.X, s, [1], [0], 0)     # target among the controls
+    with pytest.raises(sb.SpinozaError):
+        sb.mc_apply_signed(Gate.SWAP(0, 1), s, [2], [3], 0)
+
+
+@pytest.mark.parametrize("fuse,exact", [(False, False), (True, False), (True, True)])
+def test_signed_controls_in_execute(fuse, exact):
+    """Controls.signed through QuantumCircuit::execute: one launch per op unfused, X . gate . X inside the fused passes."""
+    n = 14
+    rng = np.random.default_rng(41)
+    qc = QuantumCircuit(QuantumRegister(n), fuse=fuse, exact=exact)
+    init = orc.gen_random_state(n, 77)
+    qc.state = to_gpu(init)
+    psi = init.amps()
+    kinds = [D.X, D.P, D.RX, D.RY, D.H, D.RZ, D.U, D.Y, D.Z]
+    for i in range(40):
+        t = int(rng.integers(n))
+        others = [q for q in range(n) if q != t]
+        cs = [int(c) for c in rng.choice(others, size=int(rng.integers(1, 4)), replace=False)]
+        zs = {c for c in cs if rng.random() < 0.5} or {cs[0]}
+        kind, p = kinds[i % len(kinds)], tuple(float(x) for x in rng.random(3) * 2 * PI)
+        qc.add(sb.QuantumTransformation(Gate(kind, p), t, sb.Controls.signed(cs, zs)))
+        psi = D.apply_matrix(psi, n, D.matrix(kind, p), t, sum(1 << c for c in cs), sum(1 << c for c in zs))
+        h = int(rng.integers(n))
+        qc.h(h)
+        psi = D.apply_matrix(psi, n, D.matrix(D.H), h)
+    before = sb.launch_count()
+    qc.execute()
+    launches = sb.launch_count() - before
+    assert (launches == 80) if not fuse else (launches < 40), launches
+    assert np.max(np.abs(qc.state.amps() - psi)) < 1e-12
+
+
 def test_async_upload_then_gates_equals_upload_then_gates():
     """spz_upload_async: gates and fused passes issued right after it follow the pieces of the state as they arrive (low targets
     chunk by chunk, high targets and controls after the last piece).  Bit-identical to the synchronous upload."""

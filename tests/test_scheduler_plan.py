@@ -45,7 +45,12 @@ def run_dense_order(n, psi, trs, order):
         if g.kind == Gate.KIND_SWAP:
             psi = D.apply_swap(psi, n, g.t0, g.t1)
         else:
-            psi = D.apply_matrix(psi, n, D.matrix(g.kind, g.params), t.target, t.controls.mask())
+            cm, zm = t.controls.mask(), t.controls.zeros_mask()
+            if t.controls.kind == t.controls.MIXED:
+                cm, zm = cm & ~zm, 0  # mc_apply drops the zeros (gates.rs:298-311)
+            elif t.controls.kind != t.controls.SIGNED:
+                zm = 0
+            psi = D.apply_matrix(psi, n, D.matrix(g.kind, g.params), t.target, cm, zm)
     return psi
 
 

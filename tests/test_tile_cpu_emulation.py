@@ -190,6 +190,51 @@ def test_reference_cells_merged_mode(emu, seed):
     assert stats.get("ctrl", 0) >= 1, stats
 
 
+class _SignedView:
+    """A circuit with SIGNED controls as run_emulated wants it: programs compiled from the list as the caller wrote it (the
+    native expansion in spz_execute), plan and dense fallback from the expanded list -- they must describe the same schedule."""
+
+    def __init__(self, qc):
+        self._qc, self._ex = qc, qc.expanded()
+        self.n_qubits, self.exact = qc.n_qubits, qc.exact
+        self.transformations = self._ex.transformations
+
+    def plan(self):
+        return self._ex.plan()
+
+    def _encode(self):
+        return self._qc._encode()
+
+    def _flags(self):
+        return self._qc._flags()
+
+
+@pytest.mark.parametrize("kernel", [1, 3], ids=["k_tile", "k_tile3"])
+def test_signed_controls_in_fused_passes(emu, kernel):
+    """Negative controls (Controls.signed, the SPZ_CTRL_SIGNED extension) inside fused passes: spz_execute schedules X on the
+    zero-controls around the all-ones gate; the compiled programs must reproduce the dense statement with the zeros at 0."""
+    n = 13
+    rng = np.random.default_rng(77)
+    qc = random_circuit(n, 60, 78)
+    kinds = [Gate.KIND_X, Gate.KIND_P, Gate.KIND_RX, Gate.KIND_RY, Gate.KIND_H, Gate.KIND_RZ, Gate.KIND_U, Gate.KIND_Z, Gate.KIND_Y]
+    for i in range(24):
+        t = int(rng.integers(n))
+        others = [q for q in range(n) if q != t]
+        cs = [int(c) for c in rng.choice(others, size=int(rng.integers(1, 4)), replace=False)]
+        zs = {c for c in cs if rng.random() < 0.5} or {cs[-1]}
+        p = tuple(float(x) for x in rng.random(3) * 2 * np.pi)
+        qc.add(sb.QuantumTransformation(Gate(kinds[i % len(kinds)], p), t, sb.Controls.signed(cs, zs)))
+        qc.h(int(rng.integers(n)))
+    with pytest.raises(sb.SpinozaError):
+        qc.plan()  # one entry per op of the caller's list cannot describe the expansion
+    psi0, re, im = start(n, 9)
+    stats = {}
+    run_emulated(emu, _SignedView(qc), re, im, stats, kernel=kernel)
+    want = run_dense_order(n, psi0.copy(), list(qc.transformations), range(len(qc.transformations)))
+    np.testing.assert_allclose(re + 1j * im, want, rtol=0, atol=1e-12)
+    assert stats.get("ctrl", 0) + stats.get("k_tile", 0) >= 1, stats
+
+
 def test_rotations_near_pi_keep_their_matrix(emu):
     """RX / RY with |cos(theta/2)| tiny are not rescaled (the factored form divides by the cosine), and a long run of strongly
     rescaled rotations must not drive the pass scale out of range."""
