@@ -177,6 +177,148 @@ def cpu_qft(n: int, threads: int):
     return {"seconds": dt, "gates": len(ops), "sec_per_gate": dt / len(ops), "threads": threads}
 
 
+CRITERION_N = 25  # benches/benchmark.rs:148
+
+
+def _qcbm_ops(n, depth=9):
+    """The op list of the reference's `qcbm` bench (workloads.qcbm) for the oracle's execute."""
+    import oracle as orc
+    from spinoza_b200 import QuantumCircuit, QuantumRegister, workloads
+    qc = QuantumCircuit(QuantumRegister(n))
+    workloads.qcbm(qc, depth=depth, seed=42)
+    return [orc.make_op(t.gate.kind, t.target, t.gate.params, ctrl_kind=t.controls.kind, ctrl_mask=t.controls.mask())
+            for t in qc.transformations]
+
+
+def cpu_criterion(threads: int, n: int = CRITERION_N):
+    """The reference's own criterion suite (benches/benchmark.rs:147-188, n = 25) on the oracle port: seconds per iteration of
+    each bench function, built as the reference builds it (h / x / rx / p / z / u / value_encoding allocate their State inside
+    the timed closure, `measure` generates its random state there).  One timed iteration after one warm-up."""
+    import oracle as orc
+    orc.set_threads(threads)
+    PI = math.pi
+
+    def fresh_loop(kind, p=()):
+        def f():
+            s = orc.State(n)
+            for t in range(n):
+                orc.apply(kind, s, t, p)
+        return f
+
+    kept = orc.State(n)
+    pairs = [(i, (i + 1) % n) for i in range(n)]
+    qcbm_ops = _qcbm_ops(n)
+    qcbm_state = orc.State(n)
+
+    def cx():
+        for c, t in pairs:
+            orc.c_apply(orc.X, kept, c, t)
+
+    def rz():
+        for t in range(n):
+            orc.apply(orc.RZ, kept, t, (1.0,))
+
+    def value_encoding():  # benches/benchmark.rs:63-76
+        s = orc.State(n)
+        for i in range(n):
+            orc.apply(orc.H, s, i)
+        for i in range(n):
+            orc.apply(orc.P, s, i, (2.0 * PI / (2.0 ** (i + 1)) * 2.4,))
+        orc.iqft(s, list(range(n - 1, -1, -1)))
+
+    def measure():  # benches/benchmark.rs:142-145
+        s = orc.gen_random_state(n, 42)
+        orc.measure_qubit(s, 0, True, None, 0.5)
+
+    fns = {"h": fresh_loop(orc.H), "x": fresh_loop(orc.X), "cx": cx, "rz": rz, "rx": fresh_loop(orc.RX, (1.0,)),
+           "qcbm": lambda: orc.execute(qcbm_state, qcbm_ops), "p": fresh_loop(orc.P, (1.0,)), "z": fresh_loop(orc.Z),
+           "u": fresh_loop(orc.U, (1.0, 2.0, 3.0)), "value_encoding": value_encoding, "measure": measure}
+    out = {}
+    fresh_loop(orc.H)()  # thread pool, page cache
+    for name, f in fns.items():
+        t0 = time.perf_counter()
+        f()
+        out[name] = time.perf_counter() - t0
+    return out
+
+
+def gpu_criterion(sb, device: int, n: int = CRITERION_N, reps: int = 5):
+    """The same suite through this engine's mirror of the reference API on one GPU: median seconds per iteration over `reps`
+    (CUDA events on the state's stream; `measure` by wall clock, it returns a value to the host).  The State is created once
+    and reset (spz_reset_zero) where the reference allocates a fresh one per iteration.  qcbm / value_encoding's iqft go
+    through QuantumCircuit::execute fused (the drop-in's default) -- qcbm_unfused is the one-pass-per-gate figure."""
+    from spinoza_b200 import Gate, QuantumCircuit, workloads
+    PI = math.pi
+    st = sb.State(n, device=device)
+    pairs = [(i, (i + 1) % n) for i in range(n)]
+
+    def fresh_loop(gate):
+        def f():
+            st.reset()
+            for t in range(n):
+                sb.apply(gate, st, t)
+        return f
+
+    def cx():
+        for c, t in pairs:
+            sb.c_apply(Gate.X, st, c, t)
+
+    def rz():
+        for t in range(n):
+            sb.apply(Gate.RZ(1.0), st, t)
+
+    def qcbm(fuse):
+        def f():
+            qc = QuantumCircuit.from_state(st, fuse=fuse)
+            workloads.qcbm(qc, depth=9, seed=42)
+            return qc
+        return f
+
+    def value_encoding():
+        st.reset()
+        for i in range(n):
+            sb.apply(Gate.H, st, i)
+        for i in range(n):
+            sb.apply(Gate.P(2.0 * PI / (2.0 ** (i + 1)) * 2.4), st, i)
+        sb.iqft(st, list(range(n - 1, -1, -1)))
+
+    out = {}
+
+    def timed(name, body, prepare=None):
+        ts = []
+        for r in range(reps + 1):
+            arg = prepare() if prepare else None
+            st.sync()
+            st.timer_start()
+            body(arg) if prepare else body()
+            ts.append(st.timer_stop() * 1e-3)
+        out[name] = statistics.median(ts[1:])
+
+    timed("h", fresh_loop(Gate.H))
+    timed("x", fresh_loop(Gate.X))
+    st.reset(); timed("cx", cx)
+    st.reset(); timed("rz", rz)
+    timed("rx", fresh_loop(Gate.RX(1.0)))
+    st.reset(); timed("qcbm", lambda qc: qc.execute(), prepare=qcbm(True))
+    st.reset(); timed("qcbm_unfused", lambda qc: qc.execute(), prepare=qcbm(False))
+    timed("p", fresh_loop(Gate.P(1.0)))
+    timed("z", fresh_loop(Gate.Z))
+    timed("u", fresh_loop(Gate.U(1.0, 2.0, 3.0)))
+    timed("value_encoding", value_encoding)
+    ts = []
+    for r in range(reps + 1):
+        st.sync()
+        t0 = time.perf_counter()
+        st.init_random(42)
+        sb.measure_qubit(st, 0, True, None)
+        ts.append(time.perf_counter() - t0)
+    out["measure"] = statistics.median(ts[1:])
+    qc = qcbm(True)()
+    out["_qcbm"] = {"gates": len(qc.transformations), "passes_fused": qc.plan()[1]}
+    del st
+    return out
+
+
 def sweep_config(n: int, n_local: int):
     """The `config` object of the headline workload: identical in both arms."""
     return {"workload": f"sweep_1q_H_RX_RZ_all_targets_n{n}", "qubits": n, "local_qubits": n_local,
@@ -223,6 +365,10 @@ def run_reference(args, rank: int, world: int):
             line["qft20"] = {"one_thread": cpu_qft(20, 1), "all_threads": cpu_qft(20, threads)}
         except Exception as e:
             line["qft20"] = {"error": repr(e)}
+        try:  # the reference's own criterion suite (benches/benchmark.rs:147-188) at its n = 25
+            line["criterion"] = {"qubits": pick_cpu_n(CRITERION_N), "seconds": cpu_criterion(threads, pick_cpu_n(CRITERION_N)), "threads": threads}
+        except Exception as e:
+            line["criterion"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
 
 
@@ -501,6 +647,17 @@ def main():
         except Exception as e:
             line["config3"] = {"error": repr(e)}
 
+    # ---- the reference's own criterion suite (benches/benchmark.rs:147-188) at its n = 25, single GPU ----
+    if rank == 0 and dist is None and not args.no_extras:
+        try:
+            gc = gpu_criterion(sb, local_rank)
+            meta = gc.pop("_qcbm")
+            line["criterion"] = {"qubits": CRITERION_N, "gpu_seconds": gc, "qcbm": meta,
+                                 "what": "benches/benchmark.rs:147-188 bench functions (one iteration each) through the mirrored API; "
+                                         "median of 5 after one warm-up; the CPU port's figures are in cpu_baseline.criterion"}
+        except Exception as e:
+            line["criterion"] = {"error": repr(e)}
+
     # ---- sharded runs: parity against the CPU oracle on real NVLink (20 qubits over all ranks) ----
     if dist is not None and not args.no_extras:
         try:
@@ -615,6 +772,14 @@ def main():
                 line["cpu_baseline"]["qft20"] = {"one_thread": cpu_qft(20, 1), "all_threads": cpu_qft(20, threads)}
             except Exception as e:
                 line["cpu_baseline"]["qft20"] = {"error": repr(e)}
+            try:  # the reference's criterion suite at n = 25 on the port, all host threads (next to line["criterion"])
+                cc = cpu_criterion(threads, pick_cpu_n(CRITERION_N))
+                line["cpu_baseline"]["criterion"] = {"seconds": cc, "threads": threads}
+                if isinstance(line.get("criterion", {}).get("gpu_seconds"), dict):
+                    gs = line["criterion"]["gpu_seconds"]
+                    line["criterion"]["speedup_vs_cpu_port"] = {k: round(cc[k] / gs[k], 1) for k in cc if gs.get(k)}
+            except Exception as e:
+                line["cpu_baseline"]["criterion"] = {"error": repr(e)}
 
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -3,6 +3,9 @@
 * `qft`                    -- config 1 / 4: QFT-n := qc.iqft(&(0..n).rev()); qc.inverse()   (n + n(n-1)/2 gates)
 * `random_layered_circuit` -- config 3: depth x [1q rotation on every qubit, entanglers on pairs (i, i+1), i = l mod 2,
                               alternating CNOT / CP(angle)], kinds and angles from splitmix64(seed)
+* `qcbm`                   -- the reference's own circuit benchmark (benches/benchmark.rs:12-58, criterion "qcbm": n = 25, depth 9,
+                              ring of CX pairs (i, i+1 mod n)): RX RZ on every qubit, entangler, depth x [RZ RX RZ, entangler], RZ RX.
+                              The reference draws its angles from StdRng(42), which only Rust reproduces; here from splitmix64(42)
 * `tiled_qasm`             -- config 5: a 4-qubit OpenQASM program repeated over disjoint 4-qubit blocks
 The generators are deterministic and shared by bench.py and the parity tests, so "the gate list is the shared input".
 """
@@ -68,6 +71,34 @@ def random_layered_circuit(qc: QuantumCircuit, depth: int = 20, seed: int = 42) 
         else:
             qc.cp(ang, c, t)
     return len(ops)
+
+
+def qcbm(qc: QuantumCircuit, depth: int = 9, seed: int = 42) -> int:
+    """benches/benchmark.rs:12-58 build_circuit(nqubits, depth, pairs) with pairs = [(i, (i + 1) % n)] (:155)."""
+    n = qc.n_qubits
+    rng = SplitMix64(seed)
+    pairs = [(i, (i + 1) % n) for i in range(n)]
+    before = len(qc.transformations)
+
+    def entangler():
+        for a, b in pairs:
+            if a != b:
+                qc.cx(a, b)
+
+    for k in range(n):                      # first_rotation
+        qc.rx(rng.u01(), k)
+        qc.rz(rng.u01(), k)
+    entangler()
+    for _ in range(depth):                  # mid_rotation + entangler
+        for k in range(n):
+            qc.rz(rng.u01(), k)
+            qc.rx(rng.u01(), k)
+            qc.rz(rng.u01(), k)
+        entangler()
+    for k in range(n):                      # last_rotation
+        qc.rz(rng.u01(), k)
+        qc.rx(rng.u01(), k)
+    return len(qc.transformations) - before
 
 
 def tiled_qasm(qc: QuantumCircuit, qasm_text: str, block: int = 4) -> int:

@@ -39,6 +39,28 @@ def test_config3_random_layered_circuit(n):
     assert abs(sb.norm2(fused) - 1.0) < 1e-10
 
 
+@pytest.mark.parametrize("n", [13, 20])
+def test_qcbm_circuit_benchmark_fused_exact_and_unfused(n):
+    """The reference's own circuit benchmark (benches/benchmark.rs:12-58 `qcbm`: RX RZ | ring of CX | depth x [RZ RX RZ | ring] |
+    RZ RX, depth 9) through execute: unfused == oracle bit for bit, fused-exact == unfused, merged within 1e-12."""
+    init = orc.State(n)  # the bench starts from |0..0> (QuantumCircuit::new)
+    states = {k: to_gpu(init) for k in ("fused", "exact", "plain")}
+    kws = {"fused": dict(fuse=True), "exact": dict(fuse=True, exact=True), "plain": dict(fuse=False)}
+    ops = None
+    for k, st in states.items():
+        qc = QuantumCircuit.from_state(st, **kws[k])
+        assert workloads.qcbm(qc, depth=9, seed=42) == 41 * n
+        ops = oracle_ops_from(qc)
+        qc.execute()
+    cpu = init.clone()
+    orc.execute(cpu, ops)
+    pr, pi = states["plain"].download(); er, ei = states["exact"].download(); fr, fi = states["fused"].download()
+    assert np.array_equal(pr, cpu.reals) and np.array_equal(pi, cpu.imags)
+    assert np.array_equal(er, pr) and np.array_equal(ei, pi)
+    assert np.max(np.abs(fr - cpu.reals)) <= 1e-12 and np.max(np.abs(fi - cpu.imags)) <= 1e-12
+    assert abs(sb.norm2(states["fused"]) - 1.0) < 1e-10
+
+
 @pytest.mark.parametrize("n", [16, 20, 22])
 def test_config3_with_chosen_tiles(n, monkeypatch):
     """From 24 qubits up the scheduler chooses each pass's tile qubits by how many ops they admit (abi.cu: choose_tile); force

@@ -425,3 +425,15 @@ def test_no_shared_memory_race_in_any_pass(emu, emu_tsan, tmp_path, case, kernel
         seen.add(out.strip())
         re, im = r2, i2  # feed the next pass with this pass's output, as execute would
     assert seen, "no fused pass was exercised"
+
+
+def test_qcbm_circuit_benchmark(emu):
+    """benches/benchmark.rs `qcbm` (ring of CX + RZ RX RZ layers, depth 3 here) through the emulated k_tile3."""
+    n = 13
+    qc = QuantumCircuit(QuantumRegister(n))
+    assert workloads.qcbm(qc, depth=3, seed=42) == n * (5 + 4 * 3)
+    psi0, re, im = start(n, 15)
+    stats = {}
+    run_emulated(emu, qc, re, im, stats)
+    np.testing.assert_allclose(re + 1j * im, dense_reference(qc, psi0), rtol=0, atol=1e-12)
+    assert stats.get("ctrl", 0) >= 1, stats
