@@ -869,7 +869,10 @@ int spz_upload_async(spz_state *st, const double *re, const double *im) {
     SPZ_CUDA(cudaSetDevice(st->device));
     SPZ_TRY(join_pending(st));
     spz_state::Arrival &a = st->arrival;
-    int K = 4;
+    // pieces: more of them shorten the lag of the first / last piece behind the bus, but every piece bit is a qubit whose
+    // non-diagonal gates need the whole state (SPZ_UPLOAD_CHUNKS = 2, 4 or 8; measured in profiles/round2_summary.md)
+    static const int want_chunks = [] { const char *e = std::getenv("SPZ_UPLOAD_CHUNKS"); const int v = e ? std::atoi(e) : 0; return (v == 2 || v == 4 || v == 8) ? v : 4; }();
+    int K = want_chunks;
     while (K > 1 && (st->len >> 12) < K) K >>= 1;
     if (!a.copy) {
         SPZ_CUDA(cudaStreamCreateWithFlags(&a.copy, cudaStreamNonBlocking));
@@ -1011,9 +1014,39 @@ int spz_mc_apply(spz_state *st, const spz_gate *gate, const int32_t *controls, i
     return apply_masked(st, gate->kind, gate->p, mask, target);
 }
 
+static int execute_impl(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_t flags, uint64_t *measured_mask,
+                        uint64_t *measured_vals, PlanSink *sink);
+
 int spz_iqft(spz_state *st, const int32_t *targets, int m) {
     SPZ_CHECK_STATE(st);
     if (m < 0 || (m && !targets)) return SPZ_ERR_INVALID_ARG;
+    // The m + m(m-1)/2 gates of core.rs:184-191 as ONE op list through the fused scheduler: a run of them shares one HBM pass
+    // (QFT-30: 4 passes instead of 465).  Default: merged mode, like QuantumCircuit::execute -- within 1e-12 of the gate-by-gate
+    // loop (the documented fused rounding difference; 30 qubits: 38 ms against ~700 ms).  SPZ_IQFT_FUSE=exact keeps every gate's
+    // reference arithmetic (bit-identical to the loop, 550 ms at 30 qubits: the exact tile kernel pays for every controlled
+    // phase on its own), SPZ_IQFT_FUSE=0 keeps the loop; so do small registers, where a pass is launch latency anyway.
+    const char *iqft_env = std::getenv("SPZ_IQFT_FUSE");
+    const bool fuse_iqft = !(iqft_env && iqft_env[0] == '0');
+    const uint32_t iqft_flags = SPZ_EXEC_FUSE | ((iqft_env && iqft_env[0] == 'e') ? SPZ_EXEC_EXACT : 0u);
+    if (fuse_iqft && m >= 3 && st->n >= 16) {
+        const int nq = total_qubits(st);
+        std::vector<spz_op> ops;
+        ops.reserve((size_t)m + (size_t)m * (m - 1) / 2);
+        for (int j = m - 1; j >= 0; --j) {
+            if (targets[j] < 0 || targets[j] >= nq) { set_error("bad iqft targets"); return SPZ_ERR_INVALID_ARG; }
+            spz_op h{};
+            h.kind = SPZ_GATE_H; h.target = targets[j]; h.ctrl_kind = SPZ_CTRL_NONE;
+            ops.push_back(h);
+            for (int k = j - 1; k >= 0; --k) {
+                if (targets[j] == targets[k] || targets[k] < 0 || targets[k] >= nq) { set_error("bad iqft targets"); return SPZ_ERR_INVALID_ARG; }
+                spz_op c{};
+                c.kind = SPZ_GATE_P; c.target = targets[k]; c.p[0] = -3.14159265358979323846 / std::ldexp(1.0, j - k);
+                c.ctrl_kind = SPZ_CTRL_SINGLE; c.ctrl_mask = 1ull << targets[j];
+                ops.push_back(c);
+            }
+        }
+        return execute_impl(st, ops.data(), (int64_t)ops.size(), iqft_flags, nullptr, nullptr, nullptr);
+    }
     // core.rs:184-191
     for (int j = m - 1; j >= 0; --j) {
         SPZ_TRY(apply_masked(st, SPZ_GATE_H, nullptr, 0, targets[j]));

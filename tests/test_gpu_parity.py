@@ -334,14 +334,31 @@ def test_qft_closed_form_and_roundtrip(n, fuse):  # QFT|x>[k] = 2^(
     assert abs(sb.norm2(s) - 1.0) < 1e-10
 
 
-def test_iqft_functional_matches_oracle():  # core.rs:184-191
-    n = 9
+@pytest.mark.parametrize("n,mode", [(9, None), (17, None), (20, None), (17, "exact"), (20, "0")])
+def test_iqft_functional_matches_oracle(n, mode, monkeypatch):  # core.rs:184-191
+    """From 16 qubits up spz_iqft hands its gate list to the fused scheduler: merged mode by default (within 1e-12, a handful of
+    passes), SPZ_IQFT_FUSE=exact bit-identical in as few passes, SPZ_IQFT_FUSE=0 the gate-by-gate loop."""
+    if mode is not None:
+        monkeypatch.setenv("SPZ_IQFT_FUSE", mode)
     cpu = orc.gen_random_state(n, 77)
     gpu = to_gpu(cpu)
     targets = list(reversed(range(n)))
     orc.iqft(cpu, targets)
+    before = sb.launch_count()
     sb.iqft(gpu, targets)
-    assert_same(gpu, cpu)
+    launches = sb.launch_count() - before
+    loop = n < 16 or mode == "0"
+    assert_same(gpu, cpu, exact=loop or mode == "exact", tol=1e-12)
+    assert launches == n + n * (n - 1) // 2 if loop else launches <= 8, launches
+    if n >= 16:  # a subset of the qubits, in an order of the caller's choosing
+        sub = [3, n - 1, 0, 8, 12]
+        orc.iqft(cpu, sub)
+        sb.iqft(gpu, sub)
+        assert_same(gpu, cpu, exact=False, tol=1e-12)
+        with pytest.raises(sb.SpinozaError):
+            sb.iqft(gpu, [0, 1, 1])
+        with pytest.raises(sb.SpinozaError):
+            sb.iqft(gpu, [0, 1, n])
 
 
 def test_value_encoding_yields_basis_state():  # circuit.rs:1076-1113
