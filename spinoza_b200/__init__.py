@@ -542,6 +542,34 @@ def sample(state: State, shots: int, seed: int = 0, u01: Optional[np.ndarray] = 
     return out
 
 
+class Reservoir:
+    """`spinoza::core::Reservoir` (core.rs:65-121): same construction and read-out.  The filling is the engine's exact
+    inverse-CDF sampler (spz_sample: one read pass over the device state) instead of `num_tests` rounds of weighted
+    replacement, so every entry is an exact draw from |amplitude|^2 whatever `num_tests` is."""
+
+    def __init__(self, k: int, seed: int = 0x9E3779B97F4A7C15):
+        self.entries = [0] * k
+        self._seed = seed
+
+    def sampling(self, state: State, num_tests: int):  # core.rs:96-113
+        u = np.random.default_rng(self._seed).random(len(self.entries))
+        self._seed += 1
+        self.entries = [int(i) for i in sample(state, len(u), u01=u)]
+
+    def get_outcome_count(self) -> dict:  # core.rs:115-121
+        out: dict = {}
+        for e in self.entries:
+            out[e] = out.get(e, 0) + 1
+        return out
+
+
+def reservoir_sampling(state: State, reservoir_size: int, num_tests: int) -> Reservoir:
+    """`reservoir_sampling(&state, reservoir_size, num_tests)` core.rs:125-129."""
+    r = Reservoir(reservoir_size)
+    r.sampling(state, num_tests)
+    return r
+
+
 from .circuit import (Controls, QuantumCircuit, QuantumRegister, QuantumTransformation,  # noqa: E402
                       EXEC_FUSE, EXEC_NO_FUSE, EXEC_EXACT)
 from . import openqasm  # noqa: E402
@@ -549,7 +577,7 @@ from . import distributed  # noqa: E402
 
 __all__ = [
     "PI", "SpinozaError", "Gate", "State", "HostBuffer", "apply", "c_apply", "cc_apply", "mc_apply", "mc_apply_mask", "mc_apply_signed", "iqft",
-    "measure_qubit", "prob0", "norm2", "qubit_expectation_value", "xyz_expectation_value", "sample", "uniforms",
+    "measure_qubit", "prob0", "norm2", "qubit_expectation_value", "xyz_expectation_value", "sample", "uniforms", "Reservoir", "reservoir_sampling",
     "Controls", "QuantumCircuit", "QuantumRegister", "QuantumTransformation", "EXEC_FUSE", "EXEC_NO_FUSE", "EXEC_EXACT",
     "openqasm", "device_count", "device_name", "mem_info", "launch_count", "library_path",
 ]
