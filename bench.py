@@ -658,6 +658,19 @@ def main():
         except Exception as e:
             line["criterion"] = {"error": repr(e)}
 
+    # ---- reductions at the bench size (single GPU): <Z> of every qubit from one read pass vs one pass per qubit ----
+    if rank == 0 and dist is None and not args.no_extras:
+        try:
+            state.init_random(42)
+            sb.xyz_expectation_value("z", state, [0, 1])  # warm
+            t0 = time.perf_counter(); zs = sb.xyz_expectation_value("z", state, list(range(n))); t_all = time.perf_counter() - t0
+            t0 = time.perf_counter(); z1 = [sb.xyz_expectation_value("z", state, [t])[0] for t in range(n)]; t_each = time.perf_counter() - t0
+            line["reductions"] = {"qubits": n, "z_all_qubits_one_pass_s": t_all, "z_one_pass_per_qubit_s": t_each,
+                                  "effective_read_GBps_one_pass": 16.0 * (1 << n) / t_all / 1e9,
+                                  "max_abs_diff": float(max(abs(a - b) for a, b in zip(zs, z1)))}
+        except Exception as e:
+            line["reductions"] = {"error": repr(e)}
+
     # ---- sharded runs: parity against the CPU oracle on real NVLink (20 qubits over all ranks) ----
     if dist is not None and not args.no_extras:
         try:

@@ -1413,6 +1413,16 @@ int spz_xyz_expectation_value(spz_state *st, char observable, const int32_t *tar
     default: set_error("observable %c not supported", observable); return SPZ_ERR_INVALID_ARG;
     }
     if (n_targets < 0 || (n_targets && (!targets || !out))) return SPZ_ERR_INVALID_ARG;
+    // 'z' on several targets: one read pass keeps the mass of every index bit (kernels_zall.cuh), instead of one pass per target
+    if (mode == 4 && n_targets >= 2 && st->n >= 2 && st->n <= kZMaxBits) {
+        if (st->dist) return dist_reduce_z_multi(st, targets, n_targets, out);
+        for (int i = 0; i < n_targets; ++i)
+            if (targets[i] < 0 || targets[i] >= st->n) { set_error("target %d out of range", targets[i]); return SPZ_ERR_INVALID_ARG; }
+        double all[kZMaxBits + 1];
+        SPZ_TRY(reduce_z_all(st, all));
+        for (int i = 0; i < n_targets; ++i) out[i] = all[0] - 2.0 * all[1 + targets[i]];
+        return SPZ_OK;
+    }
     for (int i = 0; i < n_targets; ++i) {
         if (st->dist) SPZ_TRY(dist_reduce_scalar(st, mode, targets[i], &out[i]));
         else SPZ_TRY(reduce_scalar(st, mode, targets[i], &out[i]));

@@ -626,6 +626,24 @@ int dist_reduce_scalar(spz_state *st, int mode, int target, double *out) {
     return dist_allreduce(st, nullptr, local, out, nullptr);
 }
 
+// <Z_t> for a list of targets: ONE read pass over the shard (reduce_z_all) serves every local target, a global target is the
+// shard's norm with the sign of this rank's bit; then one scalar all-reduce per target.
+int dist_reduce_z_multi(spz_state *st, const int32_t *targets, int k, double *out) {
+    DistCtx *c = ctx_of(st);
+    for (int i = 0; i < k; ++i)
+        if (targets[i] < 0 || targets[i] >= c->plan.n) { set_error("target %d out of range", targets[i]); return SPZ_ERR_INVALID_ARG; }
+    double loc[kZMaxBits + 1];
+    SPZ_TRY(reduce_z_all(st, loc));
+    for (int i = 0; i < k; ++i) {
+        const int pt = c->plan.perm[targets[i]];
+        double local;
+        if (pt < c->plan.n_local) local = loc[0] - 2.0 * loc[1 + pt];
+        else local = ((c->rank >> (pt - c->plan.n_local)) & 1) ? -loc[0] : loc[0];
+        SPZ_TRY(dist_allreduce(st, nullptr, local, &out[i], nullptr));
+    }
+    return SPZ_OK;
+}
+
 int dist_collapse(spz_state *st, int target, int outcome, double scale) {
     DistCtx *c = ctx_of(st);
     const int pt = c->plan.perm[target];

@@ -104,6 +104,8 @@ int launch_init_random(spz_state *st, uint64_t seed);
 // mode: 0 = sum |amp|^2 over amps with bit `target` clear (prob0); 1 = all amps (norm2; target ignored)
 // 2/3/4 = <X>/<Y>/<Z> on `target`
 int reduce_scalar(spz_state *st, int mode, int target, double *out);
+// every qubit at once, one read pass: out[0] = sum |amp|^2, out[1 + t] = the mass at indices with bit t set (out: n + 1 doubles)
+int reduce_z_all(spz_state *st, double *out);
 int launch_collapse(spz_state *st, int target, int outcome, int reset, double scale);
 int launch_scale(spz_state *st, double scale); // every amplitude *= scale
 // gen_random_state split in two so that a sharded register can insert its cross-rank sum between the halves
@@ -204,6 +206,8 @@ bool lanes_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int h
 // the same constant-factor pass on one contiguous piece of the state (launched on st->stream; no join)
 int diag_const_on(spz_state *st, double *re, double *im, long long len, const GateK &g, uint64_t cmask, int hi);
 int dist_reduce_scalar(spz_state *st, int mode, int target, double *out);
+int dist_reduce_z_multi(spz_state *st, const int32_t *targets, int k, double *out); // <Z> of k targets from one pass per shard
+constexpr int kZMaxBits = 40; // reduce_z_all / kernels_zall.cuh
 int dist_collapse(spz_state *st, int target, int outcome, double scale);
 int dist_fill_basis(spz_state *st, uint64_t logical_index);
 int dist_init_random(spz_state *st, uint64_t seed);

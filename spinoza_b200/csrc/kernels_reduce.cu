@@ -9,11 +9,13 @@
 #include <vector>
 
 #include "gate_math.cuh"
+#include "kernels_zall.cuh"
 
 namespace spz {
 
 constexpr int kRedThreads = 256;
 constexpr int kRedBlocks = 148 * 8; // grid sized in multiples of the SM count
+constexpr int kZGrid = 148 * 2;     // the all-qubit <Z> pass: two CTAs per SM (its accumulators take ~100 registers per thread)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -37,8 +39,9 @@ __device__ __forceinline__ double block_sum(double v) {
 
 int ensure_scratch(spz_state *st) {
     if (!st->scratch.partials) {
-        SPZ_CUDA(cudaMalloc(&st->scratch.partials, sizeof(double) * (kRedBlocks + 8)));
-        st->scratch.n_partials = kRedBlocks + 8;
+        // [0, kRedBlocks + 8): one-target reductions.  Behind it: the all-qubit <Z> pass, (kZMaxBits + 1) values per CTA + its result
+        SPZ_CUDA(cudaMalloc(&st->scratch.partials, sizeof(double) * (kRedBlocks + 8 + (size_t)(kZGrid + 1) * (kZMaxBits + 1))));
+        st->scratch.n_partials = kRedBlocks + 8 + (size_t)(kZGrid + 1) * (kZMaxBits + 1);
     }
     if (!st->scratch.h_result) SPZ_CUDA(cudaMallocHost(&st->scratch.h_result, sizeof(double) * 64));
     return SPZ_OK;
@@ -114,6 +117,57 @@ int reduce_scalar(spz_state *st, int mode, int target, double *out) {
     SPZ_CUDA(cudaMemcpyAsync(st->scratch.h_result, part + kRedBlocks, sizeof(double), cudaMemcpyDeviceToHost, st->stream));
     SPZ_CUDA(cudaStreamSynchronize(st->stream));
     *out = st->scratch.h_result[0];
+    return SPZ_OK;
+}
+
+// ---- <Z_t> for every qubit at once (kernels_zall.cuh) -------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(kRedThreads, 2) k_z_all(const double *__restrict__ re, const double *__restrict__ im, long long nvec,
+                                                          int n, double *__restrict__ partials) {
+    double total = 0.0, s1[NB];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) s1[t] = 0.0;
+    z_all_accumulate<NB>(re, im, nvec, n, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, total, s1);
+    double *mine = partials + (size_t)blockIdx.x * (kZMaxBits + 1);
+    total = block_sum(total);
+    if (threadIdx.x == 0) mine[0] = total;
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+        if (t < n) { // (uniform over the CTA)
+            const double v = block_sum(s1[t]);
+            if (threadIdx.x == 0) mine[1 + t] = v;
+        }
+    }
+}
+// block j: sum of value j over the CTAs of k_z_all
+__global__ void __launch_bounds__(kRedThreads) k_z_final(const double *__restrict__ partials, int n_cta, double *__restrict__ out) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_cta; i += blockDim.x) acc += partials[(size_t)i * (kZMaxBits + 1) + blockIdx.x];
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}
+
+// out[0] = sum |amp|^2 over the handle's amplitudes, out[1 + t] = the part of it at indices with bit t set, t < st->n.
+// One read pass (needs st->n >= 2: a vector is four amplitudes).
+int reduce_z_all(spz_state *st, double *out) {
+    SPZ_TRY(join_pending(st));
+    SPZ_TRY(ensure_scratch(st));
+    const int n = st->n;
+    if (n < 2 || n > kZMaxBits) { set_error("all-qubit <Z> pass needs 2..%d qubits", kZMaxBits); return SPZ_ERR_INVALID_ARG; }
+    const long long nvec = st->len / 4;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((nvec + kRedThreads - 1) / kRedThreads, kZGrid));
+    double *part = st->scratch.partials + kRedBlocks + 8;
+    double *res = part + (size_t)kZGrid * (kZMaxBits + 1);
+    if (n <= 16) k_z_all<16><<<grid, kRedThreads, 0, st->stream>>>(st->re, st->im, nvec, n, part);
+    else if (n <= 24) k_z_all<24><<<grid, kRedThreads, 0, st->stream>>>(st->re, st->im, nvec, n, part);
+    else if (n <= 32) k_z_all<32><<<grid, kRedThreads, 0, st->stream>>>(st->re, st->im, nvec, n, part);
+    else k_z_all<kZMaxBits><<<grid, kRedThreads, 0, st->stream>>>(st->re, st->im, nvec, n, part);
+    k_z_final<<<n + 1, kRedThreads, 0, st->stream>>>(part, grid, res);
+    count_launch(2);
+    SPZ_CUDA(cudaGetLastError());
+    SPZ_CUDA(cudaMemcpyAsync(st->scratch.h_result, res, sizeof(double) * (n + 1), cudaMemcpyDeviceToHost, st->stream));
+    SPZ_CUDA(cudaStreamSynchronize(st->stream));
+    for (int i = 0; i <= n; ++i) out[i] = st->scratch.h_result[i];
     return SPZ_OK;
 }
 

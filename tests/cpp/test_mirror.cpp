@@ -104,6 +104,24 @@ int main() {
             close_to(a[0].re * a[2].re + a[0].im * a[2].im + a[1].re * a[3].re + a[1].im * a[3].im, 0.0, 1e-14, "rows orthogonal (re)");
         }
     }
+    { // extension: signed controls.  X on target 2 when qubit 0 is 1 and qubit 1 is 0, through mc_apply_signed and through
+      // Controls::Signed in a circuit; from |001> that fires, from |011> it does not
+        for (unsigned start : {1u, 3u}) {
+            State s(3);
+            for (std::size_t q = 0; q < 3; ++q) if ((start >> q) & 1u) apply(Gate::X(), s, q);
+            mc_apply_signed(Gate::X(), s, {0}, {1}, 2);
+            const std::size_t want = start == 1u ? 5u : 3u;
+            auto re = s.reals();
+            for (std::size_t i = 0; i < 8; ++i) close_to(re[i], i == want ? 1.0 : 0.0, 0.0, "signed functional");
+            QuantumRegister qr(3);
+            QuantumCircuit qc({&qr});
+            for (std::size_t q = 0; q < 3; ++q) if ((start >> q) & 1u) qc.x(q);
+            qc.add(QuantumTransformation{Gate::X(), 2, Controls::Signed({0, 1}, {1})});
+            qc.execute();
+            auto rc = qc.state.reals();
+            for (std::size_t i = 0; i < 8; ++i) close_to(rc[i], i == want ? 1.0 : 0.0, 1e-15, "signed circuit");
+        }
+    }
     { // Reservoir / reservoir_sampling core.rs:65-129: a basis state has one outcome; a uniform state spreads
         State s(10);
         apply(Gate::X(), s, 3); apply(Gate::X(), s, 7);

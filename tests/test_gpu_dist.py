@@ -170,6 +170,30 @@ def test_qft_sharded_closed_form_and_reductions(n, world):
     assert res[0]["ex"] == int(math.log2(world)) + 1  # revolving door: g + 1 exchanges for the whole QFT
 
 
+@pytest.mark.parametrize("n,world", [(6, 4), (13, 2), (15, 8)])
+def test_z_expectation_of_every_qubit_sharded(n, world):
+    """xyz_expectation_value('z', all qubits) on a sharded register: one read pass per shard for the local qubits, the rank's
+    bit for the global ones -- also after exchanges have permuted the qubits."""
+    cpu = orc.gen_random_state(n, 23 + n)
+    states = DistState.create_local_group(n, world)
+    upload_shards(states, cpu)
+
+    def body(rank, s):
+        first = sb.xyz_expectation_value("z", s, list(range(n)))
+        sb.apply(Gate.H, s, n - 1)          # an exchange: qubit n-1 becomes local, another one global
+        sb.apply(Gate.RX(0.4), s, 1)
+        second = sb.xyz_expectation_value("z", s, list(reversed(range(n))))
+        s.sync()
+        return first, second
+    res = run_group(states, body)
+    assert all(r == res[0] for r in res)
+    assert np.max(np.abs(np.array(res[0][0]) - orc.xyz_expectation_value("z", cpu, list(range(n))))) < 1e-12
+    orc.apply(orc.H, cpu, n - 1)
+    orc.apply(orc.RX, cpu, 1, (0.4,))
+    assert np.max(np.abs(np.array(res[0][1]) - orc.xyz_expectation_value("z", cpu, list(reversed(range(n)))))) < 1e-12
+    assert states[0].stats()["exchanges"] >= 1
+
+
 @pytest.mark.parametrize("n,world", [(7, 4), (11, 2)])
 def test_measure_sharded(n, world):
     cpu = orc.gen_random_state(n, 19 + n)

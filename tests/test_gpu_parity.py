@@ -377,7 +377,7 @@ def test_value_encoding_yields_basis_state():  # circuit.rs:1076-1113
 
 
 # ---- reductions / measurement -----------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [1, 2, 7, 14, 19])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 11, 14, 19, 22])
 def test_prob0_norm_expectations(n):
     cpu = orc.gen_random_state(n, 900 + n)
     gpu = to_gpu(cpu)
@@ -390,6 +390,13 @@ def test_prob0_norm_expectations(n):
         got = sb.xyz_expectation_value(obs, gpu, targets)
         want = orc.xyz_expectation_value(obs, cpu, targets)
         assert np.max(np.abs(np.array(got) - want)) < 1e-12, obs
+    if n >= 2:  # 'z' on several targets is ONE read pass for all of them (csrc/kernels_zall.cuh): pass + final sum
+        before = sb.launch_count()
+        got = sb.xyz_expectation_value("z", gpu, list(range(n)))
+        assert sb.launch_count() - before == 2
+        assert np.max(np.abs(np.array(got) - orc.xyz_expectation_value("z", cpu, list(range(n))))) < 1e-12
+        with pytest.raises(sb.SpinozaError):
+            sb.xyz_expectation_value("z", gpu, [0, n])
     re, im = gpu.download()  # reductions must not modify the state (the reference clones, core.rs:227)
     assert np.array_equal(re, cpu.reals) and np.array_equal(im, cpu.imags)
 
