@@ -112,7 +112,7 @@ int main() {
             mc_apply_signed(Gate::X(), s, {0}, {1}, 2);
             const std::size_t want = start == 1u ? 5u : 3u;
             auto re = s.reals();
-            for (std::size_t i = 0; i < 8; ++i) close_to(re[i], i == want ? 1.0 : 0.0, 0.0, "signed functional");
+            for (std::size_t i = 0; i < 8; ++i) close_to(re[i], i == want ? 1.0 : 0.0, 1e-15, "signed functional");
             QuantumRegister qr(3);
             QuantumCircuit qc({&qr});
             for (std::size_t q = 0; q < 3; ++q) if ((start >> q) & 1u) qc.x(q);
