@@ -114,7 +114,7 @@ extern "C" long long emu_tile3_smem(int n_qubits, const void *blob, long long bl
     return (long long)spz::tile3_smem_bytes(a);
 }
 
-// The lowered k_tile3 program of one pass, for tools/dump_tile3.py: copies up to max_ins 16-byte instructions, returns their
+// The lowered k_tile3 program of one pass, for tools/dump_tile3.py: copies up to max_ins instructions (sizeof(Ins3) = 32 bytes each), returns their
 // number (-1: parse error, 0: the lowering refuses the pass).  info <- {in-tile control, instructions, groups, terms}.
 extern "C" int emu_tile3_dump(int n_qubits, const void *blob, long long blob_bytes, void *out_ins, int max_ins, int *info) {
     Program P;

@@ -55,7 +55,7 @@ for p in range(n_pass):
     if int(np.frombuffer(blob, dtype="<i4", count=1)[0]) == 1:
         print(f"pass {p}: single op (direct kernel)")
         continue
-    ins = np.zeros((4096, 16), dtype=np.uint8)
+    ins = np.zeros((4096, 32), dtype=np.uint8)  # Ins3 is 32 bytes: operand words, then the instruction's own two scalars
     info = (C.c_int * 4)()
     k = h.emu_tile3_dump(n, blob, len(blob), ins.ctypes.data, 4096, info)
     ops = [name(int(o)) for o in ins[:k, 0]]
@@ -67,7 +67,7 @@ for p in range(n_pass):
         print("   " + " ".join(ops))
     if "-d" in sys.argv:
         rec = ins[:k].copy().view(np.dtype([("op", "u1"), ("kind", "u1"), ("rpos", "u1"), ("flags", "u1"), ("km", "<u2"), ("thr", "<u2"),
-                                            ("a", "<u4"), ("b", "<u4")])).ravel()
+                                            ("a", "<u4"), ("b", "<u4"), ("s0", "<f8"), ("s1", "<f8")])).ravel()
         for r in rec:
             print(f"      {name(int(r['op'])):8s} cls/r {r['rpos']} flags {int(r['flags']):08b} km {int(r['km']):016b} thr {int(r['thr']):08b} a {r['a']:#x} b {r['b']}")
 print("total", dict(total))
