@@ -67,6 +67,8 @@ h = C.CDLL(sys.argv[1])
 h.emu_apply.restype = C.c_int
 h.emu_apply.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_ulonglong, C.c_int]
 h.emu_swap.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+h.emu_apply_signed.restype = C.c_int
+h.emu_apply_signed.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_ulonglong, C.c_ulonglong, C.c_int]
 rng = np.random.default_rng(0)
 cnt = 0
 for n in range(1, 12):
@@ -79,11 +81,44 @@ for n in range(1, 12):
                 re = np.ascontiguousarray(rng.random(1 << n)); im = np.ascontiguousarray(rng.random(1 << n))
                 assert h.emu_apply(n, re.ctypes.data, im.ctypes.data, kind, (C.c_double * 3)(0.3, 0.5, 0.7), cm, t) == 0
                 cnt += 1
+                if cm:  # the same mask with some controls negative (spz_mc_apply_signed)
+                    neg = cm & int(rng.integers(1, 1 << n))
+                    assert h.emu_apply_signed(n, re.ctypes.data, im.ctypes.data, kind, (C.c_double * 3)(0.3, 0.5, 0.7), cm, neg, t) == 0
+                    cnt += 1
     for a, b in itertools.product(range(n), range(n)):
         re = np.ascontiguousarray(rng.random(1 << n)); im = np.ascontiguousarray(rng.random(1 << n))
         assert h.emu_swap(n, re.ctypes.data, im.ctypes.data, a, b) == 0
 print("direct kernels:", cnt, "sanitised gate applications, 0 reports")
 '''
+
+
+ZALL_DRIVER = r'''
+import ctypes as C, sys
+import numpy as np
+h = C.CDLL(sys.argv[1])
+h.emu_z_all.restype = C.c_int
+h.emu_z_all.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+rng = np.random.default_rng(1)
+cnt = 0
+for n in range(2, 19):
+    for grid in (1, 2, 5, 296):
+        re = np.ascontiguousarray(rng.random(1 << n)); im = np.ascontiguousarray(rng.random(1 << n))
+        out = np.zeros(n + 1)
+        assert h.emu_z_all(n, re.ctypes.data, im.ctypes.data, grid, 256, out.ctypes.data) == 0
+        assert abs(out[0] - (re @ re + im @ im)) < 1e-9 * (1 << n)
+        cnt += 1
+print("all-qubit <Z> pass:", cnt, "sanitised runs, 0 reports")
+'''
+
+
+def zall(tmp):
+    lib = tmp / "libzall_emu_asan.so"
+    subprocess.run([GXX, *COMMON, "-shared", "-fPIC", str(ROOT / "tests/emu/zall_emu.cpp"), "-o", str(lib)], check=True, cwd=ROOT)
+    asan = subprocess.run(["/usr/bin/gcc", "-print-file-name=libasan.so"], capture_output=True, text=True, check=True).stdout.strip()
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([sys.executable, "-c", ZALL_DRIVER, str(lib)], env=env, capture_output=True, text=True, timeout=900)
+    print(r.stdout.strip() or r.stderr[-1500:])
+    return 0 if r.returncode == 0 and "ERROR" not in r.stderr and "runtime error" not in r.stderr else 1
 
 
 def direct(tmp):
@@ -99,4 +134,4 @@ def direct(tmp):
 if __name__ == "__main__":
     with tempfile.TemporaryDirectory() as d:
         tmp = Path(d)
-        sys.exit(1 if tile(tmp) + direct(tmp) else 0)
+        sys.exit(1 if tile(tmp) + direct(tmp) + zall(tmp) else 0)
