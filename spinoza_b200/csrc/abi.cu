@@ -135,11 +135,16 @@ static int swap_impl(spz_state *st, int t0, int t1) {
     return launch_swap(st, t0, t1);
 }
 
-static int measure_impl(spz_state *st, int target, int reset, int forced_v, int *out_bit) {
+// zero_mask: qubits known to be exactly |0> (measured with reset earlier in the same run of measurements, see execute_impl);
+// single-GPU registers then visit only the indices where those bits are 0.
+static int measure_impl(spz_state *st, int target, int reset, int forced_v, int *out_bit, uint64_t zero_mask = 0) {
     if (target < 0 || target >= total_qubits(st)) { set_error("target %d out of range", target); return SPZ_ERR_INVALID_ARG; }
     if (forced_v > 1) { set_error("forced outcome must be 0, 1 or -1"); return SPZ_ERR_INVALID_ARG; } // assert measurement.rs:32
+    zero_mask &= ~(1ull << target);
+    if (st->dist || st->n > kZMaxBits) zero_mask = 0;
     double prob0 = 0.0;
     if (st->dist) SPZ_TRY(dist_reduce_scalar(st, 0, target, &prob0));
+    else if (zero_mask) SPZ_TRY(reduce_prob0_sub(st, target, zero_mask, &prob0));
     else SPZ_TRY(reduce_scalar(st, 0, target, &prob0));
     int val;
     if (forced_v >= 0) val = forced_v;
@@ -150,6 +155,8 @@ static int measure_impl(spz_state *st, int target, int reset, int forced_v, int 
     if (st->dist) {
         SPZ_TRY(dist_collapse(st, target, val, k));
         if (val == 1 && reset) SPZ_TRY(apply_masked(st, SPZ_GATE_X, nullptr, 0, target)); // measurement.rs:87-89
+    } else if (zero_mask) {
+        SPZ_TRY(launch_collapse_sub(st, target, val, reset, k, zero_mask));
     } else {
         SPZ_TRY(launch_collapse(st, target, val, reset, k));
     }
@@ -1187,6 +1194,10 @@ static int execute_impl(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_
         return SPZ_OK;
     };
 
+    // A run of consecutive M ops (typically "measure everything" at the end of a circuit): every measurement resets its qubit
+    // to |0>, so the later ones of the run visit only the subspace where the earlier qubits are 0 (kernels_reduce.cu).
+    uint64_t run_zero = 0;
+    int64_t run_end = -2; // index of the last op of the run so far (a measurement that was skipped as already measured counts)
     for (int64_t i = 0; i < n_ops; ++i) {
         const spz_op &op = ops[i];
         const int kind = op.kind;
@@ -1202,10 +1213,15 @@ static int execute_impl(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_
                     SPZ_TRY(fuser.flush());
                     if (sink) { ROp m{}; m.kind = SPZ_GATE_M; m.target = op.target; m.src = (int)i; sink->take(std::vector<ROp>{m}); continue; }
                     int bit = 0;
-                    SPZ_TRY(measure_impl(st, op.target, 1, -1, &bit));
+                    if (run_end != i - 1) run_zero = 0; // some other op ran since the last measurement: nothing is known to be 0
+                    SPZ_TRY(measure_impl(st, op.target, 1, -1, &bit, run_zero));
+                    run_zero |= 1ull << op.target; // measured with reset: |0> from here on
+                    run_end = i;
                     *mm |= 1ull << op.target;
                     *mv &= ~(1ull << op.target);
                     *mv |= (uint64_t)bit << op.target;
+                } else if (run_end == i - 1) {
+                    run_end = i; // measured before (nothing happens, circuit.rs:560): the run goes on
                 }
             } else if (kind == SPZ_GATE_BITFLIP) { // gates.rs:1365-1374
                 const double eps = next_u01(st);

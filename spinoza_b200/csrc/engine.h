@@ -107,6 +107,9 @@ int reduce_scalar(spz_state *st, int mode, int target, double *out);
 // every qubit at once, one read pass: out[0] = sum |amp|^2, out[1 + t] = the mass at indices with bit t set (out: n + 1 doubles)
 int reduce_z_all(spz_state *st, double *out);
 int launch_collapse(spz_state *st, int target, int outcome, int reset, double scale);
+// the same two steps of a measurement restricted to the indices where every qubit of zero_mask is 0 (the rest is known to be 0)
+int reduce_prob0_sub(spz_state *st, int target, uint64_t zero_mask, double *out);
+int launch_collapse_sub(spz_state *st, int target, int outcome, int reset, double scale, uint64_t zero_mask);
 int launch_scale(spz_state *st, double scale); // every amplitude *= scale
 // gen_random_state split in two so that a sharded register can insert its cross-rank sum between the halves
 int launch_rand_probs(spz_state *st, uint64_t seed, long long index_offset, double **d_local_total);

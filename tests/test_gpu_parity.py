@@ -460,6 +460,49 @@ def test_measure_all_twice_gives_identical_bits():  # circuit.rs:825-889 (N = 21
     assert abs(s.amp(0)) == pytest.approx(1.0, abs=1e-9)  # reset=true collapses to |0..0>
 
 
+@pytest.mark.parametrize("n,order", [(5, "up"), (12, "down"), (17, "mixed"), (21, "up")])
+def test_run_of_measurements_visits_only_the_live_subspace(n, order):
+    """A run of M ops inside one execute (measure everything, circuit.rs:825-889): each measurement resets its qubit to |0>, so
+    the later ones read only the indices where the earlier qubits are 0.  Same seed, same outcomes and -- the partial sums differ
+    only in order -- the same state within 1e-12 as measuring with one execute per qubit (no run, full passes)."""
+    qs = {"up": list(range(n)), "down": list(reversed(range(n))), "mixed": [(7 * i + 3) % n for i in range(n)]}[order]
+    init = orc.gen_random_state(n, 600 + n)
+    a, b = to_gpu(init), to_gpu(init)
+    a.set_seed(99); b.set_seed(99)
+    qa = QuantumCircuit.from_state(a)
+    qa.h(0)                                  # something before the run ...
+    for t in qs[: n - 1]:
+        qa.measure(t)
+    qa.measure(qs[0])                        # ... a qubit measured twice inside it ...
+    qa.measure(qs[n - 1])
+    qa.execute()
+    qb = QuantumCircuit.from_state(b)
+    qb.h(0)
+    qb.execute()
+    for t in qs:
+        qb.measure(t)
+        qb.execute()                         # one execute per measurement: every pass is a full one
+    va = [qa.get_qubit_measured_val(t) for t in range(n)]
+    vb = [qb.get_qubit_measured_val(t) for t in range(n)]
+    assert va == vb and all(v in (0, 1) for v in va)
+    ra, ia = a.download(); rb, ib = b.download()
+    assert np.max(np.abs(ra - rb)) <= 1e-12 and np.max(np.abs(ia - ib)) <= 1e-12
+    assert abs(abs(a.amp(0)) - 1.0) < 1e-9 and np.count_nonzero(ra) + np.count_nonzero(ia) <= 2   # |0..0> up to a phase
+    # a gate between two measurements ends the run: the next measurement must see the whole state again
+    c = to_gpu(init); c.set_seed(5)
+    d = to_gpu(init); d.set_seed(5)
+    qc1 = QuantumCircuit.from_state(c)
+    qc1.measure(1); qc1.h(1); qc1.measure(0); qc1.x(1); qc1.measure(2 % n)
+    qc1.execute()
+    for build in (lambda q: q.measure(1), lambda q: q.h(1), lambda q: q.measure(0), lambda q: q.x(1), lambda q: q.measure(2 % n)):
+        q = QuantumCircuit.from_state(d)
+        build(q)
+        q.execute()
+    rc, ic = c.download(); rd, idd = d.download()
+    assert np.max(np.abs(rc - rd)) <= 1e-12 and np.max(np.abs(ic - idd)) <= 1e-12
+    assert abs(sb.norm2(c) - 1.0) < 1e-10
+
+
 def test_measurement_statistics_follow_born_rule():
     n = 3
     cpu = orc.gen_random_state(n, 3)
