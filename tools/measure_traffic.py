@@ -4,7 +4,7 @@
 
 Runs `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum` on this same script in worker mode (H, RX,
 RZ on a middle and on a low target), and records per kernel launch: bytes read + written, against the algorithmic 32 * 2^n
-(16 * 2^n for the diagonal RZ).  Times under ncu are not bench values.
+(RZ included: rz_apply multiplies every amplitude, gates.rs:930-947).  Times under ncu are not bench values.
 """
 import csv
 import io
@@ -45,11 +45,11 @@ for r in rows[1:]:
 names = ["H@mid", "H@1", "RX@mid", "RX@1", "RZ@mid", "RZ@1"]
 res = {"qubits": n, "algorithmic_bytes_full_pass": 32.0 * (1 << n), "launches": []}
 for (k, rec), nm in zip(sorted(launches.items(), key=lambda kv: int(kv[0])), names):
-    alg = (16.0 if nm.startswith("RZ") else 32.0) * (1 << n)
+    alg = 32.0 * (1 << n)
     tr = rec.get("dram__bytes_read.sum", 0.0) + rec.get("dram__bytes_write.sum", 0.0)
     res["launches"].append({"gate": nm, "kernel": rec["kernel"], "dram_read": rec.get("dram__bytes_read.sum"), "dram_write": rec.get("dram__bytes_write.sum"),
                             "traffic": tr, "algorithmic": alg, "traffic_over_algorithmic": tr / alg, "ms_under_ncu": rec.get("gpu__time_duration.sum")})
-full = [l["traffic"] for l in res["launches"] if not l["gate"].startswith("RZ")]
+full = [l["traffic"] for l in res["launches"]]
 res["traffic_full_pass_mean"] = sum(full) / len(full) if full else None
 res["source"] = "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum (tools/measure_traffic.py)"
 path = ROOT / "profiles" / f"round2_traffic_n{n}.json"
