@@ -219,6 +219,14 @@ struct PlanSink {
         st.type = 2; st.gbit = gbit; st.lq = lq;
         steps.push_back(std::move(st));
     }
+    int32_t relabel_perm[64];
+    void relabel(const int32_t *perm) { // the basis state was re-placed before the first op (dist_place_basis): type 4
+        if (!capture_all) return;
+        for (int q = 0; q < 64; ++q) relabel_perm[q] = perm[q];
+        Step st;
+        st.type = 4;
+        steps.push_back(std::move(st));
+    }
 };
 
 struct Fuser {
@@ -861,6 +869,7 @@ int spz_upload(spz_state *st, const double *re, const double *im, int64_t offset
     if (offset < 0 || count < 0 || offset + count > st->len) { set_error("upload range [%lld, +%lld) outside the state", (long long)offset, (long long)count); return SPZ_ERR_INVALID_ARG; }
     SPZ_TRY(join_pending(st));
     st->arrival.streaming = false;
+    dist_note_modified(st);
     const size_t bytes = sizeof(double) * (size_t)count;
     if (re) SPZ_CUDA(cudaMemcpyAsync(st->re + offset, re, bytes, cudaMemcpyHostToDevice, st->stream));
     if (im) SPZ_CUDA(cudaMemcpyAsync(st->im + offset, im, bytes, cudaMemcpyHostToDevice, st->stream));
@@ -873,6 +882,7 @@ int spz_upload(spz_state *st, const double *re, const double *im, int64_t offset
 // The host buffers must be page-locked (spz_alloc_host) and stay untouched until the next spz_sync / spz_download.
 int spz_upload_async(spz_state *st, const double *re, const double *im) {
     if (!st || !re || !im) { set_error("spz_upload_async: null argument"); return SPZ_ERR_INVALID_ARG; }
+    dist_note_modified(st);
     SPZ_CUDA(cudaSetDevice(st->device));
     SPZ_TRY(join_pending(st));
     spz_state::Arrival &a = st->arrival;
@@ -1092,6 +1102,18 @@ static int execute_impl(spz_state *st, const spz_op *ops, int64_t n_ops, uint32_
             if (o.kind == SPZ_GATE_SWAP || is_diagonal_kind(o.kind) || o.kind == SPZ_GATE_UNITARY) continue;
             if (o.target >= 0 && o.target < 64) uses[o.target].push_back(j);
         }
+    if (st->dist && n_ops > 0) { // a register that is still a basis state: its qubit permutation is free, choose it from the list
+        int64_t first_use[64];
+        for (int q = 0; q < 64; ++q) first_use[q] = uses[q].empty() ? INT64_MAX : uses[q][0];
+        bool changed = false;
+        SPZ_TRY(dist_place_basis(st, first_use, sink != nullptr, &changed));
+        if (changed && sink) {
+            int32_t perm[64];
+            for (int q = 0; q < 64; ++q) perm[q] = q;
+            spz_dist_perm(st, perm);
+            sink->relabel(perm);
+        }
+    }
     auto next_uses = [&](uint64_t *nu) {
         for (int q = 0; q < 64; ++q) {
             size_t &c = use_cursor[q];
@@ -1333,6 +1355,8 @@ int spz_debug_compile_pass(int n_qubits, const spz_op *ops, int64_t n_ops, uint3
 //     h[0] = 1 single op    : h[1..4] = kind, target, t2, const_hi; payload = u64 cmask, double s[7]
 //     h[0] = 2 exchange     : h[1] = bit of the rank, h[2] = local physical bit it trades places with
 //     h[0] = 3 measurement  : h[1] = target
+//     h[0] = 4 re-placement : the register was a basis state (SPZ_DEBUG_BASIS) and its qubits were relabelled before the first op
+//                             (dist_place_basis); payload = the new permutation, 64 x int32
 //   then int32 perm[64] (logical -> physical after the last op).  world = 1 describes an unsharded register.
 int spz_debug_compile_sharded(int n_total, int world, int rank, const spz_op *ops, int64_t n_ops, uint32_t flags, void *out,
                               int64_t out_bytes, int64_t *out_used) {
@@ -1379,6 +1403,9 @@ int spz_debug_compile_sharded(int n_total, int world, int rank, const spz_op *op
             h[1] = st.op.kind; h[2] = st.op.target; h[3] = st.op.t2; h[4] = st.op.const_hi;
             h[16] = (int32_t)(sizeof(uint64_t) + 7 * sizeof(double));
             ok = ok && put(h, sizeof h) && put(&st.op.cmask, sizeof(uint64_t)) && put(st.op.g.s, 7 * sizeof(double));
+        } else if (st.type == 4) { // the basis state was re-placed: payload = the new permutation (64 x int32)
+            h[16] = (int32_t)sizeof sink.relabel_perm;
+            ok = ok && put(h, sizeof h) && put(sink.relabel_perm, sizeof sink.relabel_perm);
         } else {
             h[1] = st.type == 2 ? st.gbit : st.op.target;
             h[2] = st.lq;

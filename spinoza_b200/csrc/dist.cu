@@ -70,6 +70,11 @@ struct DistCtx {
     // fused exchange + gate (opt-in, SPZ_DIST_FUSE_GATE=1): flag values already used, and the size of its persistent grid
     unsigned long long xg_base = 0;
     int xg_ctas = 128;  // SPZ_XG_CTAS; every CTA must be resident at once, so <= the number of SMs
+    // The register is (very likely) still the basis state |basis_index> it was set to (spz_dist_create, spz_reset_zero,
+    // spz_set_basis): a hint only -- dist_place_basis checks the amplitudes before it relies on it
+    bool basis_hint = false;
+    uint64_t basis_index = 0;
+    double n_placements = 0;
     // stats
     double n_exchanges = 0, bytes_sent = 0, ms_accum = 0, n_overlapped = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, free_events;
@@ -94,6 +99,7 @@ void dist_debug_attach(spz_state *st, int n_total, int world, int rank) {
     c->world = world;
     st->dist = c;
 }
+void dist_note_modified(spz_state *st) { if (st->dist) ctx_of(st)->basis_hint = false; } // (uploads: abi.cu)
 void dist_debug_detach(spz_state *st) {
     delete ctx_of(st);
     st->dist = nullptr;
@@ -360,6 +366,7 @@ static int take_timing_events(DistCtx *c, std::pair<cudaEvent_t, cudaEvent_t> *e
 
 int dist_exchange(spz_state *st, int gbit, int lq) {
     DistCtx *c = ctx_of(st);
+    c->basis_hint = false;
     if (!c->connected) { set_error("dist state used before spz_dist_connect"); return SPZ_ERR_COMM; }
     const int partner = c->rank ^ (1 << gbit);
     const int my_bit = (c->rank >> gbit) & 1;
@@ -433,6 +440,7 @@ bool dist_fuse_gate_enabled() {
 
 int dist_exchange_gate(spz_state *st, int gbit, int lq, const GateK &g) {
     DistCtx *c = ctx_of(st);
+    c->basis_hint = false;
     if (!c->connected) { set_error("dist state used before spz_dist_connect"); return SPZ_ERR_COMM; }
     // Bytes in flight decide the NVLink rate: a step of one CTA reads THREADS * U * W * 16 B = 64 KB from the partner, and a
     // step lasts a remote-load latency plus a flag round trip (several microseconds), so ~128 CTAs x 64 KB per step are
@@ -568,6 +576,7 @@ int dist_diag_const(spz_state *st, const GateK &g, uint64_t local_cmask, int hi)
 // Lower one logical gate and run the resulting actions immediately (the unfused path).
 int dist_apply_masked(spz_state *st, int kind, const double *p, int t0, int t1, uint64_t cmask, int target) {
     DistCtx *c = ctx_of(st);
+    c->basis_hint = false;
     std::vector<spz_dist_action> acts;
     int rc = c->plan.lower(c->rank, kind, p, t0, t1, cmask, target, nullptr, acts);
     if (rc != SPZ_OK) { set_error("cannot lower gate kind %d target %d onto the sharded register", kind, target); return rc; }
@@ -596,6 +605,7 @@ int dist_apply_masked(spz_state *st, int kind, const double *p, int t0, int t1, 
 int dist_lower(spz_state *st, int kind, const double *p, int t0, int t1, uint64_t cmask, int target, const uint64_t *next_use,
                std::vector<spz_dist_action> &acts) {
     DistCtx *c = ctx_of(st);
+    c->basis_hint = false; // whatever is lowered here will be applied
     return c->plan.lower(c->rank, kind, p, t0, t1, cmask, target, next_use, acts);
 }
 
@@ -644,8 +654,103 @@ int dist_reduce_z_multi(spz_state *st, const int32_t *targets, int k, double *ou
     return SPZ_OK;
 }
 
+// ---- free placement of a basis state ----------------------------------------------------------------------------------
+// While the register is a computational basis state (|0..0> after State::new, spz_set_basis) the assignment of logical qubits to
+// physical bits is free: relabelling costs two scalar writes (the single 1 moves).  execute() therefore picks the permutation
+// from its op list before the first gate: the g qubits whose first non-diagonal use comes LATEST become the rank bits, so that
+// everything before runs without communication and only those g qubits ever need an exchange (QFT-36 on 8 GPUs: 3 exchanges
+// instead of 4; QFT-34 on 2: 1 instead of 2).  The hint that the state is a basis state is never trusted: every rank checks
+// its shard (norm exactly 1 with the amplitude exactly 1 on the owner, norm exactly 0 elsewhere: one read pass) and the
+// ranks agree through an all-reduce; on any doubt nothing is relabelled.  SPZ_DIST_PLACE=0 switches it off.
+// first_use[q]: index of the first op with a non-diagonal action on logical qubit q (INT64_MAX: none).  dry: planning only
+// (spz_debug_compile_sharded; the hint comes from SPZ_DEBUG_BASIS there).  *changed: the permutation is a new one.
+static __global__ void k_store_double(double *p, double v) { *p = v; }
+
+int dist_place_basis(spz_state *st, const int64_t *first_use, bool dry, bool *changed) {
+    DistCtx *c = ctx_of(st);
+    DistPlan &pl = c->plan;
+    *changed = false;
+    if (pl.g == 0) return SPZ_OK;
+    if (const char *e = std::getenv("SPZ_DIST_PLACE")) if (e[0] == '0') return SPZ_OK;
+    uint64_t x = c->basis_index;
+    if (dry) {
+        const char *e = std::getenv("SPZ_DEBUG_BASIS");
+        if (!e) return SPZ_OK;
+        x = std::strtoull(e, nullptr, 0);
+    } else if (!c->basis_hint || !c->connected) {
+        return SPZ_OK;
+    }
+    // the g logical qubits with the latest first use; among equals those that are global already, then the highest
+    std::vector<int> order(pl.n);
+    for (int q = 0; q < pl.n; ++q) order[q] = q;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (first_use[a] != first_use[b]) return first_use[a] > first_use[b];
+        const bool ga = pl.is_global_phys(pl.perm[a]), gb = pl.is_global_phys(pl.perm[b]);
+        if (ga != gb) return ga;
+        return a > b;
+    });
+    uint64_t want = 0, have = 0;
+    for (int k = 0; k < pl.g; ++k) want |= 1ull << order[k];
+    for (int q = 0; q < pl.n; ++q) if (pl.is_global_phys(pl.perm[q])) have |= 1ull << q;
+    // a qubit that is global now and first used no later than every wanted one gains nothing by moving: keep the set unless
+    // it really postpones a use
+    int64_t worst_have = INT64_MAX, worst_want = INT64_MAX;
+    for (int q = 0; q < pl.n; ++q) {
+        if ((have >> q) & 1ull) worst_have = std::min(worst_have, first_use[q]);
+        if ((want >> q) & 1ull) worst_want = std::min(worst_want, first_use[q]);
+    }
+    if (want == have || worst_want <= worst_have) return SPZ_OK;
+    auto phys_of = [&](uint64_t logical) {
+        uint64_t p = 0;
+        for (int q = 0; q < pl.n; ++q) if ((logical >> q) & 1ull) p |= 1ull << pl.perm[q];
+        return p;
+    };
+    const uint64_t old_phys = phys_of(x);
+    const int old_owner = (int)(old_phys >> pl.n_local);
+    const uint64_t local_mask = (1ull << pl.n_local) - 1ull;
+    if (!dry) { // is it really |x>?  (every rank takes part in the all-reduce, whatever it found)
+        double nrm = -1.0, amp[2] = {0.0, 0.0};
+        SPZ_TRY(reduce_scalar(st, 1, 0, &nrm));
+        bool ok;
+        if (old_owner == c->rank) {
+            SPZ_CUDA(cudaMemcpyAsync(&amp[0], st->re + (old_phys & local_mask), sizeof(double), cudaMemcpyDeviceToHost, st->stream));
+            SPZ_CUDA(cudaMemcpyAsync(&amp[1], st->im + (old_phys & local_mask), sizeof(double), cudaMemcpyDeviceToHost, st->stream));
+            SPZ_CUDA(cudaStreamSynchronize(st->stream));
+            ok = nrm == 1.0 && amp[0] == 1.0 && amp[1] == 0.0;
+        } else {
+            ok = nrm == 0.0;
+        }
+        double bad = 0.0;
+        SPZ_TRY(dist_allreduce(st, nullptr, ok ? 0.0 : 1.0, &bad, nullptr));
+        if (bad != 0.0) { c->basis_hint = false; return SPZ_OK; }
+    }
+    // relabel: wanted qubits that are local trade places with global qubits that are not wanted
+    std::vector<int> in_q, out_q;
+    for (int q = 0; q < pl.n; ++q) {
+        if (((want >> q) & 1ull) && !((have >> q) & 1ull)) in_q.push_back(q);
+        if (((have >> q) & 1ull) && !((want >> q) & 1ull)) out_q.push_back(q);
+    }
+    for (size_t i = 0; i < in_q.size() && i < out_q.size(); ++i) {
+        const int a = in_q[i], b = out_q[i], pa = pl.perm[a], pb = pl.perm[b];
+        pl.perm[a] = pb; pl.inv[pb] = a;
+        pl.perm[b] = pa; pl.inv[pa] = b;
+    }
+    *changed = true;
+    if (dry) return SPZ_OK;
+    const uint64_t new_phys = phys_of(x);
+    const int new_owner = (int)(new_phys >> pl.n_local);
+    if (new_phys != old_phys) {
+        if (old_owner == c->rank) k_store_double<<<1, 1, 0, st->stream>>>(st->re + (old_phys & local_mask), 0.0);
+        if (new_owner == c->rank) k_store_double<<<1, 1, 0, st->stream>>>(st->re + (new_phys & local_mask), 1.0);
+        SPZ_CUDA(cudaGetLastError());
+    }
+    c->n_placements += 1;
+    return SPZ_OK;
+}
+
 int dist_collapse(spz_state *st, int target, int outcome, double scale) {
     DistCtx *c = ctx_of(st);
+    c->basis_hint = false;
     const int pt = c->plan.perm[target];
     if (pt < c->plan.n_local) return launch_collapse(st, pt, outcome, 0, scale);
     const int bit = (c->rank >> (pt - c->plan.n_local)) & 1;
@@ -665,14 +770,21 @@ int dist_fill_basis(spz_state *st, uint64_t logical_index) {
     // Every rank joins first: an overlapped exchange (second stream) may still be moving amplitudes of this shard, and the
     // memsets of the non-owner ranks do not go through a launch_* helper that would wait for it.
     SPZ_TRY(join_pending(st));
-    if (owner == c->rank) return launch_fill_basis(st, phys & ((1ull << c->plan.n_local) - 1ull));
-    SPZ_CUDA(cudaMemsetAsync(st->re, 0, sizeof(double) * (size_t)st->len, st->stream));
-    SPZ_CUDA(cudaMemsetAsync(st->im, 0, sizeof(double) * (size_t)st->len, st->stream));
+    c->basis_hint = false;
+    if (owner == c->rank) {
+        SPZ_TRY(launch_fill_basis(st, phys & ((1ull << c->plan.n_local) - 1ull)));
+    } else {
+        SPZ_CUDA(cudaMemsetAsync(st->re, 0, sizeof(double) * (size_t)st->len, st->stream));
+        SPZ_CUDA(cudaMemsetAsync(st->im, 0, sizeof(double) * (size_t)st->len, st->stream));
+    }
+    c->basis_hint = true;
+    c->basis_index = logical_index;
     return SPZ_OK;
 }
 
 int dist_init_random(spz_state *st, uint64_t seed) {
     DistCtx *c = ctx_of(st);
+    c->basis_hint = false;
     const long long total_len = 1ll << c->plan.n;
     double *d_local = nullptr, *d_total = nullptr;
     SPZ_TRY(launch_rand_probs(st, seed, (long long)c->rank * st->len, &d_local));
@@ -871,6 +983,7 @@ int spz_dist_copy_from(spz_state *dst, const spz_state *csrc) {
     spz_state *src = const_cast<spz_state *>(csrc);
     if (!dst || !src || !dst->dist || !src->dist) { set_error("both handles must be shards"); return SPZ_ERR_INVALID_ARG; }
     DistCtx *d = ctx_of(dst), *s = ctx_of(src);
+    d->basis_hint = false;
     if (dst->len != src->len || d->plan.n != s->plan.n || d->world != s->world || d->rank != s->rank) {
         set_error("shards of different registers or ranks"); return SPZ_ERR_INVALID_ARG;
     }

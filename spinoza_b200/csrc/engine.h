@@ -215,6 +215,9 @@ int dist_collapse(spz_state *st, int target, int outcome, double scale);
 int dist_fill_basis(spz_state *st, uint64_t logical_index);
 int dist_init_random(spz_state *st, uint64_t seed);
 int dist_sample(spz_state *st, const double *u01, int64_t shots, int64_t *out_index);
+// execute(): choose the qubit permutation of a register that is still a basis state from the op list (see dist.cu)
+int dist_place_basis(spz_state *st, const int64_t *first_use, bool dry, bool *changed);
+void dist_note_modified(spz_state *st); // the amplitudes were written by something dist.cu does not see (an upload)
 void dist_destroy(spz_state *st);
 void dist_debug_attach(spz_state *st, int n_total, int world, int rank); // host-only plan context for dry runs
 void dist_debug_detach(spz_state *st);

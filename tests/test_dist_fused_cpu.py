@@ -52,6 +52,9 @@ def steps_of_rank(qc, world, rank):
             steps.append(("op", int(h[1]), int(h[2]), int(h[3]), int(h[4]), cmask, s))
         elif kind == 2:
             steps.append(("exchange", int(h[1]), int(h[2])))
+        elif kind == 4:  # the basis state was re-placed before the first op: the new permutation
+            steps.append(("relabel", tuple(int(x) for x in np.frombuffer(raw, dtype="<i4", count=64, offset=off))))
+            off += 256
         else:
             raise AssertionError("measurement steps are not replayed here")
     perm = [int(x) for x in np.frombuffer(raw, dtype="<i4", count=64, offset=off)]
@@ -90,7 +93,24 @@ def replay(qc, world, psi0):
     assert all(p == perms[0] for p in perms), "the plan must evolve identically on every rank"
     shards = [psi0[r << n_local:(r + 1) << n_local].copy() for r in range(world)]
     cursors = [0] * world
-    stats = {"tile": 0, "op": 0, "exchange": 0}
+    stats = {"tile": 0, "op": 0, "exchange": 0, "relabel": 0}
+    if per_rank[0][0] and per_rank[0][0][0][0] == "relabel":
+        # free placement of a basis state (dist_place_basis): every rank relabels the same way before its first op; the
+        # physical layout of the (basis) state follows the new permutation
+        first = [steps[0] for steps, _ in per_rank]
+        assert all(f == first[0] for f in first)
+        new_perm = first[0][1][:n]
+        assert sorted(new_perm) == list(range(n))
+        i = np.arange(1 << n, dtype=np.int64)
+        p_idx = np.zeros_like(i)
+        for q in range(n):
+            p_idx |= ((i >> q) & 1) << new_perm[q]
+        phys = np.zeros_like(psi0)
+        phys[p_idx] = psi0
+        assert np.count_nonzero(psi0) == 1, "only a basis state may be re-placed"
+        shards = [phys[r << n_local:(r + 1) << n_local].copy() for r in range(world)]
+        cursors = [1] * world
+        stats["relabel"] = 1
     while True:
         pending = []
         for r in range(world):
@@ -249,3 +269,50 @@ def test_signed_controls_on_a_sharded_register(world, fuse):
     psi0 = D.random_state(n, 14)
     got, stats = replay(qc, world, psi0)
     np.testing.assert_allclose(got, dense(qc, psi0), rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("select", ["0", "1"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_basis_state_is_placed_by_looking_ahead(world, select, monkeypatch):
+    """Free placement (dist_place_basis): a register that is still a basis state gets its qubit permutation from the op list --
+    the g qubits whose first non-diagonal use comes latest become the rank bits.  QFT then needs g exchanges, not g + 1."""
+    monkeypatch.setenv("SPZ_TILE_SELECT", select)
+    g = world.bit_length() - 1
+    n = 13 + g
+    x = 0x9E3779B97F4A7C15 % (1 << n)
+    psi0 = np.zeros(1 << n, dtype=complex)
+    psi0[x] = 1.0
+    qc = qft(n)
+    want = dense(qc, psi0)
+    _, plain = replay(qc, world, psi0)                     # no hint: the qubits stay where they are
+    assert plain["relabel"] == 0 and plain["exchange"] == g + 1
+    monkeypatch.setenv("SPZ_DEBUG_BASIS", str(x))
+    got, stats = replay(qc, world, psi0)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+    assert stats["relabel"] == 1 and stats["exchange"] == g, stats
+    steps, perm = steps_of_rank(qc, world, 0)
+    assert sorted(steps[0][1][q] for q in range(g)) == list(range(n - g, n))   # QFT uses qubits 0 .. g-1 last: they start global
+    # switched off, or a circuit whose global qubits are already the last ones used: nothing is relabelled
+    monkeypatch.setenv("SPZ_DIST_PLACE", "0")
+    _, off = replay(qc, world, psi0)
+    assert off["relabel"] == 0 and off["exchange"] == g + 1
+    monkeypatch.delenv("SPZ_DIST_PLACE")
+    qc2 = QuantumCircuit(QuantumRegister(n))
+    for t in range(n):
+        qc2.h(t)                                           # ascending: the top qubits come last anyway
+    got2, st2 = replay(qc2, world, psi0)
+    np.testing.assert_allclose(got2, dense(qc2, psi0), rtol=0, atol=1e-12)
+    assert st2["relabel"] == 0
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_placement_with_layered_and_random_circuits(world, monkeypatch):
+    g = world.bit_length() - 1
+    n = 13 + g
+    x = 12345 % (1 << n)
+    psi0 = np.zeros(1 << n, dtype=complex)
+    psi0[x] = 1.0
+    monkeypatch.setenv("SPZ_DEBUG_BASIS", str(x))
+    for qc in (layered(n, 6, 9), random_circuit(n, 150, 5), random_circuit(n, 60, 6, fuse=False)):
+        got, stats = replay(qc, world, psi0)
+        np.testing.assert_allclose(got, dense(qc, psi0), rtol=0, atol=1e-12)

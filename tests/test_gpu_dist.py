@@ -167,7 +167,55 @@ def test_qft_sharded_closed_form_and_reductions(n, world):
         assert abs(res[0]["p0"][t] - orc.prob0(cpu, t)) < 1e-12
     assert np.max(np.abs(np.array(res[0]["x"]) - orc.xyz_expectation_value("x", cpu, [0, n - 1]))) < 1e-12
     assert abs(res[0]["z"][0] - orc.xyz_expectation_value("z", cpu, [n - 1])[0]) < 1e-12
-    assert res[0]["ex"] == int(math.log2(world)) + 1  # revolving door: g + 1 exchanges for the whole QFT
+    # the register was a basis state when execute() started: its qubits were placed by looking ahead (dist_place_basis), QFT's
+    # last g qubits start as the rank bits and only they are ever exchanged (the revolving door alone needs g + 1)
+    assert res[0]["ex"] == int(math.log2(world))
+
+
+@pytest.mark.parametrize("n,world", [(13, 2), (15, 8)])
+def test_placement_is_only_used_while_the_register_is_a_basis_state(n, world):
+    """dist_place_basis: free relabelling needs a basis state.  A gate before execute(), an upload, or a state that merely
+    started as a basis state must leave the permutation alone -- and every variant must give the same amplitudes."""
+    g = int(math.log2(world))
+    x = 0x5DEECE66D % (1 << n)
+    want = None
+    for variant in ("placed", "gate-first", "uploaded", "switched-off"):
+        if variant == "switched-off":
+            os.environ["SPZ_DIST_PLACE"] = "0"
+        try:
+            states = DistState.create_local_group(n, world)
+            if variant == "uploaded":
+                cpu = orc.State(n)
+                cpu.reals[0] = 0.0
+                cpu.reals[x] = 1.0
+                upload_shards(states, cpu)        # the same amplitudes, but the engine was not told it is a basis state
+
+            def body(rank, s):
+                if variant != "uploaded":
+                    s.set_basis(x)
+                if variant == "gate-first":
+                    sb.apply(Gate.Z, s, 0)        # any gate ends the freedom (Z leaves |x> alone up to a sign)
+                qc = QuantumCircuit.from_state(s, fuse=True)
+                qc.qft()
+                qc.execute()
+                s.sync()
+                return s.stats()["exchanges"], s.perm()
+            res = run_group(states, body)
+            assert all(r == res[0] for r in res)
+            re, im = gather(states)
+            got = re + 1j * im
+            if variant == "gate-first" and (x & 1):
+                got = -got
+            if want is None:
+                k = np.arange(1 << n)
+                rev = np.zeros_like(k)
+                for b in range(n):
+                    rev |= ((k >> b) & 1) << (n - 1 - b)
+                want = 2.0 ** (-n / 2) * np.exp(2j * np.pi * ((x * rev) % (1 << n)) / (1 << n))
+            assert np.max(np.abs(got - want)) < 1e-12, variant
+            assert res[0][0] == (g if variant == "placed" else g + 1), (variant, res[0][0])
+        finally:
+            os.environ.pop("SPZ_DIST_PLACE", None)
 
 
 @pytest.mark.parametrize("n,world", [(6, 4), (13, 2), (15, 8)])
