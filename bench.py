@@ -762,7 +762,10 @@ def main():
                     "exchanges": s1["exchanges"] - s0["exchanges"], "overlapped_exchanges": s1["overlapped"] - s0["overlapped"],
                     "exchange_kernel_ms": xms, "nvlink_GBps_per_direction_per_gpu": (sent / (xms * 1e-3) / 1e9) if xms > 0 else None,
                     "max_abs_err_vs_closed_form": qft_closed_form_err(np, big, nn, x, dist), "norm2_after": sb.norm2(big),
-                    "alloc_seconds": alloc_s}
+                    "alloc_seconds": alloc_s,
+                    "placement": ("the register was still a basis state when execute started, so its qubit permutation was chosen from the "
+                                  "op list (dist_place_basis): g exchanges instead of g + 1; SPZ_DIST_PLACE=0 restores the identity placement")
+                                 if os.environ.get("SPZ_DIST_PLACE", "1")[:1] != "0" else "off (SPZ_DIST_PLACE=0)"}
                 del big
         except Exception as e:
             line["qft_northstar"] = {"error": repr(e)}
