@@ -91,7 +91,19 @@ def main():
             elif engine == "sharded":
                 world = int(2 ** rng.integers(1, max(2, min(4, n - 3))))  # at least 4 local qubits per rank
                 desc["world"] = world
-                got, _ = replay(qc, world, psi0)
+                os.environ.pop("SPZ_DEBUG_BASIS", None)
+                if rng.random() < 0.5:  # a register that is still a basis state: its qubits are placed by look-ahead first
+                    bx = int(rng.integers(1 << n))
+                    psi0 = np.zeros(1 << n, dtype=complex)
+                    psi0[bx] = 1.0
+                    want = run_dense_order(n, psi0.copy(), trs, range(len(trs)))
+                    os.environ["SPZ_DEBUG_BASIS"] = str(bx)
+                    desc["basis"] = bx
+                try:
+                    got, st_ = replay(qc, world, psi0)
+                    desc["relabel"] = st_["relabel"]
+                finally:
+                    os.environ.pop("SPZ_DEBUG_BASIS", None)
             else:
                 kernel = 3 if n >= 12 and not exact and rng.random() < 0.7 else 1
                 re, im = np.ascontiguousarray(psi0.real), np.ascontiguousarray(psi0.imag)
