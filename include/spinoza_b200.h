@@ -181,7 +181,10 @@ SPZ_API int spz_sample(spz_state *st, const double *u01, int64_t shots, int64_t 
 /* The reference has no distributed layer; this is the engine's own.  Every rank calls the
    same sequence of spz_* functions on its handle (SPMD).  Local-qubit gates and all diagonal gates need no
    communication; a non-diagonal gate on a global qubit first trades that qubit for a local one by a pairwise
-   half-shard exchange written directly into the partner's HBM through CUDA IPC peer pointers over NVLink. */
+   half-shard exchange written directly into the partner's HBM through CUDA IPC peer pointers over NVLink.
+   The qubit permutation (spz_dist_perm) is the engine's to choose: exchanges update it, and spz_execute on a register that is
+   still a computational basis state (spz_dist_create, spz_reset_zero, spz_set_basis) first picks it from the op list so that
+   the qubits used last are the global ones (checked on the device before it is relied on; SPZ_DIST_PLACE=0 disables). */
 typedef struct {
     int32_t type;    /* 0 skip, 1 local gate, 2 diagonal constant factor, 3 exchange */
     int32_t kind;    /* spz_gate_kind */
