@@ -668,6 +668,12 @@ def main():
             line["reductions"] = {"qubits": n, "z_all_qubits_one_pass_s": t_all, "z_one_pass_per_qubit_s": t_each,
                                   "effective_read_GBps_one_pass": 16.0 * (1 << n) / t_all / 1e9,
                                   "max_abs_diff": float(max(abs(a - b) for a, b in zip(zs, z1)))}
+            # <X> of every qubit: tiles staged in shared memory, up to twelve targets per read pass, vs one pass per qubit
+            sb.xyz_expectation_value("x", state, [0, 1, 2])  # warm (kernel attribute)
+            t0 = time.perf_counter(); xs = sb.xyz_expectation_value("x", state, list(range(n))); t_xall = time.perf_counter() - t0
+            t0 = time.perf_counter(); x1 = [sb.xyz_expectation_value("x", state, [t])[0] for t in range(n)]; t_xeach = time.perf_counter() - t0
+            line["reductions"].update({"x_all_qubits_tiled_s": t_xall, "x_one_pass_per_qubit_s": t_xeach,
+                                       "x_max_abs_diff": float(max(abs(a - b) for a, b in zip(xs, x1)))})
         except Exception as e:
             line["reductions"] = {"error": repr(e)}
 

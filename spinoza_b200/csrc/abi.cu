@@ -1466,6 +1466,10 @@ int spz_xyz_expectation_value(spz_state *st, char observable, const int32_t *tar
         for (int i = 0; i < n_targets; ++i) out[i] = all[0] - 2.0 * all[1 + targets[i]];
         return SPZ_OK;
     }
+    // 'x' / 'y' on three or more targets of a single-GPU register: the targets share tiles staged in shared memory, up to
+    // twelve per read pass (kernels_xyall.cuh)
+    if ((mode == 2 || mode == 3) && n_targets >= 3 && !st->dist && st->n >= 7 && st->n <= 40)
+        return reduce_xy_multi(st, mode - 2, targets, n_targets, out);
     for (int i = 0; i < n_targets; ++i) {
         if (st->dist) SPZ_TRY(dist_reduce_scalar(st, mode, targets[i], &out[i]));
         else SPZ_TRY(reduce_scalar(st, mode, targets[i], &out[i]));

@@ -106,6 +106,8 @@ int launch_init_random(spz_state *st, uint64_t seed);
 int reduce_scalar(spz_state *st, int mode, int target, double *out);
 // every qubit at once, one read pass: out[0] = sum |amp|^2, out[1 + t] = the mass at indices with bit t set (out: n + 1 doubles)
 int reduce_z_all(spz_state *st, double *out);
+// <X> (obs 0) or <Y> (obs 1) of k targets of a single-GPU register, up to twelve targets per read pass (kernels_xyall.cuh)
+int reduce_xy_multi(spz_state *st, int obs, const int32_t *targets, int k, double *out);
 int launch_collapse(spz_state *st, int target, int outcome, int reset, double scale);
 // the same two steps of a measurement restricted to the indices where every qubit of zero_mask is 0 (the rest is known to be 0)
 int reduce_prob0_sub(spz_state *st, int target, uint64_t zero_mask, double *out);

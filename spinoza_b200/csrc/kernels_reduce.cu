@@ -10,6 +10,7 @@
 
 #include "gate_math.cuh"
 #include "kernels_zall.cuh"
+#include "kernels_xyall.cuh"
 
 namespace spz {
 
@@ -168,6 +169,94 @@ int reduce_z_all(spz_state *st, double *out) {
     SPZ_CUDA(cudaMemcpyAsync(st->scratch.h_result, res, sizeof(double) * (n + 1), cudaMemcpyDeviceToHost, st->stream));
     SPZ_CUDA(cudaStreamSynchronize(st->stream));
     for (int i = 0; i <= n; ++i) out[i] = st->scratch.h_result[i];
+    return SPZ_OK;
+}
+
+// ---- <X_t> / <Y_t> for up to twelve qubits at once (kernels_xyall.cuh) ------------------------------------------------
+__global__ void __launch_bounds__(kXYThreads) k_xy_all(const XYArgs a) {
+    extern __shared__ __align__(16) unsigned char xy_smem[];
+    double *sre = reinterpret_cast<double *>(xy_smem);
+    double *sim = sre + (1u << (a.L + a.H));
+    double acc[kXYBits];
+#pragma unroll
+    for (int b = 0; b < kXYBits; ++b) acc[b] = 0.0;
+    __shared__ unsigned long long hoff[64];
+    xy_prepare(a, hoff);
+    for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) xy_tile_accumulate(a, t, hoff, sre, sim, acc);
+#pragma unroll
+    for (int b = 0; b < kXYBits; ++b) {
+        if ((a.tmask >> b) & 1u) { // (uniform over the CTA)
+            const double v = block_sum(acc[b]);
+            if (threadIdx.x == 0) a.partials[(size_t)blockIdx.x * kXYBits + b] = v;
+        }
+    }
+}
+__global__ void __launch_bounds__(kRedThreads) k_xy_final(const double *__restrict__ partials, int n_cta, unsigned tmask, double *__restrict__ out) {
+    double acc = 0.0;
+    if ((tmask >> blockIdx.x) & 1u)
+        for (int i = threadIdx.x; i < n_cta; i += blockDim.x) acc += partials[(size_t)i * kXYBits + blockIdx.x];
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) out[blockIdx.x] = 2.0 * acc;
+}
+
+// <X> (obs 0) or <Y> (obs 1) of k targets, grouped into tiles: the targets below bit 12 share one pass (a tile of 2^12
+// contiguous amplitudes), the higher ones go six at a time (64 contiguous amplitudes x 2^6 combinations of the six qubits).
+int reduce_xy_multi(spz_state *st, int obs, const int32_t *targets, int k, double *out) {
+    SPZ_TRY(join_pending(st));
+    SPZ_TRY(ensure_scratch(st));
+    const int n = st->n;
+    for (int i = 0; i < k; ++i)
+        if (targets[i] < 0 || targets[i] >= n) { set_error("target %d out of range", targets[i]); return SPZ_ERR_INVALID_ARG; }
+    static bool attr_set[64] = {false}; // 64 KB of dynamic shared memory needs the opt-in, once per device
+    if (st->device >= 0 && st->device < 64 && !attr_set[st->device]) {
+        SPZ_CUDA(cudaFuncSetAttribute(k_xy_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2u * kXYTile * sizeof(double))));
+        attr_set[st->device] = true;
+    }
+    uint64_t want = 0;
+    for (int i = 0; i < k; ++i) want |= 1ull << targets[i];
+    double value[64];
+    double *part = st->scratch.partials + kRedBlocks + 8; // (the all-qubit <Z> pass uses the same region; never at the same time)
+    double *res = part + (size_t)kZGrid * (kZMaxBits + 1);
+    static_assert(kXYBits <= kZMaxBits + 1, "the <X>/<Y> partials fit the region sized for the <Z> pass");
+    auto run = [&](const XYArgs &proto, const int *tile_qubit) -> int { // tile_qubit[b]: the qubit tile bit b stands for
+        XYArgs a = proto;
+        a.re = st->re; a.im = st->im; a.obs = obs; a.partials = part;
+        const int tb = a.L + a.H;
+        a.n_tiles = (long long)st->len >> tb;
+        constexpr int kXYGrid = 148 * 3; // three CTAs per SM: 64 KB of staging each
+        static_assert((size_t)kXYGrid * kXYBits <= (size_t)kZGrid * (kZMaxBits + 1), "partials region");
+        const int grid = (int)std::max<long long>(1, std::min<long long>(a.n_tiles, kXYGrid));
+        const size_t smem = 2u * sizeof(double) << tb;
+        k_xy_all<<<grid, kXYThreads, smem, st->stream>>>(a);
+        k_xy_final<<<kXYBits, kRedThreads, 0, st->stream>>>(part, grid, a.tmask, res);
+        count_launch(2);
+        SPZ_CUDA(cudaGetLastError());
+        SPZ_CUDA(cudaMemcpyAsync(st->scratch.h_result, res, sizeof(double) * kXYBits, cudaMemcpyDeviceToHost, st->stream));
+        SPZ_CUDA(cudaStreamSynchronize(st->stream));
+        for (int b = 0; b < tb; ++b)
+            if ((a.tmask >> b) & 1u) value[tile_qubit[b]] = st->scratch.h_result[b];
+        return SPZ_OK;
+    };
+    const int low_bits = std::min(n, kXYBits);
+    if (want & ((1ull << low_bits) - 1ull)) { // the targets inside one tile of contiguous amplitudes
+        XYArgs a{};
+        a.L = low_bits; a.H = 0;
+        a.tmask = (unsigned)(want & ((1ull << low_bits) - 1ull));
+        int tq[kXYBits];
+        for (int b = 0; b < kXYBits; ++b) tq[b] = b;
+        SPZ_TRY(run(a, tq));
+    }
+    std::vector<int> high;
+    for (int q = low_bits; q < n; ++q) if ((want >> q) & 1ull) high.push_back(q);
+    for (size_t i = 0; i < high.size(); i += 6) { // six high qubits per pass, on top of 64 contiguous amplitudes
+        XYArgs a{};
+        a.L = 6;
+        a.H = (int)std::min<size_t>(6, high.size() - i);
+        int tq[kXYBits] = {0};
+        for (int h = 0; h < a.H; ++h) { a.high[h] = (unsigned char)high[i + h]; tq[a.L + h] = high[i + h]; a.tmask |= 1u << (a.L + h); }
+        SPZ_TRY(run(a, tq));
+    }
+    for (int i = 0; i < k; ++i) out[i] = value[targets[i]];
     return SPZ_OK;
 }
 

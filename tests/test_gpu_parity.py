@@ -397,6 +397,17 @@ def test_prob0_norm_expectations(n):
         assert np.max(np.abs(np.array(got) - orc.xyz_expectation_value("z", cpu, list(range(n))))) < 1e-12
         with pytest.raises(sb.SpinozaError):
             sb.xyz_expectation_value("z", gpu, [0, n])
+    if 7 <= n <= 19:  # 'x' / 'y' on three or more targets: tiles staged in shared memory, up to twelve targets per read pass
+        every = list(range(n))
+        for obs in "xy":
+            before = sb.launch_count()
+            got = sb.xyz_expectation_value(obs, gpu, every)
+            assert sb.launch_count() - before == 2 * (1 + (max(0, n - 12) + 5) // 6)   # (pass + final sum) per group of targets
+            assert np.max(np.abs(np.array(got) - orc.xyz_expectation_value(obs, cpu, every))) < 1e-12, obs
+        mixed = [n - 1, 0, n - 1, 3, n - 2]           # duplicates and any order
+        assert np.max(np.abs(np.array(sb.xyz_expectation_value("y", gpu, mixed)) - orc.xyz_expectation_value("y", cpu, mixed))) < 1e-12
+        with pytest.raises(sb.SpinozaError):
+            sb.xyz_expectation_value("x", gpu, [0, 1, n])
     re, im = gpu.download()  # reductions must not modify the state (the reference clones, core.rs:227)
     assert np.array_equal(re, cpu.reals) and np.array_equal(im, cpu.imags)
 
