@@ -173,7 +173,7 @@ int reduce_z_all(spz_state *st, double *out) {
 }
 
 // ---- <X_t> / <Y_t> for up to twelve qubits at once (kernels_xyall.cuh) ------------------------------------------------
-__global__ void __launch_bounds__(kXYThreads) k_xy_all(const XYArgs a) {
+__global__ void __launch_bounds__(kXYThreads, 2) k_xy_all(const XYArgs a) {
     extern __shared__ __align__(16) unsigned char xy_smem[];
     double *sre = reinterpret_cast<double *>(xy_smem);
     double *sim = sre + (1u << (a.L + a.H));
