@@ -121,6 +121,40 @@ def zall(tmp):
     return 0 if r.returncode == 0 and "ERROR" not in r.stderr and "runtime error" not in r.stderr else 1
 
 
+XY_DRIVER = r'''
+import ctypes as C, sys
+import numpy as np
+h = C.CDLL(sys.argv[1])
+h.emu_xy_tile.restype = C.c_int
+h.emu_xy_tile.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_void_p]
+rng = np.random.default_rng(2)
+cnt = 0
+cases = [(7, 7, []), (8, 8, []), (11, 11, []), (12, 12, []), (13, 12, []), (13, 6, [6]), (14, 6, [9, 13]), (15, 6, [6, 7, 8, 9, 10, 11]),
+         (16, 6, [12, 13, 14, 15]), (15, 6, [8, 10, 12, 13, 14])]
+for n, L, high in cases:
+    # exact-size buffers: any read past the state is an ASan report
+    re = np.ascontiguousarray(rng.random(1 << n)); im = np.ascontiguousarray(rng.random(1 << n))
+    hi = np.array(high + [0] * (8 - len(high)), dtype=np.int32)
+    for obs in (0, 1):
+        for grid, threads in ((1, 32), (3, 64)):
+            out = np.zeros(12)
+            tmask = (1 << (L + len(high))) - 1
+            assert h.emu_xy_tile(n, re.ctypes.data, im.ctypes.data, L, len(high), hi.ctypes.data, tmask, obs, grid, threads, out.ctypes.data) == 0
+            cnt += 1
+print("batched <X>/<Y> tiles:", cnt, "sanitised runs, 0 reports")
+'''
+
+
+def xyall(tmp):
+    lib = tmp / "libxyall_emu_asan.so"
+    subprocess.run([GXX, *COMMON, "-shared", "-fPIC", "-pthread", str(ROOT / "tests/emu/xyall_emu.cpp"), "-o", str(lib)], check=True, cwd=ROOT)
+    asan = subprocess.run(["/usr/bin/gcc", "-print-file-name=libasan.so"], capture_output=True, text=True, check=True).stdout.strip()
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([sys.executable, "-c", XY_DRIVER, str(lib)], env=env, capture_output=True, text=True, timeout=900)
+    print(r.stdout.strip() or r.stderr[-1500:])
+    return 0 if r.returncode == 0 and "ERROR" not in r.stderr and "runtime error" not in r.stderr else 1
+
+
 def direct(tmp):
     lib = tmp / "libdirect_emu_asan.so"
     subprocess.run([GXX, *COMMON, "-shared", "-fPIC", str(ROOT / "tests/emu/direct_emu.cpp"), "-o", str(lib)], check=True, cwd=ROOT)
@@ -134,4 +168,4 @@ def direct(tmp):
 if __name__ == "__main__":
     with tempfile.TemporaryDirectory() as d:
         tmp = Path(d)
-        sys.exit(1 if tile(tmp) + direct(tmp) + zall(tmp) else 0)
+        sys.exit(1 if tile(tmp) + direct(tmp) + zall(tmp) + xyall(tmp) else 0)
